@@ -1,0 +1,200 @@
+"""ctypes binding of libblockcopy_sm100.so (include/blockcopy_b200.h).
+
+This is the only place where the Python package touches native code.  There is no fallback:
+if the library is missing or a call fails, an exception is raised (the reference behaves the
+same way -- its block path asserts CUDA tensors, core/tensorwrapper.py:35).
+
+Every wrapper launches on torch's current stream, exactly as the reference does
+(utils/block_funcs.py:48), never synchronises and never allocates.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libblockcopy_sm100.so")
+
+BC_F16, BC_F32 = 0, 1
+BC_NCHW, BC_NHWC = 0, 1
+
+_lib: Optional[ctypes.CDLL] = None
+
+_vp, _i, _ip = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+_SIGNATURES = {
+    "bc_version": ([], _i),
+    "bc_last_error_string": ([], ctypes.c_char_p),
+    "bc_build_info": ([], ctypes.c_char_p),
+    "bc_set_tma_enabled": ([_i], _i),
+    "bc_compact_mask": ([_vp, _i, _ip, _ip, _ip, _ip, _ip, _vp], _i),
+    "bc_gather": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_scatter": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_copy_blocks": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_transfer": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_gather_halo_tiles": ([_vp, _vp, _vp, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+}
+
+
+class BlockCopyNativeError(RuntimeError):
+    """A libblockcopy_sm100 entry point returned a non-zero status."""
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing. Build it with "
+                "`python blockcopy-video-processing-pytorch_b200/build.py` (nvcc, sm_100a). "
+                "blockcopy has no CPU / eager fallback."
+            )
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the build is stale
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if l.bc_version() != 1:
+            raise ImportError(f"ABI mismatch: library reports version {l.bc_version()}, binding expects 1")
+        _lib = l
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().bc_last_error_string().decode()
+        if rc == -2:
+            # the reference raises AttributeError for shapes that are not divisible by the block size
+            # (core/tensorwrapper.py:351-354)
+            raise AttributeError(f"{what}: {msg}")
+        raise BlockCopyNativeError(f"{what} failed with status {rc}: {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype(t: torch.Tensor) -> int:
+    es = t.element_size()
+    if t.dtype in (torch.float16, torch.bfloat16) or (es == 2 and not t.dtype.is_complex):
+        return BC_F16
+    if es == 4:
+        return BC_F32
+    raise NotImplementedError(t.dtype)  # utils/cuda.py:17-23 raises the same for other dtypes
+
+
+def layout_of(t: torch.Tensor) -> int:
+    """BC_NHWC for channels_last-dense 4-D tensors, BC_NCHW for contiguous ones."""
+    if t.is_contiguous():
+        # a (N,1,H,W) / (N,C,1,1) tensor is both; NCHW is the reference's reading
+        return BC_NCHW
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return BC_NHWC
+    raise AssertionError(f"tensor must be dense NCHW or channels_last, got strides {t.stride()}")
+
+
+def set_tma_enabled(flag: bool):
+    _check(lib().bc_set_tma_enabled(int(flag)), "bc_set_tma_enabled")
+
+
+def build_info() -> str:
+    return lib().bc_build_info().decode()
+
+
+def _dev(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise AssertionError("blockcopy kernels need CUDA tensors (there is no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------- index
+def compact_mask(grid_u8: torch.Tensor, grid_idx: torch.Tensor, mapping_exec: torch.Tensor,
+                 counts: torch.Tensor, prev_grid_idx: Optional[torch.Tensor] = None,
+                 transfer_idx: Optional[torch.Tensor] = None):
+    _dev(grid_u8, grid_idx, mapping_exec, counts)
+    assert grid_u8.dtype in (torch.uint8, torch.bool) and grid_u8.is_contiguous()
+    G = grid_u8.numel()
+    assert grid_idx.numel() >= G and mapping_exec.numel() >= G and counts.numel() >= 2
+    _check(lib().bc_compact_mask(grid_u8.data_ptr(), G, grid_idx.data_ptr(), mapping_exec.data_ptr(),
+                                 counts.data_ptr(),
+                                 prev_grid_idx.data_ptr() if prev_grid_idx is not None else None,
+                                 transfer_idx.data_ptr() if transfer_idx is not None else None, _stream()),
+           "bc_compact_mask")
+
+
+# ------------------------------------------------------------------------------------------- movement
+def gather(blocks: torch.Tensor, image: torch.Tensor, mapping_exec: torch.Tensor, E: int):
+    _dev(blocks, image, mapping_exec)
+    N, C, H, W = image.shape
+    BS = blocks.shape[-1]
+    lay = layout_of(image)
+    assert E == 0 or layout_of(blocks) == lay or C == 1, "tiles and plane must share a layout"
+    _check(lib().bc_gather(blocks.data_ptr(), image.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS,
+                           _dtype(image), lay, _stream()), "bc_gather")
+    return blocks
+
+
+def scatter(blocks: torch.Tensor, image: torch.Tensor, mapping_exec: torch.Tensor, E: int):
+    _dev(blocks, image, mapping_exec)
+    N, C, H, W = image.shape
+    BS = blocks.shape[-1]
+    lay = layout_of(image)
+    assert E == 0 or layout_of(blocks) == lay or C == 1, "tiles and plane must share a layout"
+    _check(lib().bc_scatter(blocks.data_ptr(), image.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS,
+                            _dtype(image), lay, _stream()), "bc_scatter")
+    return image
+
+
+def copy_blocks(out: torch.Tensor, prev: torch.Tensor, blocks: torch.Tensor, grid_idx: torch.Tensor):
+    _dev(out, prev, blocks, grid_idx)
+    N, C, H, W = out.shape
+    BS = blocks.shape[-1]
+    lay = layout_of(out)
+    assert layout_of(prev) == lay and prev.shape == out.shape
+    _check(lib().bc_copy_blocks(out.data_ptr(), prev.data_ptr(), blocks.data_ptr() if blocks.numel() else None,
+                                grid_idx.data_ptr(), N, C, H, W, BS, _dtype(out), lay, _stream()),
+           "bc_copy_blocks")
+    return out
+
+
+def transfer(out: torch.Tensor, prev_exec: torch.Tensor, prev_transfer: torch.Tensor,
+             transfer_idx: torch.Tensor, G: int, padding: int):
+    _dev(out, prev_exec, prev_transfer, transfer_idx)
+    T, C, BS, _ = out.shape
+    lay = layout_of(out) if T > 0 else BC_NCHW
+    _check(lib().bc_transfer(out.data_ptr(), prev_exec.data_ptr(),
+                             prev_transfer.data_ptr() if prev_transfer.numel() else None,
+                             transfer_idx.data_ptr(), transfer_idx.numel(), G, C, BS, padding, _dtype(out), lay,
+                             _stream()), "bc_transfer")
+    return out
+
+
+def gather_halo_tiles(out: torch.Tensor, exec_t: torch.Tensor, transfer_t: torch.Tensor, grid_idx: torch.Tensor,
+                      mapping_exec: torch.Tensor, E: int, pad: int):
+    _dev(out, exec_t, transfer_t, grid_idx, mapping_exec)
+    N, _, GH, GW = grid_idx.shape
+    _, C, BS, _ = exec_t.shape
+    lay = layout_of(exec_t) if E > 0 else BC_NCHW
+    _check(lib().bc_gather_halo_tiles(out.data_ptr(), exec_t.data_ptr(),
+                                      transfer_t.data_ptr() if transfer_t.numel() else None,
+                                      grid_idx.data_ptr(), mapping_exec.data_ptr(), E, N, C, GH, GW, BS, pad,
+                                      _dtype(out), lay, _stream()), "bc_gather_halo_tiles")
+    return out
+
+
+def gather_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Tensor, E: int, BS: int, pad: int):
+    _dev(out, plane, mapping_exec)
+    N, C, H, W = plane.shape
+    lay = layout_of(plane)
+    assert E == 0 or layout_of(out) == lay or C == 1
+    _check(lib().bc_gather_halo(out.data_ptr(), plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS, pad,
+                                _dtype(plane), lay, _stream()), "bc_gather_halo")
+    return out

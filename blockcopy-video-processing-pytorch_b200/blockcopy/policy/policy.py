@@ -1,0 +1,281 @@
+"""Block-execution policies (reference policy/policy.py:14-370).
+
+A policy maps ``policy_meta`` (inputs, previous outputs, frame state, previous grid) to a boolean
+execution grid ``(N,1,GH,GW)``; ``Policy`` is the plug-in interface -- consumers either build one
+from the settings dict or assign ``model.policy = MyPolicy(...)``.  ``forward`` must set ``grid``
+and call ``self.stats.add_policy_meta``; ``optim`` is called once per frame after the model ran.
+
+Numerics follow SURVEY.md A.5: Bernoulli sampling of the logits, executed-block count rounded UP
+to a multiple of ``int(G/16)`` with Python's ``random`` module (so that ``random.seed`` reproduces
+the reference's masks), REINFORCE with reward = information gain + gamma * s|s|,
+s = -(running_cost - target), RMSprop.
+"""
+import abc
+import logging
+import random
+from abc import abstractmethod
+
+import torch
+import torch.nn.functional as F
+from torch.distributions import Bernoulli
+
+from blockcopy.policy.information_gain import InformationGain, InformationGainObjectDetection, InformationGainSemSeg
+from blockcopy.policy.net import PolicyNet, build_policy_net_from_settings
+from blockcopy.utils.profiler import timings
+
+
+def build_policy_from_settings(settings: dict):
+    """Policy object for ``settings['block_policy']`` in {all, none, random, rl_semseg, rl_objectdetection}."""
+    name = settings["block_policy"]
+    logging.info(f"> Policy: {name} with execution percentage target {settings['block_target']} "
+                 f"and block size {settings['block_size']}")
+    quantize = 1 / 16
+    common = dict(block_size=settings["block_size"], verbose=settings["block_policy_verbose"])
+    if name == "all":
+        return PolicyAll(**common)
+    if name == "none":
+        return PolicyNone(**common)
+    if name == "random":
+        return PolicyRandom(quantize_number_exec=quantize, **common)
+    if name.startswith("rl_"):
+        net = build_policy_net_from_settings(settings)
+        optimizer = build_policy_optimizer_from_settings(settings, net)
+        if name == "rl_semseg":
+            ig = InformationGainSemSeg(num_classes=settings["block_num_classes"])
+        elif name == "rl_objectdetection":
+            ig = InformationGainObjectDetection(num_classes=settings["block_num_classes"])
+        else:
+            raise AttributeError(f'Policy with name "{name}" not defined!')
+        return PolicyTrainRL(block_target=settings["block_target"], cost_momentum=settings["block_cost_momentum"],
+                             optimizer=optimizer, complexity_weight=settings["block_complexity_weight"],
+                             quantize_number_exec=quantize, policy_net=net, information_gain=ig, **common)
+    raise NotImplementedError(f"Policy {name} not implemented")
+
+
+def build_policy_optimizer_from_settings(settings: dict, net: PolicyNet) -> torch.optim.Optimizer:
+    return torch.optim.RMSprop(net.parameters(), lr=settings["block_optim_lr"],
+                               weight_decay=settings["block_optim_wd"], centered=False,
+                               momentum=settings["block_optim_momentum"])
+
+
+class PolicyStats:
+    """Running executed-block fraction; also fills num_exec / num_total / perc_exec of policy_meta."""
+
+    def __init__(self):
+        self.count_images = 0
+        self.exec = 0
+        self.total = 0
+
+    def add_policy_meta(self, policy_meta: dict) -> dict:
+        grid = policy_meta["grid"]
+        num_exec = getattr(grid, "_bc_num_exec", None)  # host-generated grids carry their count
+        if num_exec is None:
+            num_exec = int(grid.sum())                 # the one host sync per frame
+            try:
+                grid._bc_num_exec = num_exec           # reused by TensorWrapper.to_blocks
+            except AttributeError:
+                pass
+        num_total = int(grid.numel())
+        policy_meta["num_exec"] = num_exec
+        policy_meta["num_total"] = num_total
+        policy_meta["perc_exec"] = float(num_exec) / num_total
+        self.count_images += grid.size(0)
+        self.exec += num_exec
+        self.total += num_total
+        return policy_meta
+
+    def get_exec_percentage(self):
+        return float(self.exec) / self.total
+
+    def __repr__(self) -> str:
+        return f"Policy stats: average exec percentage [0 - 1] : {self.get_exec_percentage():0.3f}"
+
+
+class Policy(torch.nn.Module, metaclass=abc.ABCMeta):
+    """Plug-in interface for execution policies."""
+
+    def __init__(self, block_size, verbose=False, quantize_number_exec=0):
+        super().__init__()
+        self.block_size = block_size
+        self.net = None
+        self.optimizer = None
+        self.verbose = verbose
+        self.stats = PolicyStats()
+        self.fp16_enabled = False
+        self.quantize_number_exec = quantize_number_exec
+
+    def is_trainable(self):
+        return self.net is not None
+
+    def _grid_shape(self, policy_meta: dict):
+        N, C, H, W = policy_meta["inputs"].shape
+        assert H % self.block_size == 0, f"input height ({H}) not a multiple of block size {self.block_size}!"
+        assert W % self.block_size == 0, f"input width  ({W}) not a multiple of block size {self.block_size}!"
+        return (N, 1, H // self.block_size, W // self.block_size)
+
+    def quantize_number_exec_grid(self, grid: torch.Tensor) -> torch.Tensor:
+        """Round the number of executed blocks UP to a multiple of ``quantize_number_exec * G`` by
+        switching on randomly chosen skipped blocks (bounded set of tile-batch shapes => bounded
+        set of CUDA graphs / cuDNN plans).  Uses ``random.sample`` like the reference
+        (policy.py:124-144), so seeding ``random`` reproduces its choice."""
+        if self.quantize_number_exec > 0:
+            with timings.env("policy/quantize_number_exec", 3):
+                flat = grid.flatten()
+                skipped = torch.nonzero(~flat.bool().cpu()).squeeze(1).tolist()
+                total = flat.numel()
+                num_exec = total - len(skipped)
+                multiple = int(total * self.quantize_number_exec)
+                target = multiple * (1 + (num_exec - 1) // multiple)
+                extra = random.sample(skipped, target - num_exec)
+                if extra:
+                    flat[torch.as_tensor(extra, device=grid.device, dtype=torch.long)] = 1
+                grid._bc_num_exec = target  # counted on the host just now: saves the device round trip
+        return grid
+
+    @abstractmethod
+    def forward(self, policy_meta: dict) -> dict:
+        raise NotImplementedError
+
+    def optim(self, policy_meta, train=True, **kwargs):
+        return policy_meta
+
+
+class PolicyAll(Policy):
+    """Execute every block of every frame."""
+
+    def forward(self, policy_meta: dict) -> dict:
+        shape = self._grid_shape(policy_meta)
+        grid = torch.ones(shape, device=policy_meta["inputs"].device, dtype=torch.bool)
+        grid._bc_num_exec = grid.numel()  # known on the host: no device round trip
+        policy_meta["grid"] = grid
+        return self.stats.add_policy_meta(policy_meta)
+
+
+class PolicyNone(Policy):
+    """Execute nothing once a previous output exists (the first TWO frames run fully: the test is
+    on ``outputs_prev``, reference policy.py:189)."""
+
+    def forward(self, policy_meta: dict) -> dict:
+        shape = self._grid_shape(policy_meta)
+        first = policy_meta.get("outputs_prev", None) is None
+        grid = torch.full(shape, bool(first), device=policy_meta["inputs"].device, dtype=torch.bool)
+        grid._bc_num_exec = grid.numel() if first else 0
+        policy_meta["grid"] = grid
+        return self.stats.add_policy_meta(policy_meta)
+
+
+class PolicyRandom(Policy):
+    """Each block executes with probability 1/2 (then quantised); first two frames run fully."""
+
+    def forward(self, policy_meta: dict) -> dict:
+        shape = self._grid_shape(policy_meta)
+        dev = policy_meta["inputs"].device
+        if policy_meta.get("outputs_prev", None) is None:
+            grid = torch.ones(shape, device=dev).type(torch.bool)
+        else:
+            grid = (torch.randn(shape, device=dev) > 0).type(torch.bool)
+        policy_meta["grid"] = self.quantize_number_exec_grid(grid)
+        return self.stats.add_policy_meta(policy_meta)
+
+
+class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
+    """REINFORCE policy trained online at test time (reference policy.py:219-370)."""
+
+    def __init__(self, block_size: int, block_target: float, optimizer: torch.optim.Optimizer,
+                 complexity_weight: float, policy_net: PolicyNet, information_gain: InformationGain,
+                 cost_momentum: float = 0.9, at_least_one: bool = False, quantize_number_exec: float = 0,
+                 verbose: bool = False):
+        super().__init__(block_size, verbose, quantize_number_exec)
+        assert 0 <= block_target <= 1
+        self.block_target = block_target
+        self.information_gain = information_gain
+        self.momentum = cost_momentum
+        self.running_cost = None
+        self.net = policy_net
+        self.complexity_weight_gamma = complexity_weight
+        self.optimizer = optimizer
+        self.at_least_one = at_least_one
+
+    def forward(self, policy_meta: dict):
+        shape = self._grid_shape(policy_meta)
+        if policy_meta["outputs"] is None:
+            # no temporal history yet: execute everything
+            grid = torch.ones(shape, device=policy_meta["inputs"].device, dtype=torch.bool)
+            grid._bc_num_exec = grid.numel()
+            policy_meta["grid"] = grid
+        else:
+            with torch.enable_grad():
+                with timings.env("policy/net", 3):
+                    assert self.net.training
+                    grid_logits = self.net(policy_meta)
+                    assert torch.all(~torch.isnan(grid_logits)), \
+                        "Policy net returned NaN's, maybe optimization problem?"
+                with timings.env("policy/sample", 3):
+                    dist = Bernoulli(logits=grid_logits)
+                    grid = dist.sample()
+                if self.at_least_one and grid.sum() == 0:
+                    grid[0, 0, 0, 0] = 1
+                grid = self.quantize_number_exec_grid(grid)
+                policy_meta["grid_log_probs"] = dist.log_prob(grid)
+                policy_meta["grid_probs"] = dist.probs
+                assert grid.dim() == 4 and dist.probs.shape == grid.shape
+                hint = getattr(grid, "_bc_num_exec", None)
+                grid = grid.bool()
+                if hint is not None:
+                    grid._bc_num_exec = hint
+                policy_meta["grid"] = grid
+        return self.stats.add_policy_meta(policy_meta)
+
+    def _get_information_gain(self, policy_meta: dict) -> torch.Tensor:
+        with timings.env("policy/information_gain", 3):
+            ig = self.information_gain(policy_meta)
+            assert ig.dim() == 4
+            return ig
+
+    def _get_reward_complexity(self, policy_meta: dict) -> float:
+        s = -float(self.running_cost - self.block_target)
+        return s * abs(s)
+
+    def optim(self, policy_meta: dict, train=True) -> dict:
+        policy_meta["output_repr"] = self.information_gain.get_output_repr(policy_meta)
+        grid = policy_meta["grid"]
+        assert grid.dim() == 4
+        block_use = policy_meta["perc_exec"]
+        if self.running_cost is None:
+            self.running_cost = block_use
+        self.running_cost = self.running_cost * self.momentum + (1 - self.momentum) * block_use
+
+        if policy_meta["outputs_prev"] is not None and train:
+            with torch.enable_grad():
+                ig = self._get_information_gain(policy_meta)
+                policy_meta["information_gain"] = ig
+                reward_complexity_weighted = self._get_reward_complexity(policy_meta) * self.complexity_weight_gamma
+                reward = ig + reward_complexity_weighted
+                assert reward.dim() == 4
+                assert not torch.any(torch.isnan(reward))
+                log_probs = policy_meta["grid_log_probs"]
+                reward = F.adaptive_max_pool2d(reward, output_size=log_probs.shape[2:])
+                reward = torch.where(grid, reward, -reward)  # skipped blocks: negated reward
+                loss_policy = (-log_probs * reward.detach()).mean()
+                assert not torch.isnan(loss_policy)
+                with timings.env("policy/optimizer_backward", 3):
+                    loss_policy.backward()
+                with timings.env("policy/optimizer_step", 3):
+                    self.optimizer.step()
+                    self.optimizer.zero_grad(set_to_none=True)
+
+                if self.verbose or self.stats.count_images > 300:
+                    exec_mean = policy_meta["grid_probs"][grid].mean()
+                    skip_mean = policy_meta["grid_probs"][~grid].mean()
+                    if self.verbose:
+                        print(f"BLOCKS/running_cost: {self.running_cost: 0.3f} \n"
+                              f"BLOCKS/block_use: {block_use:0.3f} \n"
+                              f"BLOCKS/information_gain_max: {ig.max()} \n"
+                              f"BLOCKS/information_gain_min: {ig.min()} \n"
+                              f"BLOCKS/reward_complexity_weighted: {reward_complexity_weighted} \n"
+                              f"BLOCKS/avg_prob_exec: {exec_mean:0.3f} \n"
+                              f"BLOCKS/avg_prob_skip: {skip_mean:0.3f} \n")
+                        print(self.stats)
+                    if self.stats.count_images > 300 and exec_mean - skip_mean < 0.3:
+                        print("Warning: Block execution policy seems not well trained yet.")
+        return policy_meta

@@ -1,0 +1,172 @@
+// bc_api.cu -- extern "C" entry points of libblockcopy_sm100.so (include/blockcopy_b200.h):
+// argument validation, SIMT/TMA path selection, error text.  No torch headers anywhere.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "bc_move.cuh"
+#include "bc_tma.cuh"
+
+namespace bc {
+
+static thread_local char g_err[512] = "no error";
+static std::atomic<int> g_tma_enabled{1};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char *what) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) return BC_OK;
+  cudaGetLastError();  // clear the sticky launch-configuration error
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return (int)e;
+}
+
+int launch_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *mapping_exec, int32_t *counts,
+                        const int32_t *prev_grid_idx, int32_t *transfer_idx, cudaStream_t s);
+
+static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
+
+}  // namespace bc
+
+using namespace bc;
+
+extern "C" {
+
+BC_API int bc_version(void) { return BC_ABI_VERSION; }
+
+BC_API const char *bc_last_error_string(void) { return g_err; }
+
+BC_API const char *bc_build_info(void) {
+  return "libblockcopy_sm100 abi " "1" " | sm_100a | nvcc " __VERSION__ " | built " __DATE__;
+}
+
+BC_API int bc_set_tma_enabled(int enabled) {
+  g_tma_enabled.store(enabled ? 1 : 0);
+  return BC_OK;
+}
+
+BC_API int bc_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *mapping_exec, int32_t *counts,
+                    const int32_t *prev_grid_idx, int32_t *transfer_idx, bc_stream_t stream) {
+  BC_REQUIRE(grid && grid_idx && mapping_exec && counts, BC_ERR_NULL, "bc_compact_mask: NULL pointer");
+  BC_REQUIRE(G > 0, BC_ERR_SHAPE, "bc_compact_mask: G=%d", G);
+  BC_REQUIRE((transfer_idx == nullptr) || (prev_grid_idx != nullptr), BC_ERR_NULL,
+             "bc_compact_mask: transfer_idx requested without prev_grid_idx");
+  BC_REQUIRE(prev_grid_idx != grid_idx, BC_ERR_UNSUPPORTED, "bc_compact_mask: prev_grid_idx must not alias grid_idx");
+  return launch_compact_mask(grid, G, grid_idx, mapping_exec, counts, prev_grid_idx, transfer_idx,
+                             (cudaStream_t)stream);
+}
+
+BC_API int bc_gather(void *blocks, const void *image, const int32_t *mapping_exec, int E, int N, int C, int H, int W, int BS,
+              bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_gather: E=%d", E);
+  if (E == 0) return BC_OK;  // reference: no launch when B == 0 (block_funcs.py:33)
+  BC_REQUIRE(blocks && image && mapping_exec, BC_ERR_NULL, "bc_gather: NULL pointer");
+  const int es = elem_size(dtype);
+  MoveGeo g;
+  const void *ptrs[2] = {blocks, image};
+  int rc = make_geo(g, E, N, C, H, W, BS, BS, 0, es, layout, false, ptrs, 2);
+  if (rc != BC_OK) return rc;
+  if (tma_on() && tma_move_eligible(blocks, image, E, C, W, BS, BS, es, layout))
+    return launch_tma_move(blocks, const_cast<void *>(image), mapping_exec, E, N, C, H, W, BS, 0, BS, es, layout,
+                           false, (cudaStream_t)stream);
+  return launch_gather_simt(blocks, image, mapping_exec, g, false, (cudaStream_t)stream);
+}
+
+BC_API int bc_scatter(const void *blocks, void *image, const int32_t *mapping_exec, int E, int N, int C, int H, int W,
+               int BS, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_scatter: E=%d", E);
+  if (E == 0) return BC_OK;
+  BC_REQUIRE(blocks && image && mapping_exec, BC_ERR_NULL, "bc_scatter: NULL pointer");
+  const int es = elem_size(dtype);
+  MoveGeo g;
+  const void *ptrs[2] = {blocks, image};
+  int rc = make_geo(g, E, N, C, H, W, BS, BS, 0, es, layout, false, ptrs, 2);
+  if (rc != BC_OK) return rc;
+  if (tma_on() && tma_move_eligible(blocks, image, E, C, W, BS, BS, es, layout))
+    return launch_tma_move(const_cast<void *>(blocks), image, mapping_exec, E, N, C, H, W, BS, 0, BS, es, layout, true,
+                           (cudaStream_t)stream);
+  return launch_scatter_simt(blocks, image, mapping_exec, g, (cudaStream_t)stream);
+}
+
+BC_API int bc_copy_blocks(void *out, const void *prev, const void *blocks, const int32_t *grid_idx, int N, int C, int H,
+                   int W, int BS, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(out && prev && grid_idx, BC_ERR_NULL, "bc_copy_blocks: NULL pointer");
+  BC_REQUIRE(out != prev, BC_ERR_UNSUPPORTED, "bc_copy_blocks: out must not alias prev (use bc_scatter in place)");
+  BC_REQUIRE(BS > 0 && H > 0 && W > 0 && H % BS == 0 && W % BS == 0, BC_ERR_SHAPE,
+             "bc_copy_blocks: plane %dx%d / block %d", H, W, BS);
+  const int es = elem_size(dtype);
+  const int G = N * (H / BS) * (W / BS);
+  MoveGeo g;
+  const void *ptrs[3] = {out, prev, blocks ? blocks : out};
+  int rc = make_geo(g, G, N, C, H, W, BS, BS, 0, es, layout, false, ptrs, 3);
+  if (rc != BC_OK) return rc;
+  return launch_copy_blocks_simt(out, prev, blocks, grid_idx, g, (cudaStream_t)stream);
+}
+
+BC_API int bc_transfer(void *out, const void *prev_exec, const void *prev_transfer, const int32_t *transfer_idx, int T, int G,
+                int C, int BS, int padding, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(T >= 0, BC_ERR_SHAPE, "bc_transfer: T=%d", T);
+  if (T == 0) return BC_OK;
+  BC_REQUIRE(out && prev_exec && transfer_idx, BC_ERR_NULL, "bc_transfer: NULL pointer");
+  BC_REQUIRE(G > 0, BC_ERR_SHAPE, "bc_transfer: G=%d", G);
+  const int es = elem_size(dtype);
+  MoveGeo g;
+  // prev_transfer may legitimately be an empty tensor on the second frame (all blocks executed on the first)
+  const void *ptrs[3] = {out, prev_exec, prev_transfer ? prev_transfer : prev_exec};
+  // tile-to-tile: the "plane" extent is irrelevant; describe a 1 x 1 cell grid of edge BS
+  int rc = make_geo(g, T, 1, C, BS, BS, BS, BS, padding, es, layout, true, ptrs, 3);
+  if (rc != BC_OK) return rc;
+  return launch_transfer_simt(out, prev_exec, prev_transfer, transfer_idx, g, G, (cudaStream_t)stream);
+}
+
+BC_API int bc_gather_halo_tiles(void *out, const void *exec, const void *transfer, const int32_t *grid_idx,
+                         const int32_t *mapping_exec, int E, int N, int C, int GH, int GW, int BS, int pad,
+                         bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_gather_halo_tiles: E=%d", E);
+  if (E == 0) return BC_OK;
+  BC_REQUIRE(out && exec && grid_idx && mapping_exec, BC_ERR_NULL, "bc_gather_halo_tiles: NULL pointer");
+  BC_REQUIRE(pad > 0, BC_ERR_SHAPE, "bc_gather_halo_tiles: pad must be > 0 (blockpad.py:32), got %d", pad);
+  BC_REQUIRE(GH > 0 && GW > 0 && N > 0, BC_ERR_SHAPE, "bc_gather_halo_tiles: grid %dx%dx%d", N, GH, GW);
+  const int es = elem_size(dtype);
+  MoveGeo g, src;
+  const void *ptrs[3] = {out, exec, transfer ? transfer : exec};
+  int rc = make_geo(g, E, N, C, GH * BS, GW * BS, BS, BS + 2 * pad, pad, es, layout, true, ptrs, 3);
+  if (rc != BC_OK) return rc;
+  rc = make_geo(src, E, N, C, GH * BS, GW * BS, BS, BS, 0, es, layout, true, ptrs, 3);
+  if (rc != BC_OK) return rc;
+  return launch_halo_tiles_simt(out, exec, transfer, grid_idx, mapping_exec, g, src, N * GH * GW,
+                                (cudaStream_t)stream);
+}
+
+BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_exec, int E, int N, int C, int H, int W,
+                   int BS, int pad, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_gather_halo: E=%d", E);
+  if (E == 0) return BC_OK;
+  BC_REQUIRE(out && plane && mapping_exec, BC_ERR_NULL, "bc_gather_halo: NULL pointer");
+  BC_REQUIRE(pad >= 0, BC_ERR_SHAPE, "bc_gather_halo: pad=%d", pad);
+  const int es = elem_size(dtype);
+  MoveGeo g;
+  const void *ptrs[2] = {out, plane};
+  int rc = make_geo(g, E, N, C, H, W, BS, BS + 2 * pad, pad, es, layout, true, ptrs, 2);
+  if (rc != BC_OK) return rc;
+  if (tma_on() && tma_move_eligible(out, plane, E, C, W, BS, BS + 2 * pad, es, layout))
+    return launch_tma_move(out, const_cast<void *>(plane), mapping_exec, E, N, C, H, W, BS, pad, BS + 2 * pad, es,
+                           layout, false, (cudaStream_t)stream);
+  return launch_gather_simt(out, plane, mapping_exec, g, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// bc_common.cuh -- shared host/device helpers of libblockcopy_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "blockcopy_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libblockcopy_sm100 is written for sm_100a only"
+#endif
+
+namespace bc {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of it
+
+// ------------------------------------------------------------------ errors (thread-local text)
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+int check_launch(const char *what);  // cudaPeekAtLastError -> positive code + message
+
+#define BC_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) return ::bc::fail((code), __VA_ARGS__); \
+  } while (0)
+
+inline int elem_size(int dtype) { return dtype == BC_F16 ? 2 : dtype == BC_F32 ? 4 : 0; }
+
+// ------------------------------------------------------------------ exact division by a runtime constant
+// q = n / d for 0 <= n < 2^31, 1 <= d < 2^31, as one mul.hi + shift (Granlund-Montgomery
+// round-up variant).  All the block kernels decode a flat index into (tile, row, pixel,
+// cell) coordinates; with runtime shapes that would otherwise be ~20-instruction divides.
+struct FastDiv {
+  uint32_t d, mul, shr;
+  FastDiv() : d(1), mul(0), shr(0) {}
+  explicit FastDiv(uint32_t div) : d(div), mul(0), shr(0) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1ull << lg) < div) ++lg;  // ceil(log2(d))
+      const uint32_t p = 31 + lg;
+      mul = (uint32_t)(((1ull << p) + div - 1) / div);
+      shr = p - 32;
+    }
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    return d == 1 ? n : (__umulhi(n, mul) >> shr);
+#else
+    return d == 1 ? n : (uint32_t)(((uint64_t)n * mul) >> 32) >> shr;
+#endif
+  }
+  __host__ __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+// flat cell id -> (n, gh, gw)
+struct CellDecode {
+  FastDiv per_image, per_row;  // GH*GW, GW
+  CellDecode() {}
+  CellDecode(int GH, int GW) : per_image((uint32_t)(GH * GW)), per_row((uint32_t)GW) {}
+  __device__ __forceinline__ void operator()(uint32_t g, uint32_t &n, uint32_t &gh, uint32_t &gw) const {
+    uint32_t r;
+    per_image.divmod(g, n, r);
+    per_row.divmod(r, gh, gw);
+  }
+};
+
+// ------------------------------------------------------------------ vector access of V bytes
+template <int V> struct Vec;
+template <> struct Vec<16> { using T = uint4; };
+template <> struct Vec<8> { using T = uint2; };
+template <> struct Vec<4> { using T = uint32_t; };
+template <> struct Vec<2> { using T = uint16_t; };
+
+template <int V> __device__ __forceinline__ typename Vec<V>::T zero_vec();
+template <> __device__ __forceinline__ uint4 zero_vec<16>() { return make_uint4(0, 0, 0, 0); }
+template <> __device__ __forceinline__ uint2 zero_vec<8>() { return make_uint2(0, 0); }
+template <> __device__ __forceinline__ uint32_t zero_vec<4>() { return 0u; }
+template <> __device__ __forceinline__ uint16_t zero_vec<2>() { return (uint16_t)0; }
+
+// streaming read through the read-only path
+template <int V> __device__ __forceinline__ typename Vec<V>::T ld_stream(const char *p) {
+  return __ldg(reinterpret_cast<const typename Vec<V>::T *>(p));
+}
+template <int V> __device__ __forceinline__ void st_vec(char *p, const typename Vec<V>::T &v) {
+  *reinterpret_cast<typename Vec<V>::T *>(p) = v;
+}
+
+inline int gcd_pow2_bytes(uint64_t a) {  // largest power of two <= 16 dividing a (a > 0)
+  int v = 16;
+  while (v > 1 && (a % (uint64_t)v)) v >>= 1;
+  return v;
+}
+
+}  // namespace bc

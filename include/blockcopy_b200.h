@@ -1,0 +1,148 @@
+/*
+ * blockcopy_b200.h -- C ABI of libblockcopy_sm100.so
+ *
+ * B200 (sm_100a) implementation of BlockCopy's block-sparse execution path.
+ * This header is the drop-in boundary: every entry point replaces one place
+ * where the reference (thomasverelst/blockcopy-video-processing-pytorch) hands
+ * raw device pointers to a JIT-compiled CuPy kernel.  The reference-side stubs
+ * a maintainer would write against it are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, PODs only: device pointers as void*, sizes as int, the CUDA stream
+ *    as an opaque handle (pass torch.cuda.current_stream().cuda_stream, exactly
+ *    what the reference passes at blockcopy/utils/block_funcs.py:48).
+ *  - every function returns 0 on success, a NEGATIVE bc_status for an argument
+ *    error detected on the host (nothing launched), a POSITIVE cudaError_t when
+ *    the CUDA runtime refused the launch.  Nothing throws, nothing synchronises,
+ *    nothing allocates device memory.  bc_last_error_string() describes the last
+ *    failure of the calling thread.
+ *  - the caller owns all buffers.  Outputs are written in place; inputs are
+ *    never modified.  Tensors must be dense in the stated layout.
+ *  - grid conventions are the reference's (core/tensorwrapper.py:108-128):
+ *    cells are numbered row-major over (n, gh, gw); mapping_exec[b] is the cell
+ *    of packed tile b; grid_idx[g] >= 0 is the packed-tile row of an executed
+ *    cell, grid_idx[g] < 0 encodes row grid_idx[g] + N*GH*GW of the "transfer"
+ *    tensor of a skipped cell.
+ */
+#ifndef BLOCKCOPY_B200_H_
+#define BLOCKCOPY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BC_API __attribute__((visibility("default")))
+#else
+#define BC_API
+#endif
+
+typedef void *bc_stream_t; /* cudaStream_t */
+
+typedef enum {
+  BC_F16 = 0, /* 2-byte elements (fp16; bf16 moves through the same path) */
+  BC_F32 = 1  /* 4-byte elements */
+} bc_dtype_t;
+
+typedef enum {
+  BC_NCHW = 0, /* the reference's layout: planes (N,C,H,W), tiles (E,C,BS,BS)      */
+  BC_NHWC = 1  /* B200 product layout: planes (N,H,W,C), tiles (E,BS,BS,C)         */
+} bc_layout_t;
+
+typedef enum {
+  BC_OK = 0,
+  BC_ERR_NULL = -1,      /* required pointer is NULL                               */
+  BC_ERR_SHAPE = -2,     /* H or W not a multiple of BS, non-positive size, ...    */
+  BC_ERR_DTYPE = -3,     /* dtype / layout enum out of range                       */
+  BC_ERR_ALIGN = -4,     /* pointer not aligned to the element size                */
+  BC_ERR_RANGE = -5,     /* problem too large for 32-bit chunk indexing            */
+  BC_ERR_UNSUPPORTED = -6,
+  BC_ERR_NO_DEVICE = -7  /* no sm_100 device / driver entry point missing          */
+} bc_status_t;
+
+/* ---- library ---------------------------------------------------------------- */
+BC_API int bc_version(void);                     /* BC_ABI_VERSION the library was built with */
+BC_API const char *bc_last_error_string(void);   /* thread-local, never NULL                  */
+BC_API const char *bc_build_info(void);          /* "sm_100a nvcc 12.9 ..."                   */
+
+/* ---- index bookkeeping -------------------------------------------------------
+ * Replaces BlockFeatures._process_grid + get_grid_mappings
+ * (core/tensorwrapper.py:150-178, :108-128), which the reference runs on the HOST
+ * (D2H of the grid, CPU TorchScript, three H2D copies).  One single-CTA kernel.
+ *   grid           uint8/bool  [G]   in   (G = N*GH*GW)
+ *   grid_idx       int32       [G]   out
+ *   mapping_exec   int32       [G]   out  (first E entries valid)
+ *   counts         int32       [2]   out  {E, G-E}
+ *   prev_grid_idx  int32       [G]   in   nullable
+ *   transfer_idx   int32       [G]   out  nullable (first G-E entries valid)
+ */
+BC_API int bc_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *mapping_exec,
+                    int32_t *counts, const int32_t *prev_grid_idx, int32_t *transfer_idx,
+                    bc_stream_t stream);
+
+/* ---- active-block gather (no halo) -------------------------------------------
+ * Replaces SplitFunction / split_kernel (utils/block_funcs.py:10-83).
+ *   blocks[b, :, h, w] = image[n, :, gh*BS+h, gw*BS+w],  (n,gh,gw) = cell mapping_exec[b]
+ */
+BC_API int bc_gather(void *blocks, const void *image, const int32_t *mapping_exec, int E, int N, int C,
+              int H, int W, int BS, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream);
+
+/* ---- scatter into the previous frame's plane, in place ------------------------
+ * Replaces CombineFunction / combine_kernel (utils/block_funcs.py:85-158).
+ */
+BC_API int bc_scatter(const void *blocks, void *image, const int32_t *mapping_exec, int E, int N, int C,
+               int H, int W, int BS, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream);
+
+/* ---- copy unchanged blocks from the previous frame, fused with the scatter ----
+ * Replaces the NON-in-place combine (clone + combine_kernel,
+ * core/tensorwrapper.py:421-434): for every cell g of the plane
+ *   out[cell g] = grid_idx[g] >= 0 ? blocks[grid_idx[g]] : prev[cell g]
+ * in one pass; out must not alias prev.
+ */
+BC_API int bc_copy_blocks(void *out, const void *prev, const void *blocks, const int32_t *grid_idx, int N,
+                   int C, int H, int W, int BS, bc_dtype_t dtype, bc_layout_t layout,
+                   bc_stream_t stream);
+
+/* ---- ring transfer from the previous frame's tiles ----------------------------
+ * Replaces TransferFunction / transfer_kernel (utils/block_funcs.py:161-237).
+ * Writes only the border ring of width `padding` of each of the T transferred
+ * tiles (all pixels if padding < 0); interiors of `out` are left untouched.
+ *   G = N*GH*GW of the grid the indices refer to.
+ */
+BC_API int bc_transfer(void *out, const void *prev_exec, const void *prev_transfer,
+                const int32_t *transfer_idx, int T, int G, int C, int BS, int padding,
+                bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream);
+
+/* ---- gather with halo, reference tile protocol --------------------------------
+ * Replaces BlockPadFunction / repad_kernel (utils/blockpad.py:14-156):
+ * (E,C,BS,BS) -> (E,C,BS+2p,BS+2p); halo from the neighbouring cell's tile in
+ * `exec` (grid_idx >= 0) or `transfer` (grid_idx < 0), zeros outside the frame.
+ */
+BC_API int bc_gather_halo_tiles(void *out, const void *exec, const void *transfer, const int32_t *grid_idx,
+                         const int32_t *mapping_exec, int E, int N, int C, int GH, int GW, int BS,
+                         int pad, bc_dtype_t dtype, bc_layout_t layout, bc_stream_t stream);
+
+/* ---- gather with halo from a dense persistent plane (B200 design) -------------
+ * Same result as transfer + repad when the plane holds, for every cell, the most
+ * recently executed tile (proven bit-identical in tests):
+ *   out[b] = zero_pad(plane, p)[n, :, gh*BS : gh*BS+BS+2p, gw*BS : gw*BS+BS+2p]
+ * NHWC + 16-byte-aligned channel runs take the TMA path (cp.async.bulk.tensor
+ * box loads with hardware zero fill -> shared memory -> bulk store).
+ */
+BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_exec, int E, int N, int C,
+                   int H, int W, int BS, int pad, bc_dtype_t dtype, bc_layout_t layout,
+                   bc_stream_t stream);
+
+/* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
+ * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
+ * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */
+BC_API int bc_set_tma_enabled(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOCKCOPY_B200_H_ */

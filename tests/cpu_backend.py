@@ -1,0 +1,90 @@
+"""TEST-ONLY: runs the host logic of the blockcopy package on CPU tensors by rebinding the
+``blockcopy._C`` entry points to the C oracle.  This exists so that the `-m "not gpu"` suite can
+exercise the wrapper / state machine / policy code in a container without a GPU; the product has
+no such path (``_C`` raises on non-CUDA tensors).  Use as a context manager."""
+import contextlib
+
+import torch
+
+from oracle import cpu_oracle as O
+
+
+def _nchw(t):
+    return t.as_subclass(torch.Tensor).contiguous()
+
+
+def _store(dst, src):
+    dst.as_subclass(torch.Tensor).copy_(src)
+
+
+@contextlib.contextmanager
+def cpu_backend():
+    import blockcopy
+    from blockcopy import _C
+    from blockcopy.core import tensorwrapper as tw
+    from blockcopy.core import blockcopy as bcm
+
+    saved = {k: getattr(_C, k) for k in ("compact_mask", "gather", "scatter", "copy_blocks", "transfer",
+                                         "gather_halo_tiles", "gather_halo")}
+    saved_tw = tw.to_tensorwrapper
+
+    def compact_mask(grid_u8, grid_idx, mapping_exec, counts, prev_grid_idx=None, transfer_idx=None):
+        g = grid_u8.view(torch.bool) if grid_u8.dtype == torch.uint8 else grid_u8
+        gi, me = O.grid_mappings(g)
+        grid_idx.copy_(gi.view_as(grid_idx))
+        mapping_exec[: me.numel()].copy_(me)
+        counts[0], counts[1] = me.numel(), g.numel() - me.numel()
+        if transfer_idx is not None:
+            ti = O.transfer_idx(g, prev_grid_idx.contiguous())
+            transfer_idx[: ti.numel()].copy_(ti)
+
+    def gather(blocks, image, mapping_exec, E):
+        if E:
+            _store(blocks, O.split(_nchw(image), mapping_exec[:E].contiguous(), blocks.shape[-1]))
+        return blocks
+
+    def scatter(blocks, image, mapping_exec, E):
+        if E:
+            tmp = _nchw(image).clone()
+            O.combine_(_nchw(blocks), tmp, mapping_exec[:E].contiguous())
+            _store(image, tmp)
+        return image
+
+    def copy_blocks(out, prev, blocks, grid_idx):
+        tmp = _nchw(prev).clone()
+        gi = grid_idx.flatten()
+        cells = torch.nonzero(gi >= 0).squeeze(1).to(torch.int32)
+        if cells.numel():
+            order = gi[cells.long()].long()
+            O.combine_(_nchw(blocks)[order].contiguous(), tmp, cells.contiguous())
+        _store(out, tmp)
+        return out
+
+    def transfer(out, prev_exec, prev_transfer, transfer_idx, G, padding):
+        tmp = _nchw(out).clone()
+        O.transfer(tmp, _nchw(prev_exec), _nchw(prev_transfer), transfer_idx.contiguous(), G, padding)
+        _store(out, tmp)
+        return out
+
+    def gather_halo_tiles(out, exec_t, transfer_t, grid_idx, mapping_exec, E, pad):
+        if E:
+            _store(out, O.repad(_nchw(exec_t), _nchw(transfer_t), grid_idx.contiguous(),
+                                mapping_exec[:E].contiguous(), pad))
+        return out
+
+    def gather_halo(out, plane, mapping_exec, E, BS, pad):
+        if E:
+            _store(out, O.plane_halo(_nchw(plane), mapping_exec[:E].contiguous(), BS, pad))
+        return out
+
+    for k, v in dict(compact_mask=compact_mask, gather=gather, scatter=scatter, copy_blocks=copy_blocks,
+                     transfer=transfer, gather_halo_tiles=gather_halo_tiles, gather_halo=gather_halo).items():
+        setattr(_C, k, v)
+    cpu_tw = lambda x: x.as_subclass(tw.TensorWrapper)  # noqa: E731  (lifts the CUDA assert)
+    tw.to_tensorwrapper = bcm.to_tensorwrapper = blockcopy.to_tensorwrapper = cpu_tw
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            setattr(_C, k, v)
+        tw.to_tensorwrapper = bcm.to_tensorwrapper = blockcopy.to_tensorwrapper = saved_tw

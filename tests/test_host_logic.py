@@ -1,0 +1,274 @@
+"""Host-side logic of the blockcopy package on CPU tensors (kernels rebound to the oracle by
+tests/cpu_backend.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden_cpu.py): wrapper state machine, plane bookkeeping, op interception, policies."""
+import argparse
+import os
+import random
+
+import pytest
+import torch
+
+from cpu_backend import cpu_backend
+
+
+def _settings(**kw):
+    from blockcopy.core.argparser import default_settings
+
+    return default_settings(**kw)
+
+
+# ------------------------------------------------------------------------------------------- API surface
+def test_public_names():
+    import blockcopy
+
+    for n in ("TensorWrapper", "is_block", "is_tensorwrapper", "to_tensorwrapper", "to_tensor", "BlockCopyModel",
+              "blockcopy_noblocks", "add_argparser_arguments", "build_policy_from_settings"):
+        assert hasattr(blockcopy, n), n
+    from blockcopy.utils.profiler import timings  # noqa: F401  consumers import these by path
+    from blockcopy.policy.policy import Policy, PolicyAll, PolicyNone, PolicyRandom, PolicyTrainRL  # noqa: F401
+    from blockcopy.policy.net import PolicyNet  # noqa: F401
+    from blockcopy.utils.block_funcs import CombineFunction, SplitFunction, TransferFunction  # noqa: F401
+    from blockcopy.utils.blockpad import BlockPadFunction, pad  # noqa: F401
+
+
+def test_argparser_flags_and_defaults():
+    import blockcopy
+
+    args = vars(blockcopy.add_argparser_arguments(argparse.ArgumentParser()).parse_args([]))
+    assert args == dict(block_policy="rl_semseg", block_num_classes=19, block_optim_lr=1e-4, block_optim_wd=1e-3,
+                        block_optim_momentum=0, block_target=0.5, block_complexity_weight=5, block_size=128,
+                        block_train_interval=4, block_cost_momentum=0.9, block_policy_verbose=False)
+    with pytest.raises(NotImplementedError):
+        blockcopy.build_policy_from_settings(dict(args, block_policy="static"))
+    with pytest.raises(KeyError):  # every key is read even for non-RL policies
+        blockcopy.build_policy_from_settings(dict(block_policy="random", block_size=128))
+
+
+def test_to_tensor_recurses_and_cuda_assert():
+    import blockcopy
+
+    t = torch.zeros(1, 1, 2, 2)
+    assert blockcopy.to_tensor([t, (t, {"a": t})])[1][1]["a"] is t
+    with pytest.raises(AssertionError):
+        blockcopy.to_tensorwrapper(t)  # CPU tensor: the block path is CUDA only
+
+
+def test_timings_api():
+    from blockcopy.utils.profiler import Timings
+
+    tm = Timings(level=0)
+    with tm.env("a", 1):
+        pass
+    assert "a" not in tm.records and repr(tm) == "## Profiler: no batches registered"
+    tm.set_level(5)
+    tm.add_cnt(2)
+    with tm.env("a", 1):
+        pass
+    assert tm.counts["a"] == 1 and "ms per image" in repr(tm)
+
+
+# ------------------------------------------------------------------------------------------- wrapper semantics
+def test_incompatible_and_error_paths():
+    import blockcopy
+    import torch.nn.functional as F
+
+    with cpu_backend():
+        x = blockcopy.to_tensorwrapper(torch.randn(1, 4, 8, 16))
+        with pytest.raises(AssertionError):
+            x.to_blocks(torch.ones(1, 1, 2, 4, dtype=torch.bool))  # process_temporal_features first
+        x.process_temporal_features(None)
+        with pytest.raises(AssertionError, match="first run should execute all blocks"):
+            x.to_blocks(torch.zeros(1, 1, 2, 4, dtype=torch.bool))
+        st = x.process_temporal_features(None)
+        b = x.to_blocks(torch.ones(1, 1, 2, 4, dtype=torch.bool))
+        assert blockcopy.is_block(b) and b.block_size == 4 and tuple(b.shape) == (8, 4, 4, 4)
+        assert not blockcopy.is_block(x) and x.block_size == -1
+        for bad in (lambda: F.adaptive_avg_pool2d(b, 1), lambda: b.view(8, -1), lambda: b.flip(0)):
+            with pytest.raises(AttributeError, match="not supported for TensorWrapper"):
+                bad()
+        with pytest.raises(AttributeError, match="already split"):
+            b._split(4)
+        with pytest.raises(AttributeError, match="Not split in blocks"):
+            x.combine()
+        with pytest.raises(NotImplementedError, match="equal paddings"):
+            F.conv2d(b, torch.randn(4, 4, 3, 3), None, 1, (1, 0))
+        y = torch.relu(b) + 1
+        assert blockcopy.is_block(y) and y.get_features() is st
+        d = y.combine()
+        assert blockcopy.is_tensorwrapper(d) and not d.is_blocks and tuple(d.shape) == (1, 4, 8, 16)
+        assert type(d.to_tensor()) is torch.Tensor
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_padded_conv_matches_dense_when_all_blocks_execute(channels_last):
+    """With every block executed, halos come from current neighbours, so a padded conv on blocks
+    equals the dense conv (no bilinear involved)."""
+    import blockcopy
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 4, 16, 24, generator=g)
+    w = torch.randn(6, 4, 3, 3, generator=g)
+    if channels_last:
+        img, w = img.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last)
+    with cpu_backend():
+        x = blockcopy.to_tensorwrapper(img)
+        x.process_temporal_features(None)
+        b = x.to_blocks(torch.ones(2, 1, 2, 3, dtype=torch.bool))
+        y = F.max_pool2d(F.conv2d(b, w, None, 1, 1), kernel_size=3, stride=2, padding=1)
+        out = y.combine().to_tensor()
+    ref = F.max_pool2d(F.pad(F.conv2d(img, w, None, 1, 1), (1, 1, 1, 1)), 3, 2, 0)  # zero (not -inf) pool halo
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_group_norm_folds_blocks_into_one_sample():
+    import blockcopy
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 8, 8, 8, generator=g)
+    with cpu_backend():
+        x = blockcopy.to_tensorwrapper(img)
+        x.process_temporal_features(None)
+        b = x.to_blocks(torch.ones(1, 1, 2, 2, dtype=torch.bool))
+        out = F.group_norm(b, 2).combine().to_tensor()
+    assert torch.allclose(out, F.group_norm(img, 2), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------- end to end
+def test_swiftnet_clip_matches_reference(golden_dir):
+    """SwiftNet-RN18 + BlockCopyModel over a seeded 6-frame clip with replayed masks (incl. an
+    empty and a full frame) == the reference's own wrapper on the same weights, fp32 CPU."""
+    import blockcopy
+    from consumers.clips import PolicyReplay, deterministic_init_, synthetic_clip
+    from consumers.swiftnet_rn18 import SwiftNetRN18, fuse_conv_bn_
+
+    fix = torch.load(os.path.join(golden_dir, "swiftnet_cpu_clip.pt"))
+    H, W, BS, T = fix["H"], fix["W"], fix["BS"], fix["T"]
+    net = deterministic_init_(SwiftNetRN18().eval(), seed=fix["init_seed"])
+    model = blockcopy.BlockCopyModel(net, _settings(block_policy="all", block_size=BS)).eval()
+    fuse_conv_bn_(model)
+    model.policy = PolicyReplay(BS, list(fix["grids"].bool()))
+    clip = synthetic_clip(T, H, W, seed=fix["clip_seed"], dtype=torch.float32)
+    with cpu_backend(), torch.no_grad():
+        model.reset_temporal()
+        for t in range(T):
+            out = model(clip[t])
+            assert type(out) is torch.Tensor and tuple(out.shape) == (1, 19, H // 4, W // 4)
+            scale = fix["logits_abs_mean"][t]
+            err = (out[:, :, ::4, ::4] - fix["logits_strided"][t]).abs().max().item()
+            assert err <= 2e-4 * scale, (t, err, scale)
+            agree = (out.argmax(1).to(torch.uint8) == fix["argmax"][t]).float().mean().item()
+            assert agree >= 0.9999, (t, agree)
+            if t in fix["logits_full"]:
+                assert torch.allclose(out, fix["logits_full"][t], atol=2e-4 * scale, rtol=0)
+            fs = model.policy_meta["frame_state"]
+            assert abs(float(fs.double().sum()) - fix["frame_state_sum"][t]) < 1e-3
+            if model.policy_meta["num_exec"] == 0:
+                assert out is model.policy_meta["outputs_prev"], "num_exec == 0 returns the previous output object"
+    # 21 padded-op planes + 3 combine points (SURVEY.md 3.2 [probe])
+    assert len(model.block_temporal_features._planes) == 21
+    assert len(model.block_temporal_features._full) == 3
+
+
+def test_reference_state_dict_names():
+    """Consumer model is state_dict-compatible with the reference SwiftNet (names from
+    lib/models/swiftnet: backbone.*, spp.spp.*, upsample.N.{bottleneck,blend_conv}.*, logits.*)."""
+    from consumers.swiftnet_rn18 import SwiftNetRN18
+
+    keys = set(SwiftNetRN18().state_dict())
+    for k in ("backbone.conv1.weight", "backbone.layer2.0.downsample.0.weight", "backbone.layer4.1.bn2.running_var",
+              "spp.spp.spp_bn.norm.weight", "spp.spp.spp2.conv.weight", "spp.spp.spp_fuse.conv.weight",
+              "upsample.0.bottleneck.conv.weight", "upsample.2.blend_conv.norm.bias", "logits.conv.bias"):
+        assert k in keys, k
+
+
+# ------------------------------------------------------------------------------------------- policies
+def test_policy_first_frames_and_quantisation():
+    import blockcopy
+
+    x = torch.zeros(1, 3, 512, 1024)
+    random.seed(0)
+    torch.manual_seed(0)
+    pol = blockcopy.build_policy_from_settings(_settings(block_policy="random"))
+    meta = pol({"inputs": x, "outputs": None, "outputs_prev": None})
+    assert meta["num_exec"] == 32 and meta["grid"].dtype == torch.bool and tuple(meta["grid"].shape) == (1, 1, 4, 8)
+    meta.update(outputs=1, outputs_prev=None)
+    assert pol(meta)["num_exec"] == 32          # `random` / `none`: the first TWO frames run fully
+    meta.update(outputs_prev=1)
+    for _ in range(5):
+        meta = pol(meta)
+        assert meta["num_exec"] % 2 == 0        # rounded up to a multiple of int(32/16)
+        assert meta["num_exec"] == int(meta["grid"].sum()) and meta["perc_exec"] == meta["num_exec"] / 32
+    none = blockcopy.build_policy_from_settings(_settings(block_policy="none"))
+    assert none({"inputs": x, "outputs_prev": 1})["num_exec"] == 0
+    with pytest.raises(ZeroDivisionError):      # fewer than 16 blocks: same failure as the reference
+        blockcopy.build_policy_from_settings(_settings(block_policy="random"))(
+            {"inputs": torch.zeros(1, 3, 256, 256), "outputs_prev": 1})
+    with pytest.raises(AssertionError, match="multiple of block size"):
+        none({"inputs": torch.zeros(1, 3, 100, 256)})
+
+
+def test_quantisation_reproduces_reference_choice():
+    """random.sample over the skipped cells, seeded: same cells as policy.py:136-143."""
+    from blockcopy.policy.policy import PolicyRandom
+
+    pol = PolicyRandom(block_size=128, quantize_number_exec=1 / 16)
+    g = torch.Generator().manual_seed(3)
+    grid = torch.rand(1, 1, 8, 16, generator=g) < 0.27
+    random.seed(11)
+    skipped = torch.nonzero(~grid.flatten()).squeeze(1).tolist()
+    n = int(grid.sum())
+    want = 8 * (1 + (n - 1) // 8)
+    expect = grid.clone()
+    expect.flatten()[random.sample(skipped, want - n)] = True
+    random.seed(11)
+    got = pol.quantize_number_exec_grid(grid.clone())
+    assert torch.equal(got, expect) and int(got.sum()) == want
+
+
+def test_policy_net_and_information_gain_match_reference(golden_dir):
+    from blockcopy.policy.information_gain import InformationGainSemSeg
+    from blockcopy.policy.net import PolicyNet
+    from consumers.clips import deterministic_init_
+
+    fix = torch.load(os.path.join(golden_dir, "policy_cpu.pt"))
+    g = torch.Generator().manual_seed(fix["input_seed"])
+    N, H, W, BS, K = 1, 256, 512, fix["BS"], fix["K"]
+    meta = dict(inputs=torch.randn(N, 3, H, W, generator=g), frame_state=torch.randn(N, 3, H, W, generator=g),
+                output_repr=torch.randn(N, K, H // 4, W // 4, generator=g),
+                grid=torch.rand(N, 1, H // BS, W // BS, generator=g) < 0.4)
+    ig_meta = dict(outputs=torch.randn(N, K, H // 4, W // 4, generator=g),
+                   outputs_prev=torch.randn(N, K, H // 4, W // 4, generator=g))
+    net = deterministic_init_(PolicyNet(block_size=BS, task_num_classes=K), seed=fix["init_seed"]).train()
+    assert sum(p.numel() for p in PolicyNet(128, 19).parameters()) == 611211  # SURVEY.md 8(a) a14 [probe]
+    with torch.no_grad():
+        logits = net(meta)
+    assert torch.allclose(logits, fix["logits"], atol=1e-4, rtol=1e-4)
+    assert torch.allclose(InformationGainSemSeg(K)(ig_meta), fix["ig"], atol=1e-6, rtol=1e-5)
+
+
+def test_rl_policy_trains_online():
+    """rl_semseg end to end on CPU: Bernoulli masks, REINFORCE step every train_interval frames."""
+    import blockcopy
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+    from consumers.clips import synthetic_clip
+
+    random.seed(0)
+    torch.manual_seed(0)
+    model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), _settings(block_policy="rl_semseg", block_size=64,
+                                                                    block_train_interval=2, block_optim_lr=1e-3)).eval()
+    model.policy.net.train()
+    before = [p.detach().clone() for p in model.policy.net.parameters()]
+    clip = synthetic_clip(5, 256, 512, seed=1, dtype=torch.float32)
+    with cpu_backend(), torch.no_grad():
+        model.reset_temporal()
+        for f in clip:
+            out = model(f)
+    meta = model.policy_meta
+    for k in ("inputs", "outputs", "outputs_prev", "grid", "num_exec", "num_total", "perc_exec", "frame_state",
+              "output_repr", "grid_log_probs", "grid_probs", "information_gain"):
+        assert k in meta, k
+    assert tuple(meta["information_gain"].shape) == (1, 1, 16, 32) and tuple(out.shape) == (1, 19, 64, 128)
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.policy.net.parameters())), "policy did not train"
+    assert 0 < model.policy.stats.get_exec_percentage() <= 1
