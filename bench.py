@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: frames/s of SwiftNet-RN18 + BlockCopy at 1024x2048 with
+~30 % active blocks on B200(s), plus the HBM roofline of the dominant block kernel and the
+reference's CPU path timed beside it.  Prints ONE JSON line (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo (CUDA, C ABI)
+    python bench.py --impl reference ...                         # reference arm: dense SwiftNet, CPU torch
+    python bench.py --microbench                                 # block kernels only (ncu target)
+
+A "step" is one frame of every stream the rank owns, through blockcopy.BlockCopyModel (policy ->
+gather -> block-sparse SwiftNet -> combine).  Streams are independent; ranks never communicate
+on the data path (weak scaling: --streams-per-gpu is fixed).  Frames cycle through a seeded
+30-frame synthetic clip; frame 0 of each clip executes every block (API contract), the others
+exactly 40 of 128 blocks (30 % rounded up to the reference's multiple of 8), masks seeded and
+generated on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "blockcopy-video-processing-pytorch_b200")
+sys.path.insert(0, PKG)
+
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=90)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--fraction", type=float, default=0.3)
+    ap.add_argument("--clip-length", type=int, default=30)
+    ap.add_argument("--streams-per-gpu", type=int, default=1)
+    ap.add_argument("--policy", default="fixed", choices=["fixed", "rl_semseg"])
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA graphs")
+    ap.add_argument("--microbench", action="store_true", help="only the block-kernel microbenchmarks")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# =============================================================================================== helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+def max_over_ranks(value: float, world: int, device) -> float:
+    if world == 1:
+        return value
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, world: int, device) -> float:
+    if world == 1:
+        return value
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# =============================================================================================== workload
+def build_model(args, device):
+    import blockcopy
+    from blockcopy.core.argparser import default_settings
+    from consumers.clips import PolicyFixedFraction
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    settings = default_settings(block_policy="rl_semseg" if args.policy == "rl_semseg" else "all",
+                                block_target=args.fraction, block_train_interval=3)
+    if not args.no_graphs:
+        settings["block_cuda_graphs"] = True
+    model = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), settings).eval().to(device).half()
+    if args.policy == "fixed":
+        model.policy = PolicyFixedFraction(128, fraction=args.fraction, quantize=8, seed=0)
+    else:
+        model.policy.net = model.policy.net.float().train()
+    return model
+
+
+def run_frames(models, clips, start, count, clip_len, h2d_stream=None, host_clips=None, d2h_buf=None):
+    """Advance every stream by `count` frames starting at global frame index `start`."""
+    out = None
+    with torch.no_grad():
+        for t in range(start, start + count):
+            k = t % clip_len
+            for s, model in enumerate(models):
+                if k == 0:
+                    model.reset_temporal()
+                    if hasattr(model.policy, "reseed"):
+                        model.policy.reseed(1000 * s + t // clip_len)
+                if host_clips is not None:
+                    frame = host_clips[s][k].to(clips[s][k].device, non_blocking=True)
+                else:
+                    frame = clips[s][k]
+                out = model(frame)
+                if d2h_buf is not None:
+                    d2h_buf[s].copy_(out, non_blocking=True)
+    return out
+
+
+def bench_ours(args):
+    from blockcopy import _C
+    from consumers.clips import synthetic_clip
+
+    world, rank, local = dist_setup(args)
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True
+    peaks = load_peaks()
+    H, W, L, S = args.height, args.width, args.clip_length, args.streams_per_gpu
+
+    models = [build_model(args, device) for _ in range(S)]
+    host_clips = [[f.pin_memory() for f in synthetic_clip(L, H, W, seed=100 * rank + s, dtype=torch.float16)]
+                  for s in range(S)]
+    clips = [[f.to(device) for f in hc] for hc in host_clips]
+    G = (H // 128) * (W // 128)
+    num_exec = models[0].policy.num_exec_for(G) if hasattr(models[0].policy, "num_exec_for") else None
+
+    # ---- device-resident throughput ("value") --------------------------------------------------------
+    run_frames(models, clips, 0, args.warmup, L)
+    torch.cuda.synchronize()
+    barrier(world)
+    n0 = _C.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        run_frames(models, clips, args.warmup, args.steps, L)
+        ev1.record()
+        torch.cuda.synchronize()
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1), world, device)
+    launches = _C.launch_count() - n0
+    barrier(world)
+    frames_total = sum_over_ranks(float(args.steps * S), world, device)
+    value = frames_total / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        out_shape = (1, 19, H // 4, W // 4)
+        d2h = [torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(S)]
+        run_frames(models, clips, 0, min(args.warmup, L), L, host_clips=host_clips, d2h_buf=d2h)
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_frames(models, clips, args.warmup, args.steps, L, host_clips=host_clips, d2h_buf=d2h)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, device)
+        e2e = {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": S * 3 * H * W * 2, "d2h_bytes_per_step": S * 19 * (H // 4) * (W // 4) * 2}
+
+    # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
+    kern = microbench(device, peaks) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cpu = cpu_dense_baseline(H, W, frames=5)
+
+    if rank == 0:
+        dom = kern["gather_halo_nhwc"]
+        line = {
+            "metric": "frames/s @1024x2048, 30% active blocks (SwiftNet-RN18 + BlockCopy)", "value": value,
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "configs[2]: SwiftNet-RN18 + BlockCopy, synthetic 1024x2048 30-frame clips, "
+                                   "random-init weights, seeded masks",
+                       "height": H, "width": W, "block_size": 128, "active_blocks": num_exec, "total_blocks": G,
+                       "clip_length": L, "streams_per_gpu": S, "policy": args.policy,
+                       "cuda_graphs": not args.no_graphs,
+                       "l2_note": "microbench rotates 8 plane sets (268 MB > 126 MB L2); frame loop inputs: "
+                                  "30 distinct 12.6 MB frames + 0.27 GB of planes per stream"},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "bc_gather_halo (NHWC, C=128, BS=32, p=1, E=38: config 2)",
+                         "achieved": dom["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": dom["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]},
+            "kernels": kern, "cpu_baseline": cpu, "clocks": clk.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+# =============================================================================================== microbench
+def microbench(device, peaks, reps=200, sets=8):
+    """BASELINE config 2 (1x128x256x512 fp16, 32-px feature blocks, E=38 of 128): achieved GB/s of
+    every block kernel.  `sets` distinct plane/tile sets are rotated (8 x 33.5 MB planes > L2) and
+    `reps` launches are timed between two CUDA events on the launching stream."""
+    from blockcopy import _C
+
+    N, C, H, W, BS, E, pad = 1, 128, 256, 512, 32, 38, 1
+    g = torch.Generator(device=device).manual_seed(0)
+    cells = torch.randperm(128, generator=torch.Generator().manual_seed(0))[:E]
+    grid = torch.zeros(128, dtype=torch.bool)
+    grid[cells] = True
+    grid = grid.view(1, 1, 8, 16).to(device)
+    gi = torch.empty(grid.shape, dtype=torch.int32, device=device)
+    me = torch.empty(128, dtype=torch.int32, device=device)
+    cnt = torch.empty(2, dtype=torch.int32, device=device)
+    _C.compact_mask(grid.view(torch.uint8), gi, me, cnt)
+    me = me[:E]
+    res = {}
+    tile_b = C * BS * BS * 2
+    algo = {"gather": 2 * E * tile_b, "gather_halo": 2 * E * C * (BS + 2 * pad) ** 2 * 2, "scatter": 2 * E * tile_b,
+            "copy_blocks": 2 * C * H * W * 2}
+    for lay, fmt in (("nhwc", torch.channels_last), ("nchw", torch.contiguous_format)):
+        planes = [torch.randn(N, C, H, W, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=fmt)
+                  for _ in range(sets)]
+        outs = [torch.empty_like(planes[0]) for _ in range(2)]
+        tiles = [torch.randn(E, C, BS, BS, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=fmt)
+                 for _ in range(sets)]
+        padded = [torch.empty(E, C, BS + 2 * pad, BS + 2 * pad, device=device, dtype=torch.float16).contiguous(memory_format=fmt)
+                  for _ in range(sets)]
+        ops = {
+            "gather": lambda i: _C.gather(tiles[i % sets], planes[i % sets], me, E),
+            "gather_halo": lambda i: _C.gather_halo(padded[i % sets], planes[i % sets], me, E, BS, pad),
+            "scatter": lambda i: _C.scatter(tiles[i % sets], planes[i % sets], me, E),
+            "copy_blocks": lambda i: _C.copy_blocks(outs[i % 2], planes[i % sets], tiles[i % sets], gi),
+        }
+        for tma in ((True, False) if lay == "nhwc" else (True, False)):
+            _C.set_tma_enabled(tma)
+            for name, fn in ops.items():
+                if name == "copy_blocks" and not tma:
+                    continue
+                for i in range(10):
+                    fn(i)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(reps):
+                    fn(i)
+                b.record()
+                torch.cuda.synchronize()
+                us = a.elapsed_time(b) * 1e3 / reps
+                key = f"{name}_{lay}" + ("" if tma else "_simt")
+                res[key] = {"us": us, "bytes": algo[name], "gbs": algo[name] / us * 1e-3,
+                            "frac_of_hbm_peak": algo[name] / us * 1e-3 / peaks["hbm_gbs"]}
+        _C.set_tma_enabled(True)
+        del planes, tiles, padded, outs
+    return res
+
+
+# =============================================================================================== CPU baseline
+def cpu_dense_baseline(H, W, frames=5, warm=2):
+    """BASELINE config 1: dense SwiftNet-RN18 forward, fp32, CPU torch on all host cores (the only
+    part of the reference that runs without CUDA).  Uses the reference's own model code when it is
+    staged in baseline/_ref (kind 'reference'), else this repo's architecture-identical consumer
+    (kind 'port')."""
+    kind = "port"
+    try:
+        from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+        net = build_swiftnet_rn18(seed=0)
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+    x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(0))
+    cores = torch.get_num_threads()
+    times = []
+    with torch.no_grad():
+        for i in range(warm + frames):
+            t0 = time.perf_counter()
+            net(x)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": 1.0 / med, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": f"dense SwiftNet-RN18 fp32 forward, 1x3x{H}x{W}, {warm} warm-up + {frames} timed, median"}
+
+
+def bench_reference(args):
+    """Reference arm: the reference's CPU-runnable path (dense SwiftNet-RN18, CPU torch, all cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = max(3, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    cpu = cpu_dense_baseline(args.height, args.width, frames=frames, warm=warm)
+    line = {"impl": "reference", "metric": "frames/s @1024x2048, 30% active blocks (SwiftNet-RN18 + BlockCopy)",
+            "value": cpu["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": frames, "warmup": warm,
+            "ms_per_step": 1000.0 / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[0]: dense SwiftNet-RN18 forward on CPU torch (the reference's block "
+                                   "path is CUDA-only)", "height": args.height, "width": args.width},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return bench_reference(args)
+    if args.microbench:
+        assert torch.cuda.is_available()
+        print(json.dumps({"kernels": microbench(torch.device("cuda", 0), load_peaks())}))
+        return
+    bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,7 +68,24 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+_n_launches = 0  # kernels handed to the GPU through this binding (bench.py: "gpu_launches")
+
+
+def launch_count() -> int:
+    return _n_launches
+
+
+def add_launches(n: int):
+    """Account for kernels replayed from a captured CUDA graph (no Python call per launch)."""
+    global _n_launches
+    _n_launches += n
+
+
 def _check(rc: int, what: str):
+    global _n_launches
+    if rc == 0:
+        _n_launches += 1
+        return
     if rc != 0:
         msg = lib().bc_last_error_string().decode()
         if rc == -2:

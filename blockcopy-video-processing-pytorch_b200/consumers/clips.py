@@ -89,10 +89,10 @@ class PolicyReplay(Policy):
         return self.stats.add_policy_meta(policy_meta)
 
 
-def deterministic_init_(model: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
+def deterministic_init_(model: torch.nn.Module, seed: int = 0, gain: float = 1.0) -> torch.nn.Module:
     """Fill every parameter and buffer from a generator seeded by (seed, tensor NAME), so that two
     implementations of the same architecture (the reference's module tree and this repo's) get
-    identical weights without shipping a checkpoint.  Conv weights ~ N(0, 2/fan_out), BatchNorm
+    identical weights without shipping a checkpoint.  Conv weights ~ N(0, gain^2 * 2/fan_out), BatchNorm
     affine / running statistics are made non-trivial on purpose."""
     import zlib
 
@@ -106,7 +106,7 @@ def deterministic_init_(model: torch.nn.Module, seed: int = 0) -> torch.nn.Modul
                 continue
             if p.dim() == 4:
                 fan_out = p.shape[0] * p.shape[2] * p.shape[3]
-                v = torch.randn(p.shape, generator=g) * (2.0 / fan_out) ** 0.5
+                v = torch.randn(p.shape, generator=g) * (gain * (2.0 / fan_out) ** 0.5)
             elif name.endswith("running_var") or (name.endswith("weight") and p.dim() == 1):
                 v = 0.75 + 0.5 * torch.rand(p.shape, generator=g)
             else:

@@ -1,0 +1,194 @@
+"""oracle/make_golden_gpu.py -- TEST INFRASTRUCTURE.  Run ON THE B200 BOX:
+
+    gpurun -- 'python oracle/make_golden_gpu.py'        (writes gpurun_out/golden/*)
+
+Runs the UNMODIFIED reference on the GPU: its CUDA C kernel strings are compiled by NVRTC for
+sm_100a and launched through a minimal ``cupy`` shim (oracle/ref_env.py), everything else is the
+reference's own Python on torch/cuDNN.  Needs baseline/_ref (staged by __graft_entry__.build()).
+The files it writes are copied to tests/golden/ and committed:
+
+  ref_kernels_<case>.npz       inputs + outputs of split / combine / transfer / repad kernels
+  swiftnet_gpu_fp16_clip.pt    SwiftNet-RN18 + BlockCopyModel, fp16, 512x1024, grid 4x8, 6 frames
+  reference_timing.json        fps of the reference BlockCopy path on this B200
+"""
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_env  # noqa: E402
+
+ref = ref_env.import_reference("gpu")
+sys.path.append(os.path.join(ROOT, "blockcopy-video-processing-pytorch_b200"))  # consumers/ only
+from consumers.clips import PolicyFixedFraction, PolicyReplay, deterministic_init_, synthetic_clip  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out", "golden")
+os.makedirs(OUT, exist_ok=True)
+dev = "cuda"
+
+
+def settings(**kw):
+    s = dict(block_policy="all", block_num_classes=19, block_optim_lr=1e-4, block_optim_wd=1e-3,
+             block_optim_momentum=0, block_target=0.5, block_complexity_weight=5, block_size=128,
+             block_train_interval=4, block_cost_momentum=0.9, block_policy_verbose=False)
+    s.update(kw)
+    return s
+
+
+def kernel_goldens():
+    from blockcopy.core.tensorwrapper import get_grid_mappings
+    from blockcopy.utils.block_funcs import CombineFunction, SplitFunction, TransferFunction
+    from blockcopy.utils.blockpad import pad as ref_pad
+
+    cases = [  # name, N, C, GH, GW, BS, pad, dtype, frac
+        ("a", 1, 4, 3, 4, 8, 1, torch.float16, 0.4),
+        ("b", 2, 6, 2, 3, 4, 1, torch.float16, 0.5),
+        ("c", 1, 3, 2, 2, 16, 3, torch.float16, 0.5),
+        ("d", 1, 8, 3, 3, 4, 2, torch.float32, 0.6),
+        ("e", 2, 5, 2, 4, 2, 1, torch.float32, 0.3),
+        ("f", 1, 16, 4, 4, 32, 1, torch.float16, 0.3),
+    ]
+    for name, N, C, GH, GW, BS, pad, dt, frac in cases:
+        g = torch.Generator().manual_seed(hash(name) % 1000)
+        H, W = GH * BS, GW * BS
+        image = torch.randn(N, C, H, W, generator=g).to(dt)
+        grid = torch.rand(N, 1, GH, GW, generator=g) < frac
+        prev_grid = torch.rand(N, 1, GH, GW, generator=g) < 0.5
+        G = grid.numel()
+
+        def maps(gr):
+            ne = int(gr.sum())
+            gi, me = get_grid_mappings(ne, gr, ~gr, G, G - ne)
+            return gi.int(), me.int()
+
+        gi, me = maps(grid)
+        pgi, pme = maps(prev_grid)
+        ti = pgi[~grid].int()
+        E, Ep = me.numel(), pme.numel()
+        split = SplitFunction.apply(torch.empty(E, C, BS, BS, dtype=dt, device=dev), image.to(dev), me.to(dev), gi.to(dev))
+        tiles_in = torch.randn(E, C, BS, BS, generator=g).to(dt)
+        combine_base = torch.randn(N, C, H, W, generator=g).to(dt)
+        combine = CombineFunction.apply(tiles_in.to(dev), combine_base.to(dev).clone(), gi.to(dev), me.to(dev))
+        prev_exec = torch.randn(Ep, C, BS, BS, generator=g).to(dt)
+        prev_transfer = torch.randn(G - Ep, C, BS, BS, generator=g).to(dt)
+        transfer_base = torch.randn(G - E, C, BS, BS, generator=g).to(dt)
+        transfer = TransferFunction.apply(transfer_base.to(dev).clone(), prev_exec.to(dev), prev_transfer.to(dev),
+                                          pgi.to(dev), ti.to(dev), pad)
+        repad = ref_pad(tiles_in.to(dev), transfer, gi.to(dev), me.to(dev), pad)
+        torch.cuda.synchronize()
+        np.savez_compressed(
+            os.path.join(OUT, f"ref_kernels_{name}.npz"), dtype=str(dt).split(".")[-1], BS=BS, pad=pad,
+            image=image.numpy(), grid=grid.numpy(), grid_idx=gi.numpy(), mapping_exec=me.numpy(),
+            split=split.cpu().numpy(), tiles_in=tiles_in.numpy(), combine_base=combine_base.numpy(),
+            combine=combine.cpu().numpy(), prev_exec=prev_exec.numpy(), prev_transfer=prev_transfer.numpy(),
+            transfer_idx=ti.numpy(), transfer_base=transfer_base.numpy(), transfer=transfer.cpu().numpy(),
+            repad=repad.cpu().numpy())
+        print("kernel golden", name, "E", E, "T", G - E)
+
+
+def build_reference_swiftnet(init_seed, gain, BS, policy="all"):
+    from lib.models.swiftnet.backbones.resnet import resnet18
+    from lib.models.swiftnet.swiftnet import SwiftNet
+    from lib.utils import bn_fusion
+
+    net = SwiftNet(resnet18(pretrained=False), num_classes=19, num_features=128, use_spp=True).eval()
+    deterministic_init_(net, seed=init_seed, gain=gain)
+    model = ref.BlockCopyModel(net, settings(block_size=BS, block_policy=policy)).eval().to(dev)
+    model = bn_fusion.fuse_bn_recursively(model)
+    model = model.half()
+    if model.policy.net is not None:
+        model.policy.net = model.policy.net.float()
+    return model
+
+
+def swiftnet_fp16_clip():
+    H, W, BS, T, gain = 512, 1024, 128, 6, 0.8
+    torch.manual_seed(0)
+    random.seed(0)
+    model = build_reference_swiftnet(0, gain, BS)
+    g = torch.Generator().manual_seed(1)
+    grids = [torch.ones(1, 1, H // BS, W // BS, dtype=torch.bool)]
+    for frac in (0.3, 0.5, 0.0, 0.25, 1.0):
+        cells = grids[0].numel()
+        m = torch.zeros(cells, dtype=torch.bool)
+        m[torch.randperm(cells, generator=g)[: round(frac * cells)]] = True
+        grids.append(m.view_as(grids[0]))
+    model.policy = PolicyReplay(BS, grids)
+    clip = synthetic_clip(T, H, W, seed=3, dtype=torch.float16, device=dev)
+    outs, states = [], []
+    with torch.no_grad():
+        model.reset_temporal()
+        for t in range(T):
+            out = model(clip[t])
+            assert torch.isfinite(out).all(), "fp16 overflow in the fixture: lower the init gain"
+            outs.append(out.clone())
+            states.append(model.policy_meta["frame_state"].clone())
+    fix = dict(H=H, W=W, BS=BS, T=T, clip_seed=3, init_seed=0, init_gain=gain,
+               grids=torch.stack(grids).to(torch.uint8),
+               argmax=torch.stack([o.argmax(1).to(torch.uint8).cpu() for o in outs]),
+               logits_strided=torch.stack([o[:, :, ::4, ::4].clone().cpu() for o in outs]),
+               frame_state_strided=torch.stack([s[:, :, ::8, ::8].clone().cpu() for s in states]),
+               logits_abs_mean=[float(o.float().abs().mean()) for o in outs],
+               logits_abs_max=[float(o.float().abs().max()) for o in outs])
+    torch.save(fix, os.path.join(OUT, "swiftnet_gpu_fp16_clip.pt"))
+    print("swiftnet fp16 clip: |logits| mean", [round(v, 3) for v in fix["logits_abs_mean"]], "max",
+          [round(v, 2) for v in fix["logits_abs_max"]])
+
+
+def time_reference(H=1024, W=2048, clips=3, T=30, fraction=0.3):
+    """fps of the reference BlockCopy path (baseline 2): SwiftNet-RN18 fp16,
+    random init, seeded ~30 % masks (frame 0 all blocks), cudnn.benchmark on, timings level 0."""
+    torch.backends.cudnn.benchmark = True
+    model = build_reference_swiftnet(0, 0.8, 128)
+    model.policy = PolicyFixedFraction(128, fraction=fraction, quantize=8, seed=0)
+    clip = synthetic_clip(T, H, W, seed=0, dtype=torch.float16, device=dev)
+
+    def run_clip():
+        model.reset_temporal()
+        with torch.no_grad():
+            for f in clip:
+                out = model(f)
+        return out
+
+    run_clip()  # warm-up: NVRTC compiles, cudnn.benchmark
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(clips):
+        run_clip()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # dense cuDNN fp16 forward of the same model for comparison (baseline 3)
+    dense = model.base_model
+    with torch.no_grad():
+        for _ in range(3):
+            dense(clip[0])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(20):
+            dense(clip[0])
+        torch.cuda.synchronize()
+        dense_dt = (time.perf_counter() - t1) / 20
+    res = dict(reference_blockcopy_fps=clips * T / dt, ms_per_frame=1000 * dt / (clips * T), frames=clips * T,
+               H=H, W=W, fraction=fraction, num_exec=model.policy.num_exec_for(128),
+               dense_cudnn_fp16_fps=1 / dense_dt, gpu=torch.cuda.get_device_name(0),
+               note="reference package unmodified; cupy -> NVRTC shim; python (not -O); timings level 0")
+    with open(os.path.join(OUT, "reference_timing.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print("reference timing:", json.dumps(res))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["kernels", "clip", "time"]
+    if "kernels" in what:
+        kernel_goldens()
+    if "clip" in what:
+        swiftnet_fp16_clip()
+    if "time" in what:
+        time_reference()
