@@ -259,10 +259,12 @@ int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int
   p.stage_bytes = (p.box_bytes + 1023u) & ~1023u;
   const size_t smem = (size_t)kStages * p.stage_bytes + 1024;
 
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(tma_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
+  // opt in to > 48 KB of dynamic shared memory (static + dynamic must stay below 227 KB)
+  static cudaError_t attr_status = cudaFuncSetAttribute(
+      tma_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  BC_REQUIRE(attr_status == cudaSuccess, (int)attr_status, "cudaFuncSetAttribute(tma_move_kernel): %s",
+             cudaGetErrorString(attr_status));
+  BC_REQUIRE(smem <= 200 * 1024, BC_ERR_UNSUPPORTED, "TMA staging ring of %zu bytes is too large", smem);
   // persistent-style launch: CTAs stride over the work items; as many CTAs per SM as shared memory allows
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
