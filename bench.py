@@ -317,24 +317,31 @@ def microbench(device, peaks, reps=200, sets=8):
             "scatter": lambda i: _C.scatter(tiles[i % sets], planes[i % sets], me, E),
             "copy_blocks": lambda i: _C.copy_blocks(outs[i % 2], planes[i % sets], tiles[i % sets], gi),
         }
-        for tma in ((True, False) if lay == "nhwc" else (True, False)):
+        for tma in (True, False):
             _C.set_tma_enabled(tma)
             for name, fn in ops.items():
                 if name == "copy_blocks" and not tma:
                     continue
-                for i in range(10):
+                for i in range(sets):
                     fn(i)
+                torch.cuda.synchronize()
+                # one CUDA graph of `reps` back-to-back launches: host launch cost is not what is measured
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for i in range(reps):
+                        fn(i)
+                graph.replay()
                 torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                for i in range(reps):
-                    fn(i)
+                graph.replay()
                 b.record()
                 torch.cuda.synchronize()
                 us = a.elapsed_time(b) * 1e3 / reps
                 key = f"{name}_{lay}" + ("" if tma else "_simt")
                 res[key] = {"us": us, "bytes": algo[name], "gbs": algo[name] / us * 1e-3,
                             "frac_of_hbm_peak": algo[name] / us * 1e-3 / peaks["hbm_gbs"]}
+                del graph
         _C.set_tma_enabled(True)
         del planes, tiles, padded, outs
     return res

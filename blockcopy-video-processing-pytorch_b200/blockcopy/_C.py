@@ -36,6 +36,7 @@ _SIGNATURES = {
     "bc_transfer": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo_tiles": ([_vp, _vp, _vp, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp], _i),
 }
 
 
@@ -214,4 +215,38 @@ def gather_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Tens
     assert E == 0 or layout_of(out) == lay or C == 1
     _check(lib().bc_gather_halo(out.data_ptr(), plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS, pad,
                                 _dtype(plane), lay, _stream()), "bc_gather_halo")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- convolution
+def conv_supported(dtype, weight: torch.Tensor, BS_in: int, stride: int, padding: int, dilation: int = 1,
+                   groups: int = 1) -> bool:
+    """True when bc_conv_igemm covers this conv: fp16, k in {1,3} with pad k//2, stride 1/2, dilation 1,
+    groups 1, Cin and Cout multiples of 64, output block edge a power of two in [4,128]."""
+    Cout, Cin, kh, kw = weight.shape
+    if dtype != torch.float16 or weight.dtype != torch.float16 or not weight.is_cuda:
+        return False
+    if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
+        return False
+    if Cin % 64 or Cout % 64 or BS_in % stride:
+        return False
+    bo = BS_in // stride
+    return 4 <= bo <= 128 and (bo & (bo - 1)) == 0
+
+
+def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],
+               residual: Optional[torch.Tensor], mapping_exec: Optional[torch.Tensor], E: int, BS_in: int,
+               stride: int, padding: int, relu: bool = False):
+    """out (E,Cout,BS_out,BS_out) channels_last <- conv(plane (N,Cin,H,W) channels_last) on the E executed
+    blocks.  weight_cl must be a channels_last (Cout,Cin,k,k) fp16 tensor."""
+    _dev(out, plane, weight_cl, bias, residual, mapping_exec)
+    N, Cin, H, W = plane.shape
+    Cout, _, k, _ = weight_cl.shape
+    assert weight_cl.is_contiguous(memory_format=torch.channels_last) or k == 1
+    _check(lib().bc_conv_igemm(out.data_ptr(), plane.data_ptr(), weight_cl.data_ptr(),
+                               bias.data_ptr() if bias is not None else None,
+                               residual.data_ptr() if residual is not None else None,
+                               mapping_exec.data_ptr() if mapping_exec is not None else None,
+                               E, N, Cin, H, W, BS_in, Cout, k, stride, padding, int(relu), _stream()),
+           "bc_conv_igemm")
     return out

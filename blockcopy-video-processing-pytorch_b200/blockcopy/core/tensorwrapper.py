@@ -20,6 +20,7 @@ What is different underneath (B200 design):
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
@@ -28,6 +29,7 @@ import torch
 from .. import _C
 from ..utils.profiler import timings
 
+FUSED_CONV = os.environ.get("BLOCKCOPY_FUSED_CONV", "1") != "0"  # route eligible convs on blocks to the tcgen05 implicit-GEMM kernel (bc_conv_igemm)
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
 
@@ -383,12 +385,61 @@ class TensorWrapper(torch.Tensor):
             out._inherit(src)
         return out
 
+    def _try_fused_conv(self, args, kwargs):
+        """conv2d on blocks through bc_conv_igemm: the operand load reads the op's persistent plane
+        by block index (halo included), bias is added in the epilogue; returns None if the conv is
+        outside the kernel's envelope (then the generic gather-halo + torch path runs)."""
+        names = ("input", "weight", "bias", "stride", "padding", "dilation", "groups")
+        a = dict(bias=None, stride=1, padding=0, dilation=1, groups=1)
+        a.update(zip(names, args))
+        a.update(kwargs)
+        one = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)  # noqa: E731
+        stride, padding, dilation = one(a["stride"]), one(a["padding"]), one(a["dilation"])
+        if stride is None or padding is None or dilation is None or isinstance(padding, str):
+            return None
+        x, weight, bias = a["input"], a["weight"], a["bias"]
+        if not isinstance(x, TensorWrapper) or not x._is_blocks or isinstance(weight, TensorWrapper):
+            return None
+        E, Cin, BS, _ = x.shape
+        if E == 0 or weight.dim() != 4 or weight.shape[1] != Cin:
+            return None
+        if not _C.conv_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
+            return None
+        if bias is not None and (bias.dtype != torch.float16 or not bias.is_contiguous()):
+            return None
+        feats = self._features
+        if padding > 0 and feats._plane_cursor < len(feats._planes) and \
+                _C.layout_of(feats._planes[feats._plane_cursor]) != _C.BC_NHWC:
+            return None  # this op's plane was created NCHW on the first frame: stay on the generic path
+        tiles = _dense(x).contiguous(memory_format=torch.channels_last)
+        w = weight.detach()
+        if not w.is_contiguous(memory_format=torch.channels_last):
+            w = w.contiguous(memory_format=torch.channels_last)
+        Cout, BSo = weight.shape[0], BS // stride
+        out = torch.empty((E, Cout, BSo, BSo), dtype=tiles.dtype, device=tiles.device,
+                          memory_format=torch.channels_last)
+        if padding > 0:
+            N, _, GH, GW = feats._grid_idx.shape
+            plane = feats._next_plane(tiles, (N, Cin, GH * BS, GW * BS))
+            with timings.env("tensorwrapper/transfer", 10):
+                _C.scatter(tiles, plane, feats._mapping_exec, E)
+            with timings.env("tensorwrapper/pad_func", 11):
+                _C.conv_igemm(out, plane, w, bias, None, feats._mapping_exec, E, BS, stride, padding)
+        else:
+            with timings.env("tensorwrapper/pad_func0", 11):
+                _C.conv_igemm(out, tiles, w, bias, None, None, E, BS, stride, 0)
+        return out.as_subclass(TensorWrapper)
+
     def _func_replace_padding(self, func, types, args, kwargs):
         """Padded op: take the padding from neighbouring blocks instead of zeros, then run the op
         itself with padding 0 (reference: _func_replace_paddding, tensorwrapper.py:529-575)."""
         if BLOCKPAD_WITH_ZEROES:
             return super().__torch_function__(func, types, args, kwargs)
         op = func.__name__
+        if FUSED_CONV and op == "conv2d":
+            fused = self._try_fused_conv(args, kwargs)
+            if fused is not None:
+                return fused
         args = list(args)
         pos = _PADDING_ARG_INDEX.get(op, 4)
         padding = kwargs.get("padding", None)

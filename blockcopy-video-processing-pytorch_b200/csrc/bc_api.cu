@@ -38,6 +38,10 @@ int check_launch(const char *what) {
 int launch_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *mapping_exec, int32_t *counts,
                         const int32_t *prev_grid_idx, int32_t *transfer_idx, cudaStream_t s);
 
+int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
+               const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
+               int pad, int relu, cudaStream_t stream);
+
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace bc
@@ -51,7 +55,7 @@ BC_API int bc_version(void) { return BC_ABI_VERSION; }
 BC_API const char *bc_last_error_string(void) { return g_err; }
 
 BC_API const char *bc_build_info(void) {
-  return "libblockcopy_sm100 abi " "1" " | sm_100a | nvcc " __VERSION__ " | built " __DATE__;
+  return "libblockcopy_sm100 abi 1 | sm_100a | built " __DATE__ " " __TIME__;
 }
 
 BC_API int bc_set_tma_enabled(int enabled) {
@@ -167,6 +171,15 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
     return launch_tma_move(out, const_cast<void *>(plane), mapping_exec, E, N, C, H, W, BS, pad, BS + 2 * pad, es,
                            layout, false, (cudaStream_t)stream);
   return launch_gather_simt(out, plane, mapping_exec, g, true, (cudaStream_t)stream);
+}
+
+BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
+                         const int32_t *mapping_exec, int E, int N, int Cin, int H, int W, int BS_in, int Cout,
+                         int ksize, int stride, int pad, int relu, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_conv_igemm: E=%d", E);
+  if (E == 0) return BC_OK;
+  return conv_igemm(out, plane, weight, bias, residual, mapping_exec, E, N, Cin, H, W, BS_in, Cout, ksize, stride,
+                    pad, relu, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,304 @@
+// bc_conv.cu -- tcgen05 / TMEM implicit-GEMM convolution on the executed blocks.
+//
+// Replaces, for one padded op of the wrapped CNN, the reference's   transfer_kernel -> repad_kernel
+// -> cuDNN conv on the padded tile batch   (core/tensorwrapper.py:529-575): the A operand is read
+// straight from the op's persistent NHWC plane with TMA box loads addressed by BLOCK INDEX
+// (mapping_exec[b] -> (n, gh, gw) -> plane coordinates); the halo is simply the box reaching into
+// the neighbouring cells, and the zeros at the frame border are TMA's out-of-bounds fill.  The
+// gathered / padded tiles never exist in HBM.  The epilogue adds the bias, optionally the residual
+// and ReLU, and writes fp16 NHWC packed tiles (E, BS_out, BS_out, Cout).
+//
+// GEMM view per CTA: D[128 x N_TILE] += A[128 x 64] * B[N_TILE x 64]^T for every (tap, 64-channel
+// chunk); 128 rows = 128 output pixels of one block (BS_out >= 16: 128/BS_out rows of the block) or
+// of 128/BS_out^2 consecutive blocks (BS_out = 4, 8).  Both operands are K-major rows of 128 bytes
+// with the 128-byte swizzle, written by TMA, consumed by tcgen05.mma.kind::f16 (M = 128, K = 16,
+// fp32 accumulator in TMEM).  Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld, one TMEM lane
+// quadrant each).  Stride 2 uses the tensor map's element strides; 1x1 convs are the 1-tap case.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "bc_common.cuh"
+#include "bc_ptx.cuh"
+#include "bc_tma.cuh"
+
+namespace bc {
+
+constexpr int kConvThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                    // channels per k-step = one 128-byte swizzled row
+constexpr uint32_t kABytes = kTileM * 128;     // 16 KB per stage
+
+struct ConvParams {
+  const int32_t *mapping;   // cell of packed tile b; nullptr = identity (input is a packed tile batch)
+  CellDecode cell;          // grid of the INPUT plane
+  const __half *bias;       // [Cout] or nullptr
+  const __half *residual;   // same layout as out, or nullptr
+  __half *out;              // (E, BS_out, BS_out, Cout) NHWC
+  int E, BS_out, BS_in, stride, pad, ksize, Cout;
+  int kc_per_tap;           // Cin / 64
+  int rows_per_tile;        // rows of BS_out pixels of ONE block in a tile (BS_out >= 16) or BS_out
+  int blocks_per_tile;      // 1, or 128 / BS_out^2 for small blocks
+  int tiles_per_block;      // BS_out^2 / 128 for big blocks, else 1
+  int relu;
+  uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(kConvThreads)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                  const ConvParams p) {
+  constexpr uint32_t kBBytes = N_TILE * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which output pixels does this CTA own -----------------------------------------------------
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * N_TILE;
+  int b0, r0, nvalid;
+  if (p.blocks_per_tile == 1) {
+    b0 = tile / p.tiles_per_block;
+    r0 = (tile - b0 * p.tiles_per_block) * p.rows_per_tile;
+    nvalid = 1;
+  } else {
+    b0 = tile * p.blocks_per_tile;
+    r0 = 0;
+    nvalid = min(p.blocks_per_tile, p.E - b0);
+  }
+  const int num_k = p.ksize * p.ksize * p.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&a_map);
+    prefetch_map(&b_map);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, N_TILE);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer =================================================
+    if (lane == 0) {
+      int cn[8], cx[8], cy[8];  // plane coordinates of the (up to 8) blocks of this tile
+      for (int i = 0; i < nvalid; ++i) {
+        const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + b0 + i) : (uint32_t)(b0 + i);
+        uint32_t n, gh, gw;
+        p.cell(cell, n, gh, gw);
+        cn[i] = (int)n;
+        cx[i] = (int)gw * p.BS_in - p.pad;
+        cy[i] = (int)gh * p.BS_in + r0 * p.stride - p.pad;
+      }
+      const uint32_t tx_bytes = (uint32_t)nvalid * p.box_bytes + kBBytes;
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
+        const int tap = ks / p.kc_per_tap, cc = ks - tap * p.kc_per_tap;
+        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+        uint8_t *sa = smem + (size_t)s * kStageBytes;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        for (int i = 0; i < nvalid; ++i)
+          tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, cx[i] + kw, cy[i] + kh, cn[i]);
+        tma_load_2d(sa + kABytes, &b_map, &full_bar[s], ks * kChunkK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE);
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        mbar_wait(&full_bar[s], (uint32_t)((ks / STAGES) & 1));
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k)
+          umma_f16_ss(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (uint32_t)((ks | k) != 0));
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(&acc_bar);  // accumulator complete
+    }
+  } else {
+    // =============================== epilogue =====================================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;
+    int blk, y, x;
+    if (p.blocks_per_tile == 1) {
+      blk = 0;
+      y = r0 + m / p.BS_out;
+      x = m % p.BS_out;
+    } else {
+      const int per = p.BS_out * p.BS_out;
+      blk = m / per;
+      const int rem = m - blk * per;
+      y = rem / p.BS_out;
+      x = rem - y * p.BS_out;
+    }
+    const bool valid = blk < nvalid;
+    const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
+    __half *orow = p.out + pix * p.Cout + n0;
+    const __half *rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
+          if (p.bias) {
+            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n0 + c0 + j));
+            const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __half22float2(bh[t]);
+              v[2 * t] += f.x;
+              v[2 * t + 1] += f.y;
+            }
+          }
+          if (rrow) {
+            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + c0 + j));
+            const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __half22float2(rh[t]);
+              v[2 * t] += f.x;
+              v[2 * t + 1] += f.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+          }
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+          *reinterpret_cast<uint4 *>(orow + c0 + j) = o;
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, N_TILE);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
+
+template <int N_TILE, int STAGES>
+static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int tiles, int ntiles_n,
+                       cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 1024;
+  static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
+  conv_igemm_kernel<N_TILE, STAGES><<<dim3((unsigned)tiles, (unsigned)ntiles_n), kConvThreads, smem, s>>>(a_map, b_map, p);
+  return check_launch("bc_conv_igemm");
+}
+
+int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
+               const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
+               int pad, int relu, cudaStream_t stream) {
+  BC_REQUIRE(out && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
+  BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
+  BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
+  BC_REQUIRE(stride == 1 || stride == 2, BC_ERR_UNSUPPORTED, "bc_conv_igemm: stride %d (1 or 2)", stride);
+  BC_REQUIRE(pad == ksize / 2, BC_ERR_UNSUPPORTED, "bc_conv_igemm: padding %d for kernel %d", pad, ksize);
+  BC_REQUIRE(Cin % kChunkK == 0, BC_ERR_UNSUPPORTED, "bc_conv_igemm: Cin=%d is not a multiple of 64", Cin);
+  BC_REQUIRE(Cout % 64 == 0, BC_ERR_UNSUPPORTED, "bc_conv_igemm: Cout=%d is not a multiple of 64", Cout);
+  BC_REQUIRE(H % BS_in == 0 && W % BS_in == 0 && BS_in % stride == 0, BC_ERR_SHAPE,
+             "bc_conv_igemm: plane %dx%d / block %d / stride %d", H, W, BS_in, stride);
+  const int BS_out = BS_in / stride;
+  const int px = BS_out * BS_out;
+  BC_REQUIRE(BS_out >= 4 && BS_out <= 128 && (px % kTileM == 0 || kTileM % px == 0) && (BS_out & (BS_out - 1)) == 0,
+             BC_ERR_UNSUPPORTED, "bc_conv_igemm: output block edge %d (power of two, 4..128)", BS_out);
+  BC_REQUIRE((((uintptr_t)out | (uintptr_t)plane | (uintptr_t)weight | (uintptr_t)bias | (uintptr_t)residual) & 15) == 0,
+             BC_ERR_ALIGN, "bc_conv_igemm: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = tensor_map_encoder();
+  BC_REQUIRE(enc != nullptr, BC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+
+  ConvParams p;
+  p.mapping = mapping;
+  p.cell = CellDecode(H / BS_in, W / BS_in);
+  p.bias = (const __half *)bias;
+  p.residual = (const __half *)residual;
+  p.out = (__half *)out;
+  p.E = E; p.BS_out = BS_out; p.BS_in = BS_in; p.stride = stride; p.pad = pad; p.ksize = ksize; p.Cout = Cout;
+  p.kc_per_tap = Cin / kChunkK;
+  p.relu = relu;
+  int tiles;
+  if (px >= kTileM) {
+    p.blocks_per_tile = 1;
+    p.tiles_per_block = px / kTileM;
+    p.rows_per_tile = kTileM / BS_out;
+    tiles = E * p.tiles_per_block;
+  } else {
+    p.blocks_per_tile = kTileM / px;
+    p.tiles_per_block = 1;
+    p.rows_per_tile = BS_out;
+    tiles = (E + p.blocks_per_tile - 1) / p.blocks_per_tile;
+  }
+  p.box_bytes = (uint32_t)(p.rows_per_tile * BS_out * 128);
+
+  // A: the plane (Cin, W, H, N), box = 64 channels x BS_out x rows (sampled every `stride` pixels)
+  CUtensorMap a_map, b_map;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)(BS_out * stride), (cuuint32_t)(p.rows_per_tile * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    const CUresult r = enc(&a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(plane), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (plane) failed: CUresult %d", (int)r);
+  }
+  const int n_tile = Cout % 128 == 0 ? 128 : 64;
+  {
+    // B: weights [Cout][tap][Cin] = channels_last (Cout, Cin, k, k) memory; K-major rows
+    const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
+    cuuint64_t gdim[2] = {K, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(weight), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
+  }
+  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, stream);
+  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, stream);
+}
+
+}  // namespace bc

@@ -137,6 +137,25 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
                    int H, int W, int BS, int pad, bc_dtype_t dtype, bc_layout_t layout,
                    bc_stream_t stream);
 
+/* ---- implicit-GEMM convolution on the executed blocks (tcgen05 / TMEM / TMA) -----
+ * Replaces, for one conv of the wrapped CNN, transfer_kernel + repad_kernel + the cuDNN call on the
+ * padded tile batch (core/tensorwrapper.py:529-575; utils/blockpad.py; utils/block_funcs.py:161-237):
+ * the operand load takes the block indices directly and reads the op's persistent NHWC fp16 plane
+ * (N,H,W,Cin) -- halos are the neighbouring cells of the plane, zeros outside the frame --
+ * so padded tiles never exist in memory.  Epilogue: + bias, + residual, ReLU, fp16 store into the
+ * packed NHWC tile batch out (E, BS_in/stride, BS_in/stride, Cout).
+ *   weight   fp16 [Cout][k][k][Cin]  (= a channels_last (Cout,Cin,k,k) tensor)
+ *   bias     fp16 [Cout] or NULL;  residual fp16, layout of out, or NULL
+ *   mapping_exec NULL: the "plane" is itself a packed tile batch (N = E images of BS_in x BS_in;
+ *                      used for the 1x1 convs, which need no halo)
+ * Supported: k in {1,3} with pad = k/2, stride in {1,2}, dilation 1, Cin % 64 == 0, Cout % 64 == 0,
+ * output block edge a power of two in [4,128]; anything else returns BC_ERR_UNSUPPORTED.
+ */
+BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias,
+                         const void *residual, const int32_t *mapping_exec, int E, int N, int Cin, int H,
+                         int W, int BS_in, int Cout, int ksize, int stride, int pad, int relu,
+                         bc_stream_t stream);
+
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
  * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */
