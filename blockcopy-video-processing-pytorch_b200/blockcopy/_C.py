@@ -119,6 +119,11 @@ def layout_of(t: torch.Tensor) -> int:
     raise AssertionError(f"tensor must be dense NCHW or channels_last, got strides {t.stride()}")
 
 
+def _dense_in(t: torch.Tensor, lay: int) -> bool:
+    """Is `t` dense in layout `lay`?  (1x1 tiles and 1-channel tensors are dense in both.)"""
+    return t.is_contiguous() if lay == BC_NCHW else t.is_contiguous(memory_format=torch.channels_last)
+
+
 def set_tma_enabled(flag: bool):
     _check(lib().bc_set_tma_enabled(int(flag)), "bc_set_tma_enabled")
 
@@ -154,7 +159,7 @@ def gather(blocks: torch.Tensor, image: torch.Tensor, mapping_exec: torch.Tensor
     N, C, H, W = image.shape
     BS = blocks.shape[-1]
     lay = layout_of(image)
-    assert E == 0 or layout_of(blocks) == lay or C == 1, "tiles and plane must share a layout"
+    assert E == 0 or _dense_in(blocks, lay), "tiles and plane must share a layout"
     _check(lib().bc_gather(blocks.data_ptr(), image.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS,
                            _dtype(image), lay, _stream()), "bc_gather")
     return blocks
@@ -165,7 +170,7 @@ def scatter(blocks: torch.Tensor, image: torch.Tensor, mapping_exec: torch.Tenso
     N, C, H, W = image.shape
     BS = blocks.shape[-1]
     lay = layout_of(image)
-    assert E == 0 or layout_of(blocks) == lay or C == 1, "tiles and plane must share a layout"
+    assert E == 0 or _dense_in(blocks, lay), "tiles and plane must share a layout"
     _check(lib().bc_scatter(blocks.data_ptr(), image.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS,
                             _dtype(image), lay, _stream()), "bc_scatter")
     return image
@@ -176,7 +181,7 @@ def copy_blocks(out: torch.Tensor, prev: torch.Tensor, blocks: torch.Tensor, gri
     N, C, H, W = out.shape
     BS = blocks.shape[-1]
     lay = layout_of(out)
-    assert layout_of(prev) == lay and prev.shape == out.shape
+    assert _dense_in(prev, lay) and prev.shape == out.shape and (blocks.numel() == 0 or _dense_in(blocks, lay))
     _check(lib().bc_copy_blocks(out.data_ptr(), prev.data_ptr(), blocks.data_ptr() if blocks.numel() else None,
                                 grid_idx.data_ptr(), N, C, H, W, BS, _dtype(out), lay, _stream()),
            "bc_copy_blocks")
@@ -212,7 +217,7 @@ def gather_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Tens
     _dev(out, plane, mapping_exec)
     N, C, H, W = plane.shape
     lay = layout_of(plane)
-    assert E == 0 or layout_of(out) == lay or C == 1
+    assert E == 0 or _dense_in(out, lay)
     _check(lib().bc_gather_halo(out.data_ptr(), plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS, pad,
                                 _dtype(plane), lay, _stream()), "bc_gather_halo")
     return out

@@ -24,6 +24,12 @@ class BlockCopyModel(nn.Module):
     Optional extra keys (absent => reference behaviour):
       block_channels_last (bool, default True): store conv weights channels_last so that packed
           tiles and planes are NHWC, the layout the sm_100a kernels are written for.
+      block_cuda_graphs (bool, default False): capture the whole block-sparse frame (index
+          compaction, gather, every layer, combines) into one CUDA graph per executed-block count and
+          replay it; the Python interception layer then runs only while capturing.  Differences to
+          the eager mode: feature planes persist across ``reset_temporal`` (the first frame of a
+          clip rewrites all of them), and the returned output tensor is one of two alternating
+          buffers -- it stays valid until the next-but-one call (clone it to keep it longer).
     """
 
     def __init__(self, base_model: nn.Module, settings: dict):
@@ -38,6 +44,7 @@ class BlockCopyModel(nn.Module):
         self.train_interval = settings["block_train_interval"]
         if settings.get("block_channels_last", True):
             self.base_model.to(memory_format=torch.channels_last)
+        self._graphs = _GraphState() if settings.get("block_cuda_graphs", False) else None
 
     def load_state_dict(self, state_dict, strict: bool = True):
         """Checkpoints are base-model checkpoints (reference core/blockcopy.py:30-32)."""
@@ -46,9 +53,13 @@ class BlockCopyModel(nn.Module):
     def reset_temporal(self):
         """Forget all temporal state; call at the start of every clip."""
         self.clip_length = 0
-        if self.block_temporal_features:
-            self.block_temporal_features.clear()
-        self.block_temporal_features = None
+        if getattr(self, "_graphs", None) is not None and self.block_temporal_features is not None:
+            # captured graphs hold the planes' addresses: keep them, only forget their content
+            self.block_temporal_features.mark_reset()
+        else:
+            if self.block_temporal_features:
+                self.block_temporal_features.clear()
+            self.block_temporal_features = None
         self.policy_meta = {"inputs": None, "outputs": None, "outputs_prev": None}
 
     def forward(self, inputs, **kwargs):
@@ -69,6 +80,8 @@ class BlockCopyModel(nn.Module):
                 # nothing to execute: the previous output object is returned, no state is touched
                 meta = self.policy_meta = meta.copy()
                 out = meta["outputs"]
+            elif self._graphs is not None and not kwargs:
+                meta["frame_state"], out = self._forward_graphed(inputs, meta["grid"], meta["num_exec"])
             else:
                 self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
                 blocks = x.to_blocks(meta["grid"])
@@ -84,6 +97,71 @@ class BlockCopyModel(nn.Module):
                 train_policy = self.clip_length % self.train_interval == 0
                 self.policy_meta = self.policy.optim(self.policy_meta, train=train_policy)
         return out
+
+
+    # ------------------------------------------------------------------ CUDA-graph mode
+    def _block_frame_inplace(self, inputs, grid):
+        """One block-sparse frame with every combine IN PLACE into persistent planes (what a graph
+        can replay): returns (frame_state plane, output plane), both persistent tensors."""
+        x = to_tensorwrapper(inputs)
+        self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
+        self.block_temporal_features.track_transfer_idx = False
+        blocks = x.to_blocks(grid)
+        frame_state = blocks.combine_().to_tensor()
+        out = self.base_model(blocks)
+        return frame_state, out.combine_().to_tensor()
+
+    def _forward_graphed(self, inputs, grid, num_exec):
+        from .. import _C
+
+        gs = self._graphs
+        if gs.static_in is None or gs.static_in.shape != inputs.shape or gs.static_in.dtype != inputs.dtype:
+            assert not gs.graphs, "input shape / dtype changed after CUDA graphs were captured"
+            gs.static_in = torch.empty_like(inputs)
+            gs.static_grid = torch.empty(grid.shape, dtype=torch.bool, device=inputs.device)
+        gs.static_in.copy_(inputs)
+        gs.static_grid.copy_(grid)
+        gs.static_grid._bc_num_exec = num_exec
+        entry = gs.graphs.get(num_exec)
+        if entry is None:
+            seen = gs.seen.get(num_exec, 0)
+            gs.seen[num_exec] = seen + 1
+            if seen == 0:
+                # first time this block count shows up: run eagerly (allocates planes on the first
+                # frame of the first clip, lets cuDNN pick its algorithms)
+                frame_state, dense = self._block_frame_inplace(gs.static_in, gs.static_grid)
+            else:
+                graph = torch.cuda.CUDAGraph()
+                n0 = _C.launch_count()
+                with torch.cuda.graph(graph, pool=gs.pool):
+                    frame_state, dense = self._block_frame_inplace(gs.static_in, gs.static_grid)
+                if gs.pool is None:
+                    gs.pool = graph.pool()
+                entry = gs.graphs[num_exec] = (graph, frame_state, dense, _C.launch_count() - n0)
+                _C.add_launches(-entry[3])  # counted again at every replay
+        if entry is not None:
+            graph, frame_state, dense, launches = entry
+            graph.replay()
+            _C.add_launches(launches)
+        if gs.out_bufs is None or gs.out_bufs[0].shape != dense.shape:
+            gs.out_bufs = [torch.empty_like(dense), torch.empty_like(dense)]
+        gs.flip ^= 1
+        out = gs.out_bufs[gs.flip]
+        out.copy_(dense)
+        return frame_state, out
+
+
+class _GraphState:
+    """Static buffers and captured graphs of one BlockCopyModel (block_cuda_graphs=True)."""
+
+    def __init__(self):
+        self.static_in = None
+        self.static_grid = None
+        self.graphs = {}   # executed-block count -> (graph, frame_state plane, output plane, kernels of ours)
+        self.seen = {}
+        self.pool = None
+        self.out_bufs = None
+        self.flip = 0
 
 
 def blockcopy_noblocks(func):

@@ -105,13 +105,15 @@ class BlockFeatures:
         self._transfer_idx: Optional[torch.Tensor] = None  # int32 (T,) reference-protocol compat
         self.num_exec = 0
         self.num_total = 0
-        self.has_history = prev is not None
+        self.has_history = prev is not None and not prev._was_reset
+        self._was_reset = False
+        self.track_transfer_idx = True  # also produce transfer_idx (reference tile protocol compat)
         # persistent planes; slot = call order within a frame
         self._planes: List[torch.Tensor] = prev._planes if prev is not None else []
         self._full: List[torch.Tensor] = prev._full if prev is not None else []
         self._plane_cursor = 0
         self._full_cursor = 0
-        self._prev_grid_idx = prev._grid_idx if prev is not None else None
+        self._prev_grid_idx = prev._grid_idx if (prev is not None and self.has_history) else None
         if prev is not None:
             prev._planes, prev._full = [], []  # ownership moved
 
@@ -125,12 +127,14 @@ class BlockFeatures:
             grid_idx = torch.empty(g.shape, dtype=torch.int32, device=self.device)
             buf = torch.empty(2 * G + 2, dtype=torch.int32, device=self.device)
             mapping, transfer, counts = buf[:G], buf[G:2 * G], buf[2 * G:]
-            prev_idx = self._prev_grid_idx if self._prev_grid_idx is not None else (
-                meta_prev._grid_idx if meta_prev is not None else None)
+            prev_idx = None
+            if self.track_transfer_idx:
+                prev_idx = self._prev_grid_idx if self._prev_grid_idx is not None else (
+                    meta_prev._grid_idx if (meta_prev is not None and self.has_history) else None)
             _C.compact_mask(g.view(torch.uint8), grid_idx, mapping, counts, prev_idx,
                             transfer if prev_idx is not None else None)
             n_exec = int(hint) if hint is not None else int(counts[0])  # the single host round trip
-            if not self.has_history and meta_prev is None:
+            if not self.has_history:
                 assert n_exec == G, "No previous features known, first run should execute all blocks!"
             self._grid, self._grid_idx = g, grid_idx
             self._mapping_exec = mapping[:n_exec]
@@ -169,6 +173,11 @@ class BlockFeatures:
         else:
             assert i == len(self._full)
             self._full.append(plane)
+
+    def mark_reset(self):
+        """Logical reset that keeps the planes allocated (CUDA-graph mode): the next frame must
+        execute every block, which rewrites all of them."""
+        self._was_reset = True
 
     def clear(self):
         """Drop all stored features."""

@@ -140,13 +140,14 @@ static int largest_divisor_leq(int n, int cap) {
 
 bool tma_move_eligible(const void *tiles, const void *plane, int E, int C, int W, int BS, int tile_edge, int es,
                        int layout) {
-  (void)BS;
   if (E <= 0) return false;
   if (((uintptr_t)tiles | (uintptr_t)plane) & 15) return false;  // tensor-map base address
   if (tile_edge > 256) return false;                              // box dims are limited to 256 elements
-  // global strides and the inner box extent must be multiples of 16 bytes
-  if (layout == BC_NHWC) return ((int64_t)C * es) % 16 == 0;
-  return ((int64_t)tile_edge * es) % 16 == 0 && ((int64_t)W * es) % 16 == 0;
+  // Global strides, the inner box extent AND the byte offset of the inner-most start coordinate must be
+  // multiples of 16 bytes (a misaligned inner coordinate raises "illegal instruction" on sm_100).
+  if (layout == BC_NHWC) return ((int64_t)C * es) % 16 == 0;  // inner dim = channels, coordinates are chunk starts
+  // NCHW: inner dim = x.  Box starts at gw*BS - pad, so a halo (tile_edge != BS) is never aligned in practice.
+  return tile_edge == BS && ((int64_t)BS * es) % 16 == 0 && ((int64_t)W * es) % 16 == 0;
 }
 
 int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int N, int C, int H, int W, int BS,

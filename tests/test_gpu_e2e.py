@@ -131,3 +131,47 @@ def test_noblocks_and_reset_isolate_clips():
     rb2, ra2 = run(model, b, 6), run(model, a, 5)
     for x, y in zip(ra1 + rb1, ra2 + rb2):
         assert torch.equal(x, y)
+
+
+def test_cuda_graph_mode_is_bit_identical_to_eager():
+    """block_cuda_graphs=True: first occurrence of a block count runs eagerly, the second is
+    captured, later ones are replayed -- outputs, frame_state and policy_meta semantics must equal
+    the eager mode bit for bit, across a clip boundary (reset_temporal keeps the planes)."""
+    import blockcopy
+    from consumers.clips import PolicyReplay, synthetic_clip
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    BS, H, W = 64, 256, 512
+    g = torch.Generator().manual_seed(0)
+    grids = [torch.ones(1, 1, 4, 8, dtype=torch.bool)]
+    for e in (8, 8, 12, 8, 0, 12, 8, 32, 8):
+        m = torch.zeros(32, dtype=torch.bool)
+        m[torch.randperm(32, generator=g)[:e]] = True
+        grids.append(m.view(1, 1, 4, 8))
+    clip = synthetic_clip(len(grids), H, W, seed=4, device="cuda")
+
+    def run(graphs):
+        model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), _settings(block_policy="all", block_size=BS,
+                                                                        block_cuda_graphs=graphs)).eval().cuda().half()
+        model.policy = PolicyReplay(BS, grids)
+        outs = []
+        with torch.no_grad():
+            for _ in range(2):  # two clips: the second one replays graphs captured during the first
+                model.reset_temporal()
+                model.policy.rewind()
+                prev = None
+                for f in clip:
+                    o = model(f)
+                    assert model.policy_meta["outputs"] is o
+                    if prev is not None and model.policy_meta["num_exec"]:
+                        assert model.policy_meta["outputs_prev"] is not o
+                    outs.append((o.clone(), model.policy_meta["frame_state"].clone()))
+                    prev = o
+        return model, outs
+
+    m_eager, eager = run(False)
+    m_graph, graphed = run(True)
+    assert len(m_graph._graphs.graphs) >= 3, "graphs were not captured"
+    for t, ((a, fa), (b, fb)) in enumerate(zip(eager, graphed)):
+        assert torch.equal(a, b), f"frame {t}: outputs differ between eager and graph mode"
+        assert torch.equal(fa, fb), f"frame {t}: frame_state differs"
