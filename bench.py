@@ -133,26 +133,6 @@ def barrier(world):
         dist.barrier()
 
 
-def max_over_ranks(value: float, world: int, device) -> float:
-    if world == 1:
-        return value
-    import torch.distributed as dist
-
-    t = torch.tensor([value], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-
-def sum_over_ranks(value: float, world: int, device) -> float:
-    if world == 1:
-        return value
-    import torch.distributed as dist
-
-    t = torch.tensor([value], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
-
-
 # =============================================================================================== workload
 def build_model(args, device):
     import blockcopy
@@ -172,30 +152,78 @@ def build_model(args, device):
     return model
 
 
-def run_frames(models, clips, start, count, clip_len, h2d_stream=None, host_clips=None, d2h_buf=None):
-    """Advance every stream by `count` frames starting at global frame index `start`."""
+def _advance(models, t, clip_len):
+    k = t % clip_len
+    if k == 0:
+        for s, model in enumerate(models):
+            model.reset_temporal()
+            if hasattr(model.policy, "reseed"):
+                model.policy.reseed(1000 * s + t // clip_len)
+    return k
+
+
+def run_frames(models, clips, start, count, clip_len):
+    """Device-resident inputs: advance every stream by `count` frames from global frame `start`."""
     out = None
     with torch.no_grad():
         for t in range(start, start + count):
-            k = t % clip_len
+            k = _advance(models, t, clip_len)
             for s, model in enumerate(models):
-                if k == 0:
-                    model.reset_temporal()
-                    if hasattr(model.policy, "reseed"):
-                        model.policy.reseed(1000 * s + t // clip_len)
-                if host_clips is not None:
-                    frame = host_clips[s][k].to(clips[s][k].device, non_blocking=True)
-                else:
-                    frame = clips[s][k]
-                out = model(frame)
-                if d2h_buf is not None:
-                    d2h_buf[s].copy_(out, non_blocking=True)
+                out = model(clips[s][k])
     return out
+
+
+class HostPipeline:
+    """End-to-end loop with HOST buffers: every step uploads that step's frame from pinned host
+    memory and reads the step's logits back to pinned host memory.  Copies run on a side stream and
+    are double-buffered so that the upload of frame t+1 overlaps the compute of frame t; all of it
+    is inside the timed region."""
+
+    def __init__(self, models, host_clips, device, out_shape):
+        self.models, self.host_clips, self.device = models, host_clips, device
+        S = len(models)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        shape = host_clips[0][0].shape
+        self.dev_in = [[torch.empty(shape, dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
+        self.host_out = [[torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(S)]
+        self.in_ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
+        self.in_free = [[None, None] for _ in range(S)]
+
+    def _upload(self, s, t, clip_len):
+        slot = t % 2
+        with torch.cuda.stream(self.copy_stream):
+            if self.in_free[s][slot] is not None:
+                self.copy_stream.wait_event(self.in_free[s][slot])
+            self.dev_in[s][slot].copy_(self.host_clips[s][t % clip_len], non_blocking=True)
+            self.in_ready[s][slot].record(self.copy_stream)
+
+    def run(self, start, count, clip_len):
+        main = torch.cuda.current_stream()
+        S = len(self.models)
+        with torch.no_grad():
+            for s in range(S):
+                self._upload(s, start, clip_len)
+            for t in range(start, start + count):
+                _advance(self.models, t, clip_len)
+                slot = t % 2
+                for s, model in enumerate(self.models):
+                    if t + 1 < start + count:
+                        self._upload(s, t + 1, clip_len)
+                    main.wait_event(self.in_ready[s][slot])
+                    out = model(self.dev_in[s][slot])
+                    done = torch.cuda.Event()
+                    done.record(main)
+                    self.in_free[s][slot] = done
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(done)
+                        self.host_out[s][slot].copy_(out, non_blocking=True)
+        main.wait_stream(self.copy_stream)
 
 
 def bench_ours(args):
     from blockcopy import _C
     from consumers.clips import synthetic_clip
+    from consumers.streams import aggregate_throughput
 
     world, rank, local = dist_setup(args)
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
@@ -224,28 +252,26 @@ def bench_ours(args):
         run_frames(models, clips, args.warmup, args.steps, L)
         ev1.record()
         torch.cuda.synchronize()
-    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1), world, device)
     launches = _C.launch_count() - n0
+    frames_total, elapsed_ms, value = aggregate_throughput(float(args.steps * S), ev0.elapsed_time(ev1), device)
     barrier(world)
-    frames_total = sum_over_ranks(float(args.steps * S), world, device)
-    value = frames_total / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
     e2e = None
     if not args.skip_e2e:
-        out_shape = (1, 19, H // 4, W // 4)
-        d2h = [torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(S)]
-        run_frames(models, clips, 0, min(args.warmup, L), L, host_clips=host_clips, d2h_buf=d2h)
+        pipe = HostPipeline(models, host_clips, device, (1, 19, H // 4, W // 4))
+        pipe.run(0, min(args.warmup, L), L)
         torch.cuda.synchronize()
         barrier(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run_frames(models, clips, args.warmup, args.steps, L, host_clips=host_clips, d2h_buf=d2h)
+        pipe.run(args.warmup, args.steps, L)
         e1.record()
         torch.cuda.synchronize()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, device)
-        e2e = {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": S * 3 * H * W * 2, "d2h_bytes_per_step": S * 19 * (H // 4) * (W // 4) * 2}
+        _, e2e_ms, e2e_fps = aggregate_throughput(float(args.steps * S), e0.elapsed_time(e1), device)
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * H * W * 2,
+               "d2h_bytes_per_step": S * 19 * (H // 4) * (W // 4) * 2,
+               "note": "pinned host frame -> H2D -> model() -> D2H of the logits, copies double-buffered on a side stream"}
 
     # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
     kern = microbench(device, peaks) if rank == 0 else None
@@ -254,7 +280,12 @@ def bench_ours(args):
         cpu = cpu_dense_baseline(H, W, frames=5)
 
     if rank == 0:
-        dom = kern["gather_halo_nhwc"]
+        hbm = kern["gather_halo_nhwc"]
+        dom = kern["conv3x3_c128_bs32(#20)"]
+        ref_gpu = None
+        rt = os.path.join(ROOT, "tests", "golden", "reference_timing.json")
+        if os.path.exists(rt):
+            ref_gpu = json.load(open(rt))
         line = {
             "metric": "frames/s @1024x2048, 30% active blocks (SwiftNet-RN18 + BlockCopy)", "value": value,
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -265,14 +296,25 @@ def bench_ours(args):
                        "height": H, "width": W, "block_size": 128, "active_blocks": num_exec, "total_blocks": G,
                        "clip_length": L, "streams_per_gpu": S, "policy": args.policy,
                        "cuda_graphs": not args.no_graphs,
-                       "l2_note": "microbench rotates 8 plane sets (268 MB > 126 MB L2); frame loop inputs: "
-                                  "30 distinct 12.6 MB frames + 0.27 GB of planes per stream"},
+                       "l2_note": "kernel microbenchmarks rotate 8 plane sets (268 MB > 126 MB L2); the frame loop "
+                                  "cycles 30 distinct 12.6 MB frames over 0.27 GB of planes per stream"},
             "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "bc_gather_halo (NHWC, C=128, BS=32, p=1, E=38: config 2)",
-                         "achieved": dom["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": dom["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                         "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]},
-            "kernels": kern, "cpu_baseline": cpu, "clocks": clk.summary(),
+            "roofline": {"bound": "tensor",
+                         "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: largest share "
+                                   "of the step, profiles/r01_frame_launch_shares.md)",
+                         "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                         "frac": dom["tflops"] / peaks["tf_burst"], "traffic": None, "peak_source": peaks["source"]
+                         + " (burst: kernel timed alone)", "algorithmic_flops_per_launch": dom["flops"],
+                         "us_per_launch": dom["us"]},
+            "roofline_hbm": {"bound": "hbm", "kernel": "bc_gather_halo TMA path (NHWC, C=128, BS=32, p=1, E=38: "
+                                                       "BASELINE config 2)",
+                             "achieved": hbm["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": hbm["gbs"] / peaks["hbm_gbs"], "traffic": 19937792,
+                             "traffic_note": "dram__bytes_read+write of one launch, profiles/r01_tma_move_ncu.md "
+                                             "(writes stay in L2)",
+                             "peak_source": peaks["source"], "algorithmic_bytes_per_launch": hbm["bytes"],
+                             "us_per_launch": hbm["us"]},
+            "kernels": kern, "cpu_baseline": cpu, "reference_gpu_path": ref_gpu, "clocks": clk.summary(),
         }
         print(json.dumps(line))
     if world > 1:
@@ -344,7 +386,49 @@ def microbench(device, peaks, reps=200, sets=8):
                 del graph
         _C.set_tma_enabled(True)
         del planes, tiles, padded, outs
+    res.update(conv_microbench(device, peaks, me_full=None))
     return res
+
+
+def conv_microbench(device, peaks, me_full=None, reps=50, sets=4, E=40):
+    """bc_conv_igemm on the four characteristic 3x3 layers of SwiftNet-RN18 at 1024x2048 (grid 8x16,
+    E = 40 executed blocks): achieved TFLOP/s = 2*9*Cin*Cout*BS^2*E / time, graph-timed, rotating
+    `sets` plane copies (the layer-#20 planes are 33.5 MB each)."""
+    from blockcopy import _C
+
+    out = {}
+    cells = torch.randperm(128, generator=torch.Generator().manual_seed(0))[:E].sort().values.to(torch.int32).to(device)
+    g = torch.Generator(device=device).manual_seed(1)
+    for name, Cin, Cout, BS in (("conv3x3_c128_bs32(#20)", 128, 128, 32), ("conv3x3_c64_bs32(layer1)", 64, 64, 32),
+                                ("conv3x3_c256_bs8(layer3)", 256, 256, 8), ("conv3x3_c512_bs4(layer4)", 512, 512, 4)):
+        H, W = 8 * BS, 16 * BS
+        planes = [torch.randn(1, Cin, H, W, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=torch.channels_last)
+                  for _ in range(sets)]
+        w = (torch.randn(Cout, Cin, 3, 3, device=device, dtype=torch.float16, generator=g) * 0.05).contiguous(memory_format=torch.channels_last)
+        bias = torch.zeros(Cout, device=device, dtype=torch.float16)
+        outs = [torch.empty(E, Cout, BS, BS, device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+                for _ in range(2)]
+        fn = lambda i: _C.conv_igemm(outs[i % 2], planes[i % sets], w, bias, None, cells, E, BS, 1, 1)  # noqa: E731
+        for i in range(sets):
+            fn(i)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(reps):
+                fn(i)
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / reps
+        flops = 2.0 * 9 * Cin * Cout * BS * BS * E
+        out[name] = {"us": us, "flops": flops, "tflops": flops / us * 1e-6,
+                     "frac_of_tensor_peak": flops / us * 1e-6 / peaks["tf_burst"]}
+        del graph, planes, outs
+    return out
 
 
 # =============================================================================================== CPU baseline
@@ -353,13 +437,28 @@ def cpu_dense_baseline(H, W, frames=5, warm=2):
     part of the reference that runs without CUDA).  Uses the reference's own model code when it is
     staged in baseline/_ref (kind 'reference'), else this repo's architecture-identical consumer
     (kind 'port')."""
-    kind = "port"
-    try:
+    kind, net = "port", None
+    ref_ss = os.path.join(ROOT, "baseline", "_ref", "semantic_segmentation")
+    if os.path.isdir(os.path.join(ref_ss, "lib", "models", "swiftnet")):
+        try:  # the reference's own model code (staged copy); `blockcopy` it imports is only used for a decorator
+            import blockcopy  # noqa: F401
+            sys.path.insert(0, ref_ss)
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                from lib.models.swiftnet.backbones.resnet import resnet18
+                from lib.models.swiftnet.swiftnet import SwiftNet
+                from lib.utils import bn_fusion
+                torch.manual_seed(0)
+                net = SwiftNet(resnet18(pretrained=False), num_classes=19, num_features=128, use_spp=True).eval()
+                net = bn_fusion.fuse_bn_recursively(net)
+            kind = "reference"
+        except Exception:
+            net = None
+    if net is None:
         from consumers.swiftnet_rn18 import build_swiftnet_rn18
 
         net = build_swiftnet_rn18(seed=0)
-    except Exception as e:  # pragma: no cover
-        return {"error": repr(e)}
     x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(0))
     cores = torch.get_num_threads()
     times = []

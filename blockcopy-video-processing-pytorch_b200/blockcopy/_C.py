@@ -205,7 +205,8 @@ def gather_halo_tiles(out: torch.Tensor, exec_t: torch.Tensor, transfer_t: torch
     _dev(out, exec_t, transfer_t, grid_idx, mapping_exec)
     N, _, GH, GW = grid_idx.shape
     _, C, BS, _ = exec_t.shape
-    lay = layout_of(exec_t) if E > 0 else BC_NCHW
+    lay = layout_of(out) if E > 0 else BC_NCHW  # the padded output is never layout-ambiguous (edge >= 3)
+    assert E == 0 or _dense_in(exec_t, lay)
     _check(lib().bc_gather_halo_tiles(out.data_ptr(), exec_t.data_ptr(),
                                       transfer_t.data_ptr() if transfer_t.numel() else None,
                                       grid_idx.data_ptr(), mapping_exec.data_ptr(), E, N, C, GH, GW, BS, pad,

@@ -174,10 +174,12 @@ def blockcopy_noblocks(func):
         was_wrapper = isinstance(x, TensorWrapper)
         if was_wrapper:
             blocks = x
-            x = x.combine_().to_tensor()
+            # dense TensorWrapper (the reference hands over a plain tensor): numerically the same
+            # object, but torch calls stay interceptable, see TensorWrapper._dense_dispatch
+            x = x.combine_()
         x = func(self, x)
         if was_wrapper:
-            x = to_tensorwrapper(x).to_blocks_like(blocks)
+            x = to_tensorwrapper(x.as_subclass(torch.Tensor)).to_blocks_like(blocks)
         return x
 
     return noblocks
