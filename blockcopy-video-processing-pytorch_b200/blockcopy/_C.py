@@ -36,7 +36,9 @@ _SIGNATURES = {
     "bc_transfer": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo_tiles": ([_vp, _vp, _vp, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
-    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp], _i),
+    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _vp, ctypes.c_int64, _vp, _i,
+                                                             _vp], _i),
+    "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
 }
 
 
@@ -240,19 +242,75 @@ def conv_supported(dtype, weight: torch.Tensor, BS_in: int, stride: int, padding
     return 4 <= bo <= 128 and (bo & (bo - 1)) == 0
 
 
+def lazy_supported(x: torch.Tensor) -> bool:
+    """Can bc_ew_fused handle this block tensor (packed fp16 NHWC tiles on the GPU, C % 8 == 0)?"""
+    return x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[1] % 8 == 0
+
+
+_WORKSPACE = {}  # device index -> (fp32 split-K workspace, uint32 tile counters); caller-owned, see the header
+
+
+def _workspace(device: torch.device):
+    ws = _WORKSPACE.get(device.index)
+    if ws is None:
+        ws = (torch.empty(16 * 1024 * 1024, dtype=torch.float32, device=device),
+              torch.zeros(4096, dtype=torch.int32, device=device))
+        _WORKSPACE[device.index] = ws
+    return ws
+
+
 def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],
                residual: Optional[torch.Tensor], mapping_exec: Optional[torch.Tensor], E: int, BS_in: int,
-               stride: int, padding: int, relu: bool = False):
+               stride: int, padding: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None,
+               out_mapping: Optional[torch.Tensor] = None, split_k: bool = True):
     """out (E,Cout,BS_out,BS_out) channels_last <- conv(plane (N,Cin,H,W) channels_last) on the E executed
-    blocks.  weight_cl must be a channels_last (Cout,Cin,k,k) fp16 tensor."""
-    _dev(out, plane, weight_cl, bias, residual, mapping_exec)
+    blocks (+bias, +residual, ReLU).  weight_cl: channels_last (Cout,Cin,k,k) fp16.  plane_out: the next padded
+    op's persistent plane (N,Cout,GH*BS_out,GW*BS_out) channels_last, written in the same epilogue."""
+    _dev(out, plane, weight_cl, bias, residual, mapping_exec, plane_out, out_mapping)
     N, Cin, H, W = plane.shape
     Cout, _, k, _ = weight_cl.shape
     assert weight_cl.is_contiguous(memory_format=torch.channels_last) or k == 1
+    oN = oGH = oGW = 0
+    if plane_out is not None:
+        BSo = BS_in // stride
+        oN, _, oH, oW = plane_out.shape
+        oGH, oGW = oH // BSo, oW // BSo
+        assert plane_out.is_contiguous(memory_format=torch.channels_last) and plane_out.shape[1] == Cout
+        if out_mapping is None:
+            out_mapping = mapping_exec
+    ws, counters = _workspace(out.device) if split_k else (None, None)
     _check(lib().bc_conv_igemm(out.data_ptr(), plane.data_ptr(), weight_cl.data_ptr(),
                                bias.data_ptr() if bias is not None else None,
                                residual.data_ptr() if residual is not None else None,
                                mapping_exec.data_ptr() if mapping_exec is not None else None,
-                               E, N, Cin, H, W, BS_in, Cout, k, stride, padding, int(relu), _stream()),
+                               E, N, Cin, H, W, BS_in, Cout, k, stride, padding, int(relu),
+                               plane_out.data_ptr() if plane_out is not None else None,
+                               out_mapping.data_ptr() if out_mapping is not None else None, oN, oGH, oGW,
+                               ws.data_ptr() if ws is not None else None,
+                               ws.numel() * 4 if ws is not None else 0,
+                               counters.data_ptr() if counters is not None else None,
+                               counters.numel() if counters is not None else 0, _stream()),
            "bc_conv_igemm")
+    return out
+
+
+def ew_fused(out: Optional[torch.Tensor], a: torch.Tensor, residual: Optional[torch.Tensor] = None, bn=None,
+             relu: bool = False, up2x: bool = False, plane_out: Optional[torch.Tensor] = None,
+             mapping_exec: Optional[torch.Tensor] = None):
+    """y = relu?(bn?(up2x?(a) + residual?)) on packed channels_last fp16 tiles, written to `out` and/or scattered
+    into `plane_out`.  bn = (mean, invstd, weight|None, shift|None), fp32 [C]."""
+    _dev(out, a, residual, plane_out, mapping_exec)
+    E, C, BSa, _ = a.shape
+    BS = BSa * 2 if up2x else BSa
+    N = H = W = 0
+    if plane_out is not None:
+        N, _, H, W = plane_out.shape
+        assert plane_out.is_contiguous(memory_format=torch.channels_last) and plane_out.shape[1] == C
+    mean = invstd = weight = shift = None
+    if bn is not None:
+        mean, invstd, weight, shift = bn
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    _check(lib().bc_ew_fused(ptr(out), ptr(plane_out), a.data_ptr(), ptr(residual), ptr(mean), ptr(invstd), ptr(weight),
+                             ptr(shift), ptr(mapping_exec), E, C, BS, N, H, W, int(up2x), int(relu), _stream()),
+           "bc_ew_fused")
     return out

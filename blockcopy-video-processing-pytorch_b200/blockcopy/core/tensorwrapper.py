@@ -30,6 +30,8 @@ from .. import _C
 from ..utils.profiler import timings
 
 FUSED_CONV = os.environ.get("BLOCKCOPY_FUSED_CONV", "1") != "0"  # route eligible convs on blocks to the tcgen05 implicit-GEMM kernel (bc_conv_igemm)
+# defer convs / elementwise ops on blocks and fuse them into epilogues (see _Pending); "0" = op-by-op execution
+LAZY_FUSION = os.environ.get("BLOCKCOPY_LAZY", "1") != "0"
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
 
@@ -144,21 +146,24 @@ class BlockFeatures:
                 print(f"TensorWrapper >> GRID {tuple(g.shape)} exec {n_exec}/{G}")
 
     # ------------------------------------------------------------------ planes
-    def _next_plane(self, like: torch.Tensor, shape) -> torch.Tensor:
-        """Plane of the next padded op in call order; allocated on the first frame."""
+    def _next_plane(self, like: Optional[torch.Tensor], shape, dtype=None, device=None, nhwc=None) -> torch.Tensor:
+        """Plane of the next padded op in call order; allocated on the first frame.  Layout / dtype
+        come from `like` (packed tiles) or from the explicit descriptor."""
+        if like is not None:
+            dtype, device, nhwc = like.dtype, like.device, _C.layout_of(like) == _C.BC_NHWC
         i = self._plane_cursor
         self._plane_cursor += 1
         if i < len(self._planes):
             plane = self._planes[i]
-            if plane.shape != tuple(shape) or plane.dtype != like.dtype:
+            if plane.shape != tuple(shape) or plane.dtype != dtype:
                 raise AssertionError(
                     f"padded op #{i}: plane {tuple(plane.shape)}/{plane.dtype} does not match this frame's "
-                    f"{tuple(shape)}/{like.dtype}; the model must issue the same ops every frame")
+                    f"{tuple(shape)}/{dtype}; the model must issue the same ops every frame")
             return plane
         assert not self.has_history or self.num_exec == self.num_total, \
             "No computed features to pop from stack, something seems wrong in the model."
-        fmt = torch.channels_last if _C.layout_of(like) == _C.BC_NHWC else torch.contiguous_format
-        plane = torch.empty(shape, dtype=like.dtype, device=like.device, memory_format=fmt)
+        fmt = torch.channels_last if nhwc else torch.contiguous_format
+        plane = torch.empty(shape, dtype=dtype, device=device, memory_format=fmt)
         self._planes.append(plane)
         return plane
 
@@ -189,8 +194,72 @@ class BlockFeatures:
         return sum(p.numel() * p.element_size() for p in self._planes + self._full)
 
 
+def _raw(t: torch.Tensor) -> torch.Tensor:
+    """Plain-tensor alias of t WITHOUT going through __torch_function__ (so it never materialises)."""
+    with torch._C.DisableTorchFunctionSubclass():
+        return t.as_subclass(torch.Tensor)
+
+
+class _Pending:
+    """Deferred producer of a block tensor (lazy epilogue fusion).
+
+    A conv2d on blocks, and the elementwise ops the model applies to its result, are not launched
+    when the model calls them: the returned TensorWrapper owns its (still unwritten) storage and
+    this descriptor.  In-place ReLU / residual add are absorbed into the descriptor; eval-mode
+    batch_norm, ReLU, add and per-block bilinear x2 on materialised tiles become an elementwise
+    descriptor.  The kernel is launched when the tensor is first needed -- and if the consumer is a
+    padded op, the same launch also writes the result into that op's persistent plane (the scatter
+    of the north-star design, fused into the producer's epilogue)."""
+
+    __slots__ = ("kind", "conv", "src", "up2x", "residual", "bn", "relu", "stage", "__weakref__")
+
+    def __init__(self, kind, conv=None, src=None, up2x=False):
+        self.kind, self.conv, self.src, self.up2x = kind, conv, src, up2x
+        self.residual, self.bn, self.relu, self.stage = None, None, False, 0
+
+    def clone(self):
+        q = _Pending(self.kind, self.conv, self.src, self.up2x)
+        q.residual, q.bn, q.relu, q.stage = self.residual, self.bn, self.relu, self.stage
+        return q
+
+    def reads(self, t: torch.Tensor) -> bool:
+        ptr = t.data_ptr()
+        for u in (self.src, self.residual, self.conv["src"] if self.conv else None):
+            if u is not None and u.data_ptr() == ptr:
+                return True
+        return False
+
+
+_META_METHODS = {"dim", "size", "stride", "numel", "is_contiguous", "element_size", "storage_offset",
+                 "is_floating_point", "is_complex", "ndimension", "nelement", "get_device", "__len__"}
+_META_PROPS = {"shape", "dtype", "device", "ndim", "is_cuda", "requires_grad", "layout", "names", "is_leaf",
+               "grad_fn", "is_sparse", "is_quantized", "is_meta"}
+_BN_CACHE: Dict[Any, Any] = {}
+
+
+def _bn_params(running_mean, running_var, weight, bias, eps):
+    """fp32 (mean, invstd, weight, shift) of an eval-mode batch norm, cached per parameter version."""
+    key = (running_mean.data_ptr(), running_var.data_ptr(), running_mean._version, running_var._version,
+           None if weight is None else (weight.data_ptr(), weight._version),
+           None if bias is None else (bias.data_ptr(), bias._version), float(eps))
+    hit = _BN_CACHE.get(key)
+    if hit is None:
+        with torch.no_grad():
+            hit = (_raw(running_mean).detach().float().contiguous(),
+                   torch.rsqrt(_raw(running_var).detach().float() + eps).contiguous(),
+                   None if weight is None else _raw(weight).detach().float().contiguous(),
+                   None if bias is None else _raw(bias).detach().float().contiguous())
+        if len(_BN_CACHE) > 4096:
+            _BN_CACHE.clear()
+        _BN_CACHE[key] = hit
+    return hit
+
+
 def _dense(t: torch.Tensor) -> torch.Tensor:
-    """Plain, dense (NCHW or channels_last) view/copy of t for the kernels."""
+    """Plain, dense (NCHW or channels_last) view/copy of t for the kernels (launches a deferred
+    producer first: Tensor.as_subclass is not routed through __torch_function__)."""
+    if isinstance(t, TensorWrapper) and t._pending is not None:
+        t._materialize()
     t = t.as_subclass(torch.Tensor)
     if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
         return t
@@ -216,6 +285,7 @@ class TensorWrapper(torch.Tensor):
     _is_blocks = False
     _features: Optional[BlockFeatures] = None
     _features_prev: Optional[BlockFeatures] = None
+    _pending: Optional[_Pending] = None  # deferred producer, see _Pending
 
     # ------------------------------------------------------------------ metadata
     @property
@@ -320,9 +390,16 @@ class TensorWrapper(torch.Tensor):
             E, C, BS, _ = self.shape
             N, _, GH, GW = grid_idx.shape
             shape = (N, C, GH * BS, GW * BS)
-            tiles = _dense(self)
             slot, prev = feats._next_full()
-            if prev is not None:
+            if (self._pending is not None and inplace and prev is not None and tuple(prev.shape) == shape
+                    and prev.is_contiguous(memory_format=torch.channels_last) and not prev.is_contiguous()):
+                self._materialize(plane_out=prev)  # producer epilogue writes the plane: no scatter kernel
+                tiles, out, done = None, prev, True
+            else:
+                tiles, done = _dense(self), False
+            if done:
+                pass
+            elif prev is not None:
                 assert tuple(prev.shape) == shape, (shape, tuple(prev.shape))
                 tiles = _match_layout(tiles, prev)
                 if inplace:
@@ -345,13 +422,22 @@ class TensorWrapper(torch.Tensor):
         frame's tiles in the op's persistent plane (the reference does store_features + transfer
         + repad here, tensorwrapper.py:551-563)."""
         feats = self._features
-        tiles = _dense(self)
-        E, C, BS, _ = tiles.shape
         N, _, GH, GW = feats._grid_idx.shape
-        plane = feats._next_plane(tiles, (N, C, GH * BS, GW * BS))
-        tiles = _match_layout(tiles, plane)
-        with timings.env("tensorwrapper/transfer", 10):
-            _C.scatter(tiles, plane, feats._mapping_exec, E)
+        if self._pending is not None:
+            E, C, BS, _ = self.shape
+            plane = feats._next_plane(None, (N, C, GH * BS, GW * BS), self.dtype, self.device, True)
+            if _C.layout_of(plane) == _C.BC_NHWC:
+                self._materialize(plane_out=plane)
+            else:
+                self._materialize()
+                _C.scatter(_match_layout(_dense(self), plane), plane, feats._mapping_exec, E)
+        else:
+            tiles = _dense(self)
+            E, C, BS, _ = tiles.shape
+            plane = feats._next_plane(tiles, (N, C, GH * BS, GW * BS))
+            tiles = _match_layout(tiles, plane)
+            with timings.env("tensorwrapper/transfer", 10):
+                _C.scatter(tiles, plane, feats._mapping_exec, E)
         with timings.env("tensorwrapper/pad", 10):
             out = _like_layout((E, C, BS + 2 * padding, BS + 2 * padding), plane)
             _C.gather_halo(out, plane, feats._mapping_exec, E, BS, padding)
@@ -361,10 +447,16 @@ class TensorWrapper(torch.Tensor):
     @classmethod
     def __torch_function__(cls, func: Callable, types: Tuple, args: Tuple = (), kwargs: Optional[Dict] = None) -> Any:
         kwargs = kwargs or {}
+        op = getattr(func, "__name__", "")
+        # shape / dtype queries never need the data (and must not launch deferred producers)
+        if op in _META_METHODS or (op == "__get__" and getattr(getattr(func, "__self__", None), "__name__", "")
+                                   in _META_PROPS):
+            return super().__torch_function__(func, types, args, kwargs)
         src = _first_wrapper(args)
         if src is None and kwargs:
             src = _first_wrapper(tuple(kwargs.values()))
         if src is None or not src._is_blocks:
+            _materialize_all(args, kwargs)
             out = cls._dense_dispatch(func, args, kwargs) if src is not None else None
             if out is None:
                 out = super().__torch_function__(func, types, args, kwargs)
@@ -372,7 +464,15 @@ class TensorWrapper(torch.Tensor):
                 out._inherit(src)
             return out
 
-        op = getattr(func, "__name__", "")
+        if LAZY_FUSION:
+            out = src._lazy_dispatch(op, args, kwargs)
+            if out is not NotImplemented:
+                return out
+        if op not in OPS["PADDED"]:  # padded ops materialise their input themselves (dual write into the plane)
+            _materialize_all(args, kwargs)
+        if op.endswith("_") or op.startswith("__i") or kwargs.get("out", None) is not None:
+            _flush_readers_of(args[0] if args else None)  # about to mutate: run deferred readers first
+
         if op in OPS_SPECIAL:
             if op in OPS["PADDED"]:
                 out = src._func_replace_padding(func, types, args, kwargs)
@@ -392,9 +492,118 @@ class TensorWrapper(torch.Tensor):
         else:
             out = super().__torch_function__(func, types, args, kwargs)
 
-        if isinstance(out, TensorWrapper) and out is not src:
+        if isinstance(out, TensorWrapper) and out is not src and out._features is None:
             out._inherit(src)
         return out
+
+    # ------------------------------------------------------------------ lazy epilogue fusion
+    def _materialize(self, plane_out: Optional[torch.Tensor] = None) -> bool:
+        """Launch the deferred producer of this tensor (if any).  With `plane_out` (the NHWC plane of
+        the padded op about to consume it) the same kernel also scatters the result into the plane.
+        Returns True if a kernel ran (and therefore wrote `plane_out`)."""
+        p = self._pending
+        if p is None:
+            return False
+        self._pending = None
+        _LIVE_PENDING.pop(id(self), None)
+        out = _raw(self)
+        feats = self._features
+        if p.kind == "conv":
+            c = p.conv
+            _C.conv_igemm(out, c["src"], c["w"], c["bias"], p.residual, c["mapping"], c["E"], c["BS_in"],
+                          c["stride"], c["pad"], relu=p.relu, plane_out=plane_out, out_mapping=feats._mapping_exec)
+        else:
+            _C.ew_fused(out, p.src, p.residual, p.bn, p.relu, p.up2x, plane_out,
+                        feats._mapping_exec if plane_out is not None else None)
+        return True
+
+    def _new_pending(self, shape, pending: _Pending) -> "TensorWrapper":
+        t = torch.empty(shape, dtype=self.dtype, device=self.device, memory_format=torch.channels_last)
+        t = t.as_subclass(TensorWrapper)._inherit(self)
+        t._pending = pending
+        _LIVE_PENDING[id(t)] = __import__("weakref").ref(t, lambda _r, k=id(t): _LIVE_PENDING.pop(k, None))
+        return t
+
+    def _tiles_nhwc(self) -> Optional[torch.Tensor]:
+        """Materialised channels_last tiles of this block tensor (copy only if the layout differs)."""
+        self._materialize()
+        t = _raw(self)
+        if t.dim() != 4:
+            return None
+        return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+    def _lazy_dispatch(self, op, args, kwargs):
+        """Absorb ReLU / add / eval batch_norm / bilinear x2 on fp16 blocks into deferred descriptors.
+        Returns NotImplemented for everything else (which then runs op by op on materialised tiles)."""
+        x = args[0] if args else None
+        if not isinstance(x, TensorWrapper) or not x._is_blocks or not _C.lazy_supported(x):
+            return NotImplemented
+        if op in ("relu", "relu_"):
+            inplace = op == "relu_" or bool(kwargs.get("inplace", args[1] if len(args) > 1 else False))
+            return x._absorb("relu", None, inplace)
+        if op in ("__iadd__", "add_", "__add__", "add"):
+            other = args[1] if len(args) > 1 else kwargs.get("other")
+            if kwargs.get("alpha", 1) != 1 or not isinstance(other, TensorWrapper) or not other._is_blocks \
+                    or other.shape != x.shape or other.dtype != x.dtype or len(args) > 2:
+                return NotImplemented
+            return x._absorb("add", other, op in ("__iadd__", "add_"))
+        if op == "batch_norm":
+            training = kwargs.get("training", args[5] if len(args) > 5 else False)
+            rm = args[1] if len(args) > 1 else kwargs.get("running_mean")
+            rv = args[2] if len(args) > 2 else kwargs.get("running_var")
+            if training or rm is None or rv is None:
+                return NotImplemented
+            w = kwargs.get("weight", args[3] if len(args) > 3 else None)
+            b = kwargs.get("bias", args[4] if len(args) > 4 else None)
+            eps = kwargs.get("eps", args[7] if len(args) > 7 else 1e-5)
+            return x._absorb("bn", _bn_params(rm, rv, w, b, eps), False)
+        if op == "interpolate":
+            if kwargs.get("mode", "nearest") != "bilinear" or kwargs.get("align_corners", None) or \
+                    kwargs.get("antialias", False):
+                return NotImplemented
+            E, C, h, w = x.shape
+            size, sf = kwargs.get("size", args[1] if len(args) > 1 else None), kwargs.get("scale_factor", None)
+            if size is not None:
+                size = (size, size) if isinstance(size, int) else tuple(size)
+                ok = size == (2 * h, 2 * w)
+            else:
+                sf = (sf, sf) if isinstance(sf, (int, float)) else tuple(sf or ())
+                ok = sf == (2, 2) or sf == (2.0, 2.0)
+            if not ok or h != w:
+                return NotImplemented
+            a = x._tiles_nhwc()
+            return x._new_pending((E, C, 2 * h, 2 * w), _Pending("ew", src=a, up2x=True))
+        return NotImplemented
+
+    def _absorb(self, what: str, operand, inplace: bool):
+        """Add one op to a deferred descriptor.  Canonical order inside a kernel: add -> bn -> relu."""
+        stage = {"add": 1, "bn": 2, "relu": 3}[what]
+        p = self._pending
+        fits = p is not None and p.stage < stage and not (what == "bn" and p.kind == "conv")
+        if inplace:
+            if not fits:
+                return NotImplemented  # materialised (or chain out of order): plain torch in-place op
+            target, q = self, p
+        else:
+            if fits:
+                q = p.clone()  # `self` stays deferred and untouched; the new tensor re-derives from the same sources
+            else:
+                a = self._tiles_nhwc()
+                if a is None:
+                    return NotImplemented
+                q = _Pending("ew", src=a)
+            target = self._new_pending(tuple(self.shape), q)
+        if what == "add":
+            r = operand._tiles_nhwc()
+            if r is None:
+                return NotImplemented
+            q.residual = r
+        elif what == "bn":
+            q.bn = operand
+        else:
+            q.relu = True
+        q.stage = stage
+        return target
 
     @staticmethod
     def _dense_dispatch(func, args, kwargs):
@@ -416,8 +625,9 @@ class TensorWrapper(torch.Tensor):
 
     def _try_fused_conv(self, args, kwargs):
         """conv2d on blocks through bc_conv_igemm: the operand load reads the op's persistent plane
-        by block index (halo included), bias is added in the epilogue; returns None if the conv is
-        outside the kernel's envelope (then the generic gather-halo + torch path runs)."""
+        by block index (halo included); bias / residual / ReLU run in the epilogue.  Returns a
+        DEFERRED tensor (see _Pending) or None if the conv is outside the kernel's envelope (then
+        the generic gather-halo + torch path runs)."""
         names = ("input", "weight", "bias", "stride", "padding", "dilation", "groups")
         a = dict(bias=None, stride=1, padding=0, dilation=1, groups=1)
         a.update(zip(names, args))
@@ -434,35 +644,36 @@ class TensorWrapper(torch.Tensor):
             return None
         if not _C.conv_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
             return None
-        if bias is not None and (bias.dtype != torch.float16 or not bias.is_contiguous()):
+        if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
             return None
         feats = self._features
         if padding > 0 and feats._plane_cursor < len(feats._planes) and \
                 _C.layout_of(feats._planes[feats._plane_cursor]) != _C.BC_NHWC:
             return None  # this op's plane was created NCHW on the first frame: stay on the generic path
-        tiles = _dense(x).contiguous(memory_format=torch.channels_last)
         w = weight.detach()
         if not w.is_contiguous(memory_format=torch.channels_last):
             w = w.contiguous(memory_format=torch.channels_last)
         Cout, BSo = weight.shape[0], BS // stride
-        out = torch.empty((E, Cout, BSo, BSo), dtype=tiles.dtype, device=tiles.device,
-                          memory_format=torch.channels_last)
         if padding > 0:
             N, _, GH, GW = feats._grid_idx.shape
-            plane = feats._next_plane(tiles, (N, Cin, GH * BS, GW * BS))
+            plane = feats._next_plane(None, (N, Cin, GH * BS, GW * BS), x.dtype, x.device, True)
             with timings.env("tensorwrapper/transfer", 10):
-                _C.scatter(tiles, plane, feats._mapping_exec, E)
-            with timings.env("tensorwrapper/pad_func", 11):
-                _C.conv_igemm(out, plane, w, bias, None, feats._mapping_exec, E, BS, stride, padding)
+                if not x._materialize(plane_out=plane):  # producer epilogue wrote the plane, else scatter now
+                    _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
+            conv = dict(src=plane, w=w, bias=bias, mapping=feats._mapping_exec, E=E, BS_in=BS, stride=stride,
+                        pad=padding)
         else:
-            with timings.env("tensorwrapper/pad_func0", 11):
-                _C.conv_igemm(out, tiles, w, bias, None, None, E, BS, stride, 0)
-        return out.as_subclass(TensorWrapper)
+            conv = dict(src=x._tiles_nhwc(), w=w, bias=bias, mapping=None, E=E, BS_in=BS, stride=stride, pad=0)
+        out = x._new_pending((E, Cout, BSo, BSo), _Pending("conv", conv=conv))
+        if not LAZY_FUSION:
+            out._materialize()
+        return out
 
     def _func_replace_padding(self, func, types, args, kwargs):
         """Padded op: take the padding from neighbouring blocks instead of zeros, then run the op
         itself with padding 0 (reference: _func_replace_paddding, tensorwrapper.py:529-575)."""
         if BLOCKPAD_WITH_ZEROES:
+            _materialize_all(args, kwargs)
             return super().__torch_function__(func, types, args, kwargs)
         op = func.__name__
         if FUSED_CONV and op == "conv2d":
@@ -493,6 +704,7 @@ class TensorWrapper(torch.Tensor):
                 args[pos] = zeros
             with timings.env("tensorwrapper/pad_func", 11):
                 return super().__torch_function__(func, types, tuple(args), kwargs)
+        _materialize_all(args, kwargs)
         with timings.env("tensorwrapper/pad_func0", 11):
             return super().__torch_function__(func, types, tuple(args), kwargs)
 
@@ -531,3 +743,29 @@ def _first_wrapper(items) -> Optional[TensorWrapper]:
                 if first is None:
                     first = w
     return first
+
+
+_LIVE_PENDING: Dict[int, Any] = {}  # id -> weakref of deferred tensors that have not been launched yet
+
+
+def _materialize_all(args, kwargs=None):
+    """Launch the deferred producers of every TensorWrapper among the operands."""
+    for a in args:
+        if isinstance(a, TensorWrapper):
+            if a._pending is not None:
+                a._materialize()
+        elif isinstance(a, (list, tuple)):
+            _materialize_all(a)
+    if kwargs:
+        _materialize_all(tuple(kwargs.values()))
+
+
+def _flush_readers_of(t):
+    """An in-place op is about to change `t`: deferred tensors that still have to READ it go first."""
+    if not isinstance(t, torch.Tensor) or not _LIVE_PENDING:
+        return
+    raw = _raw(t)
+    for ref in list(_LIVE_PENDING.values()):
+        h = ref()
+        if h is not None and h is not t and h._pending is not None and h._pending.reads(raw):
+            h._materialize()

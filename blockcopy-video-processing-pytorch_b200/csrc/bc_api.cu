@@ -40,7 +40,11 @@ int launch_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *
 
 int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
-               int pad, int relu, cudaStream_t stream);
+               int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
+               void *ws, size_t ws_bytes, void *counters, int n_counters, cudaStream_t stream);
+int ew_fused(void *out, void *plane, const void *a, const void *residual, const float *mean, const float *invstd,
+             const float *weight, const float *shift, const int32_t *mapping, int E, int C, int BS, int N, int H,
+             int W, int up2x, int relu, cudaStream_t stream);
 
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
@@ -175,11 +179,24 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
 
 BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                          const int32_t *mapping_exec, int E, int N, int Cin, int H, int W, int BS_in, int Cout,
-                         int ksize, int stride, int pad, int relu, bc_stream_t stream) {
+                         int ksize, int stride, int pad, int relu, void *plane_out, const int32_t *out_mapping,
+                         int out_N, int out_GH, int out_GW, void *workspace, int64_t workspace_bytes,
+                         void *counters, int n_counters, bc_stream_t stream) {
   BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_conv_igemm: E=%d", E);
   if (E == 0) return BC_OK;
   return conv_igemm(out, plane, weight, bias, residual, mapping_exec, E, N, Cin, H, W, BS_in, Cout, ksize, stride,
-                    pad, relu, (cudaStream_t)stream);
+                    pad, relu, plane_out, out_mapping, out_N, out_GH, out_GW, workspace,
+                    workspace_bytes > 0 ? (size_t)workspace_bytes : 0, counters, n_counters, (cudaStream_t)stream);
+}
+
+BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *residual, const float *bn_mean,
+                       const float *bn_invstd, const float *bn_weight, const float *bn_shift,
+                       const int32_t *mapping_exec, int E, int C, int BS, int N, int H, int W, int up2x, int relu,
+                       bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_ew_fused: E=%d", E);
+  if (E == 0) return BC_OK;
+  return ew_fused(out, plane_out, a, residual, bn_mean, bn_invstd, bn_weight, bn_shift, mapping_exec, E, C, BS, N, H,
+                  W, up2x, relu, (cudaStream_t)stream);
 }
 
 }  // extern "C"

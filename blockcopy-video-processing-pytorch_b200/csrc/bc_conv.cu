@@ -42,6 +42,16 @@ struct ConvParams {
   int tiles_per_block;      // BS_out^2 / 128 for big blocks, else 1
   int relu;
   uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
+  // optional second destination: the next padded op's persistent plane (N, GH*BS_out, GW*BS_out, Cout)
+  __half *plane_out;
+  const int32_t *out_mapping;  // cell of packed tile b in the OUTPUT grid (== mapping unless mapping is null)
+  CellDecode out_cell;
+  int out_H, out_W;
+  // split-K: grid.z CTAs share one output tile; partial accumulators go through `ws`, the CTA that
+  // arrives last (per-tile counter) reduces them in split order (deterministic) and runs the epilogue
+  int splits, ksteps_per_split;
+  float *ws;
+  unsigned int *counters;
 };
 
 template <int N_TILE, int STAGES>
@@ -55,6 +65,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ unsigned int split_flag;
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +83,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     r0 = 0;
     nvalid = min(p.blocks_per_tile, p.E - b0);
   }
-  const int num_k = p.ksize * p.ksize * p.kc_per_tap;
+  const int total_k = p.ksize * p.ksize * p.kc_per_tap;
+  const int k_begin = (int)blockIdx.z * p.ksteps_per_split;
+  const int num_k = min(p.ksteps_per_split, total_k - k_begin);
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
@@ -106,13 +119,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       for (int ks = 0; ks < num_k; ++ks) {
         const int s = ks % STAGES;
         mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
-        const int tap = ks / p.kc_per_tap, cc = ks - tap * p.kc_per_tap;
+        const int kg = k_begin + ks;  // global k-step
+        const int tap = kg / p.kc_per_tap, cc = kg - tap * p.kc_per_tap;
         const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
         uint8_t *sa = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full_bar[s], tx_bytes);
         for (int i = 0; i < nvalid; ++i)
           tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, cx[i] + kw, cy[i] + kh, cn[i]);
-        tma_load_2d(sa + kABytes, &b_map, &full_bar[s], ks * kChunkK, n0);
+        tma_load_2d(sa + kABytes, &b_map, &full_bar[s], kg * kChunkK, n0);
       }
     }
   } else if (warp == 1) {
@@ -153,49 +167,105 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
     __half *orow = p.out + pix * p.Cout + n0;
     const __half *rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+    __half *prow = nullptr;
+    if (p.plane_out && valid) {
+      uint32_t n, gh, gw;
+      p.out_cell((uint32_t)__ldg(p.out_mapping + b0 + blk), n, gh, gw);
+      prow = p.plane_out + (((size_t)n * p.out_H + gh * p.BS_out + y) * p.out_W + gw * p.BS_out + x) * p.Cout + n0;
+    }
 
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
+
+    bool finalize = true;
+    float *ws_tile = nullptr;
+    if (p.splits > 1) {
+      // ---- publish this CTA's partial accumulator, elect the last-arriving CTA of the tile ----------
+      const size_t tile_id = (size_t)blockIdx.x * gridDim.y + blockIdx.y;
+      ws_tile = p.ws + tile_id * p.splits * (size_t)(kTileM * N_TILE);
+      float *mine = ws_tile + (size_t)blockIdx.z * (kTileM * N_TILE) + (size_t)m * N_TILE;
 #pragma unroll 1
-    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      tmem_ld_wait();
-      if (valid) {
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float v[8];
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4 *>(mine + c0 + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const unsigned int prev = atomicAdd(p.counters + tile_id, 1u);
+        const unsigned int last = prev == (unsigned int)(p.splits - 1);
+        if (last) p.counters[tile_id] = 0;  // self-resetting for the next launch
+        split_flag = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      finalize = split_flag != 0;
+      if (finalize) __threadfence();
+    }
+
+    if (finalize) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        float accf[32];
+        if (p.splits > 1) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
-          if (p.bias) {
-            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n0 + c0 + j));
-            const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
+          for (int j = 0; j < 32; ++j) accf[j] = 0.f;
+          for (int z = 0; z < p.splits; ++z) {
+            const float *src = ws_tile + (size_t)z * (kTileM * N_TILE) + (size_t)m * N_TILE + c0;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __half22float2(bh[t]);
-              v[2 * t] += f.x;
-              v[2 * t + 1] += f.y;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldcg(reinterpret_cast<const float4 *>(src + j));
+              accf[j] += t.x; accf[j + 1] += t.y; accf[j + 2] += t.z; accf[j + 3] += t.w;
             }
           }
-          if (rrow) {
-            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + c0 + j));
-            const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
+        } else {
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+          tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __half22float2(rh[t]);
-              v[2 * t] += f.x;
-              v[2 * t + 1] += f.y;
+          for (int j = 0; j < 32; ++j) accf[j] = __uint_as_float(acc[j]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = accf[j + t];
+            if (p.bias) {
+              const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n0 + c0 + j));
+              const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(bh[t]);
+                v[2 * t] += f.x;
+                v[2 * t + 1] += f.y;
+              }
             }
-          }
-          if (p.relu) {
+            if (rrow) {
+              // unfused sequence: conv output is rounded to fp16, then `out += identity` rounds again
+              const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + c0 + j));
+              const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
-          }
-          uint4 o;
-          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(rh[t]);
+                v[2 * t] = __half2float(__float2half_rn(v[2 * t])) + f.x;
+                v[2 * t + 1] = __half2float(__float2half_rn(v[2 * t + 1])) + f.y;
+              }
+            }
+            if (p.relu) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-          *reinterpret_cast<uint4 *>(orow + c0 + j) = o;
+              for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+            }
+            uint4 o;
+            __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+            *reinterpret_cast<uint4 *>(orow + c0 + j) = o;
+            if (prow) *reinterpret_cast<uint4 *>(prow + c0 + j) = o;
+          }
         }
       }
     }
@@ -218,19 +288,36 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
 
 template <int N_TILE, int STAGES>
-static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int tiles, int ntiles_n,
-                       cudaStream_t s) {
+static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvParams &p, int tiles, int ntiles_n,
+                       size_t ws_bytes, int n_counters, cudaStream_t s) {
+  // split-K when the output tiles alone cannot fill the GPU (deep layers: 4..8-px blocks)
+  const int total_k = p.ksize * p.ksize * p.kc_per_tap;
+  const int ctas = tiles * ntiles_n;
+  p.splits = 1;
+  p.ksteps_per_split = total_k;
+  if (p.ws != nullptr && p.counters != nullptr && ctas < 96 && total_k >= 8 && ctas <= n_counters) {
+    int want = (kNumSMs + ctas - 1) / ctas;
+    if (want > total_k / 2) want = total_k / 2;   // at least 2 k-steps per split
+    if (want > 16) want = 16;
+    while (want > 1 && (size_t)ctas * want * kTileM * N_TILE * sizeof(float) > ws_bytes) --want;
+    if (want > 1) {
+      p.ksteps_per_split = (total_k + want - 1) / want;
+      p.splits = (total_k + p.ksteps_per_split - 1) / p.ksteps_per_split;
+    }
+  }
   constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 1024;
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
-  conv_igemm_kernel<N_TILE, STAGES><<<dim3((unsigned)tiles, (unsigned)ntiles_n), kConvThreads, smem, s>>>(a_map, b_map, p);
+  conv_igemm_kernel<N_TILE, STAGES><<<dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits), kConvThreads, smem, s>>>(
+      a_map, b_map, p);
   return check_launch("bc_conv_igemm");
 }
 
 int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
-               int pad, int relu, cudaStream_t stream) {
+               int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
+               void *ws, size_t ws_bytes, void *counters, int n_counters, cudaStream_t stream) {
   BC_REQUIRE(out && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
   BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
@@ -258,6 +345,18 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   p.E = E; p.BS_out = BS_out; p.BS_in = BS_in; p.stride = stride; p.pad = pad; p.ksize = ksize; p.Cout = Cout;
   p.kc_per_tap = Cin / kChunkK;
   p.relu = relu;
+  p.plane_out = (__half *)plane_out;
+  p.out_mapping = out_mapping ? out_mapping : mapping;
+  p.out_cell = CellDecode(out_GH > 0 ? out_GH : 1, out_GW > 0 ? out_GW : 1);
+  p.out_H = out_GH * BS_out;
+  p.out_W = out_GW * BS_out;
+  if (plane_out) {
+    BC_REQUIRE(p.out_mapping != nullptr && out_GH > 0 && out_GW > 0 && out_N > 0, BC_ERR_NULL,
+               "bc_conv_igemm: plane_out needs out_mapping and the output grid");
+    BC_REQUIRE(((uintptr_t)plane_out & 15) == 0, BC_ERR_ALIGN, "bc_conv_igemm: plane_out must be 16-byte aligned");
+  }
+  p.ws = (float *)ws;
+  p.counters = (unsigned int *)counters;
   int tiles;
   if (px >= kTileM) {
     p.blocks_per_tile = 1;
@@ -297,8 +396,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
   }
-  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, stream);
-  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, stream);
+  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, ws_bytes, n_counters, stream);
+  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, ws_bytes, n_counters, stream);
 }
 
 }  // namespace bc

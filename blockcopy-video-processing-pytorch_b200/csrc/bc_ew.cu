@@ -1,0 +1,136 @@
+// bc_ew.cu -- fused elementwise stage between two convolutions of the wrapped CNN, on packed NHWC
+// fp16 tiles:   y = relu?( affine?( up2x?(a) + residual? ) )   written to the packed tile batch and,
+// in the same pass, scattered into the next padded op's persistent plane.
+//
+// One launch replaces what the reference issues as separate torch kernels on the tile batch
+// (core/tensorwrapper.py:519-520 pass-through ops and :577-598 bilinear): per-block bilinear x2
+// (taps clamped at the BLOCK edge), `x += skip`, eval-mode BatchNorm (3 kernels in ATen), ReLU, plus
+// this repo's scatter into the plane.  Every intermediate is rounded to fp16 exactly where the
+// unfused op sequence rounds, so results match the op-by-op path.
+#include <cuda_fp16.h>
+
+#include "bc_common.cuh"
+
+namespace bc {
+
+struct EwParams {
+  const __half *a;         // (E, BSa, BSa, C), BSa = BS/2 if up2x else BS
+  const __half *residual;  // (E, BS, BS, C) or nullptr
+  const float *mean, *invstd, *weight, *shift;  // [C] fp32 or nullptr (weight/shift may be null individually)
+  __half *out;             // (E, BS, BS, C) or nullptr
+  __half *plane;           // (N, H, W, C) or nullptr
+  const int32_t *mapping;  // cell of tile b (needed when plane != nullptr)
+  CellDecode cell;
+  FastDiv chunks_per_pixel, bs_div, px_per_tile;
+  int E, C, BS, H, W, up2x, relu, has_affine;
+  uint32_t total;          // E * BS * BS * C / 8
+};
+
+__device__ __forceinline__ void load8(const __half *p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+  const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+
+__global__ void __launch_bounds__(256) ew_fused_kernel(const EwParams p) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
+    uint32_t pix, ch, b, rem, y, x;
+    p.chunks_per_pixel.divmod(i, pix, ch);
+    p.px_per_tile.divmod(pix, b, rem);
+    p.bs_div.divmod(rem, y, x);
+    const int c0 = (int)ch * 8;
+    float v[8];
+    if (p.up2x) {
+      // PyTorch upsample_bilinear2d, align_corners = False, scale 0.5: src = 0.5 * (dst + 0.5) - 0.5, clamped at 0
+      const int hs = p.BS >> 1;
+      const float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.f);
+      const int y1 = (int)sy, x1 = (int)sx;
+      const int yp = y1 < hs - 1 ? 1 : 0, xp = x1 < hs - 1 ? 1 : 0;
+      const float ly1 = sy - (float)y1, ly0 = 1.f - ly1, lx1 = sx - (float)x1, lx0 = 1.f - lx1;
+      const __half *base = p.a + (((size_t)b * hs + y1) * hs + x1) * p.C + c0;
+      float v00[8], v01[8], v10[8], v11[8];
+      load8(base, v00);
+      load8(base + (size_t)xp * p.C, v01);
+      load8(base + (size_t)yp * hs * p.C, v10);
+      load8(base + ((size_t)yp * hs + xp) * p.C, v11);
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        v[t] = round_h(ly0 * (lx0 * v00[t] + lx1 * v01[t]) + ly1 * (lx0 * v10[t] + lx1 * v11[t]));
+    } else {
+      load8(p.a + (size_t)pix * p.C + c0, v);
+    }
+    if (p.residual) {
+      float r[8];
+      load8(p.residual + (size_t)pix * p.C + c0, r);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = round_h(v[t] + r[t]);
+    }
+    if (p.has_affine) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = c0 + t;
+        const float w = p.weight ? __ldg(p.weight + c) : 1.f, s = p.shift ? __ldg(p.shift + c) : 0.f;
+        v[t] = round_h(w * (v[t] - __ldg(p.mean + c)) * __ldg(p.invstd + c) + s);  // ATen's eval-BN expression
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+    }
+    uint4 o;
+    __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+    if (p.out) *reinterpret_cast<uint4 *>(p.out + (size_t)pix * p.C + c0) = o;
+    if (p.plane) {
+      uint32_t n, gh, gw;
+      p.cell((uint32_t)__ldg(p.mapping + b), n, gh, gw);
+      const size_t off = (((size_t)n * p.H + gh * p.BS + y) * p.W + gw * p.BS + x) * p.C + c0;
+      *reinterpret_cast<uint4 *>(p.plane + off) = o;
+    }
+  }
+}
+
+int ew_fused(void *out, void *plane, const void *a, const void *residual, const float *mean, const float *invstd,
+             const float *weight, const float *shift, const int32_t *mapping, int E, int C, int BS, int N, int H,
+             int W, int up2x, int relu, cudaStream_t stream) {
+  BC_REQUIRE(a && (out || plane), BC_ERR_NULL, "bc_ew_fused: NULL pointer");
+  BC_REQUIRE(E > 0 && C > 0 && BS > 0, BC_ERR_SHAPE, "bc_ew_fused: empty problem");
+  BC_REQUIRE(C % 8 == 0, BC_ERR_UNSUPPORTED, "bc_ew_fused: C=%d is not a multiple of 8", C);
+  BC_REQUIRE(!up2x || BS % 2 == 0, BC_ERR_SHAPE, "bc_ew_fused: up2x needs an even output block edge");
+  BC_REQUIRE((mean == nullptr) == (invstd == nullptr), BC_ERR_NULL, "bc_ew_fused: mean and invstd come together");
+  BC_REQUIRE((((uintptr_t)out | (uintptr_t)plane | (uintptr_t)a | (uintptr_t)residual) & 15) == 0, BC_ERR_ALIGN,
+             "bc_ew_fused: pointers must be 16-byte aligned");
+  if (plane) {
+    BC_REQUIRE(mapping != nullptr, BC_ERR_NULL, "bc_ew_fused: plane output needs mapping_exec");
+    BC_REQUIRE(N > 0 && H > 0 && W > 0 && H % BS == 0 && W % BS == 0, BC_ERR_SHAPE,
+               "bc_ew_fused: plane %dx%d / block %d", H, W, BS);
+  }
+  EwParams p;
+  p.a = (const __half *)a; p.residual = (const __half *)residual;
+  p.mean = mean; p.invstd = invstd; p.weight = weight; p.shift = shift;
+  p.out = (__half *)out; p.plane = (__half *)plane; p.mapping = mapping;
+  p.cell = plane ? CellDecode(H / BS, W / BS) : CellDecode(1, 1);
+  p.chunks_per_pixel = FastDiv((uint32_t)(C / 8));
+  p.bs_div = FastDiv((uint32_t)BS);
+  p.px_per_tile = FastDiv((uint32_t)(BS * BS));
+  p.E = E; p.C = C; p.BS = BS; p.H = H; p.W = W; p.up2x = up2x; p.relu = relu; p.has_affine = mean != nullptr;
+  const int64_t total = (int64_t)E * BS * BS * (C / 8);
+  BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_ew_fused: problem too large");
+  p.total = (uint32_t)total;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (grid > cap) grid = cap;
+  ew_fused_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  return check_launch("bc_ew_fused");
+}
+
+}  // namespace bc

@@ -148,13 +148,38 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
  *   bias     fp16 [Cout] or NULL;  residual fp16, layout of out, or NULL
  *   mapping_exec NULL: the "plane" is itself a packed tile batch (N = E images of BS_in x BS_in;
  *                      used for the 1x1 convs, which need no halo)
+ * Optional fused scatter (north-star item (b)/(c)): when plane_out != NULL the epilogue ALSO writes
+ * every output pixel into the NEXT padded op's persistent plane (out_N, out_GH*BS_out, out_GW*BS_out,
+ * Cout) at the block's position (out_mapping = mapping_exec of the output grid), so no separate
+ * scatter kernel runs and cells that were not executed keep the previous frame's values.
+ * Optional split-K: with a caller-owned fp32 workspace (workspace_bytes) and n_counters zero-
+ * initialised uint32 counters, layers whose output tiles cannot fill 148 SMs are split along K over
+ * grid.z; partials are reduced in split order by the last CTA of each tile (deterministic), counters
+ * reset themselves.  Pass NULL / 0 to disable.
  * Supported: k in {1,3} with pad = k/2, stride in {1,2}, dilation 1, Cin % 64 == 0, Cout % 64 == 0,
  * output block edge a power of two in [4,128]; anything else returns BC_ERR_UNSUPPORTED.
  */
 BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias,
                          const void *residual, const int32_t *mapping_exec, int E, int N, int Cin, int H,
                          int W, int BS_in, int Cout, int ksize, int stride, int pad, int relu,
+                         void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
+                         void *workspace, int64_t workspace_bytes, void *counters, int n_counters,
                          bc_stream_t stream);
+
+/* ---- fused elementwise stage between two convs, on packed NHWC fp16 tiles ----------------------
+ * Replaces the pass-through torch ops the reference issues on the tile batch between padded ops
+ * (core/tensorwrapper.py:519-520, :577-598): per-block bilinear x2 (taps clamped at the block edge),
+ * `x += skip`, eval-mode batch_norm, ReLU -- and this design's scatter into the next plane:
+ *   y = relu?( bn?( up2x?(a) + residual? ) );   out <- y (if out);  plane_out[cells] <- y (if plane_out)
+ * a: (E, BS/2, BS/2, C) if up2x else (E, BS, BS, C); residual/out: (E, BS, BS, C); plane_out:
+ * (N, H, W, C) with H, W multiples of BS; bn_*: fp32 [C] (bn_weight / bn_shift may be NULL), NULL
+ * bn_mean = no batch norm.  Intermediates are rounded to fp16 where the unfused sequence rounds.
+ * out may alias a (when !up2x) or residual.  C % 8 == 0.
+ */
+BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *residual, const float *bn_mean,
+                       const float *bn_invstd, const float *bn_weight, const float *bn_shift,
+                       const int32_t *mapping_exec, int E, int C, int BS, int N, int H, int W, int up2x, int relu,
+                       bc_stream_t stream);
 
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the

@@ -25,7 +25,8 @@ def cpu_backend():
     from blockcopy.core import blockcopy as bcm
 
     saved = {k: getattr(_C, k) for k in ("compact_mask", "gather", "scatter", "copy_blocks", "transfer",
-                                         "gather_halo_tiles", "gather_halo")}
+                                         "gather_halo_tiles", "gather_halo", "conv_igemm", "ew_fused",
+                                         "conv_supported", "lazy_supported")}
     saved_tw = tw.to_tensorwrapper
 
     def compact_mask(grid_u8, grid_idx, mapping_exec, counts, prev_grid_idx=None, transfer_idx=None):
@@ -77,6 +78,66 @@ def cpu_backend():
             _store(out, O.plane_halo(_nchw(plane), mapping_exec[:E].contiguous(), BS, pad))
         return out
 
+    # --- torch restatements of the two compute kernels, so that the lazy-fusion bookkeeping of the wrapper
+    #     (deferred convs, absorbed ReLU / add / BN / bilinear, dual write into planes) runs on CPU as well
+    import torch.nn.functional as F
+
+    def _scatter_plane(plane_out, tiles, mapping):
+        tmp = _nchw(plane_out).clone()
+        O.combine_(_nchw(tiles), tmp, mapping.contiguous())
+        _store(plane_out, tmp)
+
+    def conv_igemm(out, plane, weight_cl, bias, residual, mapping_exec, E, BS_in, stride, padding, relu=False,
+                   plane_out=None, out_mapping=None, split_k=True):
+        if mapping_exec is None:
+            y = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding)
+        else:
+            full = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding)
+            y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), BS_in // stride)
+        if residual is not None:
+            y = y + _nchw(residual)
+        if relu:
+            y = y.relu()
+        _store(out, y)
+        if plane_out is not None:
+            _scatter_plane(plane_out, y, (out_mapping if out_mapping is not None else mapping_exec)[:E])
+        return out
+
+    def ew_fused(out, a, residual=None, bn=None, relu=False, up2x=False, plane_out=None, mapping_exec=None):
+        y = _nchw(a)
+        if up2x:
+            y = F.interpolate(y, scale_factor=2, mode="bilinear")
+        if residual is not None:
+            y = y + _nchw(residual)
+        if bn is not None:
+            mean, invstd, w, s = bn
+            v = lambda t: t.view(1, -1, 1, 1).to(y.dtype)  # noqa: E731
+            y = (y - v(mean)) * v(invstd)
+            if w is not None:
+                y = y * v(w)
+            if s is not None:
+                y = y + v(s)
+        if relu:
+            y = y.relu()
+        if out is not None:
+            _store(out, y)
+        if plane_out is not None:
+            _scatter_plane(plane_out, y, mapping_exec[: y.shape[0]])
+        return out
+
+    def conv_supported(dtype, weight, BS_in, stride, padding, dilation=1, groups=1):
+        Cout, Cin, kh, kw = weight.shape
+        if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
+            return False
+        bo = BS_in // stride
+        return Cin % 64 == 0 and Cout % 64 == 0 and BS_in % stride == 0 and bo >= 1
+
+    def lazy_supported(x):
+        return x.dim() == 4 and x.shape[1] % 8 == 0
+
+    for k, v in dict(conv_igemm=conv_igemm, ew_fused=ew_fused, conv_supported=conv_supported,
+                     lazy_supported=lazy_supported).items():
+        setattr(_C, k, v)
     for k, v in dict(compact_mask=compact_mask, gather=gather, scatter=scatter, copy_blocks=copy_blocks,
                      transfer=transfer, gather_halo_tiles=gather_halo_tiles, gather_halo=gather_halo).items():
         setattr(_C, k, v)

@@ -82,3 +82,91 @@ def test_unsupported_shapes_are_refused_not_miscomputed():
     out = torch.zeros(1, 64, 8, 8, dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
     with pytest.raises(_C.BlockCopyNativeError, match="multiple of 64"):
         _C.conv_igemm(out, t, w, None, None, None, 1, 8, 1, 1)
+
+
+def test_conv_dual_write_and_residual_relu():
+    """Epilogue fusion: + residual, ReLU, and the scatter into the next op's plane in one launch.
+    Cells that were not executed keep the previous content of the plane (= previous frame)."""
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(3)
+    N, C, GH, GW, BS = 2, 64, 2, 3, 16
+    plane = torch.randn(N, C, GH * BS, GW * BS, generator=g).half()
+    w = (torch.randn(C, C, 3, 3, generator=g) * 0.05).half()
+    b = (0.1 * torch.randn(C, generator=g)).half()
+    grid = torch.rand(N, 1, GH, GW, generator=g) < 0.5
+    gi, me = O.grid_mappings(grid)
+    E = me.numel()
+    res = torch.randn(E, C, BS, BS, generator=g).half()
+    nxt = torch.randn(N, C, GH * BS, GW * BS, generator=g).half()
+    d = lambda t: t.to(dev).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    out, d_next = d(torch.zeros(E, C, BS, BS).half()), d(nxt)
+    _C.conv_igemm(out, d(plane), d(w), b.to(dev), d(res), me.to(dev), E, BS, 1, 1, relu=True, plane_out=d_next)
+    conv = F.conv2d(plane.to(dev).float(), w.to(dev).float(), b.to(dev).float(), padding=1).half()
+    ref = (O.split(conv.cpu().contiguous(), me, BS).to(dev) + res.to(dev)).relu()
+    err = (out.float() - ref.float()).abs().max().item()
+    assert err <= 2 ** -9 * float(ref.abs().max()) + 2e-3, err
+    want_plane = nxt.clone()
+    O.combine_(out.cpu().contiguous(), want_plane, me)
+    assert torch.equal(d_next.cpu().contiguous(), want_plane), "plane != scatter of the tiles / untouched cells changed"
+
+
+@pytest.mark.parametrize("Cin,Cout,BS", [(256, 256, 8), (512, 512, 4), (128, 128, 8)])
+def test_split_k_is_deterministic_and_close(Cin, Cout, BS):
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(Cin + BS)
+    plane = torch.randn(1, Cin, 8 * BS, 16 * BS, generator=g).half().to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).half().to(dev).contiguous(memory_format=torch.channels_last)
+    me = torch.randperm(128, generator=g)[:40].sort().values.to(torch.int32).to(dev)
+    outs = []
+    for split in (True, True, False):
+        o = torch.empty(40, Cout, BS, BS, dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+        _C.conv_igemm(o, plane, w, None, None, me, 40, BS, 1, 1, split_k=split)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]), "split-K must be run-to-run deterministic (ordered reduction)"
+    ref = outs[2].float()
+    assert (outs[0].float() - ref).abs().max().item() <= 2 ** -9 * float(ref.abs().max()) + 2e-3
+
+
+@pytest.mark.parametrize("up2x,res,bn,relu", [(False, True, False, True), (True, True, True, True), (False, False, True, True),
+                                              (True, False, False, False), (False, True, True, False)])
+def test_ew_fused_matches_op_by_op(up2x, res, bn, relu):
+    """bc_ew_fused == the torch op sequence it replaces (bilinear x2 per tile, add, eval batch_norm,
+    ReLU), each rounded to fp16 like the separate kernels; <= 1 fp16 ulp, plane scatter bit-exact."""
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(7)
+    N, C, GH, GW, BS = 1, 128, 3, 4, 16
+    grid = torch.rand(N, 1, GH, GW, generator=g) < 0.5
+    gi, me = O.grid_mappings(grid)
+    E = me.numel()
+    d = lambda t: t.to(dev).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    a = d(torch.randn(E, C, BS // 2 if up2x else BS, BS // 2 if up2x else BS, generator=g).half())
+    r = d(torch.randn(E, C, BS, BS, generator=g).half()) if res else None
+    mean, var = torch.randn(C, generator=g).half().to(dev), (0.5 + torch.rand(C, generator=g)).half().to(dev)
+    wt, bs = (0.5 + torch.rand(C, generator=g)).half().to(dev), torch.randn(C, generator=g).half().to(dev)
+    y = a
+    if up2x:
+        y = F.interpolate(y, size=(BS, BS), mode="bilinear")
+    if res:
+        y = y + r
+    if bn:
+        y = F.batch_norm(y, mean, var, wt, bs, False, 0.1, 1e-5)
+    if relu:
+        y = y.relu()
+    bnp = (mean.float(), torch.rsqrt(var.float() + 1e-5), wt.float(), bs.float()) if bn else None
+    out = d(torch.zeros(E, C, BS, BS).half())
+    base = torch.randn(N, C, GH * BS, GW * BS, generator=g).half()
+    plane = d(base)
+    _C.ew_fused(out, a, r, bnp, relu, up2x, plane, me.to(dev))
+    torch.cuda.synchronize()
+    ulp = (out.float() - y.float()).abs() / (y.float().abs() * 2 ** -10 + 2 ** -14)
+    assert ulp.max().item() <= 1.01, ulp.max().item()
+    want = base.clone()
+    O.combine_(out.cpu().contiguous(), want, me)
+    assert torch.equal(plane.cpu().contiguous(), want)

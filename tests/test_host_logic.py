@@ -272,3 +272,42 @@ def test_rl_policy_trains_online():
     assert tuple(meta["information_gain"].shape) == (1, 1, 16, 32) and tuple(out.shape) == (1, 19, 64, 128)
     assert any(not torch.equal(a, b) for a, b in zip(before, model.policy.net.parameters())), "policy did not train"
     assert 0 < model.policy.stats.get_exec_percentage() <= 1
+
+
+def test_lazy_fusion_removes_scatters_and_elementwise_kernels(monkeypatch):
+    """Bookkeeping of the deferred-epilogue engine (kernels emulated on CPU): with fusion on, convs
+    write the next op's plane themselves and ReLU / add / BN / bilinear never run as separate ops."""
+    import blockcopy
+    from blockcopy import _C
+    from blockcopy.core import tensorwrapper as tw
+    from consumers.clips import PolicyReplay, deterministic_init_, synthetic_clip
+    from consumers.swiftnet_rn18 import SwiftNetRN18, fuse_conv_bn_
+
+    grids = [torch.ones(1, 1, 4, 8, dtype=torch.bool), torch.rand(1, 1, 4, 8, generator=torch.Generator().manual_seed(0)) < 0.4]
+    clip = synthetic_clip(2, 256, 512, seed=1, dtype=torch.float32)
+
+    def run(lazy):
+        monkeypatch.setattr(tw, "LAZY_FUSION", lazy)
+        net = deterministic_init_(SwiftNetRN18().eval(), seed=0)
+        model = blockcopy.BlockCopyModel(net, _settings(block_policy="all", block_size=64)).eval()
+        fuse_conv_bn_(model)
+        model.policy = PolicyReplay(64, grids)
+        counts = {}
+        with cpu_backend(), torch.no_grad():
+            for name in ("scatter", "conv_igemm", "ew_fused", "gather_halo"):
+                orig = getattr(_C, name)
+                def counted(*a, _o=orig, _n=name, **k):
+                    counts[_n] = counts.get(_n, 0) + 1
+                    return _o(*a, **k)
+                setattr(_C, name, counted)
+            model.reset_temporal()
+            outs = [model(f).clone() for f in clip]
+        return outs, counts
+
+    eager, c0 = run(False)
+    lazy, c1 = run(True)
+    for a, b in zip(eager, lazy):
+        assert torch.allclose(a, b, atol=1e-3 * float(a.abs().mean()))
+    assert c0["conv_igemm"] == c1["conv_igemm"] == 2 * 25       # 20 3x3 + 3 downsample + 3 skip 1x1 - (logits: Cout 19)
+    assert c1["ew_fused"] == 2 * 7, c1                           # 3 skip BN-ReLU, 3 upsample+add+BN+ReLU, 1 logits BN-ReLU
+    assert c0["scatter"] - c1["scatter"] >= 2 * 18, (c0, c1)     # planes are written by producer epilogues instead
