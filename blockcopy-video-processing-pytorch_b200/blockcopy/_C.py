@@ -36,8 +36,7 @@ _SIGNATURES = {
     "bc_transfer": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo_tiles": ([_vp, _vp, _vp, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
-    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _vp, ctypes.c_int64, _vp, _i,
-                                                             _vp], _i),
+    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp], _i),
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
 }
 
@@ -247,18 +246,6 @@ def lazy_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[1] % 8 == 0
 
 
-_WORKSPACE = {}  # device index -> (fp32 split-K workspace, uint32 tile counters); caller-owned, see the header
-
-
-def _workspace(device: torch.device):
-    ws = _WORKSPACE.get(device.index)
-    if ws is None:
-        ws = (torch.empty(16 * 1024 * 1024, dtype=torch.float32, device=device),
-              torch.zeros(4096, dtype=torch.int32, device=device))
-        _WORKSPACE[device.index] = ws
-    return ws
-
-
 def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],
                residual: Optional[torch.Tensor], mapping_exec: Optional[torch.Tensor], E: int, BS_in: int,
                stride: int, padding: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None,
@@ -278,7 +265,6 @@ def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, 
         assert plane_out.is_contiguous(memory_format=torch.channels_last) and plane_out.shape[1] == Cout
         if out_mapping is None:
             out_mapping = mapping_exec
-    ws, counters = _workspace(out.device) if split_k else (None, None)
     _check(lib().bc_conv_igemm(out.data_ptr(), plane.data_ptr(), weight_cl.data_ptr(),
                                bias.data_ptr() if bias is not None else None,
                                residual.data_ptr() if residual is not None else None,
@@ -286,10 +272,7 @@ def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, 
                                E, N, Cin, H, W, BS_in, Cout, k, stride, padding, int(relu),
                                plane_out.data_ptr() if plane_out is not None else None,
                                out_mapping.data_ptr() if out_mapping is not None else None, oN, oGH, oGW,
-                               ws.data_ptr() if ws is not None else None,
-                               ws.numel() * 4 if ws is not None else 0,
-                               counters.data_ptr() if counters is not None else None,
-                               counters.numel() if counters is not None else 0, _stream()),
+                               int(split_k), _stream()),
            "bc_conv_igemm")
     return out
 

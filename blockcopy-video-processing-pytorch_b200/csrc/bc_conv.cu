@@ -17,6 +17,7 @@
 // quadrant each).  Stride 2 uses the tensor map's element strides; 1x1 convs are the 1-tap case.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "bc_common.cuh"
 #include "bc_ptx.cuh"
@@ -47,12 +48,93 @@ struct ConvParams {
   const int32_t *out_mapping;  // cell of packed tile b in the OUTPUT grid (== mapping unless mapping is null)
   CellDecode out_cell;
   int out_H, out_W;
-  // split-K: grid.z CTAs share one output tile; partial accumulators go through `ws`, the CTA that
-  // arrives last (per-tile counter) reduces them in split order (deterministic) and runs the epilogue
+  // split-K: the `splits` CTAs of one thread-block CLUSTER (1,1,splits) share an output tile.  Each
+  // keeps its partial accumulator (fp32) in its own shared memory; after a cluster barrier CTA r
+  // reduces rows [r*128/splits, ...) over all peers through distributed shared memory, in rank
+  // order (deterministic), and runs the epilogue for those rows.
   int splits, ksteps_per_split;
-  float *ws;
-  unsigned int *counters;
 };
+
+template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)
+
+// accumulator row m of a tile -> (block within the tile, y, x) of the output pixel
+__device__ __forceinline__ void pixel_of_row(const ConvParams &p, int m, int r0, int &blk, int &y, int &x) {
+  if (p.blocks_per_tile == 1) {
+    blk = 0;
+    y = r0 + m / p.BS_out;
+    x = m % p.BS_out;
+  } else {
+    const int per = p.BS_out * p.BS_out;
+    blk = m / per;
+    const int rem = m - blk * per;
+    y = rem / p.BS_out;
+    x = rem - y * p.BS_out;
+  }
+}
+
+// address of channel 0 of pixel (y, x) of packed tile b in the next op's plane
+__device__ __forceinline__ __half *plane_row(const ConvParams &p, int b, int y, int x) {
+  uint32_t n, gh, gw;
+  p.out_cell((uint32_t)__ldg(p.out_mapping + b), n, gh, gw);
+  return p.plane_out + (((size_t)n * p.out_H + gh * p.BS_out + y) * p.out_W + gw * p.BS_out + x) * p.Cout;
+}
+
+// bias -> (round, + residual) -> ReLU -> fp16, for 8 consecutive channels of one output pixel; stores
+// to the packed tile batch and, if given, to the next op's plane
+__device__ __forceinline__ void epilogue_store8(float (&v)[8], const __half *bias8, const __half *res8, int relu,
+                                                __half *out8, __half *plane8) {
+  if (bias8) {
+    const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(bias8));
+    const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(bh[t]);
+      v[2 * t] += f.x;
+      v[2 * t + 1] += f.y;
+    }
+  }
+  if (res8) {
+    // unfused sequence: the conv output is rounded to fp16, then `out += identity` rounds again
+    const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(res8));
+    const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(rh[t]);
+      v[2 * t] = __half2float(__float2half_rn(v[2 * t])) + f.x;
+      v[2 * t + 1] = __half2float(__float2half_rn(v[2 * t + 1])) + f.y;
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+  }
+  uint4 o;
+  __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4 *>(out8) = o;
+  if (plane8) *reinterpret_cast<uint4 *>(plane8) = o;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(remote)
+               : "memory");
+  return v;
+}
 
 template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(kConvThreads)
@@ -65,7 +147,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ unsigned int split_flag;
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,40 +231,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   } else {
     // =============================== epilogue =====================================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const int m = q * 32 + lane;
-    int blk, y, x;
-    if (p.blocks_per_tile == 1) {
-      blk = 0;
-      y = r0 + m / p.BS_out;
-      x = m % p.BS_out;
-    } else {
-      const int per = p.BS_out * p.BS_out;
-      blk = m / per;
-      const int rem = m - blk * per;
-      y = rem / p.BS_out;
-      x = rem - y * p.BS_out;
-    }
-    const bool valid = blk < nvalid;
-    const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
-    __half *orow = p.out + pix * p.Cout + n0;
-    const __half *rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-    __half *prow = nullptr;
-    if (p.plane_out && valid) {
-      uint32_t n, gh, gw;
-      p.out_cell((uint32_t)__ldg(p.out_mapping + b0 + blk), n, gh, gw);
-      prow = p.plane_out + (((size_t)n * p.out_H + gh * p.BS_out + y) * p.out_W + gw * p.BS_out + x) * p.Cout + n0;
-    }
-
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
-
-    bool finalize = true;
-    float *ws_tile = nullptr;
-    if (p.splits > 1) {
-      // ---- publish this CTA's partial accumulator, elect the last-arriving CTA of the tile ----------
-      const size_t tile_id = (size_t)blockIdx.x * gridDim.y + blockIdx.y;
-      ws_tile = p.ws + tile_id * p.splits * (size_t)(kTileM * N_TILE);
-      float *mine = ws_tile + (size_t)blockIdx.z * (kTileM * N_TILE) + (size_t)m * N_TILE;
+    if (p.splits == 1) {
+      const int m = q * 32 + lane;  // thread <-> accumulator row <-> output pixel
+      int blk, y, x;
+      pixel_of_row(p, m, r0, blk, y, x);
+      const bool valid = blk < nvalid;
+      const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
+      __half *orow = p.out + pix * p.Cout + n0;
+      const __half *rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
+      __half *prow = nullptr;
+      if (p.plane_out && valid) prow = plane_row(p, b0 + blk, y, x) + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
+            epilogue_store8(v, p.bias ? p.bias + n0 + c0 + j : nullptr, rrow ? rrow + c0 + j : nullptr, p.relu,
+                            orow + c0 + j, prow ? prow + c0 + j : nullptr);
+          }
+        }
+      }
+    } else {
+      // ---- split-K, phase 1: park this CTA's partial accumulator in its own shared memory ----------
+      // (the pipeline stages are free: acc_bar says every MMA, hence every TMA load, has completed)
+      float *part = reinterpret_cast<float *>(smem);
+      const int m = q * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t acc[32];
@@ -191,85 +271,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4 *>(mine + c0 + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const unsigned int prev = atomicAdd(p.counters + tile_id, 1u);
-        const unsigned int last = prev == (unsigned int)(p.splits - 1);
-        if (last) p.counters[tile_id] = 0;  // self-resetting for the next launch
-        split_flag = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      finalize = split_flag != 0;
-      if (finalize) __threadfence();
-    }
-
-    if (finalize) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        float accf[32];
-        if (p.splits > 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) accf[j] = 0.f;
-          for (int z = 0; z < p.splits; ++z) {
-            const float *src = ws_tile + (size_t)z * (kTileM * N_TILE) + (size_t)m * N_TILE + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = __ldcg(reinterpret_cast<const float4 *>(src + j));
-              accf[j] += t.x; accf[j + 1] += t.y; accf[j + 2] += t.z; accf[j + 3] += t.w;
-            }
-          }
-        } else {
-          uint32_t acc[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) accf[j] = __uint_as_float(acc[j]);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = accf[j + t];
-            if (p.bias) {
-              const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n0 + c0 + j));
-              const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __half22float2(bh[t]);
-                v[2 * t] += f.x;
-                v[2 * t + 1] += f.y;
-              }
-            }
-            if (rrow) {
-              // unfused sequence: conv output is rounded to fp16, then `out += identity` rounds again
-              const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + c0 + j));
-              const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = __half22float2(rh[t]);
-                v[2 * t] = __half2float(__float2half_rn(v[2 * t])) + f.x;
-                v[2 * t + 1] = __half2float(__float2half_rn(v[2 * t + 1])) + f.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
-            }
-            uint4 o;
-            __half2 *oh = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-            *reinterpret_cast<uint4 *>(orow + c0 + j) = o;
-            if (prow) *reinterpret_cast<uint4 *>(prow + c0 + j) = o;
-          }
-        }
+          *reinterpret_cast<uint4 *>(part + (size_t)m * kPartStride<N_TILE> + c0 + j) =
+              make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }
     tc_fence_before_sync();
+  }
+
+  if (p.splits > 1) {
+    cluster_sync_all();  // every CTA's partial is visible cluster-wide
+    if (warp >= 2) {
+      // ---- phase 2: reduce-scatter over the cluster; this CTA owns 128/splits accumulator rows -----
+      const uint32_t rank = cluster_ctarank();
+      const int rows = kTileM / p.splits;
+      constexpr int kThreadsPerRow = N_TILE / 8;            // 8 channels (16 bytes of fp16) per thread
+      constexpr int kRowsPerPass = 128 / kThreadsPerRow;
+      const int t = threadIdx.x - 64;
+      const int c8 = (t % kThreadsPerRow) * 8;
+      const uint32_t part_addr = smem_u32(smem);
+      for (int rr = t / kThreadsPerRow; rr < rows; rr += kRowsPerPass) {
+        const int m = (int)rank * rows + rr;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int z = 0; z < p.splits; ++z) {  // fixed order: bit-reproducible sums
+          const uint32_t a = part_addr + (uint32_t)(((size_t)m * kPartStride<N_TILE> + c8) * sizeof(float));
+          const float4 lo = ld_dsmem_f4(a, (uint32_t)z), hi = ld_dsmem_f4(a + 16, (uint32_t)z);
+          v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
+          v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+        }
+        int blk, y, x;
+        pixel_of_row(p, m, r0, blk, y, x);
+        if (blk < nvalid) {
+          const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
+          const size_t off = pix * p.Cout + n0 + c8;
+          epilogue_store8(v, p.bias ? p.bias + n0 + c8 : nullptr, p.residual ? p.residual + off : nullptr, p.relu,
+                          p.out + off, p.plane_out ? plane_row(p, b0 + blk, y, x) + n0 + c8 : nullptr);
+        }
+      }
+    }
+    cluster_sync_all();  // nobody leaves (and frees its shared memory) while peers still read it
   }
 
   __syncthreads();
@@ -289,35 +330,56 @@ EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
 
 template <int N_TILE, int STAGES>
 static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvParams &p, int tiles, int ntiles_n,
-                       size_t ws_bytes, int n_counters, cudaStream_t s) {
-  // split-K when the output tiles alone cannot fill the GPU (deep layers: 4..8-px blocks)
+                       bool allow_split, cudaStream_t s) {
+  // split-K over a cluster when the output tiles alone cannot fill the GPU (deep layers: 4..8-px blocks)
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
   const int ctas = tiles * ntiles_n;
   p.splits = 1;
   p.ksteps_per_split = total_k;
-  if (p.ws != nullptr && p.counters != nullptr && ctas < 96 && total_k >= 8 && ctas <= n_counters) {
-    int want = (kNumSMs + ctas - 1) / ctas;
-    if (want > total_k / 2) want = total_k / 2;   // at least 2 k-steps per split
-    if (want > 16) want = 16;
-    while (want > 1 && (size_t)ctas * want * kTileM * N_TILE * sizeof(float) > ws_bytes) --want;
-    if (want > 1) {
-      p.ksteps_per_split = (total_k + want - 1) / want;
-      p.splits = (total_k + p.ksteps_per_split - 1) / p.ksteps_per_split;
+  if (allow_split && ctas < 96 && total_k >= 8) {
+    int want = (kNumSMs * 2 + ctas - 1) / ctas;  // aim at ~2 CTAs per SM
+    int splits = 8;                              // portable cluster size limit
+    while (splits > 1 && (splits > want || splits * 2 > total_k)) splits >>= 1;
+    while (splits > 1) {
+      const int kpp = (total_k + splits - 1) / splits;
+      if (kpp * (splits - 1) < total_k) break;   // every CTA of the cluster gets at least one k-step
+      splits >>= 1;
+    }
+    if (splits > 1) {
+      p.splits = splits;
+      p.ksteps_per_split = (total_k + splits - 1) / splits;
     }
   }
   constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 1024;
+  static_assert((size_t)kTileM * kPartStride<N_TILE> * sizeof(float) <= (size_t)STAGES * (kABytes + N_TILE * 128),
+                "parked accumulator must fit in the pipeline stages");
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
-  conv_igemm_kernel<N_TILE, STAGES><<<dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits), kConvThreads, smem, s>>>(
-      a_map, b_map, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = (unsigned)p.splits;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<N_TILE, STAGES>, a_map, b_map, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+  }
   return check_launch("bc_conv_igemm");
 }
 
 int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
                int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
-               void *ws, size_t ws_bytes, void *counters, int n_counters, cudaStream_t stream) {
+               int allow_split_k, cudaStream_t stream) {
   BC_REQUIRE(out && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
   BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
@@ -355,8 +417,6 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                "bc_conv_igemm: plane_out needs out_mapping and the output grid");
     BC_REQUIRE(((uintptr_t)plane_out & 15) == 0, BC_ERR_ALIGN, "bc_conv_igemm: plane_out must be 16-byte aligned");
   }
-  p.ws = (float *)ws;
-  p.counters = (unsigned int *)counters;
   int tiles;
   if (px >= kTileM) {
     p.blocks_per_tile = 1;
@@ -396,8 +456,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
   }
-  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, ws_bytes, n_counters, stream);
-  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, ws_bytes, n_counters, stream);
+  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, allow_split_k != 0, stream);
+  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, allow_split_k != 0, stream);
 }
 
 }  // namespace bc

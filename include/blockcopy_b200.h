@@ -152,10 +152,9 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
  * every output pixel into the NEXT padded op's persistent plane (out_N, out_GH*BS_out, out_GW*BS_out,
  * Cout) at the block's position (out_mapping = mapping_exec of the output grid), so no separate
  * scatter kernel runs and cells that were not executed keep the previous frame's values.
- * Optional split-K: with a caller-owned fp32 workspace (workspace_bytes) and n_counters zero-
- * initialised uint32 counters, layers whose output tiles cannot fill 148 SMs are split along K over
- * grid.z; partials are reduced in split order by the last CTA of each tile (deterministic), counters
- * reset themselves.  Pass NULL / 0 to disable.
+ * allow_split_k != 0: layers whose output tiles cannot fill 148 SMs (4..8-px blocks) are split along K
+ * over a thread-block cluster (1,1,S<=8); partial accumulators stay in shared memory and are reduced
+ * through distributed shared memory in rank order, so results are run-to-run reproducible.
  * Supported: k in {1,3} with pad = k/2, stride in {1,2}, dilation 1, Cin % 64 == 0, Cout % 64 == 0,
  * output block edge a power of two in [4,128]; anything else returns BC_ERR_UNSUPPORTED.
  */
@@ -163,8 +162,7 @@ BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const
                          const void *residual, const int32_t *mapping_exec, int E, int N, int Cin, int H,
                          int W, int BS_in, int Cout, int ksize, int stride, int pad, int relu,
                          void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
-                         void *workspace, int64_t workspace_bytes, void *counters, int n_counters,
-                         bc_stream_t stream);
+                         int allow_split_k, bc_stream_t stream);
 
 /* ---- fused elementwise stage between two convs, on packed NHWC fp16 tiles ----------------------
  * Replaces the pass-through torch ops the reference issues on the tile batch between padded ops
