@@ -38,6 +38,7 @@ _SIGNATURES = {
     "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp], _i),
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
+    "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
 }
 
 
@@ -283,7 +284,11 @@ def ew_fused(out: Optional[torch.Tensor], a: torch.Tensor, residual: Optional[to
     """y = relu?(bn?(up2x?(a) + residual?)) on packed channels_last fp16 tiles, written to `out` and/or scattered
     into `plane_out`.  bn = (mean, invstd, weight|None, shift|None), fp32 [C]."""
     _dev(out, a, residual, plane_out, mapping_exec)
-    E, C, BSa, _ = a.shape
+    E, C, BSa, Wa = a.shape
+    if not up2x and plane_out is None:
+        E, BSa = E * BSa * Wa, 1  # purely per-pixel: any dense (N,C,H,W) channels_last tensor
+    else:
+        assert BSa == Wa, "tiles must be square"
     BS = BSa * 2 if up2x else BSa
     N = H = W = 0
     if plane_out is not None:
@@ -296,4 +301,17 @@ def ew_fused(out: Optional[torch.Tensor], a: torch.Tensor, residual: Optional[to
     _check(lib().bc_ew_fused(ptr(out), ptr(plane_out), a.data_ptr(), ptr(residual), ptr(mean), ptr(invstd), ptr(weight),
                              ptr(shift), ptr(mapping_exec), E, C, BS, N, H, W, int(up2x), int(relu), _stream()),
            "bc_ew_fused")
+    return out
+
+
+def maxpool_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Tensor, E: int, BS_in: int, k: int,
+                 stride: int, padding: int, plane_out: Optional[torch.Tensor] = None):
+    """out (E,C,BS_in/stride,..) channels_last <- max-pool of the E executed blocks of `plane` (halo from the
+    neighbouring cells, zeros outside the frame); optionally also scattered into `plane_out`."""
+    _dev(out, plane, mapping_exec, plane_out)
+    N, C, H, W = plane.shape
+    assert plane.is_contiguous(memory_format=torch.channels_last) and out.is_contiguous(memory_format=torch.channels_last)
+    _check(lib().bc_maxpool_halo(out.data_ptr(), plane_out.data_ptr() if plane_out is not None else None,
+                                 plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS_in, k, stride, padding,
+                                 _stream()), "bc_maxpool_halo")
     return out

@@ -456,6 +456,10 @@ class TensorWrapper(torch.Tensor):
         if src is None and kwargs:
             src = _first_wrapper(tuple(kwargs.values()))
         if src is None or not src._is_blocks:
+            if LAZY_FUSION and src is not None and op in ("relu", "relu_", "batch_norm"):
+                out = src._lazy_dispatch(op, args, kwargs)  # dense planes of a noblocks region: BN+ReLU in one kernel
+                if out is not NotImplemented:
+                    return out
             _materialize_all(args, kwargs)
             out = cls._dense_dispatch(func, args, kwargs) if src is not None else None
             if out is None:
@@ -512,6 +516,10 @@ class TensorWrapper(torch.Tensor):
             c = p.conv
             _C.conv_igemm(out, c["src"], c["w"], c["bias"], p.residual, c["mapping"], c["E"], c["BS_in"],
                           c["stride"], c["pad"], relu=p.relu, plane_out=plane_out, out_mapping=feats._mapping_exec)
+        elif p.kind == "pool":
+            c = p.conv
+            _C.maxpool_halo(out, c["src"], c["mapping"], c["E"], c["BS_in"], c["k"], c["stride"], c["pad"],
+                            plane_out=plane_out)
         else:
             _C.ew_fused(out, p.src, p.residual, p.bn, p.relu, p.up2x, plane_out,
                         feats._mapping_exec if plane_out is not None else None)
@@ -536,7 +544,9 @@ class TensorWrapper(torch.Tensor):
         """Absorb ReLU / add / eval batch_norm / bilinear x2 on fp16 blocks into deferred descriptors.
         Returns NotImplemented for everything else (which then runs op by op on materialised tiles)."""
         x = args[0] if args else None
-        if not isinstance(x, TensorWrapper) or not x._is_blocks or not _C.lazy_supported(x):
+        if not isinstance(x, TensorWrapper) or not _C.lazy_supported(x):
+            return NotImplemented
+        if not x._is_blocks and op not in ("relu", "relu_", "batch_norm"):
             return NotImplemented
         if op in ("relu", "relu_"):
             inplace = op == "relu_" or bool(kwargs.get("inplace", args[1] if len(args) > 1 else False))
@@ -669,6 +679,38 @@ class TensorWrapper(torch.Tensor):
             out._materialize()
         return out
 
+    def _try_fused_pool(self, args, kwargs):
+        """max_pool2d with padding on fp16 NHWC blocks through bc_maxpool_halo (reads the op's plane,
+        halo included); deferred like the convs so that its result lands in the next op's plane."""
+        names = ("input", "kernel_size", "stride", "padding", "dilation", "ceil_mode", "return_indices")
+        a = dict(stride=None, padding=0, dilation=1, ceil_mode=False, return_indices=False)
+        a.update(zip(names, args))
+        a.update(kwargs)
+        one = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)  # noqa: E731
+        k, padding, dilation = one(a["kernel_size"]), one(a["padding"]), one(a["dilation"])
+        stride = k if a["stride"] is None or a["stride"] == [] else one(a["stride"])
+        x = a["input"]
+        if None in (k, padding, dilation, stride) or dilation != 1 or a["ceil_mode"] or a["return_indices"] \
+                or padding <= 0 or not isinstance(x, TensorWrapper) or not x._is_blocks or not _C.lazy_supported(x):
+            return None
+        E, C, BS, _ = x.shape
+        if E == 0 or BS % stride or (BS + 2 * padding - k) // stride + 1 != BS // stride:
+            return None
+        feats = self._features
+        if feats._plane_cursor < len(feats._planes) and _C.layout_of(feats._planes[feats._plane_cursor]) != _C.BC_NHWC:
+            return None
+        N, _, GH, GW = feats._grid_idx.shape
+        plane = feats._next_plane(None, (N, C, GH * BS, GW * BS), x.dtype, x.device, True)
+        if not x._materialize(plane_out=plane):
+            _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
+        pend = _Pending("pool", conv=dict(src=plane, mapping=feats._mapping_exec, E=E, BS_in=BS, k=k, stride=stride,
+                                          pad=padding))
+        pend.stage = 3  # nothing is absorbed into a pooling kernel
+        out = x._new_pending((E, C, BS // stride, BS // stride), pend)
+        if not LAZY_FUSION:
+            out._materialize()
+        return out
+
     def _func_replace_padding(self, func, types, args, kwargs):
         """Padded op: take the padding from neighbouring blocks instead of zeros, then run the op
         itself with padding 0 (reference: _func_replace_paddding, tensorwrapper.py:529-575)."""
@@ -676,8 +718,8 @@ class TensorWrapper(torch.Tensor):
             _materialize_all(args, kwargs)
             return super().__torch_function__(func, types, args, kwargs)
         op = func.__name__
-        if FUSED_CONV and op == "conv2d":
-            fused = self._try_fused_conv(args, kwargs)
+        if FUSED_CONV and op in ("conv2d", "max_pool2d"):
+            fused = self._try_fused_conv(args, kwargs) if op == "conv2d" else self._try_fused_pool(args, kwargs)
             if fused is not None:
                 return fused
         args = list(args)

@@ -46,6 +46,9 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
              const float *weight, const float *shift, const int32_t *mapping, int E, int C, int BS, int N, int H,
              int W, int up2x, int relu, cudaStream_t stream);
 
+int maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *mapping, int E, int N, int C, int H,
+                 int W, int BS_in, int k, int stride, int pad, cudaStream_t stream);
+
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace bc
@@ -195,6 +198,14 @@ BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *re
   if (E == 0) return BC_OK;
   return ew_fused(out, plane_out, a, residual, bn_mean, bn_invstd, bn_weight, bn_shift, mapping_exec, E, C, BS, N, H,
                   W, up2x, relu, (cudaStream_t)stream);
+}
+
+BC_API int bc_maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *mapping_exec, int E, int N,
+                           int C, int H, int W, int BS_in, int ksize, int stride, int pad, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_maxpool_halo: E=%d", E);
+  if (E == 0) return BC_OK;
+  return maxpool_halo(out, plane_out, plane, mapping_exec, E, N, C, H, W, BS_in, ksize, stride, pad,
+                      (cudaStream_t)stream);
 }
 
 }  // extern "C"

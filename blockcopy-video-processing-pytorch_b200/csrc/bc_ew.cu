@@ -134,3 +134,85 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
 }
 
 }  // namespace bc
+
+// ---------------------------------------------------------------------------------------------------
+// max-pool on the executed blocks, reading the op's persistent plane (halo = neighbouring cells,
+// ZEROS outside the frame: the reference pads the tile with zeros -- not -inf -- and pools with
+// padding 0, utils/blockpad.py:114-120 + core/tensorwrapper.py:565-571).  Replaces transfer + repad +
+// at::max_pool2d + this repo's scatter of the result.
+// ---------------------------------------------------------------------------------------------------
+namespace bc {
+
+struct PoolParams {
+  const __half *plane;  // (N, H, W, C)
+  __half *out;          // (E, BSo, BSo, C)
+  __half *plane_out;    // (N, GH*BSo, GW*BSo, C) or nullptr
+  const int32_t *mapping;
+  CellDecode cell;
+  FastDiv chunks_per_pixel, bs_div, px_per_tile;
+  int C, H, W, BS_in, BSo, k, stride, pad;
+  uint32_t total;
+};
+
+__global__ void __launch_bounds__(256) maxpool_halo_kernel(const PoolParams p) {
+  const uint32_t gstride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gstride) {
+    uint32_t pix, ch, b, rem, oy, ox, n, gh, gw;
+    p.chunks_per_pixel.divmod(i, pix, ch);
+    p.px_per_tile.divmod(pix, b, rem);
+    p.bs_div.divmod(rem, oy, ox);
+    p.cell((uint32_t)__ldg(p.mapping + b), n, gh, gw);
+    const int c0 = (int)ch * 8;
+    const int y0 = (int)(gh * p.BS_in + oy * p.stride) - p.pad, x0 = (int)(gw * p.BS_in + ox * p.stride) - p.pad;
+    __half2 m[4];
+    bool first = true;
+    for (int dy = 0; dy < p.k; ++dy)
+      for (int dx = 0; dx < p.k; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        uint4 u = make_uint4(0, 0, 0, 0);  // zero padding outside the frame
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+          u = __ldg(reinterpret_cast<const uint4 *>(p.plane + (((size_t)n * p.H + yy) * p.W + xx) * p.C + c0));
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m[t] = first ? h[t] : __hmax2_nan(m[t], h[t]);
+        first = false;
+      }
+    const uint4 o = *reinterpret_cast<uint4 *>(m);
+    *reinterpret_cast<uint4 *>(p.out + (size_t)pix * p.C + c0) = o;
+    if (p.plane_out) {
+      const int Wo = p.W / p.BS_in * p.BSo, Ho = p.H / p.BS_in * p.BSo;
+      const size_t off = (((size_t)n * Ho + gh * p.BSo + oy) * Wo + gw * p.BSo + ox) * p.C + c0;
+      *reinterpret_cast<uint4 *>(p.plane_out + off) = o;
+    }
+  }
+}
+
+int maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *mapping, int E, int N, int C, int H,
+                 int W, int BS_in, int k, int stride, int pad, cudaStream_t stream) {
+  BC_REQUIRE(out && plane && mapping, BC_ERR_NULL, "bc_maxpool_halo: NULL pointer");
+  BC_REQUIRE(E > 0 && N > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0, BC_ERR_SHAPE, "bc_maxpool_halo: bad sizes");
+  BC_REQUIRE(C % 8 == 0, BC_ERR_UNSUPPORTED, "bc_maxpool_halo: C=%d is not a multiple of 8", C);
+  BC_REQUIRE(H % BS_in == 0 && W % BS_in == 0, BC_ERR_SHAPE, "bc_maxpool_halo: plane %dx%d / block %d", H, W, BS_in);
+  BC_REQUIRE(BS_in % stride == 0 && (BS_in + 2 * pad - k) / stride + 1 == BS_in / stride, BC_ERR_UNSUPPORTED,
+             "bc_maxpool_halo: kernel %d stride %d pad %d does not map a %d-px block onto a %d-px block", k, stride, pad,
+             BS_in, BS_in / stride);
+  BC_REQUIRE((((uintptr_t)out | (uintptr_t)plane | (uintptr_t)plane_out) & 15) == 0, BC_ERR_ALIGN,
+             "bc_maxpool_halo: pointers must be 16-byte aligned");
+  PoolParams p;
+  p.plane = (const __half *)plane; p.out = (__half *)out; p.plane_out = (__half *)plane_out; p.mapping = mapping;
+  p.cell = CellDecode(H / BS_in, W / BS_in);
+  p.C = C; p.H = H; p.W = W; p.BS_in = BS_in; p.BSo = BS_in / stride; p.k = k; p.stride = stride; p.pad = pad;
+  p.chunks_per_pixel = FastDiv((uint32_t)(C / 8));
+  p.bs_div = FastDiv((uint32_t)p.BSo);
+  p.px_per_tile = FastDiv((uint32_t)(p.BSo * p.BSo));
+  const int64_t total = (int64_t)E * p.BSo * p.BSo * (C / 8);
+  BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_maxpool_halo: problem too large");
+  p.total = (uint32_t)total;
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (grid > cap) grid = cap;
+  maxpool_halo_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  return check_launch("bc_maxpool_halo");
+}
+
+}  // namespace bc

@@ -179,6 +179,16 @@ BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *re
                        const int32_t *mapping_exec, int E, int C, int BS, int N, int H, int W, int up2x, int relu,
                        bc_stream_t stream);
 
+/* ---- max-pool on the executed blocks, straight from the op's persistent plane -------------------
+ * Replaces transfer + repad + at::max_pool2d(padding=0) of a padded pooling op
+ * (core/tensorwrapper.py:529-575 with func = max_pool2d): out[b] = maxpool_k,stride(zero_pad(plane, pad))
+ * on block b; halo = neighbouring cells, ZEROS (not -inf) outside the frame, as in the reference.
+ * NHWC fp16, C % 8 == 0; (BS_in + 2*pad - k)/stride + 1 must equal BS_in/stride.  plane_out (optional):
+ * the next padded op's plane (N, H/stride, W/stride, C), written in the same pass.
+ */
+BC_API int bc_maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *mapping_exec, int E, int N,
+                           int C, int H, int W, int BS_in, int ksize, int stride, int pad, bc_stream_t stream);
+
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
  * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */

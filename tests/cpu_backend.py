@@ -25,7 +25,7 @@ def cpu_backend():
     from blockcopy.core import blockcopy as bcm
 
     saved = {k: getattr(_C, k) for k in ("compact_mask", "gather", "scatter", "copy_blocks", "transfer",
-                                         "gather_halo_tiles", "gather_halo", "conv_igemm", "ew_fused",
+                                         "gather_halo_tiles", "gather_halo", "conv_igemm", "ew_fused", "maxpool_halo",
                                          "conv_supported", "lazy_supported")}
     saved_tw = tw.to_tensorwrapper
 
@@ -125,6 +125,14 @@ def cpu_backend():
             _scatter_plane(plane_out, y, mapping_exec[: y.shape[0]])
         return out
 
+    def maxpool_halo(out, plane, mapping_exec, E, BS_in, k, stride, padding, plane_out=None):
+        full = F.max_pool2d(F.pad(_nchw(plane), (padding,) * 4), k, stride, 0)  # zero (not -inf) halo at the frame edge
+        y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), BS_in // stride)
+        _store(out, y)
+        if plane_out is not None:
+            _scatter_plane(plane_out, y, mapping_exec[:E])
+        return out
+
     def conv_supported(dtype, weight, BS_in, stride, padding, dilation=1, groups=1):
         Cout, Cin, kh, kw = weight.shape
         if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
@@ -136,7 +144,7 @@ def cpu_backend():
         return x.dim() == 4 and x.shape[1] % 8 == 0
 
     for k, v in dict(conv_igemm=conv_igemm, ew_fused=ew_fused, conv_supported=conv_supported,
-                     lazy_supported=lazy_supported).items():
+                     lazy_supported=lazy_supported, maxpool_halo=maxpool_halo).items():
         setattr(_C, k, v)
     for k, v in dict(compact_mask=compact_mask, gather=gather, scatter=scatter, copy_blocks=copy_blocks,
                      transfer=transfer, gather_halo_tiles=gather_halo_tiles, gather_halo=gather_halo).items():

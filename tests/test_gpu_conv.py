@@ -170,3 +170,29 @@ def test_ew_fused_matches_op_by_op(up2x, res, bn, relu):
     want = base.clone()
     O.combine_(out.cpu().contiguous(), want, me)
     assert torch.equal(plane.cpu().contiguous(), want)
+
+
+@pytest.mark.parametrize("C,BS,k,stride,pad", [(64, 64, 3, 2, 1), (64, 16, 3, 1, 1), (128, 8, 3, 2, 1)])
+def test_maxpool_halo_matches_zero_padded_pool(C, BS, k, stride, pad):
+    """bc_maxpool_halo == max_pool2d(padding=0) of the zero-padded plane crop (the reference's padded-tile
+    pooling: zeros, not -inf, outside the frame), bit-exact, incl. the scatter into the next plane."""
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(C + BS)
+    N, GH, GW = 2, 2, 3
+    plane = (torch.randn(N, C, GH * BS, GW * BS, generator=g) - 0.5).half()   # mostly negative at the border too
+    grid = torch.rand(N, 1, GH, GW, generator=g) < 0.6
+    gi, me = O.grid_mappings(grid)
+    E, BSo = me.numel(), BS // stride
+    d = lambda t: t.to(dev).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    out = d(torch.zeros(E, C, BSo, BSo).half())
+    base = torch.randn(N, C, GH * BSo, GW * BSo, generator=g).half()
+    nxt = d(base)
+    _C.maxpool_halo(out, d(plane), me.to(dev), E, BS, k, stride, pad, plane_out=nxt)
+    full = F.max_pool2d(F.pad(plane.float(), (pad,) * 4), k, stride, 0).half()
+    ref = O.split(full.contiguous(), me, BSo)
+    assert torch.equal(out.cpu().contiguous(), ref)
+    want = base.clone()
+    O.combine_(ref, want, me)
+    assert torch.equal(nxt.cpu().contiguous(), want)
