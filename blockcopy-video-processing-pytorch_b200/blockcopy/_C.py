@@ -39,6 +39,8 @@ _SIGNATURES = {
     "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp], _i),
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
     "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
+    "bc_stem_pack": ([_vp, _vp, _ip] + [_i] * 5 + [_vp], _i),
+    "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
 }
 
 
@@ -314,4 +316,67 @@ def maxpool_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Ten
     _check(lib().bc_maxpool_halo(out.data_ptr(), plane_out.data_ptr() if plane_out is not None else None,
                                  plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS_in, k, stride, padding,
                                  _stream()), "bc_maxpool_halo")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- stem (7x7 s2, 3 ch)
+_STEM_W = {}
+
+
+def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout,3,7,7) -> (Cout,256): the 7x7 stride-2 kernel as a zero-extended 4x4 kernel over the
+    space-to-depth(2) image with 16 (12 used) channels; cached per weight version."""
+    key = (w.data_ptr(), w._version, w.dtype)
+    hit = _STEM_W.get(key)
+    if hit is None:
+        Cout = w.shape[0]
+        wd = w.detach()
+        wp = torch.zeros(Cout, 4, 4, 16, dtype=w.dtype, device=w.device)
+        for dy in range(2):
+            for dx in range(2):
+                ch = (dy * 2 + dx) * 3
+                for kh in range(4):
+                    t = 2 * kh + dy - 1
+                    if not 0 <= t < 7:
+                        continue
+                    for kw in range(4):
+                        u = 2 * kw + dx - 1
+                        if 0 <= u < 7:
+                            wp[:, kh, kw, ch:ch + 3] = wd[:, :, t, u]
+        hit = wp.reshape(Cout, 256).contiguous()
+        if len(_STEM_W) > 64:
+            _STEM_W.clear()
+        _STEM_W[key] = hit
+    return hit
+
+
+def stem_supported(dtype, weight: torch.Tensor, BS_in: int, stride, padding, dilation=1, groups=1) -> bool:
+    Cout, Cin, kh, kw = weight.shape
+    bo = BS_in // 2
+    return (dtype == torch.float16 and weight.dtype == torch.float16 and weight.is_cuda and Cin == 3 and kh == kw == 7
+            and stride == 2 and padding == 3 and dilation == 1 and groups == 1 and Cout % 64 == 0 and BS_in % 2 == 0
+            and 16 <= bo <= 128 and (bo & (bo - 1)) == 0)
+
+
+def stem_pack(s2d_plane: torch.Tensor, tiles: torch.Tensor, mapping_exec: torch.Tensor, E: int):
+    """Executed NCHW input tiles (E,3,BS,BS) -> cells of the space-to-depth plane (N,16,H/2,W/2) channels_last."""
+    _dev(s2d_plane, tiles, mapping_exec)
+    N, C16, Hs, Ws = s2d_plane.shape
+    assert C16 == 16 and s2d_plane.is_contiguous(memory_format=torch.channels_last) and tiles.is_contiguous()
+    assert tiles.shape[1] == 3
+    _check(lib().bc_stem_pack(s2d_plane.data_ptr(), tiles.data_ptr(), mapping_exec.data_ptr(), E, N, Hs * 2, Ws * 2,
+                              tiles.shape[-1], _stream()), "bc_stem_pack")
+    return s2d_plane
+
+
+def conv_stem(out: torch.Tensor, s2d_plane: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor],
+              mapping_exec: torch.Tensor, E: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None):
+    _dev(out, s2d_plane, weight_packed, bias, mapping_exec, plane_out)
+    N, _, Hs, Ws = s2d_plane.shape
+    Cout, BSo = out.shape[1], out.shape[-1]
+    assert out.is_contiguous(memory_format=torch.channels_last) and weight_packed.shape == (Cout, 256)
+    _check(lib().bc_conv_stem(out.data_ptr(), s2d_plane.data_ptr(), weight_packed.data_ptr(),
+                              bias.data_ptr() if bias is not None else None, mapping_exec.data_ptr(), E, N, Hs, Ws, BSo,
+                              Cout, int(relu), plane_out.data_ptr() if plane_out is not None else None, _stream()),
+           "bc_conv_stem")
     return out

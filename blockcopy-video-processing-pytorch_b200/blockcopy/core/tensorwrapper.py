@@ -516,6 +516,9 @@ class TensorWrapper(torch.Tensor):
             c = p.conv
             _C.conv_igemm(out, c["src"], c["w"], c["bias"], p.residual, c["mapping"], c["E"], c["BS_in"],
                           c["stride"], c["pad"], relu=p.relu, plane_out=plane_out, out_mapping=feats._mapping_exec)
+        elif p.kind == "stem":
+            c = p.conv
+            _C.conv_stem(out, c["src"], c["w"], c["bias"], c["mapping"], c["E"], relu=p.relu, plane_out=plane_out)
         elif p.kind == "pool":
             c = p.conv
             _C.maxpool_halo(out, c["src"], c["mapping"], c["E"], c["BS_in"], c["k"], c["stride"], c["pad"],
@@ -589,7 +592,8 @@ class TensorWrapper(torch.Tensor):
         """Add one op to a deferred descriptor.  Canonical order inside a kernel: add -> bn -> relu."""
         stage = {"add": 1, "bn": 2, "relu": 3}[what]
         p = self._pending
-        fits = p is not None and p.stage < stage and not (what == "bn" and p.kind == "conv")
+        fits = p is not None and p.stage < stage and not (what == "bn" and p.kind in ("conv", "stem")) \
+            and not (what == "add" and p.kind == "stem")
         if inplace:
             if not fits:
                 return NotImplemented  # materialised (or chain out of order): plain torch in-place op
@@ -652,11 +656,24 @@ class TensorWrapper(torch.Tensor):
         E, Cin, BS, _ = x.shape
         if E == 0 or weight.dim() != 4 or weight.shape[1] != Cin:
             return None
-        if not _C.conv_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
-            return None
         if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
             return None
         feats = self._features
+        if _C.stem_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
+            # ResNet stem: 7x7/s2 on 3 channels as a 4x4/s1 implicit GEMM over a space-to-depth plane
+            N, _, GH, GW = feats._grid_idx.shape
+            if feats._plane_cursor < len(feats._planes) and feats._planes[feats._plane_cursor].shape[1] != 16:
+                return None
+            plane = feats._next_plane(None, (N, 16, GH * BS // 2, GW * BS // 2), x.dtype, x.device, True)
+            _C.stem_pack(plane, _dense(x).contiguous(), feats._mapping_exec, E)
+            pend = _Pending("stem", conv=dict(src=plane, w=_C.pack_stem_weight(weight), bias=bias,
+                                              mapping=feats._mapping_exec, E=E))
+            out = x._new_pending((E, weight.shape[0], BS // 2, BS // 2), pend)
+            if not LAZY_FUSION:
+                out._materialize()
+            return out
+        if not _C.conv_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
+            return None
         if padding > 0 and feats._plane_cursor < len(feats._planes) and \
                 _C.layout_of(feats._planes[feats._plane_cursor]) != _C.BC_NHWC:
             return None  # this op's plane was created NCHW on the first frame: stay on the generic path

@@ -49,6 +49,11 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
 int maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *mapping, int E, int N, int C, int H,
                  int W, int BS_in, int k, int stride, int pad, cudaStream_t stream);
 
+int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int N, int H, int W, int BS,
+              cudaStream_t stream);
+int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias, const int32_t *mapping, int E,
+              int N, int Hs, int Ws, int BS_out, int Cout, int relu, void *plane_out, cudaStream_t stream);
+
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace bc
@@ -206,6 +211,22 @@ BC_API int bc_maxpool_halo(void *out, void *plane_out, const void *plane, const 
   if (E == 0) return BC_OK;
   return maxpool_halo(out, plane_out, plane, mapping_exec, E, N, C, H, W, BS_in, ksize, stride, pad,
                       (cudaStream_t)stream);
+}
+
+BC_API int bc_stem_pack(void *s2d_plane, const void *tiles, const int32_t *mapping_exec, int E, int N, int H, int W,
+                        int BS, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_stem_pack: E=%d", E);
+  if (E == 0) return BC_OK;
+  return stem_pack(s2d_plane, tiles, mapping_exec, E, N, H, W, BS, (cudaStream_t)stream);
+}
+
+BC_API int bc_conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias,
+                        const int32_t *mapping_exec, int E, int N, int Hs, int Ws, int BS_out, int Cout, int relu,
+                        void *plane_out, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_conv_stem: E=%d", E);
+  if (E == 0) return BC_OK;
+  return conv_stem(out, s2d_plane, weight, bias, mapping_exec, E, N, Hs, Ws, BS_out, Cout, relu, plane_out,
+                   (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -19,122 +19,10 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
-#include "bc_common.cuh"
-#include "bc_ptx.cuh"
+#include "bc_conv.cuh"
 #include "bc_tma.cuh"
 
 namespace bc {
-
-constexpr int kConvThreads = 192;
-constexpr int kTileM = 128;
-constexpr int kChunkK = 64;                    // channels per k-step = one 128-byte swizzled row
-constexpr uint32_t kABytes = kTileM * 128;     // 16 KB per stage
-
-struct ConvParams {
-  const int32_t *mapping;   // cell of packed tile b; nullptr = identity (input is a packed tile batch)
-  CellDecode cell;          // grid of the INPUT plane
-  const __half *bias;       // [Cout] or nullptr
-  const __half *residual;   // same layout as out, or nullptr
-  __half *out;              // (E, BS_out, BS_out, Cout) NHWC
-  int E, BS_out, BS_in, stride, pad, ksize, Cout;
-  int kc_per_tap;           // Cin / 64
-  int rows_per_tile;        // rows of BS_out pixels of ONE block in a tile (BS_out >= 16) or BS_out
-  int blocks_per_tile;      // 1, or 128 / BS_out^2 for small blocks
-  int tiles_per_block;      // BS_out^2 / 128 for big blocks, else 1
-  int relu;
-  uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
-  // optional second destination: the next padded op's persistent plane (N, GH*BS_out, GW*BS_out, Cout)
-  __half *plane_out;
-  const int32_t *out_mapping;  // cell of packed tile b in the OUTPUT grid (== mapping unless mapping is null)
-  CellDecode out_cell;
-  int out_H, out_W;
-  // split-K: the `splits` CTAs of one thread-block CLUSTER (1,1,splits) share an output tile.  Each
-  // keeps its partial accumulator (fp32) in its own shared memory; after a cluster barrier CTA r
-  // reduces rows [r*128/splits, ...) over all peers through distributed shared memory, in rank
-  // order (deterministic), and runs the epilogue for those rows.
-  int splits, ksteps_per_split;
-};
-
-template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)
-
-// accumulator row m of a tile -> (block within the tile, y, x) of the output pixel
-__device__ __forceinline__ void pixel_of_row(const ConvParams &p, int m, int r0, int &blk, int &y, int &x) {
-  if (p.blocks_per_tile == 1) {
-    blk = 0;
-    y = r0 + m / p.BS_out;
-    x = m % p.BS_out;
-  } else {
-    const int per = p.BS_out * p.BS_out;
-    blk = m / per;
-    const int rem = m - blk * per;
-    y = rem / p.BS_out;
-    x = rem - y * p.BS_out;
-  }
-}
-
-// address of channel 0 of pixel (y, x) of packed tile b in the next op's plane
-__device__ __forceinline__ __half *plane_row(const ConvParams &p, int b, int y, int x) {
-  uint32_t n, gh, gw;
-  p.out_cell((uint32_t)__ldg(p.out_mapping + b), n, gh, gw);
-  return p.plane_out + (((size_t)n * p.out_H + gh * p.BS_out + y) * p.out_W + gw * p.BS_out + x) * p.Cout;
-}
-
-// bias -> (round, + residual) -> ReLU -> fp16, for 8 consecutive channels of one output pixel; stores
-// to the packed tile batch and, if given, to the next op's plane
-__device__ __forceinline__ void epilogue_store8(float (&v)[8], const __half *bias8, const __half *res8, int relu,
-                                                __half *out8, __half *plane8) {
-  if (bias8) {
-    const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(bias8));
-    const __half2 *bh = reinterpret_cast<const __half2 *>(&bb);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __half22float2(bh[t]);
-      v[2 * t] += f.x;
-      v[2 * t + 1] += f.y;
-    }
-  }
-  if (res8) {
-    // unfused sequence: the conv output is rounded to fp16, then `out += identity` rounds again
-    const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(res8));
-    const __half2 *rh = reinterpret_cast<const __half2 *>(&rr);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __half22float2(rh[t]);
-      v[2 * t] = __half2float(__float2half_rn(v[2 * t])) + f.x;
-      v[2 * t + 1] = __half2float(__float2half_rn(v[2 * t + 1])) + f.y;
-    }
-  }
-  if (relu) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
-  }
-  uint4 o;
-  __half2 *oh = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-  *reinterpret_cast<uint4 *>(out8) = o;
-  if (plane8) *reinterpret_cast<uint4 *>(plane8) = o;
-}
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(remote)
-               : "memory");
-  return v;
-}
 
 template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(kConvThreads)

@@ -1,0 +1,247 @@
+// bc_stem.cu -- the ResNet stem (conv 7x7, stride 2, padding 3, 3 input channels) on executed blocks,
+// on the tensor cores.
+//
+// A 7x7/s2 conv on 3 channels is a 4x4/s1 conv on the space-to-depth(2) image with 12 channels (kernel
+// zero-extended to 8x8): tap (kh', kw') of output (oy, ox) reads s2d pixel (oy+kh'-2, ox+kw'-2).  With
+// the 12 channels padded to 16 one s2d pixel is 32 bytes = one K=16 slab of tcgen05.mma.kind::f16, so
+// the implicit GEMM is M = 128 output pixels, N = 64, K = 16 taps x 16.
+//   stem_pack_kernel : executed NCHW input tiles (E,3,BS,BS) -> persistent s2d plane (N,H/2,W/2,16) NHWC
+//                      (this plane is the op's temporal state: skipped cells keep older frames' pixels)
+//   conv_stem_kernel : per kernel row kh' one pipeline stage of 4 TMA A boxes (16 ch x BS_out x rows, halo =
+//                      neighbouring cells, OOB = zeros) + 4 weight boxes, SWIZZLE_32B operands, 4 MMAs;
+//                      epilogue = bias + ReLU -> NHWC tiles (+ scatter into the next op's plane)
+// Replaces transfer + repad + cuDNN's 3-channel fprop + bias + ReLU (+ NCHW<->NHWC conversions) of the
+// reference path (core/tensorwrapper.py:529-575 for backbone.conv1).
+#include "bc_conv.cuh"
+#include "bc_tma.cuh"
+
+namespace bc {
+
+// ------------------------------------------------------------------ pack: NCHW tiles -> s2d plane
+struct PackParams {
+  const __half *tiles;  // (E, 3, BS, BS) NCHW
+  __half *plane;        // (N, H/2, W/2, 16) NHWC
+  const int32_t *mapping;
+  CellDecode cell;
+  FastDiv half_bs, px_per_tile;
+  int BS, Hh, Wh;       // BS of the input tiles; s2d plane extent
+  uint32_t total;       // E * (BS/2)^2
+};
+
+__global__ void __launch_bounds__(256) stem_pack_kernel(const PackParams p) {
+  const uint32_t gstride = gridDim.x * blockDim.x;
+  const int hb = p.BS >> 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gstride) {
+    uint32_t b, rem, Y, X, n, gh, gw;
+    p.px_per_tile.divmod(i, b, rem);
+    p.half_bs.divmod(rem, Y, X);
+    p.cell((uint32_t)__ldg(p.mapping + b), n, gh, gw);
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const __half2 pr = __ldg(reinterpret_cast<const __half2 *>(
+            p.tiles + (((size_t)b * 3 + c) * p.BS + 2 * Y + dy) * p.BS + 2 * X));
+        v[(dy * 2 + 0) * 3 + c] = __low2half(pr);
+        v[(dy * 2 + 1) * 3 + c] = __high2half(pr);
+      }
+#pragma unroll
+    for (int t = 12; t < 16; ++t) v[t] = __float2half(0.f);
+    __half *dst = p.plane + (((size_t)n * p.Hh + gh * hb + Y) * p.Wh + gw * hb + X) * 16;
+    reinterpret_cast<uint4 *>(dst)[0] = reinterpret_cast<const uint4 *>(v)[0];
+    reinterpret_cast<uint4 *>(dst)[1] = reinterpret_cast<const uint4 *>(v)[1];
+  }
+}
+
+int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int N, int H, int W, int BS,
+              cudaStream_t stream) {
+  BC_REQUIRE(plane && tiles && mapping, BC_ERR_NULL, "bc_stem_pack: NULL pointer");
+  BC_REQUIRE(E > 0 && BS % 2 == 0 && H % BS == 0 && W % BS == 0, BC_ERR_SHAPE, "bc_stem_pack: %dx%d / block %d", H, W, BS);
+  BC_REQUIRE((((uintptr_t)plane & 15) | ((uintptr_t)tiles & 3)) == 0, BC_ERR_ALIGN, "bc_stem_pack: alignment");
+  PackParams p;
+  p.tiles = (const __half *)tiles; p.plane = (__half *)plane; p.mapping = mapping;
+  p.cell = CellDecode(H / BS, W / BS);
+  p.half_bs = FastDiv((uint32_t)(BS / 2));
+  p.px_per_tile = FastDiv((uint32_t)((BS / 2) * (BS / 2)));
+  p.BS = BS; p.Hh = H / 2; p.Wh = W / 2;
+  const int64_t total = (int64_t)E * (BS / 2) * (BS / 2);
+  BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_stem_pack: problem too large");
+  p.total = (uint32_t)total;
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
+  stem_pack_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  return check_launch("bc_stem_pack");
+}
+
+// ------------------------------------------------------------------ conv on the s2d plane
+constexpr int kStemN = 64;
+constexpr int kStemStages = 4;                       // = the 4 kernel rows: everything is in flight at once
+constexpr uint32_t kStemABox = kTileM * 32;          // 128 pixels x 16 ch x 2 B
+constexpr uint32_t kStemBBox = kStemN * 32;
+constexpr uint32_t kStemStage = 4 * (kStemABox + kStemBBox);  // 24 KB
+
+// K-major operand tile of rows of 32 bytes, 32-byte swizzle: 8-row groups are 256 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((256u >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 6ull << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                 const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStemStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, n0 = blockIdx.y * kStemN;
+  const int b0 = tile / p.tiles_per_block;
+  const int r0 = (tile - b0 * p.tiles_per_block) * p.rows_per_tile;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&a_map);
+    prefetch_map(&b_map);
+    for (int s = 0; s < kStemStages; ++s) mbar_init(&full_bar[s], 1);
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kStemN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t n, gh, gw;
+      p.cell((uint32_t)__ldg(p.mapping + b0), n, gh, gw);
+      const int x0 = (int)gw * p.BS_out - 2, y0 = (int)gh * p.BS_out + r0 - 2;
+      for (int kh = 0; kh < 4; ++kh) {  // no ring: each stage is used exactly once
+        uint8_t *sa = smem + (size_t)kh * kStemStage;
+        mbar_expect_tx(&full_bar[kh], 4 * (kStemABox + kStemBBox));
+        for (int kw = 0; kw < 4; ++kw) {
+          tma_load_4d(sa + kw * kStemABox, &a_map, &full_bar[kh], 0, x0 + kw, y0 + kh, (int)n);
+          tma_load_2d(sa + 4 * kStemABox + kw * kStemBBox, &b_map, &full_bar[kh], (kh * 4 + kw) * 16, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, kStemN);
+      for (int kh = 0; kh < 4; ++kh) {
+        mbar_wait(&full_bar[kh], 0);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + (size_t)kh * kStemStage);
+        const uint32_t b_addr = a_addr + 4 * kStemABox;
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw)
+          umma_f16_ss(tmem_base, umma_desc_sw32(a_addr + kw * kStemABox), umma_desc_sw32(b_addr + kw * kStemBBox), idesc,
+                      (uint32_t)((kh | kw) != 0));
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int blk, y, x;
+    pixel_of_row(p, m, r0, blk, y, x);
+    const size_t pix = ((size_t)b0 * p.BS_out + y) * p.BS_out + x;
+    __half *orow = p.out + pix * p.Cout + n0;
+    __half *prow = p.plane_out ? plane_row(p, b0, y, x) + n0 : nullptr;
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < kStemN; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
+        epilogue_store8(v, p.bias ? p.bias + n0 + c0 + j : nullptr, nullptr, p.relu, orow + c0 + j,
+                        prow ? prow + c0 + j : nullptr);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kStemN);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
+
+// s2d_plane (N, Hs, Ws, 16) fp16 NHWC; weight fp16 [Cout][4][4][16] (see blockcopy/_C.py: pack_stem_weight)
+int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias, const int32_t *mapping, int E,
+              int N, int Hs, int Ws, int BS_out, int Cout, int relu, void *plane_out, cudaStream_t stream) {
+  BC_REQUIRE(out && s2d_plane && weight && mapping, BC_ERR_NULL, "bc_conv_stem: NULL pointer");
+  BC_REQUIRE(E > 0 && N > 0, BC_ERR_SHAPE, "bc_conv_stem: empty problem");
+  BC_REQUIRE(Cout % kStemN == 0, BC_ERR_UNSUPPORTED, "bc_conv_stem: Cout=%d is not a multiple of 64", Cout);
+  const int px = BS_out * BS_out;
+  BC_REQUIRE(BS_out >= 16 && BS_out <= 128 && (BS_out & (BS_out - 1)) == 0 && px % kTileM == 0, BC_ERR_UNSUPPORTED,
+             "bc_conv_stem: output block edge %d (power of two, 16..128)", BS_out);
+  BC_REQUIRE(Hs % BS_out == 0 && Ws % BS_out == 0, BC_ERR_SHAPE, "bc_conv_stem: plane %dx%d / block %d", Hs, Ws, BS_out);
+  BC_REQUIRE((((uintptr_t)out | (uintptr_t)s2d_plane | (uintptr_t)weight | (uintptr_t)bias | (uintptr_t)plane_out) & 15) == 0,
+             BC_ERR_ALIGN, "bc_conv_stem: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = tensor_map_encoder();
+  BC_REQUIRE(enc != nullptr, BC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+
+  ConvParams p = {};
+  p.mapping = mapping;
+  p.cell = CellDecode(Hs / BS_out, Ws / BS_out);
+  p.bias = (const __half *)bias;
+  p.out = (__half *)out;
+  p.E = E; p.BS_out = BS_out; p.BS_in = BS_out; p.stride = 1; p.pad = 2; p.ksize = 4; p.Cout = Cout;
+  p.blocks_per_tile = 1;
+  p.tiles_per_block = px / kTileM;
+  p.rows_per_tile = kTileM / BS_out;
+  p.relu = relu;
+  p.plane_out = (__half *)plane_out;
+  p.out_mapping = mapping;
+  p.out_cell = p.cell;
+  p.out_H = Hs; p.out_W = Ws;
+  p.splits = 1;
+
+  CUtensorMap a_map, b_map;
+  {
+    cuuint64_t gdim[4] = {16, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {32, (cuuint64_t)Ws * 32, (cuuint64_t)Hs * Ws * 32};
+    cuuint32_t box[4] = {16, (cuuint32_t)BS_out, (cuuint32_t)p.rows_per_tile, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(s2d_plane), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_stem: tensor map (plane) failed: CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[2] = {256, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {512};
+    cuuint32_t box[2] = {16, (cuuint32_t)kStemN};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(weight), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_stem: tensor map (weights) failed: CUresult %d", (int)r);
+  }
+  constexpr size_t smem = (size_t)kStemStages * kStemStage + 1024;
+  static cudaError_t attr = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_stem_kernel): %s", cudaGetErrorString(attr));
+  conv_stem_kernel<<<dim3((unsigned)(E * p.tiles_per_block), (unsigned)(Cout / kStemN)), kConvThreads, smem, stream>>>(
+      a_map, b_map, p);
+  return check_launch("bc_conv_stem");
+}
+
+}  // namespace bc

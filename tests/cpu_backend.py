@@ -26,7 +26,7 @@ def cpu_backend():
 
     saved = {k: getattr(_C, k) for k in ("compact_mask", "gather", "scatter", "copy_blocks", "transfer",
                                          "gather_halo_tiles", "gather_halo", "conv_igemm", "ew_fused", "maxpool_halo",
-                                         "conv_supported", "lazy_supported")}
+                                         "conv_supported", "lazy_supported", "stem_supported", "stem_pack", "conv_stem")}
     saved_tw = tw.to_tensorwrapper
 
     def compact_mask(grid_u8, grid_idx, mapping_exec, counts, prev_grid_idx=None, transfer_idx=None):
@@ -133,6 +133,33 @@ def cpu_backend():
             _scatter_plane(plane_out, y, mapping_exec[:E])
         return out
 
+    def stem_supported(dtype, weight, BS_in, stride, padding, dilation=1, groups=1):
+        Cout, Cin, kh, kw = weight.shape
+        return Cin == 3 and kh == kw == 7 and stride == 2 and padding == 3 and Cout % 64 == 0 and BS_in % 2 == 0
+
+    def stem_pack(s2d_plane, tiles, mapping_exec, E):
+        t = _nchw(tiles)                                   # (E,3,BS,BS)
+        E_, _, BS, _ = t.shape
+        s2d = torch.zeros(E_, 16, BS // 2, BS // 2, dtype=t.dtype)
+        for dy in range(2):
+            for dx in range(2):
+                ch = (dy * 2 + dx) * 3
+                s2d[:, ch:ch + 3] = t[:, :, dy::2, dx::2]
+        _scatter_plane(s2d_plane, s2d, mapping_exec[:E])
+        return s2d_plane
+
+    def conv_stem(out, s2d_plane, weight_packed, bias, mapping_exec, E, relu=False, plane_out=None):
+        Cout = weight_packed.shape[0]
+        w = weight_packed.view(Cout, 4, 4, 16).permute(0, 3, 1, 2).contiguous()
+        full = F.conv2d(F.pad(_nchw(s2d_plane), (2, 1, 2, 1)), w, bias)  # taps oy-2 .. oy+1
+        y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), out.shape[-1])
+        if relu:
+            y = y.relu()
+        _store(out, y)
+        if plane_out is not None:
+            _scatter_plane(plane_out, y, mapping_exec[:E])
+        return out
+
     def conv_supported(dtype, weight, BS_in, stride, padding, dilation=1, groups=1):
         Cout, Cin, kh, kw = weight.shape
         if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
@@ -144,7 +171,8 @@ def cpu_backend():
         return x.dim() == 4 and x.shape[1] % 8 == 0
 
     for k, v in dict(conv_igemm=conv_igemm, ew_fused=ew_fused, conv_supported=conv_supported,
-                     lazy_supported=lazy_supported, maxpool_halo=maxpool_halo).items():
+                     lazy_supported=lazy_supported, maxpool_halo=maxpool_halo, stem_supported=stem_supported,
+                     stem_pack=stem_pack, conv_stem=conv_stem).items():
         setattr(_C, k, v)
     for k, v in dict(compact_mask=compact_mask, gather=gather, scatter=scatter, copy_blocks=copy_blocks,
                      transfer=transfer, gather_halo_tiles=gather_halo_tiles, gather_halo=gather_halo).items():

@@ -196,3 +196,41 @@ def test_maxpool_halo_matches_zero_padded_pool(C, BS, k, stride, pad):
     want = base.clone()
     O.combine_(ref, want, me)
     assert torch.equal(nxt.cpu().contiguous(), want)
+
+
+@pytest.mark.parametrize("N,GH,GW,BS,Cout,frac", [(1, 2, 3, 128, 64, 0.5), (2, 2, 2, 64, 64, 1.0), (1, 3, 2, 32, 128, 0.4)])
+def test_stem_conv_7x7_s2(N, GH, GW, BS, Cout, frac):
+    """bc_stem_pack + bc_conv_stem == relu(conv2d(frame, w, b, stride 2, padding 3)) on the executed blocks
+    (halo from the neighbouring cells of the persistent space-to-depth plane, zeros outside the frame)."""
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(BS + Cout)
+    H, W = GH * BS, GW * BS
+    frame = torch.randn(N, 3, H, W, generator=g).half()
+    w = (torch.randn(Cout, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5).half()
+    b = (0.1 * torch.randn(Cout, generator=g)).half()
+    # the plane holds an OLDER frame in the cells that are not executed now
+    old = torch.randn(N, 3, H, W, generator=g).half()
+    grid = torch.rand(N, 1, GH, GW, generator=g) < frac if frac < 1 else torch.ones(N, 1, GH, GW, dtype=torch.bool)
+    gi, me = O.grid_mappings(grid)
+    all_gi, all_me = O.grid_mappings(torch.ones_like(grid))
+    E, G = me.numel(), grid.numel()
+    plane = torch.zeros(N, 16, H // 2, W // 2, dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+    _C.stem_pack(plane, O.split(old, all_me, BS).to(dev), all_me.to(dev), G)
+    _C.stem_pack(plane, O.split(frame, me, BS).to(dev), me.to(dev), E)
+    mixed = old.clone()
+    O.combine_(O.split(frame, me, BS), mixed, me)      # what the reference's frame_state would hold
+    out = torch.full((E, Cout, BS // 2, BS // 2), float("nan"), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+    nxt_base = torch.randn(N, Cout, H // 2, W // 2, generator=g).half()
+    nxt = nxt_base.to(dev).contiguous(memory_format=torch.channels_last)
+    _C.conv_stem(out, plane, _C.pack_stem_weight(w.to(dev)), b.to(dev), me.to(dev), E, relu=True, plane_out=nxt)
+    ref_full = F.conv2d(mixed.to(dev).float(), w.to(dev).float(), b.to(dev).float(), stride=2, padding=3).relu()
+    ref = O.split(ref_full.cpu().contiguous(), me, BS // 2)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 2 ** -9 * float(ref.abs().max()) + 2e-3, err
+    want = nxt_base.clone()
+    O.combine_(out.cpu().contiguous(), want, me)
+    assert torch.equal(nxt.cpu().contiguous(), want)
