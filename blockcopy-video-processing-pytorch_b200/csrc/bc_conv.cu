@@ -224,8 +224,10 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
   const int ctas = tiles * ntiles_n;
   p.splits = 1;
   p.ksteps_per_split = total_k;
-  if (allow_split && ctas < 96 && total_k >= 8) {
-    int want = (kNumSMs * 2 + ctas - 1) / ctas;  // aim at ~2 CTAs per SM
+  // Measured (profiles/): the cluster reduction + the per-CTA fixed costs pay off only when the unsplit
+  // grid covers less than a third of the GPU; keep the split grid within ~one wave of 2 CTAs per SM.
+  if (allow_split && ctas <= 48 && total_k >= 8) {
+    const int want = 240 / ctas;
     int splits = 8;                              // portable cluster size limit
     while (splits > 1 && (splits > want || splits * 2 > total_k)) splits >>= 1;
     while (splits > 1) {
