@@ -41,6 +41,8 @@ _SIGNATURES = {
     "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
     "bc_stem_pack": ([_vp, _vp, _ip] + [_i] * 5 + [_vp], _i),
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
+    "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
+    "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
 }
 
 
@@ -379,4 +381,41 @@ def conv_stem(out: torch.Tensor, s2d_plane: torch.Tensor, weight_packed: torch.T
                               bias.data_ptr() if bias is not None else None, mapping_exec.data_ptr(), E, N, Hs, Ws, BSo,
                               Cout, int(relu), plane_out.data_ptr() if plane_out is not None else None, _stream()),
            "bc_conv_stem")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- policy features
+def policy_features(frame: torch.Tensor, frame_state: torch.Tensor, output_repr: torch.Tensor, grid: torch.Tensor,
+                    scale_factor: float) -> torch.Tensor:
+    """(N, 3+3+K+1, H*s, W*s) fp32 input of the policy net (reference policy/net.py:84-113) in one kernel."""
+    _dev(frame, frame_state, output_repr, grid)
+    N, _, H, W = frame.shape
+    K, h, w = output_repr.shape[1:]
+    Ho, Wo = int(H * scale_factor), int(W * scale_factor)  # F.interpolate(scale_factor=...) floors
+    assert frame.is_contiguous() and frame_state.is_contiguous() and frame_state.dtype == frame.dtype
+    if output_repr.dtype != frame.dtype:
+        output_repr = output_repr.to(frame.dtype)
+    g = grid.to(torch.bool).contiguous()
+    out = torch.empty((N, 7 + K, Ho, Wo), dtype=torch.float32, device=frame.device)
+    strides = (ctypes.c_int64 * 4)(*output_repr.stride())
+    _check(lib().bc_policy_features(out.data_ptr(), frame.data_ptr(), frame_state.data_ptr(), output_repr.data_ptr(),
+                                    g.data_ptr(), N, K, H, W, h, w, g.shape[2], g.shape[3], Ho, Wo,
+                                    ctypes.cast(strides, ctypes.c_void_p), 1.0 / scale_factor, 1.0 / scale_factor,
+                                    _dtype(frame), _stream()), "bc_policy_features")
+    return out
+
+
+def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor:
+    """InformationGainSemSeg.forward for fp16 logits (N,K,h,w) in one kernel -> (N,1,h/4,w/4) fp16."""
+    _dev(outputs, outputs_prev)
+    assert outputs.dtype == torch.float16 and outputs_prev.dtype == torch.float16
+    if outputs_prev.stride() != outputs.stride():
+        outputs_prev = outputs_prev.contiguous(memory_format=torch.channels_last) if not outputs.is_contiguous() \
+            else outputs_prev.contiguous()
+        assert outputs_prev.stride() == outputs.stride()
+    N, K, h, w = outputs.shape
+    out = torch.empty((N, 1, h // 4, w // 4), dtype=torch.float16, device=outputs.device)
+    strides = (ctypes.c_int64 * 4)(*outputs.stride())
+    _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
+                              ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
     return out

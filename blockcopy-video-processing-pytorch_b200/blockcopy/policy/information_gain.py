@@ -38,6 +38,12 @@ class InformationGainSemSeg(InformationGain):
     def forward(self, policy_meta: Dict) -> torch.Tensor:
         cur, prev = policy_meta["outputs"], policy_meta["outputs_prev"]
         assert cur is not None and prev is not None
+        if cur.is_cuda and cur.dtype == torch.float16 and prev.dtype == torch.float16 and cur.shape == prev.shape \
+                and cur.dim() == 4 and cur.shape[1] <= 64 and cur.shape[2] % 4 == 0 and cur.shape[3] % 4 == 0 \
+                and self.scale_factor == 1 / 4:
+            from blockcopy import _C
+
+            return _C.info_gain(cur, prev)  # one sm_100a kernel (bc_info_gain) instead of six
         cur = F.interpolate(cur, scale_factor=self.scale_factor, mode="bilinear")
         prev = F.interpolate(prev, scale_factor=self.scale_factor, mode="bilinear")
         # elementwise p_prev * (log p_prev - log p_cur), then mean over classes

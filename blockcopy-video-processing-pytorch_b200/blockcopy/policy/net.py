@@ -47,6 +47,9 @@ class PolicyNet(nn.Module):
         previous output - 0.5 | previous grid - 0.5   (reference net.py:84-113)."""
         frame = policy_meta["inputs"]
         assert frame.dim() == 4 and frame.size(1) == 3
+        fused = self._fused_features(policy_meta)
+        if fused is not None:
+            return fused
         feats = [F.interpolate(frame, scale_factor=self.scale_factor, mode="nearest").float()]
         size = feats[0].shape[2:]
         if self.use_frame_state:
@@ -62,6 +65,23 @@ class PolicyNet(nn.Module):
             assert g.dim() == 4
             feats.append(F.interpolate(g, size=size, mode="nearest") - 0.5)
         return torch.cat(feats, dim=1).detach()
+
+    def _fused_features(self, policy_meta: dict):
+        """One sm_100a kernel (bc_policy_features) instead of 4 interpolates + casts + cat, when the
+        inputs are the usual CUDA tensors; same values bit for bit (pure gathers and `- 0.5` in fp32)."""
+        frame, state = policy_meta["inputs"], policy_meta.get("frame_state", None)
+        rep, grid = policy_meta.get("output_repr", None), policy_meta.get("grid", None)
+        if not (self.use_frame_state and self.use_prev_output and self.use_prev_grid) or not frame.is_cuda:
+            return None
+        if state is None or rep is None or grid is None or rep.dim() != 4 or grid.dim() != 4:
+            return None
+        if frame.dtype not in (torch.float16, torch.float32) or state.dtype != frame.dtype or state.shape != frame.shape:
+            return None
+        if not frame.is_contiguous() or not state.is_contiguous() or rep.dtype not in (torch.float16, torch.float32):
+            return None
+        from blockcopy import _C
+
+        return _C.policy_features(frame, state, rep, grid, self.scale_factor)
 
     def forward(self, policy_meta: dict):
         N, C, H, W = policy_meta["inputs"].shape

@@ -54,6 +54,12 @@ int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int
 int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias, const int32_t *mapping, int E,
               int N, int Hs, int Ws, int BS_out, int Cout, int relu, void *plane_out, cudaStream_t stream);
 
+int policy_features(float *out, const void *frame, const void *state, const void *repr, const uint8_t *grid, int N,
+                    int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
+                    float sy_frame, float sx_frame, int dtype, cudaStream_t stream);
+int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
+              cudaStream_t stream);
+
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace bc
@@ -227,6 +233,19 @@ BC_API int bc_conv_stem(void *out, const void *s2d_plane, const void *weight, co
   if (E == 0) return BC_OK;
   return conv_stem(out, s2d_plane, weight, bias, mapping_exec, E, N, Hs, Ws, BS_out, Cout, relu, plane_out,
                    (cudaStream_t)stream);
+}
+
+BC_API int bc_policy_features(float *out, const void *frame, const void *frame_state, const void *output_repr,
+                              const uint8_t *grid, int N, int K, int H, int W, int h, int w, int GH, int GW, int Ho,
+                              int Wo, const int64_t *repr_strides, float inv_scale_y, float inv_scale_x,
+                              bc_dtype_t dtype, bc_stream_t stream) {
+  return policy_features(out, frame, frame_state, output_repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo, repr_strides,
+                         inv_scale_y, inv_scale_x, dtype, (cudaStream_t)stream);
+}
+
+BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
+                        const int64_t *strides, bc_stream_t stream) {
+  return info_gain(out, outputs, outputs_prev, N, K, h, w, strides, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -205,6 +205,25 @@ BC_API int bc_conv_stem(void *out, const void *s2d_plane, const void *weight, co
                         const int32_t *mapping_exec, int E, int N, int Hs, int Ws, int BS_out, int Cout, int relu,
                         void *plane_out, bc_stream_t stream);
 
+/* ---- policy network input (replaces PolicyNet.forward's feature building, policy/net.py:84-113) ---
+ * out (N, 3+3+K+1, Ho, Wo) fp32 NCHW = [ nearest(frame) | nearest(frame_state) | nearest(output_repr) - 0.5 |
+ * nearest(grid) - 0.5 ].  frame / frame_state: (N,3,H,W) NCHW, dtype F16 or F32; output_repr: (N,K,h,w) of the
+ * same dtype with ELEMENT strides repr_strides[4] (NCHW or channels_last); grid: (N,1,GH,GW) bool.
+ * inv_scale_*: 1/scale_factor of the frame resize (ATen's nearest index = floor(dst * inv_scale)).
+ */
+BC_API int bc_policy_features(float *out, const void *frame, const void *frame_state, const void *output_repr,
+                              const uint8_t *grid, int N, int K, int H, int W, int h, int w, int GH, int GW, int Ho,
+                              int Wo, const int64_t *repr_strides, float inv_scale_y, float inv_scale_x,
+                              bc_dtype_t dtype, bc_stream_t stream);
+
+/* ---- information gain of semantic segmentation (policy/information_gain.py:32-41) ------------------
+ * out (N,1,h/4,w/4) fp16 = mean_c[ p_prev * (log p_prev - log p_cur) ] of the bilinearly 1/4-resized
+ * logits (align_corners False); outputs / outputs_prev: fp16 (N,K,h,w) with element strides[4];
+ * h, w multiples of 4; K <= 64.  Intermediates are rounded to fp16 where the op-by-op sequence rounds.
+ */
+BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
+                        const int64_t *strides, bc_stream_t stream);
+
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
  * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */
