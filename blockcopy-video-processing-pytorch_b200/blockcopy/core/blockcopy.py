@@ -143,6 +143,8 @@ class BlockCopyModel(nn.Module):
             graph, frame_state, dense, launches = entry
             graph.replay()
             _C.add_launches(launches)
+            # a replayed frame creates no new BlockFeatures: the kept one now holds this frame's history
+            self.block_temporal_features._was_reset = False
         if gs.out_bufs is None or gs.out_bufs[0].shape != dense.shape:
             gs.out_bufs = [torch.empty_like(dense), torch.empty_like(dense)]
         gs.flip ^= 1
