@@ -43,11 +43,14 @@ def parse_args():
     ap.add_argument("--fraction", type=float, default=0.3)
     ap.add_argument("--clip-length", type=int, default=30)
     ap.add_argument("--streams-per-gpu", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=1, help="streams batched along N in one model call "
+                    "(the reference's speed configs use --batch-size 2)")
     ap.add_argument("--policy", default="fixed", choices=["fixed", "rl_semseg"])
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA graphs")
     ap.add_argument("--microbench", action="store_true", help="only the block-kernel microbenchmarks")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-batched", action="store_true", help="skip the extra batch-8 throughput measurement")
     return ap.parse_args()
 
 
@@ -231,10 +234,10 @@ def bench_ours(args):
     device = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
     peaks = load_peaks()
-    H, W, L, S = args.height, args.width, args.clip_length, args.streams_per_gpu
+    H, W, L, S, B = args.height, args.width, args.clip_length, args.streams_per_gpu, args.batch
 
     models = [build_model(args, device) for _ in range(S)]
-    host_clips = [[f.pin_memory() for f in synthetic_clip(L, H, W, seed=100 * rank + s, dtype=torch.float16)]
+    host_clips = [[f.pin_memory() for f in synthetic_clip(L, H, W, seed=100 * rank + s, batch=B, dtype=torch.float16)]
                   for s in range(S)]
     clips = [[f.to(device) for f in hc] for hc in host_clips]
     G = (H // 128) * (W // 128)
@@ -256,13 +259,13 @@ def bench_ours(args):
         ev1.record()
         torch.cuda.synchronize()
     launches = _C.launch_count() - n0
-    frames_total, elapsed_ms, value = aggregate_throughput(float(args.steps * S), ev0.elapsed_time(ev1), device)
+    frames_total, elapsed_ms, value = aggregate_throughput(float(args.steps * S * B), ev0.elapsed_time(ev1), device)
     barrier(world)
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
-    e2e = None
+    e2e, pipe = None, None
     if not args.skip_e2e:
-        pipe = HostPipeline(models, host_clips, device, (1, 19, H // 4, W // 4))
+        pipe = HostPipeline(models, host_clips, device, (B, 19, H // 4, W // 4))
         pipe.run(0, min(args.warmup, L), L)
         torch.cuda.synchronize()
         barrier(world)
@@ -271,10 +274,30 @@ def bench_ours(args):
         pipe.run(args.warmup, args.steps, L)
         e1.record()
         torch.cuda.synchronize()
-        _, e2e_ms, e2e_fps = aggregate_throughput(float(args.steps * S), e0.elapsed_time(e1), device)
-        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": S * 3 * H * W * 2,
-               "d2h_bytes_per_step": S * 19 * (H // 4) * (W // 4) * 2,
+        _, e2e_ms, e2e_fps = aggregate_throughput(float(args.steps * S * B), e0.elapsed_time(e1), device)
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": S * B * 3 * H * W * 2,
+               "d2h_bytes_per_step": S * B * 19 * (H // 4) * (W // 4) * 2,
                "note": "pinned host frame -> H2D -> model() -> D2H of the logits, copies double-buffered on a side stream"}
+
+    # ---- same path with 8 streams batched along N (secondary number; config 4 packs 64/ngpu streams per GPU) ---
+    batched = None
+    if not args.skip_batched and B == 1 and S == 1 and world == 1:
+        pipe = None
+        models.clear()
+        torch.cuda.empty_cache()
+        B8 = 8
+        m8 = build_model(args, device)
+        clip8 = [f.to(device) for f in synthetic_clip(L, H, W, seed=7, batch=B8, dtype=torch.float16)]
+        run_frames([m8], [clip8], 0, 2 * L + 2, L)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        run_frames([m8], [clip8], 2, L, L)
+        b1.record()
+        torch.cuda.synchronize()
+        batched = {"batch": B8, "value": B8 * L / (b0.elapsed_time(b1) * 1e-3), "unit": "frames/s",
+                   "ms_per_step": b0.elapsed_time(b1) / L, "steps": L}
+        del m8, clip8
 
     # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
     kern = microbench(device, peaks) if rank == 0 else None
@@ -297,14 +320,14 @@ def bench_ours(args):
             "config": {"workload": "configs[2]: SwiftNet-RN18 + BlockCopy, synthetic 1024x2048 30-frame clips, "
                                    "random-init weights, seeded masks",
                        "height": H, "width": W, "block_size": 128, "active_blocks": num_exec, "total_blocks": G,
-                       "clip_length": L, "streams_per_gpu": S, "policy": args.policy,
+                       "clip_length": L, "streams_per_gpu": S, "batch": B, "policy": args.policy,
                        "cuda_graphs": not args.no_graphs,
                        "l2_note": "kernel microbenchmarks rotate 8 plane sets (268 MB > 126 MB L2); the frame loop "
                                   "cycles 30 distinct 12.6 MB frames over 0.27 GB of planes per stream"},
-            "e2e": e2e, "gpu_launches": int(launches),
+            "e2e": e2e, "gpu_launches": int(launches), "batched": batched,
             "roofline": {"bound": "tensor",
                          "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: largest share "
-                                   "of the step, profiles/r01_frame_launch_shares.md)",
+                                   "of the step, profiles/r01b_frame_launch_shares.md)",
                          "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                          "frac": dom["tflops"] / peaks["tf_burst"], "traffic": None, "peak_source": peaks["source"]
                          + " (burst: kernel timed alone)", "algorithmic_flops_per_launch": dom["flops"],
