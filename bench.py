@@ -339,7 +339,9 @@ def bench_ours(args):
                              "traffic_note": "dram__bytes_read+write of one launch, profiles/r01_tma_move_ncu.md "
                                              "(writes stay in L2)",
                              "peak_source": peaks["source"], "algorithmic_bytes_per_launch": hbm["bytes"],
-                             "us_per_launch": hbm["us"]},
+                             "us_per_launch": hbm["us"],
+                             "at_config5_size": {k: kern[k] for k in ("gather_halo_nhwc_cfg5", "gather_nhwc_cfg5",
+                                                                      "scatter_nhwc_cfg5") if k in kern}},
             "kernels": kern, "cpu_baseline": cpu, "reference_gpu_path": ref_gpu, "clocks": clk.summary(),
         }
         print(json.dumps(line))
@@ -412,8 +414,45 @@ def microbench(device, peaks, reps=200, sets=8):
                 del graph
         _C.set_tma_enabled(True)
         del planes, tiles, padded, outs
+    res.update(large_gather_microbench(device, peaks))
     res.update(conv_microbench(device, peaks, me_full=None))
     return res
+
+
+def large_gather_microbench(device, peaks, reps=100, sets=2):
+    """Same kernels at BASELINE config-5 size (2048x4096 image => 128x512x1024 plane = 134 MB, 154 of 512 blocks,
+    ~90 MB per launch): long enough that the launch ramp no longer dominates."""
+    from blockcopy import _C
+
+    C, H, W, BS, E, G = 128, 512, 1024, 32, 154, 512
+    cells = torch.randperm(G, generator=torch.Generator().manual_seed(0))[:E].sort().values.to(torch.int32).to(device)
+    fmt = torch.channels_last
+    planes = [torch.randn(1, C, H, W, device=device, dtype=torch.float16).contiguous(memory_format=fmt) for _ in range(sets)]
+    padded = [torch.empty(E, C, BS + 2, BS + 2, device=device, dtype=torch.float16).contiguous(memory_format=fmt) for _ in range(sets)]
+    tiles = [torch.empty(E, C, BS, BS, device=device, dtype=torch.float16).contiguous(memory_format=fmt) for _ in range(sets)]
+    out = {}
+    for name, fn, nbytes in (
+            ("gather_halo_nhwc_cfg5", lambda i: _C.gather_halo(padded[i % sets], planes[i % sets], cells, E, BS, 1), 2 * E * C * (BS + 2) ** 2 * 2),
+            ("gather_nhwc_cfg5", lambda i: _C.gather(tiles[i % sets], planes[i % sets], cells, E), 2 * E * C * BS * BS * 2),
+            ("scatter_nhwc_cfg5", lambda i: _C.scatter(tiles[i % sets], planes[i % sets], cells, E), 2 * E * C * BS * BS * 2)):
+        for i in range(sets):
+            fn(i)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(reps):
+                fn(i)
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / reps
+        out[name] = {"us": us, "bytes": nbytes, "gbs": nbytes / us * 1e-3, "frac_of_hbm_peak": nbytes / us * 1e-3 / peaks["hbm_gbs"]}
+        del graph
+    return out
 
 
 def conv_microbench(device, peaks, me_full=None, reps=50, sets=4, E=40):

@@ -9,6 +9,7 @@
 //   NCHW  plane (W, H, C, N)  tile (TE, TE, C, E)  box (TE, R, Cc, 1)
 // TE = tile edge (BS, or BS+2p for the halo gather), R rows and Cc channels per box.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -19,7 +20,7 @@
 namespace bc {
 
 // ------------------------------------------------------------------ kernel
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;  // ring depth is a launch parameter (p.stages <= kMaxStages)
 
 struct TmaMoveParams {
   const int32_t *mapping;  // cell of packed tile b
@@ -30,19 +31,21 @@ struct TmaMoveParams {
   int nhwc;     // coordinate order
   int to_plane; // 0: plane -> tiles (gather), 1: tiles -> plane (scatter)
   uint32_t box_bytes, stage_bytes;
+  int stages;
 };
 
 __global__ void __launch_bounds__(32)
 tma_move_kernel(const __grid_constant__ CUtensorMap plane_map, const __grid_constant__ CUtensorMap tile_map,
                 const TmaMoveParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   if (threadIdx.x != 0) return;
 
   // 1024-byte aligned staging ring
   uint8_t *ring = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   prefetch_map(&plane_map);
   prefetch_map(&tile_map);
+  const int kStages = p.stages;
   for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
   fence_mbar_init();
 
@@ -155,7 +158,12 @@ int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int
   const int TE = tile_edge;
   BC_REQUIRE(H % BS == 0 && W % BS == 0, BC_ERR_SHAPE, "plane %dx%d is not divisible by block size %d", H, W, BS);
   // Box selection: <= 32 KB per stage, inner box dim <= 256 elements and a multiple of 16 bytes.
-  const int64_t kBoxBudget = 32 * 1024;
+  // tunables (env: BC_TMA_BOX_KB, BC_TMA_STAGES, BC_TMA_CTAS_PER_SM), defaults chosen on B200 (profiles/)
+  static const int env_box_kb = getenv("BC_TMA_BOX_KB") ? atoi(getenv("BC_TMA_BOX_KB")) : 16;
+  static const int env_stages = getenv("BC_TMA_STAGES") ? atoi(getenv("BC_TMA_STAGES")) : 4;
+  static const int env_ctas = getenv("BC_TMA_CTAS_PER_SM") ? atoi(getenv("BC_TMA_CTAS_PER_SM")) : 4;
+  const int64_t kBoxBudget = (int64_t)(env_box_kb < 1 ? 1 : env_box_kb > 48 ? 48 : env_box_kb) * 1024;
+  const int kStages = env_stages < 2 ? 2 : env_stages > kMaxStages ? kMaxStages : env_stages;
   int Cc, R;
   if (layout == BC_NHWC) {
     int cap_c = 256;  // elements
@@ -212,6 +220,7 @@ int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int
   p.to_plane = to_plane ? 1 : 0;
   p.box_bytes = (uint32_t)((int64_t)R * row_bytes);
   p.stage_bytes = (p.box_bytes + 1023u) & ~1023u;
+  p.stages = kStages;
   const size_t smem = (size_t)kStages * p.stage_bytes + 1024;
 
   // opt in to > 48 KB of dynamic shared memory (static + dynamic must stay below 227 KB)
@@ -223,7 +232,7 @@ int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int
   // persistent-style launch: CTAs stride over the work items; as many CTAs per SM as shared memory allows
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > env_ctas) per_sm = env_ctas > 0 ? env_ctas : 1;
   int64_t grid = (int64_t)kNumSMs * per_sm;
   if (grid > n_items) grid = n_items;
   tma_move_kernel<<<(unsigned)grid, 32, smem, s>>>(plane_map, tile_map, p);

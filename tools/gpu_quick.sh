@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for b in 1 2 4 8; do timeout 600 python bench.py --skip-cpu-baseline --batch $b --steps 60 --warmup 30 > gpurun_out/bench_b$b.json 2> gpurun_out/bench_b$b.err; done
+timeout 1500 python tools/tma_sweep.py > gpurun_out/tma_sweep.log 2>&1
 echo done
