@@ -43,6 +43,9 @@ _SIGNATURES = {
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_spp_pool": ([_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp], _i),
+    "bc_spp_levels": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _vp], _i),
+    "bc_spp_prep": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _i, _vp], _i),
 }
 
 
@@ -419,3 +422,37 @@ def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor
     _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
                               ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
     return out
+
+
+# ------------------------------------------------------------------------------------------- dense pyramid pooling
+def _grids(gh, gw):
+    L = len(gh)
+    return (ctypes.c_int32 * L)(*gh), (ctypes.c_int32 * L)(*gw), L
+
+
+def spp_pool(pooled, x0, gh, gw):
+    _dev(pooled, x0)
+    N, C, H, W = x0.shape
+    a, b, L = _grids(gh, gw)
+    _check(lib().bc_spp_pool(pooled.data_ptr(), x0.data_ptr(), N, C, H, W, L, ctypes.cast(a, _vp), ctypes.cast(b, _vp),
+                             _stream()), "bc_spp_pool")
+    return pooled
+
+
+def spp_levels(out, pooled, bn, weights, x0_shape, gh, gw):
+    _dev(out, pooled, bn, weights)
+    N, C, H, W = x0_shape
+    a, b, L = _grids(gh, gw)
+    _check(lib().bc_spp_levels(out.data_ptr(), pooled.data_ptr(), bn.data_ptr(), weights.data_ptr(), N, C, H, W, L,
+                               ctypes.cast(a, _vp), ctypes.cast(b, _vp), weights.shape[1], _stream()), "bc_spp_levels")
+    return out
+
+
+def spp_prep(y, x0, levels, bn, gh, gw):
+    _dev(y, x0, levels, bn)
+    N, C, H, W = x0.shape
+    a, b, L = _grids(gh, gw)
+    _check(lib().bc_spp_prep(y.data_ptr(), x0.data_ptr(), levels.data_ptr(), bn.data_ptr(), N, C, H, W, L,
+                             ctypes.cast(a, _vp), ctypes.cast(b, _vp), levels.shape[1], y.shape[1], _stream()),
+           "bc_spp_prep")
+    return y

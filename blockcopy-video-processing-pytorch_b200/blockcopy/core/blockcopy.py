@@ -166,6 +166,17 @@ class _GraphState:
         self.flip = 0
 
 
+def _try_fused_dense(module, x):
+    """Fused sm_100a implementation of a known dense module (today: SwiftNet-style pyramid pooling)."""
+    import os
+
+    if os.environ.get("BLOCKCOPY_FUSED_SPP", "1") == "0":
+        return None
+    from .fused_spp import try_fused_spp
+
+    return try_fused_spp(module, x)
+
+
 def blockcopy_noblocks(func):
     """Decorator for ``forward`` methods that cannot run on blocks (e.g. global pooling): the
     blocks are combined in place into the dense tensor, the method runs densely, and its result
@@ -179,6 +190,9 @@ def blockcopy_noblocks(func):
             # dense TensorWrapper (the reference hands over a plain tensor): numerically the same
             # object, but torch calls stay interceptable, see TensorWrapper._dense_dispatch
             x = x.combine_()
+            fused = _try_fused_dense(self, x)
+            if fused is not None:
+                return to_tensorwrapper(fused).to_blocks_like(blocks)
         x = func(self, x)
         if was_wrapper:
             x = to_tensorwrapper(x.as_subclass(torch.Tensor)).to_blocks_like(blocks)

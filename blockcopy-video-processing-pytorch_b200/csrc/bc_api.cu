@@ -60,6 +60,12 @@ int policy_features(float *out, const void *frame, const void *state, const void
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
 
+int spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int *gh, const int *gw, cudaStream_t s);
+int spp_levels(void *out, const void *pooled, const float *bn, const void *w, int N, int C, int H, int W, int L,
+               const int *gh, const int *gw, int Lc, cudaStream_t s);
+int spp_prep(void *y, const void *x0, const void *lev, const float *bn, int N, int C, int H, int W, int L, const int *gh,
+             const int *gw, int Lc, int Cp, cudaStream_t s);
+
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace bc
@@ -246,6 +252,23 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream) {
   return info_gain(out, outputs, outputs_prev, N, K, h, w, strides, (cudaStream_t)stream);
+}
+
+BC_API int bc_spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int32_t *grid_h,
+                       const int32_t *grid_w, bc_stream_t stream) {
+  return spp_pool(pooled, x0, N, C, H, W, L, grid_h, grid_w, (cudaStream_t)stream);
+}
+
+BC_API int bc_spp_levels(void *out, const void *pooled, const float *bn, const void *weights, int N, int C, int H, int W,
+                         int L, const int32_t *grid_h, const int32_t *grid_w, int level_channels, bc_stream_t stream) {
+  return spp_levels(out, pooled, bn, weights, N, C, H, W, L, grid_h, grid_w, level_channels, (cudaStream_t)stream);
+}
+
+BC_API int bc_spp_prep(void *y, const void *x0, const void *levels, const float *bn, int N, int C, int H, int W, int L,
+                       const int32_t *grid_h, const int32_t *grid_w, int level_channels, int padded_channels,
+                       bc_stream_t stream) {
+  return spp_prep(y, x0, levels, bn, N, C, H, W, L, grid_h, grid_w, level_channels, padded_channels,
+                  (cudaStream_t)stream);
 }
 
 }  // extern "C"

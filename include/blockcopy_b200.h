@@ -224,6 +224,23 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream);
 
+/* ---- dense pyramid pooling (the @blockcopy_noblocks module of SwiftNet, swiftnet/util.py:85-138) ----------
+ * Everything between the module's first and last 1x1 conv, on dense NHWC fp16 planes; grid_h/grid_w are HOST
+ * arrays of L <= 4 pooling grids that must divide (H, W).  "cells" = sum_i N*grid_h[i]*grid_w[i], level-major.
+ *   bc_spp_pool   pooled[cells][C]   = average pools of x0 (N,H,W,C) for all levels (one launch)
+ *   bc_spp_levels out[cells][Lc]     = conv1x1_i(relu(bn_i(pooled)))   bn: fp32 [L][4][C] = mean,invstd,weight,shift
+ *                                      weights: fp16 [L][Lc][C]
+ *   bc_spp_prep   y (N,H,W,Cp)       = relu(bn(cat[x0, bilinear_up(level_0), ...])), channels >= C+L*Lc are 0;
+ *                                      bn: fp32 [4][Cp]
+ */
+BC_API int bc_spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int32_t *grid_h,
+                       const int32_t *grid_w, bc_stream_t stream);
+BC_API int bc_spp_levels(void *out, const void *pooled, const float *bn, const void *weights, int N, int C, int H, int W,
+                         int L, const int32_t *grid_h, const int32_t *grid_w, int level_channels, bc_stream_t stream);
+BC_API int bc_spp_prep(void *y, const void *x0, const void *levels, const float *bn, int N, int C, int H, int W, int L,
+                       const int32_t *grid_h, const int32_t *grid_w, int level_channels, int padded_channels,
+                       bc_stream_t stream);
+
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
  * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */
