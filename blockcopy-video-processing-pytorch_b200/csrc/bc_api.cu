@@ -1,6 +1,7 @@
 // bc_api.cu -- extern "C" entry points of libblockcopy_sm100.so (include/blockcopy_b200.h):
 // argument validation, SIMT/TMA path selection, error text.  No torch headers anywhere.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -65,6 +66,11 @@ int spp_levels(void *out, const void *pooled, const float *bn, const void *w, in
                const int *gh, const int *gw, int Lc, cudaStream_t s);
 int spp_prep(void *y, const void *x0, const void *lev, const float *bn, int N, int C, int H, int W, int L, const int *gh,
              const int *gw, int Lc, int Cp, cudaStream_t s);
+
+bool pdl_enabled() {
+  static const bool on = getenv("BC_PDL") && getenv("BC_PDL")[0] == '1';  // measured: no gain inside CUDA graphs -> opt-in
+  return on;
+}
 
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 

@@ -88,6 +88,43 @@ template <int V> __device__ __forceinline__ void st_vec(char *p, const typename 
   *reinterpret_cast<typename Vec<V>::T *>(p) = v;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the
+// next kernel's CTAs may be scheduled (and run their prologue: barrier init, TMEM alloc, descriptor
+// prefetch) while this one drains.  Contract inside every kernel: pdl_trigger() first, then pdl_wait()
+// BEFORE the first global-memory access that could depend on (or be read by) an earlier kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // BC_PDL=0 disables the launch attribute (bc_api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 unsigned cluster_z, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_z > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 1;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = cluster_z;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int gcd_pow2_bytes(uint64_t a) {  // largest power of two <= 16 dividing a (a > 0)
   int v = 16;
   while (v > 1 && (a % (uint64_t)v)) v >>= 1;

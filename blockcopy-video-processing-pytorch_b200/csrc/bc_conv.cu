@@ -35,6 +35,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[N_TILE];  // this CTA's slice of the bias, staged while the main loop runs
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -54,7 +55,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   }
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
   const int k_begin = (int)blockIdx.z * p.ksteps_per_split;
-  const int num_k = min(p.ksteps_per_split, total_k - k_begin);
+  const int num_k = (p.debug & 1) ? 1 : min(p.ksteps_per_split, total_k - k_begin);
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
@@ -71,6 +72,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();
+  pdl_wait();  // barrier init, TMEM alloc and descriptor prefetch above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // =============================== TMA producer =================================================
@@ -119,32 +122,79 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   } else {
     // =============================== epilogue =====================================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    for (int c = threadIdx.x - 64; c < N_TILE; c += 128) bias_s[c] = p.bias ? __half2float(__ldg(p.bias + n0 + c)) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     mbar_wait(&acc_bar, 0);
     tc_fence_after_sync();
     if (p.splits == 1) {
-      const int m = q * 32 + lane;  // thread <-> accumulator row <-> output pixel
-      int blk, y, x;
-      pixel_of_row(p, m, r0, blk, y, x);
-      const bool valid = blk < nvalid;
-      const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
-      __half *orow = p.out + pix * p.Cout + n0;
-      const __half *rrow = p.residual ? p.residual + pix * p.Cout + n0 : nullptr;
-      __half *prow = nullptr;
-      if (p.plane_out && valid) prow = plane_row(p, b0 + blk, y, x) + n0;
+      // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's private
+      //      staging rows (the pipeline stages are free: acc_bar says every MMA and TMA load completed)
+      constexpr int kRowB = N_TILE * 2 + 16;  // +16 B: rows start in different bank groups
+      uint8_t *stage = smem + (size_t)q * 32 * kRowB;
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
+        for (int j = 0; j < 32; j += 8) {
+          float v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
-            epilogue_store8(v, p.bias ? p.bias + n0 + c0 + j : nullptr, rrow ? rrow + c0 + j : nullptr, p.relu,
-                            orow + c0 + j, prow ? prow + c0 + j : nullptr);
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]) + bias_s[c0 + j + t];
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+          *reinterpret_cast<uint4 *>(stage + (size_t)lane * kRowB + (c0 + j) * 2) = o;
+        }
+      }
+      __syncwarp();
+      // ---- phase B: coalesced: kTPR lanes cover one pixel's N_TILE channels (16 B each), so every
+      //      global access of the warp is a run of full 32-byte sectors: (+ residual) -> ReLU -> tiles, plane
+      constexpr int kTPR = N_TILE / 8, kRPI = 32 / kTPR;
+      const int c8 = (lane % kTPR) * 8;
+      constexpr int kBatch = 4;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += kRPI * kBatch) {
+        size_t off[kBatch];
+        __half *pl[kBatch];
+        uint4 res[kBatch];
+        bool ok[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {  // addresses + residual loads of the whole batch first (latency overlap)
+          const int r = i0 + u * kRPI + lane / kTPR;
+          int blk, y, x;
+          pixel_of_row(p, q * 32 + r, r0, blk, y, x);
+          ok[u] = blk < nvalid && !(p.debug & 2);
+          off[u] = (((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x) * p.Cout + n0 + c8;
+          pl[u] = (p.plane_out && ok[u]) ? plane_row(p, b0 + blk, y, x) + n0 + c8 : nullptr;
+          res[u] = make_uint4(0, 0, 0, 0);
+          if (p.residual && ok[u]) res[u] = __ldg(reinterpret_cast<const uint4 *>(p.residual + off[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (!ok[u]) continue;
+          const int r = i0 + u * kRPI + lane / kTPR;
+          const uint4 uu = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kRowB + c8 * 2);
+          const __half2 *uh = reinterpret_cast<const __half2 *>(&uu);
+          const __half2 *rh = reinterpret_cast<const __half2 *>(&res[u]);
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {  // staged value = fp16-rounded conv output, as in the unfused sequence
+            const float2 f = __half22float2(uh[t]), g = __half22float2(rh[t]);
+            v[2 * t] = f.x + g.x;
+            v[2 * t + 1] = f.y + g.y;
           }
+          if (p.relu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+          }
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+          *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
+          if (pl[u]) *reinterpret_cast<uint4 *>(pl[u]) = o;
         }
       }
     } else {
@@ -246,19 +296,8 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits);
-  cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 1;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = (unsigned)p.splits;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<N_TILE, STAGES>, a_map, b_map, p);
+  const cudaError_t e = launch_kernel(conv_igemm_kernel<N_TILE, STAGES>, dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits),
+                                      dim3(kConvThreads), smem, s, (unsigned)p.splits, a_map, b_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -297,6 +336,10 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   p.E = E; p.BS_out = BS_out; p.BS_in = BS_in; p.stride = stride; p.pad = pad; p.ksize = ksize; p.Cout = Cout;
   p.kc_per_tap = Cin / kChunkK;
   p.relu = relu;
+  {
+    static const char *dbg = getenv("BC_CONV_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   p.plane_out = (__half *)plane_out;
   p.out_mapping = out_mapping ? out_mapping : mapping;
   p.out_cell = CellDecode(out_GH > 0 ? out_GH : 1, out_GW > 0 ? out_GW : 1);

@@ -36,6 +36,7 @@ struct ConvParams {
   // reduces rows [r*128/splits, ...) over all peers through distributed shared memory, in rank
   // order (deterministic), and runs the epilogue for those rows.
   int splits, ksteps_per_split;
+  int debug;  // BC_CONV_DEBUG (timing experiments only): 1 = one k-step, 2 = no epilogue stores, 3 = both
 };
 
 template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)

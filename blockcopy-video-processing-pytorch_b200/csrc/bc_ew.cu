@@ -40,6 +40,8 @@ __device__ __forceinline__ void load8(const __half *p, float (&v)[8]) {
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
 __global__ void __launch_bounds__(256) ew_fused_kernel(const EwParams p) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
     uint32_t pix, ch, b, rem, y, x;
@@ -129,7 +131,7 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
   int64_t grid = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (grid > cap) grid = cap;
-  ew_fused_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  launch_kernel(ew_fused_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_ew_fused");
 }
 
@@ -155,6 +157,8 @@ struct PoolParams {
 };
 
 __global__ void __launch_bounds__(256) maxpool_halo_kernel(const PoolParams p) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t gstride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gstride) {
     uint32_t pix, ch, b, rem, oy, ox, n, gh, gw;
@@ -211,7 +215,7 @@ int maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *m
   int64_t grid = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (grid > cap) grid = cap;
-  maxpool_halo_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  launch_kernel(maxpool_halo_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_maxpool_halo");
 }
 

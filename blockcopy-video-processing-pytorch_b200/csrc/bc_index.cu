@@ -16,6 +16,8 @@ compact_mask_kernel(const uint8_t *__restrict__ grid, int G, int32_t *__restrict
                     const int32_t *__restrict__ prev_grid_idx, int32_t *__restrict__ transfer_idx) {
   __shared__ int warp_sums[kScanThreads / 32];
   __shared__ int total_exec;
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int per = (G + kScanThreads - 1) / kScanThreads;
   const int lo = min(tid * per, G), hi = min(lo + per, G);
@@ -64,7 +66,8 @@ compact_mask_kernel(const uint8_t *__restrict__ grid, int G, int32_t *__restrict
 
 int launch_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *mapping_exec, int32_t *counts,
                         const int32_t *prev_grid_idx, int32_t *transfer_idx, cudaStream_t s) {
-  compact_mask_kernel<<<1, kScanThreads, 0, s>>>(grid, G, grid_idx, mapping_exec, counts, prev_grid_idx, transfer_idx);
+  launch_kernel(compact_mask_kernel, dim3(1), dim3(kScanThreads), 0, s, 1, grid, G, grid_idx, mapping_exec, counts,
+                prev_grid_idx, transfer_idx);
   return check_launch("bc_compact_mask");
 }
 

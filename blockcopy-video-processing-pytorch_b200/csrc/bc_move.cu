@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(kThreads)
 gather_kernel(char *__restrict__ tiles, const char *__restrict__ plane,
               const int32_t *__restrict__ mapping, const MoveGeo g) {
   using T = typename Vec<V>::T;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * kThreads;
   for (uint32_t base = blockIdx.x * kThreads + threadIdx.x; base < g.total; base += stride * kUnroll) {
     T v[kUnroll];
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(kThreads)
 scatter_kernel(const char *__restrict__ tiles, char *__restrict__ plane,
                const int32_t *__restrict__ mapping, const MoveGeo g) {
   using T = typename Vec<V>::T;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * kThreads;
   for (uint32_t base = blockIdx.x * kThreads + threadIdx.x; base < g.total; base += stride * kUnroll) {
     T v[kUnroll];
@@ -127,6 +131,8 @@ __global__ void __launch_bounds__(kThreads)
 copy_blocks_kernel(char *__restrict__ out, const char *__restrict__ prev, const char *__restrict__ tiles,
                    const int32_t *__restrict__ grid_idx, const MoveGeo g) {
   using T = typename Vec<V>::T;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * kThreads;
   for (uint32_t base = blockIdx.x * kThreads + threadIdx.x; base < g.total; base += stride * kUnroll) {
     T v[kUnroll];
@@ -160,6 +166,8 @@ __global__ void __launch_bounds__(kThreads)
 transfer_kernel(char *__restrict__ out, const char *__restrict__ prev_exec,
                 const char *__restrict__ prev_transfer, const int32_t *__restrict__ transfer_idx,
                 const MoveGeo g, const int G) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * kThreads;
   const int lo = g.pad, hi = g.BS - g.pad - 1;
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < g.total; i += stride) {
@@ -188,6 +196,8 @@ halo_tiles_kernel(char *__restrict__ out, const char *__restrict__ exec, const c
                   const MoveGeo g, const int64_t src_stride_b, const int64_t src_stride_c,
                   const int64_t src_row_bytes, const int G) {
   using T = typename Vec<V>::T;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t stride = gridDim.x * kThreads;
   const int BS = g.BS, P = g.pad, BP = BS + 2 * P;
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < g.total; i += stride) {
@@ -303,9 +313,9 @@ int launch_gather_simt(void *tiles, const void *plane, const int32_t *mapping, c
   const int grid = grid_for(g.total, kUnroll);
   BC_DISPATCH_VEC(g.vec, {
     if (halo)
-      gather_kernel<VV, true><<<grid, kThreads, 0, s>>>((char *)tiles, (const char *)plane, mapping, g);
+      launch_kernel(gather_kernel<VV, true>, dim3(grid), dim3(kThreads), 0, s, 1, (char *)tiles, (const char *)plane, mapping, g);
     else
-      gather_kernel<VV, false><<<grid, kThreads, 0, s>>>((char *)tiles, (const char *)plane, mapping, g);
+      launch_kernel(gather_kernel<VV, false>, dim3(grid), dim3(kThreads), 0, s, 1, (char *)tiles, (const char *)plane, mapping, g);
   });
   return check_launch(halo ? "bc_gather_halo" : "bc_gather");
 }
@@ -313,7 +323,7 @@ int launch_gather_simt(void *tiles, const void *plane, const int32_t *mapping, c
 int launch_scatter_simt(const void *tiles, void *plane, const int32_t *mapping, const MoveGeo &g, cudaStream_t s) {
   if (g.total == 0) return BC_OK;
   const int grid = grid_for(g.total, kUnroll);
-  BC_DISPATCH_VEC(g.vec, { scatter_kernel<VV><<<grid, kThreads, 0, s>>>((const char *)tiles, (char *)plane, mapping, g); });
+  BC_DISPATCH_VEC(g.vec, { launch_kernel(scatter_kernel<VV>, dim3(grid), dim3(kThreads), 0, s, 1, (const char *)tiles, (char *)plane, mapping, g); });
   return check_launch("bc_scatter");
 }
 
@@ -322,7 +332,8 @@ int launch_copy_blocks_simt(void *out, const void *prev, const void *tiles, cons
   if (g.total == 0) return BC_OK;
   const int grid = grid_for(g.total, kUnroll);
   BC_DISPATCH_VEC(g.vec, {
-    copy_blocks_kernel<VV><<<grid, kThreads, 0, s>>>((char *)out, (const char *)prev, (const char *)tiles, grid_idx, g);
+    launch_kernel(copy_blocks_kernel<VV>, dim3(grid), dim3(kThreads), 0, s, 1, (char *)out, (const char *)prev,
+                  (const char *)tiles, grid_idx, g);
   });
   return check_launch("bc_copy_blocks");
 }
@@ -332,8 +343,8 @@ int launch_transfer_simt(void *out, const void *prev_exec, const void *prev_tran
   if (g.total == 0) return BC_OK;
   const int grid = grid_for(g.total, 1);
   BC_DISPATCH_VEC(g.vec, {
-    transfer_kernel<VV><<<grid, kThreads, 0, s>>>((char *)out, (const char *)prev_exec, (const char *)prev_transfer,
-                                                 transfer_idx, g, G);
+    launch_kernel(transfer_kernel<VV>, dim3(grid), dim3(kThreads), 0, s, 1, (char *)out, (const char *)prev_exec,
+                  (const char *)prev_transfer, transfer_idx, g, G);
   });
   return check_launch("bc_transfer");
 }
@@ -343,9 +354,9 @@ int launch_halo_tiles_simt(void *out, const void *exec, const void *transfer, co
   if (g.total == 0) return BC_OK;
   const int grid = grid_for(g.total, 1);
   BC_DISPATCH_VEC(g.vec, {
-    halo_tiles_kernel<VV><<<grid, kThreads, 0, s>>>((char *)out, (const char *)exec, (const char *)transfer, grid_idx,
-                                                   mapping, g, src.tile_stride_b, src.tile_stride_c,
-                                                   src.tile_row_bytes, G);
+    launch_kernel(halo_tiles_kernel<VV>, dim3(grid), dim3(kThreads), 0, s, 1, (char *)out, (const char *)exec,
+                  (const char *)transfer, grid_idx, mapping, g, src.tile_stride_b, src.tile_stride_c,
+                  src.tile_row_bytes, G);
   });
   return check_launch("bc_gather_halo_tiles");
 }

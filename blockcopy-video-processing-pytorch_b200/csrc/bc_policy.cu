@@ -31,6 +31,8 @@ __device__ __forceinline__ int nearest_src(float scale, int dst, int in_size) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) policy_features_kernel(const FeatParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int C = 7 + p.K;
   const uint32_t gstride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gstride) {
@@ -74,9 +76,9 @@ int policy_features(float *out, const void *frame, const void *state, const void
   int64_t gridsz = (total + 255) / 256;
   if (gridsz > (int64_t)kNumSMs * 16) gridsz = (int64_t)kNumSMs * 16;
   if (dtype == BC_F16)
-    policy_features_kernel<__half><<<(unsigned)gridsz, 256, 0, stream>>>(p);
+    launch_kernel(policy_features_kernel<__half>, dim3((unsigned)gridsz), dim3(256), 0, stream, 1, p);
   else
-    policy_features_kernel<float><<<(unsigned)gridsz, 256, 0, stream>>>(p);
+    launch_kernel(policy_features_kernel<float>, dim3((unsigned)gridsz), dim3(256), 0, stream, 1, p);
   return check_launch("bc_policy_features");
 }
 
@@ -104,6 +106,8 @@ __device__ __forceinline__ float quarter_tap(const __half *t, const IgParams &p,
 }
 
 __global__ void __launch_bounds__(128) info_gain_kernel(const IgParams p) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.total) return;
   const int x = (int)(i % (uint32_t)p.wo), y = (int)((i / (uint32_t)p.wo) % (uint32_t)p.ho);
@@ -142,7 +146,7 @@ int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h,
   const int64_t total = (int64_t)N * p.ho * p.wo;
   BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_info_gain: problem too large");
   p.total = (uint32_t)total;
-  info_gain_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(p);
+  launch_kernel(info_gain_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, stream, 1, p);
   return check_launch("bc_info_gain");
 }
 

@@ -28,6 +28,8 @@ __device__ __forceinline__ float rh_(float x) { return __half2float(__float2half
 __global__ void __launch_bounds__(256) spp_pool_kernel(const __half *__restrict__ x0, __half *__restrict__ pooled,
                                                         const SppGeo g) {
   __shared__ float red[256 * 8];
+  pdl_trigger();
+  pdl_wait();
   int lvl = 0;
   while (lvl + 1 < g.L && (int)blockIdx.x >= g.cell_off[lvl + 1]) ++lvl;
   const int cell = (int)blockIdx.x - g.cell_off[lvl];
@@ -78,6 +80,8 @@ struct LevelParams {
 
 __global__ void __launch_bounds__(128) spp_levels_kernel(const LevelParams p) {
   extern __shared__ float act[];  // C
+  pdl_trigger();
+  pdl_wait();
   int lvl = 0;
   while (lvl + 1 < p.g.L && (int)blockIdx.x >= p.g.cell_off[lvl + 1]) ++lvl;
   const int C = p.g.C;
@@ -116,6 +120,8 @@ struct PrepParams {
 };
 
 __global__ void __launch_bounds__(256) spp_prep_kernel(const PrepParams p) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.total) return;
   const int chunks = p.Cp / 8;
@@ -173,7 +179,7 @@ int spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, co
   int rc = make_geo(g, N, C, H, W, L, gh, gw);
   if (rc != BC_OK) return rc;
   BC_REQUIRE(C / 8 <= 256, BC_ERR_UNSUPPORTED, "bc_spp_pool: C=%d too large", C);
-  spp_pool_kernel<<<(unsigned)g.cell_off[L], 256, 0, s>>>((const __half *)x0, (__half *)pooled, g);
+  launch_kernel(spp_pool_kernel, dim3((unsigned)g.cell_off[L]), dim3(256), 0, s, 1, (const __half *)x0, (__half *)pooled, g);
   return check_launch("bc_spp_pool");
 }
 
@@ -185,7 +191,7 @@ int spp_levels(void *out, const void *pooled, const float *bn, const void *w, in
   if (rc != BC_OK) return rc;
   BC_REQUIRE(Lc > 0, BC_ERR_SHAPE, "bc_spp_levels: level size %d", Lc);
   p.pooled = (const __half *)pooled; p.out = (__half *)out; p.bn = bn; p.w = (const __half *)w; p.Lc = Lc;
-  spp_levels_kernel<<<(unsigned)p.g.cell_off[L], 128, (size_t)C * sizeof(float), s>>>(p);
+  launch_kernel(spp_levels_kernel, dim3((unsigned)p.g.cell_off[L]), dim3(128), (size_t)C * sizeof(float), s, 1, p);
   return check_launch("bc_spp_levels");
 }
 
@@ -200,7 +206,7 @@ int spp_prep(void *y, const void *x0, const void *lev, const float *bn, int N, i
   const int64_t total = (int64_t)N * H * W * (Cp / 8);
   BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_spp_prep: problem too large");
   p.total = (uint32_t)total;
-  spp_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  launch_kernel(spp_prep_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 1, p);
   return check_launch("bc_spp_prep");
 }
 

@@ -29,6 +29,8 @@ struct PackParams {
 };
 
 __global__ void __launch_bounds__(256) stem_pack_kernel(const PackParams p) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t gstride = gridDim.x * blockDim.x;
   const int hb = p.BS >> 1;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += gstride) {
@@ -70,7 +72,7 @@ int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int
   p.total = (uint32_t)total;
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
-  stem_pack_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+  launch_kernel(stem_pack_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_stem_pack");
 }
 
@@ -116,6 +118,8 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -239,8 +243,8 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
   constexpr size_t smem = (size_t)kStemStages * kStemStage + 1024;
   static cudaError_t attr = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_stem_kernel): %s", cudaGetErrorString(attr));
-  conv_stem_kernel<<<dim3((unsigned)(E * p.tiles_per_block), (unsigned)(Cout / kStemN)), kConvThreads, smem, stream>>>(
-      a_map, b_map, p);
+  launch_kernel(conv_stem_kernel, dim3((unsigned)(E * p.tiles_per_block), (unsigned)(Cout / kStemN)), dim3(kConvThreads),
+                smem, stream, 1, a_map, b_map, p);
   return check_launch("bc_conv_stem");
 }
 

@@ -48,6 +48,8 @@ tma_move_kernel(const __grid_constant__ CUtensorMap plane_map, const __grid_cons
   const int kStages = p.stages;
   for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
   fence_mbar_init();
+  pdl_trigger();
+  pdl_wait();
 
   const CUtensorMap *src = p.to_plane ? &tile_map : &plane_map;
   const CUtensorMap *dst = p.to_plane ? &plane_map : &tile_map;
@@ -235,7 +237,7 @@ int launch_tma_move(void *tiles, void *plane, const int32_t *mapping, int E, int
   if (per_sm > env_ctas) per_sm = env_ctas > 0 ? env_ctas : 1;
   int64_t grid = (int64_t)kNumSMs * per_sm;
   if (grid > n_items) grid = n_items;
-  tma_move_kernel<<<(unsigned)grid, 32, smem, s>>>(plane_map, tile_map, p);
+  launch_kernel(tma_move_kernel, dim3((unsigned)grid), dim3(32), smem, s, 1, plane_map, tile_map, p);
   return check_launch(to_plane ? "bc_scatter[tma]" : "bc_gather[tma]");
 }
 
