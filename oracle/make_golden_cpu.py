@@ -151,7 +151,33 @@ def policy_pieces():
     print("policy_cpu.pt: logits", tuple(logits.shape), "ig", tuple(ig.shape))
 
 
+# ------------------------------------------------------------------------------------------- 4. CSP stand-in
+def csp_standin_clip():
+    """Second consumer (Pedestron CSPBlockCopy op set, tests/csp_standin.py) on the reference package."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from csp_standin import StandinDetector
+
+    H, W, BS = 128, 256, 64
+    det = StandinDetector(settings(block_size=BS)).eval()
+    deterministic_init_(det, seed=4)
+    g = torch.Generator().manual_seed(2)
+    grids = [torch.ones(1, 1, H // BS, W // BS, dtype=torch.bool)]
+    for frac in (0.5, 0.25, 0.0, 0.75):
+        cells = grids[0].numel()
+        m = torch.zeros(cells, dtype=torch.bool)
+        m[torch.randperm(cells, generator=g)[: round(frac * cells)]] = True
+        grids.append(m.view_as(grids[0]))
+    det.policy = PolicyReplay(BS, grids)
+    clip = synthetic_clip(len(grids), H, W, seed=6, dtype=torch.float32)
+    with torch.no_grad():
+        outs = [det.simple_test(f).clone() for f in clip]
+    torch.save(dict(H=H, W=W, BS=BS, init_seed=4, clip_seed=6, grids=torch.stack(grids).to(torch.uint8),
+                    outs=torch.stack(outs)), os.path.join(GOLD, "csp_standin_cpu.pt"))
+    print("csp_standin_cpu.pt:", tuple(outs[0].shape), [round(float(o.abs().mean()), 4) for o in outs])
+
+
 if __name__ == "__main__":
+    csp_standin_clip()
     index_kats()
     policy_pieces()
     swiftnet_clip()
