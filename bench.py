@@ -465,7 +465,8 @@ def conv_microbench(device, peaks, me_full=None, reps=50, sets=4, E=40):
     cells = torch.randperm(128, generator=torch.Generator().manual_seed(0))[:E].sort().values.to(torch.int32).to(device)
     g = torch.Generator(device=device).manual_seed(1)
     for name, Cin, Cout, BS in (("conv3x3_c128_bs32(#20)", 128, 128, 32), ("conv3x3_c64_bs32(layer1)", 64, 64, 32),
-                                ("conv3x3_c256_bs8(layer3)", 256, 256, 8), ("conv3x3_c512_bs4(layer4)", 512, 512, 4)):
+                                ("conv3x3_c128_bs16(layer2)", 128, 128, 16), ("conv3x3_c256_bs8(layer3)", 256, 256, 8),
+                                ("conv3x3_c512_bs4(layer4)", 512, 512, 4)):
         H, W = 8 * BS, 16 * BS
         planes = [torch.randn(1, Cin, H, W, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=torch.channels_last)
                   for _ in range(sets)]

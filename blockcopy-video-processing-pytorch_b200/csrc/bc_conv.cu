@@ -25,7 +25,7 @@
 namespace bc {
 
 template <int N_TILE, int STAGES>
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kConvThreadsV1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                   const ConvParams p) {
   constexpr uint32_t kBBytes = N_TILE * 128;
@@ -61,7 +61,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     prefetch_map(&a_map);
     prefetch_map(&b_map);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      // producers: activations by TMA (warp 0, one arrive.expect_tx) + weights either by TMA (warp 6 lane 0,
+      // one arrive.expect_tx) or by cp.async (all 32 lanes of warp 6, one deferred arrive each)
+      mbar_init(&full_bar[s], p.b_via_tma ? 2 : 33);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
@@ -87,7 +89,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         cx[i] = (int)gw * p.BS_in - p.pad;
         cy[i] = (int)gh * p.BS_in + r0 * p.stride - p.pad;
       }
-      const uint32_t tx_bytes = (uint32_t)nvalid * p.box_bytes + kBBytes;
+      const uint32_t tx_bytes = (uint32_t)nvalid * p.box_bytes;
       for (int ks = 0; ks < num_k; ++ks) {
         const int s = ks % STAGES;
         mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
@@ -98,8 +100,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         mbar_expect_tx(&full_bar[s], tx_bytes);
         for (int i = 0; i < nvalid; ++i)
           tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, cx[i] + kw, cy[i] + kh, cn[i]);
-        tma_load_2d(sa + kABytes, &b_map, &full_bar[s], kg * kChunkK, n0);
       }
+    }
+  } else if (warp == 6) {
+    // =============================== weight producer =============================================
+    // One CTA's TMA queue tops out at ~35 B/clk (profiles/r01b_conv_experiments.md), so the weights take
+    // the other road into shared memory: 16-byte cp.async through the LSU, written with the same 128-byte
+    // swizzle the TMA would apply (16-byte chunk j of row n lands at chunk j ^ (n & 7)).
+    if (p.b_via_tma) {
+      if (lane == 0) {
+        for (int ks = 0; ks < num_k; ++ks) {
+          const int s = ks % STAGES;
+          mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
+          mbar_expect_tx(&full_bar[s], kBBytes);
+          tma_load_2d(smem + (size_t)s * kStageBytes + kABytes, &b_map, &full_bar[s], (k_begin + ks) * kChunkK, n0);
+        }
+      }
+    } else {
+      const __half *wbase = p.weight + (size_t)n0 * p.ktot + (lane & 7) * 8;
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
+        const uint32_t sb = smem_u32(smem + (size_t)s * kStageBytes + kABytes);
+        const __half *wk = wbase + (size_t)(k_begin + ks) * kChunkK;
+#pragma unroll 8
+        for (int it = 0; it < N_TILE / 4; ++it) {  // 4 rows of 128 bytes per warp instruction
+          const int n = it * 4 + (lane >> 3), j = lane & 7;
+          const uint32_t dst = sb + (uint32_t)n * 128u + (uint32_t)((j ^ (n & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(wk + (size_t)n * p.ktot) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===================================================
@@ -108,6 +140,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       for (int ks = 0; ks < num_k; ++ks) {
         const int s = ks % STAGES;
         mbar_wait(&full_bar[s], (uint32_t)((ks / STAGES) & 1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) wrote B
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
@@ -218,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
 
   if (p.splits > 1) {
     cluster_sync_all();  // every CTA's partial is visible cluster-wide
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       // ---- phase 2: reduce-scatter over the cluster; this CTA owns 128/splits accumulator rows -----
       const uint32_t rank = cluster_ctarank();
       const int rows = kTileM / p.splits;
@@ -291,13 +324,15 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
     }
   }
   constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 1024;
-  static_assert((size_t)kTileM * kPartStride<N_TILE> * sizeof(float) <= (size_t)STAGES * (kABytes + N_TILE * 128),
-                "parked accumulator must fit in the pipeline stages");
+  if ((size_t)kTileM * kPartStride<N_TILE> * sizeof(float) > (size_t)STAGES * (kABytes + N_TILE * 128)) {
+    p.splits = 1;  // the parked accumulator of the split-K path would not fit in this variant's pipeline stages
+    p.ksteps_per_split = total_k;
+  }
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
   const cudaError_t e = launch_kernel(conv_igemm_kernel<N_TILE, STAGES>, dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits),
-                                      dim3(kConvThreads), smem, s, (unsigned)p.splits, a_map, b_map, p);
+                                      dim3(kConvThreadsV1), smem, s, (unsigned)p.splits, a_map, b_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -339,7 +374,11 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   {
     static const char *dbg = getenv("BC_CONV_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+    static const char *btma = getenv("BC_CONV_B_TMA");
+    p.b_via_tma = btma ? atoi(btma) : 1;  // cp.async path (0) measured slower on B200: opt-in
   }
+  p.weight = (const __half *)weight;
+  p.ktot = ksize * ksize * Cin;
   p.plane_out = (__half *)plane_out;
   p.out_mapping = out_mapping ? out_mapping : mapping;
   p.out_cell = CellDecode(out_GH > 0 ? out_GH : 1, out_GW > 0 ? out_GW : 1);
@@ -376,7 +415,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (plane) failed: CUresult %d", (int)r);
   }
-  const int n_tile = Cout % 128 == 0 ? 128 : 64;
+  static const int env_ntile = getenv("BC_CONV_NTILE") ? atoi(getenv("BC_CONV_NTILE")) : 0;  // experiments
+  const int n_tile = env_ntile == 64 ? 64 : (Cout % 128 == 0 ? 128 : 64);
   {
     // B: weights [Cout][tap][Cin] = channels_last (Cout, Cin, k, k) memory; K-major rows
     const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
@@ -389,8 +429,37 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
   }
-  if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, allow_split_k != 0, stream);
-  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, allow_split_k != 0, stream);
+  // Variant selection (B200 sweep, profiles/r01b_conv_experiments.md): what counts is how many CTAs an SM can
+  // keep in flight -- one CTA's operand stream tops out near 35 B/clk whatever the pipeline depth -- so
+  // big grids trade stages for co-residency (2 stages -> 3-4 CTAs/SM, single wave), mid-size grids
+  // take 64-wide N tiles to double the CTA count, small grids split K over a cluster.
+  static const int env_stages = getenv("BC_CONV_STAGES") ? atoi(getenv("BC_CONV_STAGES")) : 0;  // experiments
+  const bool split = allow_split_k != 0;
+  if (env_stages || env_ntile) {
+    if (n_tile == 128 && env_stages == 6) return launch_conv<128, 6>(a_map, b_map, p, tiles, Cout / 128, split, stream);
+    if (n_tile == 128 && env_stages == 2) return launch_conv<128, 2>(a_map, b_map, p, tiles, Cout / 128, split, stream);
+    if (n_tile == 64 && env_stages == 2) return launch_conv<64, 2>(a_map, b_map, p, tiles, Cout / 64, split, stream);
+    if (n_tile == 128) return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, split, stream);
+    return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, split, stream);
+  }
+  if (n_tile == 128) {
+    const int ctas = tiles * (Cout / 128);
+    if (ctas > 2 * kNumSMs) return launch_conv<128, 2>(a_map, b_map, p, tiles, Cout / 128, split, stream);
+    if (ctas >= kNumSMs || (split && ctas <= 48))
+      return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, split, stream);
+    // 48 < ctas < 148: re-encode the weight map for 64-wide tiles
+    cuuint64_t gdim[2] = {(cuuint64_t)ksize * ksize * Cin, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {gdim[0] * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kChunkK, 64u};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(weight), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
+    return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, split, stream);
+  }
+  if (tiles * (Cout / 64) > 2 * kNumSMs) return launch_conv<64, 2>(a_map, b_map, p, tiles, Cout / 64, split, stream);
+  return launch_conv<64, 4>(a_map, b_map, p, tiles, Cout / 64, split, stream);
 }
 
 }  // namespace bc

@@ -8,7 +8,8 @@
 
 namespace bc {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;      // stem kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kConvThreadsV1 = 224;    // conv_igemm: + a second TMA producer warp (weights)
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                    // channels per k-step = one 128-byte swizzled row
 constexpr uint32_t kABytes = kTileM * 128;     // 16 KB per stage
@@ -36,6 +37,9 @@ struct ConvParams {
   // reduces rows [r*128/splits, ...) over all peers through distributed shared memory, in rank
   // order (deterministic), and runs the epilogue for those rows.
   int splits, ksteps_per_split;
+  const __half *weight;  // [Cout][ksize*ksize*Cin] (same memory the weight tensor map describes)
+  int ktot;              // ksize*ksize*Cin
+  int b_via_tma;         // 1: weights through TMA like the activations; 0: through cp.async (LSU path)
   int debug;  // BC_CONV_DEBUG (timing experiments only): 1 = one k-step, 2 = no epilogue stores, 3 = both
 };
 

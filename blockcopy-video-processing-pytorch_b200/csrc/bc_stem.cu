@@ -78,7 +78,7 @@ int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int
 
 // ------------------------------------------------------------------ conv on the s2d plane
 constexpr int kStemN = 64;
-constexpr int kStemStages = 4;                       // = the 4 kernel rows: everything is in flight at once
+constexpr int kStemStages = 2;                       // ring over the 4 kernel rows; 49 KB of smem -> 4 CTAs per SM
 constexpr uint32_t kStemABox = kTileM * 32;          // 128 pixels x 16 ch x 2 B
 constexpr uint32_t kStemBBox = kStemN * 32;
 constexpr uint32_t kStemStage = 4 * (kStemABox + kStemBBox);  // 24 KB
@@ -98,6 +98,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                  const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStemStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStemStages];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -109,7 +110,10 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
-    for (int s = 0; s < kStemStages; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < kStemStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
@@ -126,12 +130,14 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
       uint32_t n, gh, gw;
       p.cell((uint32_t)__ldg(p.mapping + b0), n, gh, gw);
       const int x0 = (int)gw * p.BS_out - 2, y0 = (int)gh * p.BS_out + r0 - 2;
-      for (int kh = 0; kh < 4; ++kh) {  // no ring: each stage is used exactly once
-        uint8_t *sa = smem + (size_t)kh * kStemStage;
-        mbar_expect_tx(&full_bar[kh], 4 * (kStemABox + kStemBBox));
+      for (int kh = 0; kh < 4; ++kh) {
+        const int s = kh % kStemStages;
+        mbar_wait(&empty_bar[s], (uint32_t)(((kh / kStemStages) & 1) ^ 1));
+        uint8_t *sa = smem + (size_t)s * kStemStage;
+        mbar_expect_tx(&full_bar[s], 4 * (kStemABox + kStemBBox));
         for (int kw = 0; kw < 4; ++kw) {
-          tma_load_4d(sa + kw * kStemABox, &a_map, &full_bar[kh], 0, x0 + kw, y0 + kh, (int)n);
-          tma_load_2d(sa + 4 * kStemABox + kw * kStemBBox, &b_map, &full_bar[kh], (kh * 4 + kw) * 16, n0);
+          tma_load_4d(sa + kw * kStemABox, &a_map, &full_bar[s], 0, x0 + kw, y0 + kh, (int)n);
+          tma_load_2d(sa + 4 * kStemABox + kw * kStemBBox, &b_map, &full_bar[s], (kh * 4 + kw) * 16, n0);
         }
       }
     }
@@ -139,14 +145,16 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, kStemN);
       for (int kh = 0; kh < 4; ++kh) {
-        mbar_wait(&full_bar[kh], 0);
+        const int s = kh % kStemStages;
+        mbar_wait(&full_bar[s], (uint32_t)((kh / kStemStages) & 1));
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + (size_t)kh * kStemStage);
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStemStage);
         const uint32_t b_addr = a_addr + 4 * kStemABox;
 #pragma unroll
         for (int kw = 0; kw < 4; ++kw)
           umma_f16_ss(tmem_base, umma_desc_sw32(a_addr + kw * kStemABox), umma_desc_sw32(b_addr + kw * kStemBBox), idesc,
                       (uint32_t)((kh | kw) != 0));
+        umma_commit(&empty_bar[s]);
       }
       umma_commit(&acc_bar);
     }
