@@ -363,10 +363,20 @@ def stem_supported(dtype, weight: torch.Tensor, BS_in: int, stride, padding, dil
             and 16 <= bo <= 128 and (bo & (bo - 1)) == 0)
 
 
+STEM_XPAD = 2  # BC_STEM_XPAD of include/blockcopy_b200.h
+
+
+def stem_plane(N: int, Hs: int, Ws: int, dtype, device) -> torch.Tensor:
+    """Zero-filled space-to-depth plane (N,16,Hs,Ws+2*STEM_XPAD) channels_last; the pad columns stay zero."""
+    return torch.zeros((N, 16, Hs, Ws + 2 * STEM_XPAD), dtype=dtype, device=device).contiguous(
+        memory_format=torch.channels_last)
+
+
 def stem_pack(s2d_plane: torch.Tensor, tiles: torch.Tensor, mapping_exec: torch.Tensor, E: int):
-    """Executed NCHW input tiles (E,3,BS,BS) -> cells of the space-to-depth plane (N,16,H/2,W/2) channels_last."""
+    """Executed NCHW input tiles (E,3,BS,BS) -> cells of the space-to-depth plane (see stem_plane)."""
     _dev(s2d_plane, tiles, mapping_exec)
     N, C16, Hs, Ws = s2d_plane.shape
+    Ws -= 2 * STEM_XPAD
     assert C16 == 16 and s2d_plane.is_contiguous(memory_format=torch.channels_last) and tiles.is_contiguous()
     assert tiles.shape[1] == 3
     _check(lib().bc_stem_pack(s2d_plane.data_ptr(), tiles.data_ptr(), mapping_exec.data_ptr(), E, N, Hs * 2, Ws * 2,
@@ -378,6 +388,7 @@ def conv_stem(out: torch.Tensor, s2d_plane: torch.Tensor, weight_packed: torch.T
               mapping_exec: torch.Tensor, E: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None):
     _dev(out, s2d_plane, weight_packed, bias, mapping_exec, plane_out)
     N, _, Hs, Ws = s2d_plane.shape
+    Ws -= 2 * STEM_XPAD
     Cout, BSo = out.shape[1], out.shape[-1]
     assert out.is_contiguous(memory_format=torch.channels_last) and weight_packed.shape == (Cout, 256)
     _check(lib().bc_conv_stem(out.data_ptr(), s2d_plane.data_ptr(), weight_packed.data_ptr(),

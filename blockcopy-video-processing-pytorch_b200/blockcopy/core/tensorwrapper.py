@@ -146,7 +146,8 @@ class BlockFeatures:
                 print(f"TensorWrapper >> GRID {tuple(g.shape)} exec {n_exec}/{G}")
 
     # ------------------------------------------------------------------ planes
-    def _next_plane(self, like: Optional[torch.Tensor], shape, dtype=None, device=None, nhwc=None) -> torch.Tensor:
+    def _next_plane(self, like: Optional[torch.Tensor], shape, dtype=None, device=None, nhwc=None,
+                    zero: bool = False) -> torch.Tensor:
         """Plane of the next padded op in call order; allocated on the first frame.  Layout / dtype
         come from `like` (packed tiles) or from the explicit descriptor."""
         if like is not None:
@@ -164,6 +165,8 @@ class BlockFeatures:
             "No computed features to pop from stack, something seems wrong in the model."
         fmt = torch.channels_last if nhwc else torch.contiguous_format
         plane = torch.empty(shape, dtype=dtype, device=device, memory_format=fmt)
+        if zero:
+            plane.zero_()
         self._planes.append(plane)
         return plane
 
@@ -664,7 +667,8 @@ class TensorWrapper(torch.Tensor):
             N, _, GH, GW = feats._grid_idx.shape
             if feats._plane_cursor < len(feats._planes) and feats._planes[feats._plane_cursor].shape[1] != 16:
                 return None
-            plane = feats._next_plane(None, (N, 16, GH * BS // 2, GW * BS // 2), x.dtype, x.device, True)
+            plane = feats._next_plane(None, (N, 16, GH * BS // 2, GW * BS // 2 + 2 * _C.STEM_XPAD), x.dtype, x.device,
+                                      True, zero=True)  # zero pad columns = the conv's horizontal frame border
             _C.stem_pack(plane, _dense(x).contiguous(), feats._mapping_exec, E)
             pend = _Pending("stem", conv=dict(src=plane, w=_C.pack_stem_weight(weight), bias=bias,
                                               mapping=feats._mapping_exec, E=E))

@@ -76,12 +76,28 @@ __global__ void __launch_bounds__(256) ew_fused_kernel(const EwParams p) {
       for (int t = 0; t < 8; ++t) v[t] = round_h(v[t] + r[t]);
     }
     if (p.has_affine) {
+      // per-channel parameters as 2 x float4 per array (8 vector loads instead of 32 scalar ones)
+      float mean[8], istd[8], w[8], sh[8];
+      *reinterpret_cast<float4 *>(mean) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0));
+      *reinterpret_cast<float4 *>(mean + 4) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0 + 4));
+      *reinterpret_cast<float4 *>(istd) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0));
+      *reinterpret_cast<float4 *>(istd + 4) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0 + 4));
+      if (p.weight) {
+        *reinterpret_cast<float4 *>(w) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0));
+        *reinterpret_cast<float4 *>(w + 4) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0 + 4));
+      } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int c = c0 + t;
-        const float w = p.weight ? __ldg(p.weight + c) : 1.f, s = p.shift ? __ldg(p.shift + c) : 0.f;
-        v[t] = round_h(w * (v[t] - __ldg(p.mean + c)) * __ldg(p.invstd + c) + s);  // ATen's eval-BN expression
+        for (int t = 0; t < 8; ++t) w[t] = 1.f;
       }
+      if (p.shift) {
+        *reinterpret_cast<float4 *>(sh) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0));
+        *reinterpret_cast<float4 *>(sh + 4) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0 + 4));
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sh[t] = 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = round_h(w[t] * (v[t] - mean[t]) * istd[t] + sh[t]);  // ATen's eval-BN expression
     }
     if (p.relu) {
 #pragma unroll
@@ -129,7 +145,7 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
   BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_ew_fused: problem too large");
   p.total = (uint32_t)total;
   int64_t grid = (total + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)kNumSMs * 16;
   if (grid > cap) grid = cap;
   launch_kernel(ew_fused_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_ew_fused");

@@ -5,10 +5,16 @@
 // zero-extended to 8x8): tap (kh', kw') of output (oy, ox) reads s2d pixel (oy+kh'-2, ox+kw'-2).  With
 // the 12 channels padded to 16 one s2d pixel is 32 bytes = one K=16 slab of tcgen05.mma.kind::f16, so
 // the implicit GEMM is M = 128 output pixels, N = 64, K = 16 taps x 16.
-//   stem_pack_kernel : executed NCHW input tiles (E,3,BS,BS) -> persistent s2d plane (N,H/2,W/2,16) NHWC
-//                      (this plane is the op's temporal state: skipped cells keep older frames' pixels)
-//   conv_stem_kernel : per kernel row kh' one pipeline stage of 4 TMA A boxes (16 ch x BS_out x rows, halo =
-//                      neighbouring cells, OOB = zeros) + 4 weight boxes, SWIZZLE_32B operands, 4 MMAs;
+//   stem_pack_kernel : executed NCHW input tiles (E,3,BS,BS) -> persistent s2d plane (N,H/2,W/2+4,16) NHWC
+//                      (this plane is the op's temporal state: skipped cells keep older frames' pixels);
+//                      every row carries BC_STEM_XPAD = 2 zero pixels on either side (zeroed once by the owner)
+//   conv_stem_kernel : the 4 taps of one kernel row are 4 CONSECUTIVE pixels = 128 contiguous bytes, so the
+//                      im2col row of output pixel ox is the 128-byte window starting at padded pixel ox.  The
+//                      A tensor map describes exactly that: inner dim 64 elements, next dim = pixels with a
+//                      stride of ONE pixel (32 B, windows overlap).  One 16 KB SWIZZLE_128B box per kernel
+//                      row (128-byte TMA rows instead of 4x as many 32-byte ones) + one 8 KB weight box,
+//                      4 MMAs of K = 16; vertical halo = neighbouring cells, OOB rows = zeros, horizontal
+//                      frame border = the physical zero columns.
 //                      epilogue = bias + ReLU -> NHWC tiles (+ scatter into the next op's plane)
 // Replaces transfer + repad + cuDNN's 3-channel fprop + bias + ReLU (+ NCHW<->NHWC conversions) of the
 // reference path (core/tensorwrapper.py:529-575 for backbone.conv1).
@@ -18,9 +24,11 @@
 namespace bc {
 
 // ------------------------------------------------------------------ pack: NCHW tiles -> s2d plane
+constexpr int kStemXPad = BC_STEM_XPAD;  // zero pixels on either side of every s2d row
+
 struct PackParams {
   const __half *tiles;  // (E, 3, BS, BS) NCHW
-  __half *plane;        // (N, H/2, W/2, 16) NHWC
+  __half *plane;        // (N, H/2, W/2 + 2*kStemXPad, 16) NHWC
   const int32_t *mapping;
   CellDecode cell;
   FastDiv half_bs, px_per_tile;
@@ -50,7 +58,7 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const PackParams p) {
       }
 #pragma unroll
     for (int t = 12; t < 16; ++t) v[t] = __float2half(0.f);
-    __half *dst = p.plane + (((size_t)n * p.Hh + gh * hb + Y) * p.Wh + gw * hb + X) * 16;
+    __half *dst = p.plane + (((size_t)n * p.Hh + gh * hb + Y) * (p.Wh + 2 * kStemXPad) + kStemXPad + gw * hb + X) * 16;
     reinterpret_cast<uint4 *>(dst)[0] = reinterpret_cast<const uint4 *>(v)[0];
     reinterpret_cast<uint4 *>(dst)[1] = reinterpret_cast<const uint4 *>(v)[1];
   }
@@ -79,19 +87,9 @@ int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int
 // ------------------------------------------------------------------ conv on the s2d plane
 constexpr int kStemN = 64;
 constexpr int kStemStages = 2;                       // ring over the 4 kernel rows; 49 KB of smem -> 4 CTAs per SM
-constexpr uint32_t kStemABox = kTileM * 32;          // 128 pixels x 16 ch x 2 B
-constexpr uint32_t kStemBBox = kStemN * 32;
-constexpr uint32_t kStemStage = 4 * (kStemABox + kStemBBox);  // 24 KB
-
-// K-major operand tile of rows of 32 bytes, 32-byte swizzle: 8-row groups are 256 bytes apart
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((256u >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;
-  d |= 6ull << 61;
-  return d;
-}
+constexpr uint32_t kStemABox = kTileM * 128;         // 128 pixels x (4 taps x 16 ch) x 2 B
+constexpr uint32_t kStemBBox = kStemN * 128;
+constexpr uint32_t kStemStage = kStemABox + kStemBBox;  // 24 KB
 
 __global__ void __launch_bounds__(kConvThreads)
 conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
@@ -129,16 +127,14 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     if (lane == 0) {
       uint32_t n, gh, gw;
       p.cell((uint32_t)__ldg(p.mapping + b0), n, gh, gw);
-      const int x0 = (int)gw * p.BS_out - 2, y0 = (int)gh * p.BS_out + r0 - 2;
+      const int x0 = (int)gw * p.BS_out, y0 = (int)gh * p.BS_out + r0 - 2;  // x in padded pixels: tap 0 of ox
       for (int kh = 0; kh < 4; ++kh) {
         const int s = kh % kStemStages;
         mbar_wait(&empty_bar[s], (uint32_t)(((kh / kStemStages) & 1) ^ 1));
         uint8_t *sa = smem + (size_t)s * kStemStage;
-        mbar_expect_tx(&full_bar[s], 4 * (kStemABox + kStemBBox));
-        for (int kw = 0; kw < 4; ++kw) {
-          tma_load_4d(sa + kw * kStemABox, &a_map, &full_bar[s], 0, x0 + kw, y0 + kh, (int)n);
-          tma_load_2d(sa + 4 * kStemABox + kw * kStemBBox, &b_map, &full_bar[s], (kh * 4 + kw) * 16, n0);
-        }
+        mbar_expect_tx(&full_bar[s], kStemStage);
+        tma_load_4d(sa, &a_map, &full_bar[s], 0, x0, y0 + kh, (int)n);
+        tma_load_2d(sa + kStemABox, &b_map, &full_bar[s], kh * 64, n0);
       }
     }
   } else if (warp == 1) {
@@ -149,10 +145,10 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
         mbar_wait(&full_bar[s], (uint32_t)((kh / kStemStages) & 1));
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * kStemStage);
-        const uint32_t b_addr = a_addr + 4 * kStemABox;
+        const uint32_t b_addr = a_addr + kStemABox;
 #pragma unroll
         for (int kw = 0; kw < 4; ++kw)
-          umma_f16_ss(tmem_base, umma_desc_sw32(a_addr + kw * kStemABox), umma_desc_sw32(b_addr + kw * kStemBBox), idesc,
+          umma_f16_ss(tmem_base, umma_desc_sw128(a_addr + kw * 32), umma_desc_sw128(b_addr + kw * 32), idesc,
                       (uint32_t)((kh | kw) != 0));
         umma_commit(&empty_bar[s]);
       }
@@ -196,7 +192,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
 
-// s2d_plane (N, Hs, Ws, 16) fp16 NHWC; weight fp16 [Cout][4][4][16] (see blockcopy/_C.py: pack_stem_weight)
+// s2d_plane (N, Hs, Ws + 2*kStemXPad, 16) fp16 NHWC, pad columns zero; weight fp16 [Cout][4][4][16] (see blockcopy/_C.py: pack_stem_weight)
 int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias, const int32_t *mapping, int E,
               int N, int Hs, int Ws, int BS_out, int Cout, int relu, void *plane_out, cudaStream_t stream) {
   BC_REQUIRE(out && s2d_plane && weight && mapping, BC_ERR_NULL, "bc_conv_stem: NULL pointer");
@@ -229,22 +225,24 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
 
   CUtensorMap a_map, b_map;
   {
-    cuuint64_t gdim[4] = {16, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {32, (cuuint64_t)Ws * 32, (cuuint64_t)Hs * Ws * 32};
-    cuuint32_t box[4] = {16, (cuuint32_t)BS_out, (cuuint32_t)p.rows_per_tile, 1};
+    // dim 1 walks WINDOWS of 4 pixels with a stride of one pixel: window x = padded pixels x .. x+3
+    const cuuint64_t Wp = (cuuint64_t)Ws + 2 * kStemXPad;
+    cuuint64_t gdim[4] = {64, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {32, Wp * 32, (cuuint64_t)Hs * Wp * 32};
+    cuuint32_t box[4] = {64, (cuuint32_t)BS_out, (cuuint32_t)p.rows_per_tile, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(&a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(s2d_plane), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_stem: tensor map (plane) failed: CUresult %d", (int)r);
   }
   {
     cuuint64_t gdim[2] = {256, (cuuint64_t)Cout};
     cuuint64_t gstr[1] = {512};
-    cuuint32_t box[2] = {16, (cuuint32_t)kStemN};
+    cuuint32_t box[2] = {64, (cuuint32_t)kStemN};
     cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(&b_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(weight), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_stem: tensor map (weights) failed: CUresult %d", (int)r);
   }

@@ -191,14 +191,17 @@ BC_API int bc_maxpool_halo(void *out, void *plane_out, const void *plane, const 
 
 /* ---- ResNet stem (conv 7x7, stride 2, padding 3, 3 input channels) on executed blocks -------------
  * Replaces transfer + repad + cuDNN conv + bias + ReLU for backbone.conv1 (core/tensorwrapper.py:529-575).
- * The op's temporal state is a space-to-depth(2) plane s2d (N, H/2, W/2, 16) fp16 NHWC:
- *   s2d[n, Y, X, (dy*2+dx)*3 + c] = frame[n, c, 2Y+dy, 2X+dx],  channels 12..15 = 0.
+ * The op's temporal state is a space-to-depth(2) plane s2d (N, H/2, W/2 + 2*BC_STEM_XPAD, 16) fp16 NHWC:
+ *   s2d[n, Y, BC_STEM_XPAD + X, (dy*2+dx)*3 + c] = frame[n, c, 2Y+dy, 2X+dx],  channels 12..15 = 0,
+ *   and the BC_STEM_XPAD pixels on either side of every row are ZERO (the owner zero-fills the plane once;
+ *   neither entry point writes them).  They are the conv's horizontal frame-border padding.
  * bc_stem_pack writes the executed cells of it from the packed NCHW input tiles (E,3,BS,BS);
  * bc_conv_stem runs the conv as a 4x4 stride-1 implicit GEMM on that plane (tcgen05, K = 16 taps x 16):
  *   weight fp16 [Cout][4][4][16], w'[o,kh',kw',(dy*2+dx)*3+c] = w[o,c,2kh'+dy-1,2kw'+dx-1] (0 outside 0..6)
  *   out    fp16 (E, BS_out, BS_out, Cout) NHWC, BS_out = BS/2;  epilogue: + bias, ReLU
  *   plane_out optional: the next padded op's plane (N, H/2, W/2, Cout) NHWC, written in the same pass.
  */
+#define BC_STEM_XPAD 2
 BC_API int bc_stem_pack(void *s2d_plane, const void *tiles, const int32_t *mapping_exec, int E, int N, int H, int W,
                         int BS, bc_stream_t stream);
 BC_API int bc_conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias,

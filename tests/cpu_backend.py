@@ -145,13 +145,13 @@ def cpu_backend():
             for dx in range(2):
                 ch = (dy * 2 + dx) * 3
                 s2d[:, ch:ch + 3] = t[:, :, dy::2, dx::2]
-        _scatter_plane(s2d_plane, s2d, mapping_exec[:E])
+        _scatter_plane(s2d_plane[..., 2:-2], s2d, mapping_exec[:E])  # BC_STEM_XPAD columns stay zero
         return s2d_plane
 
     def conv_stem(out, s2d_plane, weight_packed, bias, mapping_exec, E, relu=False, plane_out=None):
         Cout = weight_packed.shape[0]
         w = weight_packed.view(Cout, 4, 4, 16).permute(0, 3, 1, 2).contiguous()
-        full = F.conv2d(F.pad(_nchw(s2d_plane), (2, 1, 2, 1)), w, bias)  # taps oy-2 .. oy+1
+        full = F.conv2d(F.pad(_nchw(s2d_plane)[..., 2:-2], (2, 1, 2, 1)), w, bias)  # taps oy-2 .. oy+1
         y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), out.shape[-1])
         if relu:
             y = y.relu()

@@ -216,7 +216,7 @@ def test_stem_conv_7x7_s2(N, GH, GW, BS, Cout, frac):
     gi, me = O.grid_mappings(grid)
     all_gi, all_me = O.grid_mappings(torch.ones_like(grid))
     E, G = me.numel(), grid.numel()
-    plane = torch.zeros(N, 16, H // 2, W // 2, dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+    plane = _C.stem_plane(N, H // 2, W // 2, torch.float16, dev)
     _C.stem_pack(plane, O.split(old, all_me, BS).to(dev), all_me.to(dev), G)
     _C.stem_pack(plane, O.split(frame, me, BS).to(dev), me.to(dev), E)
     mixed = old.clone()
