@@ -39,6 +39,7 @@ _SIGNATURES = {
     "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp], _i),
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
     "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
+    "bc_debug_trace": ([_vp], _i),
     "bc_stem_pack": ([_vp, _vp, _ip] + [_i] * 5 + [_vp], _i),
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),

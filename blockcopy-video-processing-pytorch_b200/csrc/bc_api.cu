@@ -74,6 +74,8 @@ bool pdl_enabled() {
 
 static inline bool tma_on() { return g_tma_enabled.load(std::memory_order_relaxed) != 0; }
 
+static std::atomic<unsigned long long *> g_trace{nullptr};
+unsigned long long *debug_trace_buffer() { return g_trace.load(); }
 }  // namespace bc
 
 using namespace bc;
@@ -90,6 +92,11 @@ BC_API const char *bc_build_info(void) {
 
 BC_API int bc_set_tma_enabled(int enabled) {
   g_tma_enabled.store(enabled ? 1 : 0);
+  return BC_OK;
+}
+
+BC_API int bc_debug_trace(void *device_buffer) {
+  bc::g_trace.store((unsigned long long *)device_buffer);
   return BC_OK;
 }
 

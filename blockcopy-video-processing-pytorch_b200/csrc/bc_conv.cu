@@ -36,6 +36,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[N_TILE];  // this CTA's slice of the bias, staged while the main loop runs
+  // element offsets of channel n0 of accumulator row m's pixel in the tile batch / in the next op's plane
+  // (-1: no such pixel / no plane).  Decoding a row costs two integer divisions and a mapping lookup; done
+  // once per row while the main loop runs instead of once per 16-byte store (profiles/r01c_cta_timeline.md).
+  __shared__ long long row_off_s[kTileM], row_pl_s[kTileM];
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -56,6 +60,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
   const int k_begin = (int)blockIdx.z * p.ksteps_per_split;
   const int num_k = (p.debug & 1) ? 1 : min(p.ksteps_per_split, total_k - k_begin);
+  if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
@@ -76,6 +81,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   const uint32_t tmem_base = tmem_base_slot;
   pdl_trigger();
   pdl_wait();  // barrier init, TMEM alloc and descriptor prefetch above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) trace_mark(p, 1);
 
   if (warp == 0) {
     // =============================== TMA producer =================================================
@@ -140,6 +146,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       for (int ks = 0; ks < num_k; ++ks) {
         const int s = ks % STAGES;
         mbar_wait(&full_bar[s], (uint32_t)((ks / STAGES) & 1));
+        if (ks == 0) trace_mark(p, 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) wrote B
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
@@ -151,13 +158,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
       }
       umma_commit(&acc_bar);  // accumulator complete
+      trace_mark(p, 3);
     }
   } else {
     // =============================== epilogue =====================================================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     for (int c = threadIdx.x - 64; c < N_TILE; c += 128) bias_s[c] = p.bias ? __half2float(__ldg(p.bias + n0 + c)) : 0.f;
+    {
+      const int m = q * 32 + lane;
+      int blk, y, x;
+      pixel_of_row(p, m, r0, blk, y, x);
+      const bool ok = blk < nvalid && !(p.debug & 2);
+      row_off_s[m] = ok ? (long long)((((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x) * p.Cout + n0) : -1ll;
+      row_pl_s[m] = (ok && p.plane_out) ? (long long)(plane_row(p, b0 + blk, y, x) - p.plane_out) + n0 : -1ll;
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     mbar_wait(&acc_bar, 0);
+    if (threadIdx.x == 64) trace_mark(p, 4);
     tc_fence_after_sync();
     if (p.splits == 1) {
       // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's private
@@ -195,12 +212,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         bool ok[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {  // addresses + residual loads of the whole batch first (latency overlap)
-          const int r = i0 + u * kRPI + lane / kTPR;
-          int blk, y, x;
-          pixel_of_row(p, q * 32 + r, r0, blk, y, x);
-          ok[u] = blk < nvalid && !(p.debug & 2);
-          off[u] = (((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x) * p.Cout + n0 + c8;
-          pl[u] = (p.plane_out && ok[u]) ? plane_row(p, b0 + blk, y, x) + n0 + c8 : nullptr;
+          const int m = q * 32 + i0 + u * kRPI + lane / kTPR;
+          const long long ro = row_off_s[m], rp = row_pl_s[m];
+          ok[u] = ro >= 0;
+          off[u] = (size_t)ro + c8;
+          pl[u] = rp >= 0 ? p.plane_out + rp + c8 : nullptr;
           res[u] = make_uint4(0, 0, 0, 0);
           if (p.residual && ok[u]) res[u] = __ldg(reinterpret_cast<const uint4 *>(p.residual + off[u]));
         }
@@ -246,6 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
               make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }
+    if (threadIdx.x == 64) trace_mark(p, 5);
     tc_fence_before_sync();
   }
 
@@ -262,22 +279,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       const uint32_t part_addr = smem_u32(smem);
       for (int rr = t / kThreadsPerRow; rr < rows; rr += kRowsPerPass) {
         const int m = (int)rank * rows + rr;
+        // peers' partials in batches (one DSMEM round trip per 4 peers instead of one per peer), then the sum
+        // in rank order: bit-reproducible
+        const uint32_t a = part_addr + (uint32_t)(((size_t)m * kPartStride<N_TILE> + c8) * sizeof(float));
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        for (int z = 0; z < p.splits; ++z) {  // fixed order: bit-reproducible sums
-          const uint32_t a = part_addr + (uint32_t)(((size_t)m * kPartStride<N_TILE> + c8) * sizeof(float));
-          const float4 lo = ld_dsmem_f4(a, (uint32_t)z), hi = ld_dsmem_f4(a + 16, (uint32_t)z);
-          v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
-          v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+#pragma unroll 1
+        for (int z0 = 0; z0 < p.splits; z0 += 4) {  // 4 peers per round trip (register budget: 4 CTAs per SM)
+          float4 lo[4], hi[4];
+#pragma unroll
+          for (int z = 0; z < 4; ++z)
+            if (z0 + z < p.splits) {
+              lo[z] = ld_dsmem_f4(a, (uint32_t)(z0 + z));
+              hi[z] = ld_dsmem_f4(a + 16, (uint32_t)(z0 + z));
+            }
+#pragma unroll
+          for (int z = 0; z < 4; ++z)
+            if (z0 + z < p.splits) {
+              v[0] += lo[z].x; v[1] += lo[z].y; v[2] += lo[z].z; v[3] += lo[z].w;
+              v[4] += hi[z].x; v[5] += hi[z].y; v[6] += hi[z].z; v[7] += hi[z].w;
+            }
         }
-        int blk, y, x;
-        pixel_of_row(p, m, r0, blk, y, x);
-        if (blk < nvalid) {
-          const size_t pix = ((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x;
-          const size_t off = pix * p.Cout + n0 + c8;
+        const long long ro = row_off_s[m], rp = row_pl_s[m];
+        if (ro >= 0) {
+          const size_t off = (size_t)ro + c8;
           epilogue_store8(v, p.bias ? p.bias + n0 + c8 : nullptr, p.residual ? p.residual + off : nullptr, p.relu,
-                          p.out + off, p.plane_out ? plane_row(p, b0 + blk, y, x) + n0 + c8 : nullptr);
+                          p.out + off, rp >= 0 ? p.plane_out + rp + c8 : nullptr);
         }
       }
     }
@@ -285,6 +313,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   }
 
   __syncthreads();
+  if (threadIdx.x == 0) { trace_mark(p, 6); trace_wall(p, 10); }
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, N_TILE);
@@ -374,6 +403,7 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   {
     static const char *dbg = getenv("BC_CONV_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+    p.trace = debug_trace_buffer();
     static const char *btma = getenv("BC_CONV_B_TMA");
     p.b_via_tma = btma ? atoi(btma) : 1;  // cp.async path (0) measured slower on B200: opt-in
   }

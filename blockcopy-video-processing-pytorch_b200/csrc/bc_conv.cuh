@@ -40,8 +40,29 @@ struct ConvParams {
   const __half *weight;  // [Cout][ksize*ksize*Cin] (same memory the weight tensor map describes)
   int ktot;              // ksize*ksize*Cin
   int b_via_tma;         // 1: weights through TMA like the activations; 0: through cp.async (LSU path)
+  unsigned long long *trace;  // bc_debug_trace buffer (16 words per CTA) or nullptr
   int debug;  // BC_CONV_DEBUG (timing experiments only): 1 = one k-step, 2 = no epilogue stores, 3 = both
 };
+
+// in-kernel timeline for profiles/ (bc_debug_trace): slot k of this CTA's 16-word record <- SM clock
+__device__ __forceinline__ void trace_mark(const ConvParams &p, int k) {
+  if (p.trace) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    p.trace[(size_t)cta * 16 + k] = (unsigned long long)clock64();
+  }
+}
+__device__ __forceinline__ void trace_wall(const ConvParams &p, int k) {  // slot k <- %globaltimer (ns), k+1 <- SM id
+  if (p.trace) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    unsigned long long t;
+    unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    p.trace[(size_t)cta * 16 + k] = t;
+    p.trace[(size_t)cta * 16 + k + 1] = sm;
+  }
+}
+unsigned long long *debug_trace_buffer();  // bc_api.cu
 
 template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)
 

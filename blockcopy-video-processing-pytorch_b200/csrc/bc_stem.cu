@@ -85,105 +85,150 @@ int stem_pack(void *plane, const void *tiles, const int32_t *mapping, int E, int
 }
 
 // ------------------------------------------------------------------ conv on the s2d plane
+// One CTA = kStemTiles vertically adjacent 128-pixel tiles of one block and 64 output channels:
+//   * ONE A box of (kStemTiles*rows + 3) pixel rows x BS_out windows (the tiles and the 4 kernel rows share
+//     pixel rows: tap kh of tile t is the SAME shared memory shifted by (t*rows + kh) * BS_out windows),
+//   * the whole 64 x 256 weight slab once (4 boxes, one per kernel row),
+//   * kStemTiles accumulators of 64 TMEM columns, 16 MMAs (K = 16) each,
+//   * epilogue through shared memory so that global stores are whole 128-byte pixel rows.
+// L1<->L2 traffic per output pixel falls from ~1.3 KB (per-tile weight reload, 4x4 window reuse from L2,
+// half-filled store sectors) to ~0.6 KB, which is what bounds this kernel (profiles/r01c_stem.md).
 constexpr int kStemN = 64;
-constexpr int kStemStages = 2;                       // ring over the 4 kernel rows; 49 KB of smem -> 4 CTAs per SM
-constexpr uint32_t kStemABox = kTileM * 128;         // 128 pixels x (4 taps x 16 ch) x 2 B
-constexpr uint32_t kStemBBox = kStemN * 128;
-constexpr uint32_t kStemStage = kStemABox + kStemBBox;  // 24 KB
+constexpr int kStemTiles = 2;
+constexpr uint32_t kStemBBox = kStemN * 128;          // one kernel row of the weights: 64 x (4 taps x 16 ch) fp16
+constexpr uint32_t kStemBBytes = 4 * kStemBBox;       // 32 KB
+constexpr int kStemRowB = kStemN * 2 + 16;            // staged output row (+16 B: bank spread)
+
+__host__ __device__ constexpr uint32_t stem_a_bytes(int BS_out) {
+  return (uint32_t)(kStemTiles * kTileM + 3 * BS_out) * 128u;
+}
 
 __global__ void __launch_bounds__(kConvThreads)
 conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                  const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStemStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStemStages];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ __align__(8) uint64_t acc_bar[kStemTiles];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[kStemN];
+  __shared__ long long row_off_s[kTileM], row_pl_s[kTileM];  // tile 0's pixel offsets (see bc_conv.cu)
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, n0 = blockIdx.y * kStemN;
-  const int b0 = tile / p.tiles_per_block;
-  const int r0 = (tile - b0 * p.tiles_per_block) * p.rows_per_tile;
+  const int group = blockIdx.x, n0 = blockIdx.y * kStemN;
+  const int groups_per_block = p.tiles_per_block / kStemTiles;
+  const int b0 = group / groups_per_block;
+  const int r0 = (group - b0 * groups_per_block) * kStemTiles * p.rows_per_tile;
+  const uint32_t a_bytes = stem_a_bytes(p.BS_out);
+  if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
-    for (int s = 0; s < kStemStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&acc_bar, 1);
+    mbar_init(&full_bar, 1);
+    for (int t = 0; t < kStemTiles; ++t) mbar_init(&acc_bar[t], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_slot, kStemN);
+  if (warp == 1) tmem_alloc(&tmem_base_slot, kStemTiles * kStemN);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
   pdl_trigger();
   pdl_wait();  // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) trace_mark(p, 1);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t n, gh, gw;
       p.cell((uint32_t)__ldg(p.mapping + b0), n, gh, gw);
-      const int x0 = (int)gw * p.BS_out, y0 = (int)gh * p.BS_out + r0 - 2;  // x in padded pixels: tap 0 of ox
-      for (int kh = 0; kh < 4; ++kh) {
-        const int s = kh % kStemStages;
-        mbar_wait(&empty_bar[s], (uint32_t)(((kh / kStemStages) & 1) ^ 1));
-        uint8_t *sa = smem + (size_t)s * kStemStage;
-        mbar_expect_tx(&full_bar[s], kStemStage);
-        tma_load_4d(sa, &a_map, &full_bar[s], 0, x0, y0 + kh, (int)n);
-        tma_load_2d(sa + kStemABox, &b_map, &full_bar[s], kh * 64, n0);
-      }
+      // x in padded pixels (window x = taps of output column x); rows r0-2 .. r0 + tiles*rows: OOB rows = zeros
+      mbar_expect_tx(&full_bar, a_bytes + kStemBBytes);
+      tma_load_4d(smem, &a_map, &full_bar, 0, (int)gw * p.BS_out, (int)gh * p.BS_out + r0 - 2, (int)n);
+      for (int kh = 0; kh < 4; ++kh) tma_load_2d(smem + a_bytes + kh * kStemBBox, &b_map, &full_bar, kh * 64, n0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, kStemN);
-      for (int kh = 0; kh < 4; ++kh) {
-        const int s = kh % kStemStages;
-        mbar_wait(&full_bar[s], (uint32_t)((kh / kStemStages) & 1));
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStemStage);
-        const uint32_t b_addr = a_addr + kStemABox;
+      mbar_wait(&full_bar, 0);
+      trace_mark(p, 2);
+      tc_fence_after_sync();
+      const uint32_t a_addr = smem_u32(smem), b_addr = a_addr + a_bytes;
+      for (int t = 0; t < kStemTiles; ++t) {
+        for (int kh = 0; kh < 4; ++kh) {
+          const uint32_t a_tap = a_addr + (uint32_t)((t * p.rows_per_tile + kh) * p.BS_out) * 128u;
 #pragma unroll
-        for (int kw = 0; kw < 4; ++kw)
-          umma_f16_ss(tmem_base, umma_desc_sw128(a_addr + kw * 32), umma_desc_sw128(b_addr + kw * 32), idesc,
-                      (uint32_t)((kh | kw) != 0));
-        umma_commit(&empty_bar[s]);
+          for (int kw = 0; kw < 4; ++kw)
+            umma_f16_ss(tmem_base + (uint32_t)(t * kStemN), umma_desc_sw128(a_tap + kw * 32),
+                        umma_desc_sw128(b_addr + kh * kStemBBox + kw * 32), idesc, (uint32_t)((kh | kw) != 0));
+        }
+        umma_commit(&acc_bar[t]);
       }
-      umma_commit(&acc_bar);
+      trace_mark(p, 3);
     }
   } else {
     const int q = warp & 3;
-    const int m = q * 32 + lane;
-    int blk, y, x;
-    pixel_of_row(p, m, r0, blk, y, x);
-    const size_t pix = ((size_t)b0 * p.BS_out + y) * p.BS_out + x;
-    __half *orow = p.out + pix * p.Cout + n0;
-    __half *prow = p.plane_out ? plane_row(p, b0, y, x) + n0 : nullptr;
-    mbar_wait(&acc_bar, 0);
+    if (threadIdx.x - 64 < kStemN) bias_s[threadIdx.x - 64] = p.bias ? __half2float(p.bias[n0 + threadIdx.x - 64]) : 0.f;
+    {
+      const int m = q * 32 + lane;
+      int blk, y, x;
+      pixel_of_row(p, m, r0, blk, y, x);
+      row_off_s[m] = (long long)((((size_t)b0 * p.BS_out + y) * p.BS_out + x) * p.Cout + n0);
+      row_pl_s[m] = p.plane_out ? (long long)(plane_row(p, b0, y, x) - p.plane_out) + n0 : -1ll;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+    // staging rows live in the A region: free once the LAST accumulator is complete (all MMAs have read smem)
+    uint8_t *stage = smem + (size_t)q * 32 * kStemRowB;
+    constexpr int kTPR = kStemN / 8, kRPI = 32 / kTPR;  // 8 lanes cover one pixel's 128 bytes, 4 pixels per access
+    const int c8 = (lane % kTPR) * 8;
+    mbar_wait(&acc_bar[kStemTiles - 1], 0);
+    if (threadIdx.x == 64) trace_mark(p, 4);
     tc_fence_after_sync();
 #pragma unroll 1
-    for (int c0 = 0; c0 < kStemN; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      tmem_ld_wait();
+    for (int t = 0; t < kStemTiles; ++t) {
+      // phase A: this thread's accumulator row -> + bias -> ReLU -> fp16 -> staging row `lane`
+#pragma unroll 1
+      for (int c0 = 0; c0 < kStemN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * kStemN + c0), acc);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float v[8];
+        for (int j = 0; j < 32; j += 8) {
+          float v[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(acc[j + t]);
-        epilogue_store8(v, p.bias ? p.bias + n0 + c0 + j : nullptr, nullptr, p.relu, orow + c0 + j,
-                        prow ? prow + c0 + j : nullptr);
+          for (int u = 0; u < 8; ++u) {
+            v[u] = __uint_as_float(acc[j + u]) + bias_s[c0 + j + u];
+            if (p.relu) v[u] = fmaxf(v[u], 0.f);
+          }
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) oh[u] = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+          *reinterpret_cast<uint4 *>(stage + (size_t)lane * kStemRowB + (c0 + j) * 2) = o;
+        }
       }
+      __syncwarp();
+      // phase B: whole 128-byte pixel rows to the tile batch and to the next op's plane
+      // tile t lies t * rows_per_tile pixel rows below tile 0
+      const long long dt_out = (long long)t * kTileM * p.Cout;
+      const long long dt_pl = (long long)t * p.rows_per_tile * p.out_W * p.Cout;
+#pragma unroll
+      for (int i0 = 0; i0 < 32; i0 += kRPI) {
+        const int r = i0 + lane / kTPR;
+        const long long ro = row_off_s[q * 32 + r], rp = row_pl_s[q * 32 + r];
+        const uint4 o = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kStemRowB + c8 * 2);
+        *reinterpret_cast<uint4 *>(p.out + ro + dt_out + c8) = o;
+        if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + dt_pl + c8) = o;
+      }
+      __syncwarp();
     }
+    if (threadIdx.x == 64) trace_mark(p, 5);
     tc_fence_before_sync();
   }
   __syncthreads();
+  if (threadIdx.x == 0) { trace_mark(p, 6); trace_wall(p, 10); }
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kStemN);
+    tmem_dealloc(tmem_base, kStemTiles * kStemN);
   }
 }
 
@@ -222,6 +267,7 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
   p.out_cell = p.cell;
   p.out_H = Hs; p.out_W = Ws;
   p.splits = 1;
+  p.trace = debug_trace_buffer();
 
   CUtensorMap a_map, b_map;
   {
@@ -229,7 +275,7 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
     const cuuint64_t Wp = (cuuint64_t)Ws + 2 * kStemXPad;
     cuuint64_t gdim[4] = {64, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
     cuuint64_t gstr[3] = {32, Wp * 32, (cuuint64_t)Hs * Wp * 32};
-    cuuint32_t box[4] = {64, (cuuint32_t)BS_out, (cuuint32_t)p.rows_per_tile, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)BS_out, (cuuint32_t)(kStemTiles * p.rows_per_tile + 3), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(&a_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(s2d_plane), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -246,11 +292,12 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_stem: tensor map (weights) failed: CUresult %d", (int)r);
   }
-  constexpr size_t smem = (size_t)kStemStages * kStemStage + 1024;
-  static cudaError_t attr = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)stem_a_bytes(BS_out) + kStemBBytes + 1024;
+  static cudaError_t attr = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(stem_a_bytes(128) + kStemBBytes + 1024));
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_stem_kernel): %s", cudaGetErrorString(attr));
-  launch_kernel(conv_stem_kernel, dim3((unsigned)(E * p.tiles_per_block), (unsigned)(Cout / kStemN)), dim3(kConvThreads),
-                smem, stream, 1, a_map, b_map, p);
+  launch_kernel(conv_stem_kernel, dim3((unsigned)(E * p.tiles_per_block / kStemTiles), (unsigned)(Cout / kStemN)),
+                dim3(kConvThreads), smem, stream, 1, a_map, b_map, p);
   return check_launch("bc_conv_stem");
 }
 

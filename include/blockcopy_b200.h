@@ -247,6 +247,12 @@ BC_API int bc_spp_prep(void *y, const void *x0, const void *levels, const float 
 /* Selects the implementation of bc_gather / bc_gather_halo / bc_scatter for NHWC
  * inputs: 0 = vectorised SIMT kernels, 1 = TMA-staged kernels (default when the
  * shape qualifies).  Process-wide; meant for benchmarking the two against each other. */
+/* Diagnostics (tools/cta_timeline.py, profiles/): while a device buffer is registered, every CTA of
+ * bc_conv_igemm / bc_conv_stem writes a 16-word (uint64) record into it at index linear_cta_id*16:
+ * [0..6] SM clock at entry / after setup / first operands landed / last MMA issued / accumulator complete /
+ * epilogue done / exit, [8] %globaltimer at entry, [9] SM id, [10] %globaltimer at exit.  NULL switches
+ * it off (default).  The buffer must hold 16*8 bytes per CTA of the largest launch made while registered. */
+BC_API int bc_debug_trace(void *device_buffer);
 BC_API int bc_set_tma_enabled(int enabled);
 
 #ifdef __cplusplus
