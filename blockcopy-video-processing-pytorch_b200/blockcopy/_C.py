@@ -36,7 +36,8 @@ _SIGNATURES = {
     "bc_transfer": ([_vp, _vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo_tiles": ([_vp, _vp, _vp, _ip, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_gather_halo": ([_vp, _vp, _ip, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
-    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp], _i),
+    "bc_conv_igemm": ([_vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 11 + [_vp, _ip, _i, _i, _i, _i, _vp, ctypes.c_longlong, _vp],
+                      _i),
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
     "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
     "bc_debug_trace": ([_vp], _i),
@@ -255,6 +256,20 @@ def lazy_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.shape[1] % 8 == 0
 
 
+_SPLITK_WS = {}
+SPLITK_WS_BYTES = 32 << 20
+
+
+def _splitk_workspace(device: torch.device, stream: int) -> torch.Tensor:
+    """Scratch for the split-K partial sums of bc_conv_igemm, one per (device, stream): launches on one
+    stream are ordered, so they may share it; concurrent streams must not."""
+    key = (device.index, stream)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = torch.empty(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
 def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],
                residual: Optional[torch.Tensor], mapping_exec: Optional[torch.Tensor], E: int, BS_in: int,
                stride: int, padding: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None,
@@ -274,6 +289,8 @@ def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, 
         assert plane_out.is_contiguous(memory_format=torch.channels_last) and plane_out.shape[1] == Cout
         if out_mapping is None:
             out_mapping = mapping_exec
+    stream = _stream()
+    ws = _splitk_workspace(out.device, int(stream)) if split_k and split_k != "dsmem" else None
     _check(lib().bc_conv_igemm(out.data_ptr(), plane.data_ptr(), weight_cl.data_ptr(),
                                bias.data_ptr() if bias is not None else None,
                                residual.data_ptr() if residual is not None else None,
@@ -281,7 +298,8 @@ def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, 
                                E, N, Cin, H, W, BS_in, Cout, k, stride, padding, int(relu),
                                plane_out.data_ptr() if plane_out is not None else None,
                                out_mapping.data_ptr() if out_mapping is not None else None, oN, oGH, oGW,
-                               int(split_k), _stream()),
+                               int(bool(split_k)), ws.data_ptr() if ws is not None else None,
+                               ws.numel() if ws is not None else 0, stream),
            "bc_conv_igemm")
     return out
 
@@ -325,15 +343,40 @@ def maxpool_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Ten
     return out
 
 
+# ------------------------------------------------------------------------------------------- derived-parameter cache
+class TensorCache:
+    """Values derived from parameter tensors (packed weights, folded batch-norm vectors), keyed by the
+    IDENTITY of the source tensors plus their in-place version counters.  Entries keep the sources alive,
+    so neither an id() nor a data_ptr() can be recycled by another tensor while the entry exists."""
+
+    def __init__(self, capacity: int):
+        self._d, self._cap = {}, capacity
+
+    @staticmethod
+    def _versions(tensors):
+        return tuple(None if t is None else t._version for t in tensors)
+
+    def get(self, tensors, extra=()):
+        e = self._d.get(tuple(id(t) for t in tensors) + tuple(extra))
+        if e is not None and all(a is b for a, b in zip(e[0], tensors)) and e[1] == self._versions(tensors):
+            return e[2]
+        return None
+
+    def put(self, tensors, extra, value):
+        if len(self._d) >= self._cap:
+            self._d.clear()
+        self._d[tuple(id(t) for t in tensors) + tuple(extra)] = (tuple(tensors), self._versions(tensors), value)
+        return value
+
+
 # ------------------------------------------------------------------------------------------- stem (7x7 s2, 3 ch)
-_STEM_W = {}
+_STEM_W = TensorCache(64)
 
 
 def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
     """(Cout,3,7,7) -> (Cout,256): the 7x7 stride-2 kernel as a zero-extended 4x4 kernel over the
     space-to-depth(2) image with 16 (12 used) channels; cached per weight version."""
-    key = (w.data_ptr(), w._version, w.dtype)
-    hit = _STEM_W.get(key)
+    hit = _STEM_W.get((w,))
     if hit is None:
         Cout = w.shape[0]
         wd = w.detach()
@@ -349,10 +392,7 @@ def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
                         u = 2 * kw + dx - 1
                         if 0 <= u < 7:
                             wp[:, kh, kw, ch:ch + 3] = wd[:, :, t, u]
-        hit = wp.reshape(Cout, 256).contiguous()
-        if len(_STEM_W) > 64:
-            _STEM_W.clear()
-        _STEM_W[key] = hit
+        hit = _STEM_W.put((w,), (), wp.reshape(Cout, 256).contiguous())
     return hit
 
 

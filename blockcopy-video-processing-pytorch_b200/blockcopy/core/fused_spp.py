@@ -9,12 +9,14 @@ CUDA, the same math runs as 7 launches: BN+ReLU (bc_ew_fused), 1x1 conv (bc_conv
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.nn as nn
 
 from .. import _C
 
-_PLANS = {}
+_PLANS = weakref.WeakKeyDictionary()  # module -> _Plan (dies with the module: no id() reuse)
 
 
 def _unit(u):
@@ -72,11 +74,14 @@ class _Plan:
 
 
 def _versions(units):
-    v = []
-    for bn, conv in units:
-        for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias, conv.weight):
-            v.append(None if t is None else (t.data_ptr(), t._version))
-    return tuple(v)
+    """(source tensors, their in-place version counters): the plan keeps the tensors, so a replaced
+    parameter is a different object even if the allocator hands out the same address again."""
+    src = [t for bn, conv in units for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias, conv.weight)]
+    return src, tuple(None if t is None else t._version for t in src)
+
+
+def _same(a, b):
+    return a[1] == b[1] and len(a[0]) == len(b[0]) and all(x is y for x, y in zip(a[0], b[0]))
 
 
 def _match(module):
@@ -98,9 +103,9 @@ def try_fused_spp(module, x: torch.Tensor):
     units = _match(module)
     if units is None:
         return None
-    plan = _PLANS.get(id(module))
-    if plan is None or plan.versions != _versions(units):
-        plan = _PLANS[id(module)] = _Plan(module, units, list(module.grids))
+    plan = _PLANS.get(module)
+    if plan is None or not _same(plan.versions, _versions(units)):
+        plan = _PLANS[module] = _Plan(module, units, list(module.grids))
     if not plan.ok or x.shape[1] != plan.C0:
         return None
     x = x.as_subclass(torch.Tensor)

@@ -237,24 +237,20 @@ _META_METHODS = {"dim", "size", "stride", "numel", "is_contiguous", "element_siz
                  "is_floating_point", "is_complex", "ndimension", "nelement", "get_device", "__len__"}
 _META_PROPS = {"shape", "dtype", "device", "ndim", "is_cuda", "requires_grad", "layout", "names", "is_leaf",
                "grad_fn", "is_sparse", "is_quantized", "is_meta"}
-_BN_CACHE: Dict[Any, Any] = {}
+_BN_CACHE = _C.TensorCache(4096)
 
 
 def _bn_params(running_mean, running_var, weight, bias, eps):
     """fp32 (mean, invstd, weight, shift) of an eval-mode batch norm, cached per parameter version."""
-    key = (running_mean.data_ptr(), running_var.data_ptr(), running_mean._version, running_var._version,
-           None if weight is None else (weight.data_ptr(), weight._version),
-           None if bias is None else (bias.data_ptr(), bias._version), float(eps))
-    hit = _BN_CACHE.get(key)
+    src = (running_mean, running_var, weight, bias)
+    hit = _BN_CACHE.get(src, (float(eps),))
     if hit is None:
         with torch.no_grad():
             hit = (_raw(running_mean).detach().float().contiguous(),
                    torch.rsqrt(_raw(running_var).detach().float() + eps).contiguous(),
                    None if weight is None else _raw(weight).detach().float().contiguous(),
                    None if bias is None else _raw(bias).detach().float().contiguous())
-        if len(_BN_CACHE) > 4096:
-            _BN_CACHE.clear()
-        _BN_CACHE[key] = hit
+        _BN_CACHE.put(src, (float(eps),), hit)
     return hit
 
 

@@ -42,7 +42,7 @@ int launch_compact_mask(const uint8_t *grid, int G, int32_t *grid_idx, int32_t *
 int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
                int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
-               int allow_split_k, cudaStream_t stream);
+               int allow_split_k, void *workspace, long long workspace_bytes, cudaStream_t stream);
 int ew_fused(void *out, void *plane, const void *a, const void *residual, const float *mean, const float *invstd,
              const float *weight, const float *shift, const int32_t *mapping, int E, int C, int BS, int N, int H,
              int W, int up2x, int relu, cudaStream_t stream);
@@ -213,11 +213,13 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
 BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                          const int32_t *mapping_exec, int E, int N, int Cin, int H, int W, int BS_in, int Cout,
                          int ksize, int stride, int pad, int relu, void *plane_out, const int32_t *out_mapping,
-                         int out_N, int out_GH, int out_GW, int allow_split_k, bc_stream_t stream) {
+                         int out_N, int out_GH, int out_GW, int allow_split_k, void *workspace,
+                         long long workspace_bytes, bc_stream_t stream) {
   BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_conv_igemm: E=%d", E);
   if (E == 0) return BC_OK;
   return conv_igemm(out, plane, weight, bias, residual, mapping_exec, E, N, Cin, H, W, BS_in, Cout, ksize, stride,
-                    pad, relu, plane_out, out_mapping, out_N, out_GH, out_GW, allow_split_k, (cudaStream_t)stream);
+                    pad, relu, plane_out, out_mapping, out_N, out_GH, out_GW, allow_split_k, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *residual, const float *bn_mean,

@@ -36,10 +36,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[N_TILE];  // this CTA's slice of the bias, staged while the main loop runs
-  // element offsets of channel n0 of accumulator row m's pixel in the tile batch / in the next op's plane
-  // (-1: no such pixel / no plane).  Decoding a row costs two integer divisions and a mapping lookup; done
-  // once per row while the main loop runs instead of once per 16-byte store (profiles/r01c_cta_timeline.md).
-  __shared__ long long row_off_s[kTileM], row_pl_s[kTileM];
+  // element offset of channel n0 of accumulator row m's pixel in the next op's plane (-1: no such pixel / no
+  // plane).  Decoding a row costs two integer divisions and a mapping lookup; done once per row while the
+  // main loop runs instead of once per 16-byte store (profiles/r01c_cta_timeline.md).  In the packed tile
+  // batch the rows of a tile are simply consecutive pixels: offset = out_base + m * Cout.
+  __shared__ long long row_pl_s[kTileM];
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,10 +169,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       const int m = q * 32 + lane;
       int blk, y, x;
       pixel_of_row(p, m, r0, blk, y, x);
-      const bool ok = blk < nvalid && !(p.debug & 2);
-      row_off_s[m] = ok ? (long long)((((size_t)(b0 + blk) * p.BS_out + y) * p.BS_out + x) * p.Cout + n0) : -1ll;
-      row_pl_s[m] = (ok && p.plane_out) ? (long long)(plane_row(p, b0 + blk, y, x) - p.plane_out) + n0 : -1ll;
+      row_pl_s[m] = (blk < nvalid && p.plane_out) ? (long long)(plane_row(p, b0 + blk, y, x) - p.plane_out) + n0 : -1ll;
     }
+    const size_t out_base = ((size_t)b0 * p.BS_out * p.BS_out + (size_t)r0 * p.BS_out) * p.Cout + n0;
+    const int m_valid = (p.debug & 2) ? 0 : (p.blocks_per_tile == 1 ? kTileM : nvalid * p.BS_out * p.BS_out);
     asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     mbar_wait(&acc_bar, 0);
     if (threadIdx.x == 64) trace_mark(p, 4);
@@ -213,9 +214,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {  // addresses + residual loads of the whole batch first (latency overlap)
           const int m = q * 32 + i0 + u * kRPI + lane / kTPR;
-          const long long ro = row_off_s[m], rp = row_pl_s[m];
-          ok[u] = ro >= 0;
-          off[u] = (size_t)ro + c8;
+          const long long rp = row_pl_s[m];
+          ok[u] = m < m_valid;
+          off[u] = out_base + (size_t)m * p.Cout + c8;
           pl[u] = rp >= 0 ? p.plane_out + rp + c8 : nullptr;
           res[u] = make_uint4(0, 0, 0, 0);
           if (p.residual && ok[u]) res[u] = __ldg(reinterpret_cast<const uint4 *>(p.residual + off[u]));
@@ -224,24 +225,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         for (int u = 0; u < kBatch; ++u) {
           if (!ok[u]) continue;
           const int r = i0 + u * kRPI + lane / kTPR;
-          const uint4 uu = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kRowB + c8 * 2);
-          const __half2 *uh = reinterpret_cast<const __half2 *>(&uu);
+          // staged value = fp16-rounded conv output, as in the unfused sequence.  fp16 + fp16 rounded once
+          // (HADD2) equals the float add + round of the eager op bit for bit (the float sum is exact unless
+          // the exponents differ by > 13, where both round to the larger operand).
+          uint4 o = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kRowB + c8 * 2);
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
           const __half2 *rh = reinterpret_cast<const __half2 *>(&res[u]);
-          float v[8];
+          if (p.residual) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {  // staged value = fp16-rounded conv output, as in the unfused sequence
-            const float2 f = __half22float2(uh[t]), g = __half22float2(rh[t]);
-            v[2 * t] = f.x + g.x;
-            v[2 * t + 1] = f.y + g.y;
+            for (int t = 0; t < 4; ++t) oh[t] = __hadd2(oh[t], rh[t]);
           }
           if (p.relu) {
+            const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+            for (int t = 0; t < 4; ++t) oh[t] = __hmax2(oh[t], zero);
           }
-          uint4 o;
-          __half2 *oh = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
           *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
           if (pl[u]) *reinterpret_cast<uint4 *>(pl[u]) = o;
         }
@@ -261,6 +259,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
           *reinterpret_cast<uint4 *>(part + (size_t)m * kPartStride<N_TILE> + c0 + j) =
               make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
+      if (p.work) {
+        // this warp's 32 parked rows -> global scratch, whole rows per access
+        __syncwarp();
+        constexpr int kLPR = N_TILE / 4, kRows = 32 / kLPR;  // lanes per row (float4 each), rows per access
+        const unsigned tile_lin = blockIdx.x + gridDim.x * blockIdx.y;
+        float *ws = p.work + ((size_t)(tile_lin * p.splits + blockIdx.z) * kTileM + q * 32) * N_TILE;
+#pragma unroll 4
+        for (int r = lane / kLPR; r < 32; r += kRows) {
+          const float4 v = *reinterpret_cast<const float4 *>(part + (size_t)(q * 32 + r) * kPartStride<N_TILE> + (lane % kLPR) * 4);
+          *reinterpret_cast<float4 *>(ws + (size_t)r * N_TILE + (lane % kLPR) * 4) = v;
+        }
+      }
     }
     if (threadIdx.x == 64) trace_mark(p, 5);
     tc_fence_before_sync();
@@ -277,11 +287,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       const int t = threadIdx.x - 64;
       const int c8 = (t % kThreadsPerRow) * 8;
       const uint32_t part_addr = smem_u32(smem);
+      const size_t out_base_all = ((size_t)b0 * p.BS_out * p.BS_out + (size_t)r0 * p.BS_out) * p.Cout + n0;
+      const int m_valid_all = p.blocks_per_tile == 1 ? kTileM : nvalid * p.BS_out * p.BS_out;
+      const unsigned tile_lin = blockIdx.x + gridDim.x * blockIdx.y;
       for (int rr = t / kThreadsPerRow; rr < rows; rr += kRowsPerPass) {
         const int m = (int)rank * rows + rr;
         // peers' partials in batches (one DSMEM round trip per 4 peers instead of one per peer), then the sum
         // in rank order: bit-reproducible
         const uint32_t a = part_addr + (uint32_t)(((size_t)m * kPartStride<N_TILE> + c8) * sizeof(float));
+        const float *wrow = p.work ? p.work + ((size_t)tile_lin * p.splits * kTileM + m) * N_TILE + c8 : nullptr;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -291,8 +305,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
 #pragma unroll
           for (int z = 0; z < 4; ++z)
             if (z0 + z < p.splits) {
-              lo[z] = ld_dsmem_f4(a, (uint32_t)(z0 + z));
-              hi[z] = ld_dsmem_f4(a + 16, (uint32_t)(z0 + z));
+              if (wrow) {  // L2 only: the peers' stores were released by the cluster barrier
+                const float *src = wrow + (size_t)(z0 + z) * kTileM * N_TILE;
+                lo[z] = __ldcg(reinterpret_cast<const float4 *>(src));
+                hi[z] = __ldcg(reinterpret_cast<const float4 *>(src) + 1);
+              } else {
+                lo[z] = ld_dsmem_f4(a, (uint32_t)(z0 + z));
+                hi[z] = ld_dsmem_f4(a + 16, (uint32_t)(z0 + z));
+              }
             }
 #pragma unroll
           for (int z = 0; z < 4; ++z)
@@ -301,15 +321,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
               v[4] += hi[z].x; v[5] += hi[z].y; v[6] += hi[z].z; v[7] += hi[z].w;
             }
         }
-        const long long ro = row_off_s[m], rp = row_pl_s[m];
-        if (ro >= 0) {
-          const size_t off = (size_t)ro + c8;
+        const long long rp = row_pl_s[m];
+        if (m < m_valid_all) {
+          const size_t off = out_base_all + (size_t)m * p.Cout + c8;
           epilogue_store8(v, p.bias ? p.bias + n0 + c8 : nullptr, p.residual ? p.residual + off : nullptr, p.relu,
                           p.out + off, rp >= 0 ? p.plane_out + rp + c8 : nullptr);
         }
       }
     }
-    cluster_sync_all();  // nobody leaves (and frees its shared memory) while peers still read it
+    if (!p.work) cluster_sync_all();  // nobody leaves (and frees its shared memory) while peers still read it
   }
 
   __syncthreads();
@@ -357,6 +377,8 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
     p.splits = 1;  // the parked accumulator of the split-K path would not fit in this variant's pipeline stages
     p.ksteps_per_split = total_k;
   }
+  if (p.splits == 1 || (long long)ctas * p.splits * kTileM * N_TILE * (long long)sizeof(float) > p.work_bytes)
+    p.work = nullptr;  // scratch absent or too small: reduce through distributed shared memory
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
@@ -372,7 +394,7 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
 int conv_igemm(void *out, const void *plane, const void *weight, const void *bias, const void *residual,
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
                int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
-               int allow_split_k, cudaStream_t stream) {
+               int allow_split_k, void *workspace, long long workspace_bytes, cudaStream_t stream) {
   BC_REQUIRE(out && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
   BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
@@ -408,6 +430,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     p.b_via_tma = btma ? atoi(btma) : 1;  // cp.async path (0) measured slower on B200: opt-in
   }
   p.weight = (const __half *)weight;
+  p.work = (((uintptr_t)workspace & 15) == 0 && workspace_bytes > 0) ? (float *)workspace : nullptr;
+  p.work_bytes = workspace_bytes;
   p.ktot = ksize * ksize * Cin;
   p.plane_out = (__half *)plane_out;
   p.out_mapping = out_mapping ? out_mapping : mapping;

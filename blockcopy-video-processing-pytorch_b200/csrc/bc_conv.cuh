@@ -37,6 +37,10 @@ struct ConvParams {
   // reduces rows [r*128/splits, ...) over all peers through distributed shared memory, in rank
   // order (deterministic), and runs the epilogue for those rows.
   int splits, ksteps_per_split;
+  // split-K through L2 instead: partials go to this global scratch ([tile][split][128][N_TILE] fp32), cluster
+  // barrier, CTA r sums its rows from there.  DSMEM moves ~20 B/clk per SM, L2 several times that.
+  float *work;
+  long long work_bytes;
   const __half *weight;  // [Cout][ksize*ksize*Cin] (same memory the weight tensor map describes)
   int ktot;              // ksize*ksize*Cin
   int b_via_tma;         // 1: weights through TMA like the activations; 0: through cp.async (LSU path)

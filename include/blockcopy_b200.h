@@ -153,8 +153,11 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
  * Cout) at the block's position (out_mapping = mapping_exec of the output grid), so no separate
  * scatter kernel runs and cells that were not executed keep the previous frame's values.
  * allow_split_k != 0: layers whose output tiles cannot fill 148 SMs (4..8-px blocks) are split along K
- * over a thread-block cluster (1,1,S<=8); partial accumulators stay in shared memory and are reduced
- * through distributed shared memory in rank order, so results are run-to-run reproducible.
+ * over a thread-block cluster (1,1,S<=8) and the partial accumulators are summed in rank order, so
+ * results are run-to-run reproducible.  workspace (optional, 16-byte aligned device memory private to the
+ * stream, workspace_bytes long): the partials travel through it (L2); 4 * 128 * Cout * ceil(pixels/128) * S
+ * bytes are needed -- 32 MiB covers every supported shape up to 64 Ki output pixels.  NULL or too small:
+ * they stay in shared memory and are reduced through distributed shared memory (slower, same result).
  * Supported: k in {1,3} with pad = k/2, stride in {1,2}, dilation 1, Cin % 64 == 0, Cout % 64 == 0,
  * output block edge a power of two in [4,128]; anything else returns BC_ERR_UNSUPPORTED.
  */
@@ -162,7 +165,7 @@ BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const
                          const void *residual, const int32_t *mapping_exec, int E, int N, int Cin, int H,
                          int W, int BS_in, int Cout, int ksize, int stride, int pad, int relu,
                          void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
-                         int allow_split_k, bc_stream_t stream);
+                         int allow_split_k, void *workspace, long long workspace_bytes, bc_stream_t stream);
 
 /* ---- fused elementwise stage between two convs, on packed NHWC fp16 tiles ----------------------
  * Replaces the pass-through torch ops the reference issues on the tile batch between padded ops

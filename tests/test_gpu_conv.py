@@ -122,12 +122,15 @@ def test_split_k_is_deterministic_and_close(Cin, Cout, BS):
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).half().to(dev).contiguous(memory_format=torch.channels_last)
     me = torch.randperm(128, generator=g)[:40].sort().values.to(torch.int32).to(dev)
     outs = []
-    for split in (True, True, False):
+    bias = (0.1 * torch.randn(Cout, generator=g)).half().to(dev)
+    res = torch.randn(40, Cout, BS, BS, generator=g).half().to(dev).contiguous(memory_format=torch.channels_last)
+    for split in (True, True, False, "dsmem"):  # True: partials through the L2 scratch; "dsmem": through DSMEM
         o = torch.empty(40, Cout, BS, BS, dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
-        _C.conv_igemm(o, plane, w, None, None, me, 40, BS, 1, 1, split_k=split)
+        _C.conv_igemm(o, plane, w, bias, res, me, 40, BS, 1, 1, relu=True, split_k=split)
         outs.append(o)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1]), "split-K must be run-to-run deterministic (ordered reduction)"
+    assert torch.equal(outs[0], outs[3]), "both reduction paths sum in rank order: identical bits"
     ref = outs[2].float()
     assert (outs[0].float() - ref).abs().max().item() <= 2 ** -9 * float(ref.abs().max()) + 2e-3
 
