@@ -24,10 +24,80 @@
 
 namespace bc {
 
-template <int N_TILE, int STAGES>
+// ---------------------------------------------------------------------------------------------------
+// split-K, phase 2 through the L2 scratch: CTA `rank` of the cluster owns 128/S accumulator rows and sums
+// them over the S partials in rank order (bit-reproducible).  Every thread owns U units of 8 channels;
+// the 2*S partial loads and the residual load of up to 8/S units are all issued before the first use, so
+// the whole reduction costs ~two L2 round trips instead of one per peer and per pass.
+template <int N_TILE, int S>
+__device__ __forceinline__ void splitk_reduce_l2(const ConvParams &p, uint32_t rank, unsigned tile_lin, int n0,
+                                                 size_t out_base, int m_valid, const long long *row_pl_s,
+                                                 const float *bias_s) {
+  constexpr int kTPRow = N_TILE / 8, kRows = kTileM / S;
+  constexpr int U = kRows * kTPRow / 128;
+  constexpr int UPB = (8 / S < U) ? 8 / S : U;
+  static_assert(U >= 1 && U % UPB == 0, "unit schedule");
+  const int t = threadIdx.x - 64;
+#pragma unroll 1
+  for (int u0 = 0; u0 < U; u0 += UPB) {
+    float4 lo[UPB][S], hi[UPB][S];
+    uint4 res[UPB];
+    int mm[UPB], cc[UPB];
+#pragma unroll
+    for (int i = 0; i < UPB; ++i) {
+      const int unit = (u0 + i) * 128 + t;
+      mm[i] = (int)rank * kRows + unit / kTPRow;
+      cc[i] = (unit % kTPRow) * 8;
+      const float4 *src = reinterpret_cast<const float4 *>(p.work + ((size_t)tile_lin * S * kTileM + mm[i]) * N_TILE + cc[i]);
+#pragma unroll
+      for (int z = 0; z < S; ++z) {  // L2 only: the peers' stores were released by the cluster barrier
+        lo[i][z] = __ldcg(src + (size_t)z * (kTileM * N_TILE / 4));
+        hi[i][z] = __ldcg(src + (size_t)z * (kTileM * N_TILE / 4) + 1);
+      }
+      res[i] = make_uint4(0, 0, 0, 0);
+      if (p.residual && mm[i] < m_valid)
+        res[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + out_base + (size_t)mm[i] * p.Cout + cc[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < UPB; ++i) {
+      if (mm[i] >= m_valid) continue;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int z = 0; z < S; ++z) {
+        v[0] += lo[i][z].x; v[1] += lo[i][z].y; v[2] += lo[i][z].z; v[3] += lo[i][z].w;
+        v[4] += hi[i][z].x; v[5] += hi[i][z].y; v[6] += hi[i][z].z; v[7] += hi[i][z].w;
+      }
+      uint4 o;
+      __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        oh[k] = __floats2half2_rn(v[2 * k] + bias_s[cc[i] + 2 * k], v[2 * k + 1] + bias_s[cc[i] + 2 * k + 1]);
+      if (p.residual) {  // fp16-rounded conv output + identity, rounded once more (see phase B above)
+        const __half2 *rh = reinterpret_cast<const __half2 *>(&res[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __hadd2(oh[k], rh[k]);
+      }
+      if (p.relu) {
+        const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
+      }
+      *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
+      const long long rp = row_pl_s[mm[i]];
+      if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + cc[i]) = o;
+    }
+  }
+}
+
+// SPLITK = false compiles the split-K epilogue out (p.splits is 1 then): the single-pass variants stay within
+// the register budget of 4 CTAs per SM; the split variant (2 CTAs per SM) may keep 64+ loads in flight.
+template <int N_TILE, int STAGES, bool SPLITK>
 __global__ void __launch_bounds__(kConvThreadsV1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                   const ConvParams p) {
+  const bool is_split = SPLITK && p.splits > 1;
   constexpr uint32_t kBBytes = N_TILE * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -63,13 +133,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   const int num_k = (p.debug & 1) ? 1 : min(p.ksteps_per_split, total_k - k_begin);
   if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
+  // Plane coordinates of the (up to 8) blocks of this tile.  The mapping lookup (an L2 round trip) is issued
+  // before the set-up barrier so that it overlaps barrier init and the TMEM allocation.  `mapping` is written
+  // once per frame by bc_compact_mask, never by the kernel just before this one, so reading it ahead of
+  // griddepcontrol.wait is safe under programmatic dependent launch as well.
+  __shared__ int4 blk_coord_s[8];  // (x0, y0, image, -) per block; private to warp 0 lane 0
+  int cx0 = 0, cy0 = 0, cn0 = 0;   // block 0 in registers (the only one when BS_out >= 16)
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
+    for (int i = 0; i < nvalid; ++i) {
+      const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + b0 + i) : (uint32_t)(b0 + i);
+      uint32_t n, gh, gw;
+      p.cell(cell, n, gh, gw);
+      const int4 c = make_int4((int)gw * p.BS_in - p.pad, (int)gh * p.BS_in + r0 * p.stride - p.pad, (int)n, 0);
+      blk_coord_s[i] = c;
+      if (i == 0) { cx0 = c.x; cy0 = c.y; cn0 = c.z; }
+    }
     for (int s = 0; s < STAGES; ++s) {
-      // producers: activations by TMA (warp 0, one arrive.expect_tx) + weights either by TMA (warp 6 lane 0,
-      // one arrive.expect_tx) or by cp.async (all 32 lanes of warp 6, one deferred arrive each)
-      mbar_init(&full_bar[s], p.b_via_tma ? 2 : 33);
+      mbar_init(&full_bar[s], 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
@@ -84,79 +166,71 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   pdl_wait();  // barrier init, TMEM alloc and descriptor prefetch above overlapped the previous kernel's tail
   if (threadIdx.x == 0) trace_mark(p, 1);
 
+  // The three single-thread loops below are the critical path of a k-step (profiles/r01c_conv_kstep_probe.md:
+  // with loads and MMAs switched off a k-step still cost ~430 clk of dependent scalar instructions): no
+  // divisions, no local-memory arrays, stage index and parity advanced incrementally.
   if (warp == 0) {
-    // =============================== TMA producer =================================================
+    // =============================== activation producer ==========================================
     if (lane == 0) {
-      int cn[8], cx[8], cy[8];  // plane coordinates of the (up to 8) blocks of this tile
-      for (int i = 0; i < nvalid; ++i) {
-        const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + b0 + i) : (uint32_t)(b0 + i);
-        uint32_t n, gh, gw;
-        p.cell(cell, n, gh, gw);
-        cn[i] = (int)n;
-        cx[i] = (int)gw * p.BS_in - p.pad;
-        cy[i] = (int)gh * p.BS_in + r0 * p.stride - p.pad;
-      }
       const uint32_t tx_bytes = (uint32_t)nvalid * p.box_bytes;
+      const int tap0 = k_begin / p.kc_per_tap;
+      int cc = k_begin - tap0 * p.kc_per_tap, kh = tap0 / p.ksize;
+      int kw = tap0 - kh * p.ksize;
+      int s = 0;
+      uint32_t parity = 1;  // first pass over the ring: the stages are free
+      uint8_t *sa = smem;
       for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
-        const int kg = k_begin + ks;  // global k-step
-        const int tap = kg / p.kc_per_tap, cc = kg - tap * p.kc_per_tap;
-        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-        uint8_t *sa = smem + (size_t)s * kStageBytes;
+        mbar_wait(&empty_bar[s], parity);
         mbar_expect_tx(&full_bar[s], tx_bytes);
-        for (int i = 0; i < nvalid; ++i)
-          tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, cx[i] + kw, cy[i] + kh, cn[i]);
+        if (nvalid == 1) {
+          tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw, cy0 + kh, cn0);
+        } else {
+          for (int i = 0; i < nvalid; ++i) {
+            const int4 c = blk_coord_s[i];
+            tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw, c.y + kh, c.z);
+          }
+        }
+        if (++cc == p.kc_per_tap) {
+          cc = 0;
+          if (++kw == p.ksize) { kw = 0; ++kh; }
+        }
+        sa += kStageBytes;
+        if (++s == STAGES) { s = 0; parity ^= 1; sa = smem; }
       }
     }
   } else if (warp == 6) {
-    // =============================== weight producer =============================================
-    // One CTA's TMA queue tops out at ~35 B/clk (profiles/r01b_conv_experiments.md), so the weights take
-    // the other road into shared memory: 16-byte cp.async through the LSU, written with the same 128-byte
-    // swizzle the TMA would apply (16-byte chunk j of row n lands at chunk j ^ (n & 7)).
-    if (p.b_via_tma) {
-      if (lane == 0) {
-        for (int ks = 0; ks < num_k; ++ks) {
-          const int s = ks % STAGES;
-          mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
-          mbar_expect_tx(&full_bar[s], kBBytes);
-          tma_load_2d(smem + (size_t)s * kStageBytes + kABytes, &b_map, &full_bar[s], (k_begin + ks) * kChunkK, n0);
-        }
-      }
-    } else {
-      const __half *wbase = p.weight + (size_t)n0 * p.ktot + (lane & 7) * 8;
+    // =============================== weight producer ==============================================
+    if (lane == 0) {
+      int s = 0, kcoord = k_begin * kChunkK;
+      uint32_t parity = 1;
+      uint8_t *sb = smem + kABytes;
       for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        mbar_wait(&empty_bar[s], (uint32_t)(((ks / STAGES) & 1) ^ 1));
-        const uint32_t sb = smem_u32(smem + (size_t)s * kStageBytes + kABytes);
-        const __half *wk = wbase + (size_t)(k_begin + ks) * kChunkK;
-#pragma unroll 8
-        for (int it = 0; it < N_TILE / 4; ++it) {  // 4 rows of 128 bytes per warp instruction
-          const int n = it * 4 + (lane >> 3), j = lane & 7;
-          const uint32_t dst = sb + (uint32_t)n * 128u + (uint32_t)((j ^ (n & 7)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(wk + (size_t)n * p.ktot) : "memory");
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        mbar_wait(&empty_bar[s], parity);
+        mbar_expect_tx(&full_bar[s], kBBytes);
+        tma_load_2d(sb, &b_map, &full_bar[s], kcoord, n0);
+        kcoord += kChunkK;
+        sb += kStageBytes;
+        if (++s == STAGES) { s = 0; parity ^= 1; sb = smem + kABytes; }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===================================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE);
+      // descriptors of stage 0; a stage / a K slab of 16 is an offset in the 16-byte-unit address field
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem)), b_desc0 = umma_desc_sw128(smem_u32(smem) + kABytes);
+      int s = 0;
+      uint32_t parity = 0, stage_off = 0;
       for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        mbar_wait(&full_bar[s], (uint32_t)((ks / STAGES) & 1));
+        mbar_wait(&full_bar[s], parity);
         if (ks == 0) trace_mark(p, 2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) wrote B
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
         for (int k = 0; k < kChunkK / 16; ++k)
-          umma_f16_ss(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                      (uint32_t)((ks | k) != 0));
+          umma_f16_ss(tmem_base, a_desc0 + stage_off + 2 * k, b_desc0 + stage_off + 2 * k, idesc, (uint32_t)((ks | k) != 0));
         umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        stage_off += kStageBytes >> 4;
+        if (++s == STAGES) { s = 0; parity ^= 1; stage_off = 0; }
       }
       umma_commit(&acc_bar);  // accumulator complete
       trace_mark(p, 3);
@@ -177,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     mbar_wait(&acc_bar, 0);
     if (threadIdx.x == 64) trace_mark(p, 4);
     tc_fence_after_sync();
-    if (p.splits == 1) {
+    if (!is_split) {
       // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's private
       //      staging rows (the pipeline stages are free: acc_bar says every MMA and TMA load completed)
       constexpr int kRowB = N_TILE * 2 + 16;  // +16 B: rows start in different bank groups
@@ -276,7 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     tc_fence_before_sync();
   }
 
-  if (p.splits > 1) {
+  if (is_split) {
     cluster_sync_all();  // every CTA's partial is visible cluster-wide
     if (warp >= 2 && warp < 6) {
       // ---- phase 2: reduce-scatter over the cluster; this CTA owns 128/splits accumulator rows -----
@@ -290,6 +364,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       const size_t out_base_all = ((size_t)b0 * p.BS_out * p.BS_out + (size_t)r0 * p.BS_out) * p.Cout + n0;
       const int m_valid_all = p.blocks_per_tile == 1 ? kTileM : nvalid * p.BS_out * p.BS_out;
       const unsigned tile_lin = blockIdx.x + gridDim.x * blockIdx.y;
+      if (p.work) {
+        if (p.splits == 8) splitk_reduce_l2<N_TILE, 8>(p, rank, tile_lin, n0, out_base_all, m_valid_all, row_pl_s, bias_s);
+        else if (p.splits == 4) splitk_reduce_l2<N_TILE, 4>(p, rank, tile_lin, n0, out_base_all, m_valid_all, row_pl_s, bias_s);
+        else splitk_reduce_l2<N_TILE, 2>(p, rank, tile_lin, n0, out_base_all, m_valid_all, row_pl_s, bias_s);
+      } else
       for (int rr = t / kThreadsPerRow; rr < rows; rr += kRowsPerPass) {
         const int m = (int)rank * rows + rr;
         // peers' partials in batches (one DSMEM round trip per 4 peers instead of one per peer), then the sum
@@ -358,8 +437,10 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
   p.ksteps_per_split = total_k;
   // Measured (profiles/): the cluster reduction + the per-CTA fixed costs pay off only when the unsplit
   // grid covers less than a third of the GPU; keep the split grid within ~one wave of 2 CTAs per SM.
-  if (allow_split && ctas <= 48 && total_k >= 8) {
-    const int want = 240 / ctas;
+  static const int max_ctas = getenv("BC_SPLIT_MAX_CTAS") ? atoi(getenv("BC_SPLIT_MAX_CTAS")) : 48;   // experiments
+  static const int target = getenv("BC_SPLIT_TARGET") ? atoi(getenv("BC_SPLIT_TARGET")) : 240;
+  if (allow_split && ctas <= max_ctas && total_k >= 8) {
+    const int want = target / ctas;
     int splits = 8;                              // portable cluster size limit
     while (splits > 1 && (splits > want || splits * 2 > total_k)) splits >>= 1;
     while (splits > 1) {
@@ -379,10 +460,14 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
   }
   if (p.splits == 1 || (long long)ctas * p.splits * kTileM * N_TILE * (long long)sizeof(float) > p.work_bytes)
     p.work = nullptr;  // scratch absent or too small: reduce through distributed shared memory
-  static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static cudaError_t attr1 = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES, false>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static cudaError_t attr2 = cudaFuncSetAttribute(conv_igemm_kernel<N_TILE, STAGES, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const cudaError_t attr = attr1 != cudaSuccess ? attr1 : attr2;
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
-  const cudaError_t e = launch_kernel(conv_igemm_kernel<N_TILE, STAGES>, dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits),
+  const cudaError_t e = launch_kernel(p.splits > 1 ? conv_igemm_kernel<N_TILE, STAGES, true> : conv_igemm_kernel<N_TILE, STAGES, false>,
+                                      dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits),
                                       dim3(kConvThreadsV1), smem, s, (unsigned)p.splits, a_map, b_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -426,13 +511,9 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     static const char *dbg = getenv("BC_CONV_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
     p.trace = debug_trace_buffer();
-    static const char *btma = getenv("BC_CONV_B_TMA");
-    p.b_via_tma = btma ? atoi(btma) : 1;  // cp.async path (0) measured slower on B200: opt-in
   }
-  p.weight = (const __half *)weight;
   p.work = (((uintptr_t)workspace & 15) == 0 && workspace_bytes > 0) ? (float *)workspace : nullptr;
   p.work_bytes = workspace_bytes;
-  p.ktot = ksize * ksize * Cin;
   p.plane_out = (__half *)plane_out;
   p.out_mapping = out_mapping ? out_mapping : mapping;
   p.out_cell = CellDecode(out_GH > 0 ? out_GH : 1, out_GW > 0 ? out_GW : 1);

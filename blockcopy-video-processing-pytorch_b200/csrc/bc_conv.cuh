@@ -41,11 +41,8 @@ struct ConvParams {
   // barrier, CTA r sums its rows from there.  DSMEM moves ~20 B/clk per SM, L2 several times that.
   float *work;
   long long work_bytes;
-  const __half *weight;  // [Cout][ksize*ksize*Cin] (same memory the weight tensor map describes)
-  int ktot;              // ksize*ksize*Cin
-  int b_via_tma;         // 1: weights through TMA like the activations; 0: through cp.async (LSU path)
   unsigned long long *trace;  // bc_debug_trace buffer (16 words per CTA) or nullptr
-  int debug;  // BC_CONV_DEBUG (timing experiments only): 1 = one k-step, 2 = no epilogue stores, 3 = both
+  int debug;  // BC_CONV_DEBUG (timing experiments only): bit 0 one k-step, bit 1 no epilogue stores
 };
 
 // in-kernel timeline for profiles/ (bc_debug_trace): slot k of this CTA's 16-word record <- SM clock
