@@ -551,7 +551,17 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (plane) failed: CUresult %d", (int)r);
   }
   static const int env_ntile = getenv("BC_CONV_NTILE") ? atoi(getenv("BC_CONV_NTILE")) : 0;  // experiments
-  const int n_tile = env_ntile == 64 ? 64 : (Cout % 128 == 0 ? 128 : 64);
+  static const int env_persist = getenv("BC_CONV_PERSIST") ? atoi(getenv("BC_CONV_PERSIST")) : 1;
+  int n_tile = env_ntile == 64 ? 64 : (Cout % 128 == 0 ? 128 : 64);
+  const int total_k_steps = ksize * ksize * (Cin / kChunkK);
+  // Tiny grids (deep layers) split K over a cluster; everything else runs on the persistent kernel, with
+  // 64-wide channel slices when 128-wide ones would leave more than half of the SMs without a tile.
+  const bool use_split = allow_split_k != 0 && tiles * (Cout / n_tile) <= 48 && total_k_steps >= 8;
+  if (!use_split && !env_ntile && n_tile == 128 && tiles * (Cout / 128) <= kNumSMs / 2) n_tile = 64;
+  // Measured on B200 (profiles/r01c_conv_persistent.md): with at most one tile per SM the deep operand ring
+  // of the persistent kernel wins; with 2+ tiles per SM three co-resident 2-stage CTAs still do better
+  // (16.9 vs 18.3 us on the 320-tile decoder conv) -- BC_CONV_PERSIST=2 forces the persistent kernel.
+  const bool persistent = !use_split && (env_persist == 2 || (env_persist == 1 && tiles * (Cout / n_tile) <= kNumSMs));
   {
     // B: weights [Cout][tap][Cin] = channels_last (Cout, Cin, k, k) memory; K-major rows
     const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
@@ -563,6 +573,14 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
+  }
+  if (persistent) {
+    p.tiles_m = tiles;
+    p.ntiles_n = Cout / n_tile;
+    p.splits = 1;
+    p.ksteps_per_split = total_k_steps;
+    p.work = nullptr;
+    return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
   }
   // Variant selection (B200 sweep, profiles/r01b_conv_experiments.md): what counts is how many CTAs an SM can
   // keep in flight -- one CTA's operand stream tops out near 35 B/clk whatever the pipeline depth -- so

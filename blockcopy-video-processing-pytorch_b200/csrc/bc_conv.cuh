@@ -25,6 +25,7 @@ struct ConvParams {
   int rows_per_tile;        // rows of BS_out pixels of ONE block in a tile (BS_out >= 16) or BS_out
   int blocks_per_tile;      // 1, or 128 / BS_out^2 for small blocks
   int tiles_per_block;      // BS_out^2 / 128 for big blocks, else 1
+  int tiles_m, ntiles_n;    // persistent kernel: number of 128-pixel tiles / of N_TILE-channel slices
   int relu;
   uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
   // optional second destination: the next padded op's persistent plane (N, GH*BS_out, GW*BS_out, Cout)
@@ -64,6 +65,8 @@ __device__ __forceinline__ void trace_wall(const ConvParams &p, int k) {  // slo
   }
 }
 unsigned long long *debug_trace_buffer();  // bc_api.cu
+int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int n_tile,
+                           cudaStream_t s);  // bc_conv_persist.cu
 
 template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)
 

@@ -1,0 +1,322 @@
+// bc_conv_persist.cu -- persistent, warp-specialised variant of the tcgen05 implicit-GEMM convolution
+// (same math, operands and epilogue semantics as conv_igemm_kernel in bc_conv.cu; see the header there).
+//
+// Why a second kernel: the per-CTA timelines (profiles/r01c_cta_timeline.md) show that one k-step is a
+// fixed-latency round trip -- TMA issue -> L2 -> full barrier -> 4 MMAs -> commit -> empty barrier ->
+// next TMA issue, ~1450 clk -- so a CTA's k-loop runs at (stages in flight) / 1450 clk, and the epilogue
+// (27-45 % of a CTA's life) leaves both the tensor pipe and the operand ring idle.  This variant
+//   * owns the SM alone: 5 (N_TILE 128) or 8 (N_TILE 64) operand stages = 160-192 KB in flight,
+//   * loops over output tiles (static round-robin, one CTA per SM), the operand ring running across tiles,
+//   * double-buffers the accumulator in TMEM (2 x N_TILE columns): the epilogue warps drain tile i
+//     (TMEM -> registers -> bias -> fp16 -> staging rows -> coalesced stores to the tile batch and to
+//     the next op's plane) while the MMA warp is already accumulating tile i+1.
+// Warp roles: 0 = activation producer (TMA), 6 = weight producer (TMA), 1 = MMA issuer + TMEM owner,
+// 2..5 = epilogue (TMEM lane quadrant = warp & 3).  All single-thread loops are division-free.
+// Split-K launches (tiny grids) stay on conv_igemm_kernel<.., true>.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "bc_conv.cuh"
+
+namespace bc {
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int b0, r0, nvalid, n0;
+};
+
+// linear tile -> (first packed block, first pixel row, blocks in the tile, first output channel); tiles
+// that differ only in the channel slice are neighbours, so concurrently running CTAs share activations in L2
+template <int N_TILE>
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams &p, int tile) {
+  TileCoord t;
+  const int m_idx = tile / p.ntiles_n;
+  t.n0 = (tile - m_idx * p.ntiles_n) * N_TILE;
+  if (p.blocks_per_tile == 1) {
+    t.b0 = m_idx / p.tiles_per_block;
+    t.r0 = (m_idx - t.b0 * p.tiles_per_block) * p.rows_per_tile;
+    t.nvalid = 1;
+  } else {
+    t.b0 = m_idx * p.blocks_per_tile;
+    t.r0 = 0;
+    t.nvalid = min(p.blocks_per_tile, p.E - t.b0);
+  }
+  return t;
+}
+
+constexpr int kAProd = 2;                              // activation producer warps
+constexpr int kPersistThreads = 224 + 32 * (kAProd - 1);  // warps 0..6 as in conv_igemm_kernel + producers 7..
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                             const ConvParams p) {
+  constexpr uint32_t kBBytes = N_TILE * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int kRowB = N_TILE * 2 + 16;  // staged output row (+16 B: rows start in different bank groups)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];   // MMA warp -> epilogue: accumulator buffer complete
+  __shared__ __align__(8) uint64_t acc_empty[2];  // epilogue -> MMA warp: buffer read out (128 arrivals)
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[N_TILE];
+  __shared__ long long row_pl_s[kTileM];  // see conv_igemm_kernel
+  __shared__ int4 blk_coord_s[8 * kAProd];
+
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *staging = smem + (size_t)STAGES * kStageBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.ntiles_n;
+  const int total_k = p.ksize * p.ksize * p.kc_per_tap;
+  if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&a_map);
+    prefetch_map(&b_map);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_slot, 2 * N_TILE);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_trigger();
+  pdl_wait();
+  if (threadIdx.x == 0) trace_mark(p, 1);
+
+  if (warp == 0 || warp >= 7) {
+    // =============================== activation producers =========================================
+    // kAProd warps (0, 7, ...), one elected lane each; producer j issues the k-steps g = j, j + kAProd, ...
+    // of the CTA's global k-step sequence (the ring position follows from g alone)
+    if (lane == 0) {
+      const int j = warp == 0 ? 0 : warp - 6;
+      int g = j;  // global k-step (over all tiles of this CTA) this producer issues next
+      int g_tile0 = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, g_tile0 += total_k) {
+        const TileCoord t = tile_coord<N_TILE>(p, tile);
+        int cx0 = 0, cy0 = 0, cn0 = 0;
+        int4 *coords = blk_coord_s + 8 * j;
+        for (int i = 0; i < t.nvalid; ++i) {
+          const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + t.b0 + i) : (uint32_t)(t.b0 + i);
+          uint32_t n, gh, gw;
+          p.cell(cell, n, gh, gw);
+          const int4 c = make_int4((int)gw * p.BS_in - p.pad, (int)gh * p.BS_in + t.r0 * p.stride - p.pad, (int)n, 0);
+          coords[i] = c;
+          if (i == 0) { cx0 = c.x; cy0 = c.y; cn0 = c.z; }
+        }
+        const uint32_t tx_bytes = (uint32_t)t.nvalid * p.box_bytes;
+        // (tap, channel chunk) of this producer's first k-step in the tile
+        int ks = g - g_tile0;
+        int tap = ks / p.kc_per_tap, cc = ks - tap * p.kc_per_tap, kh = tap / p.ksize;
+        int kw = tap - kh * p.ksize;
+        for (; ks < total_k; ks += kAProd, g += kAProd) {
+          const int s = g % STAGES;
+          const uint32_t parity = (uint32_t)(((g / STAGES) & 1) ^ 1);
+          uint8_t *sa = smem + (size_t)s * kStageBytes;
+          mbar_wait(&empty_bar[s], parity);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          if (t.nvalid == 1) {
+            tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw, cy0 + kh, cn0);
+          } else {
+            for (int i = 0; i < t.nvalid; ++i) {
+              const int4 c = coords[i];
+              tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw, c.y + kh, c.z);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kAProd; ++u)
+            if (++cc == p.kc_per_tap) {
+              cc = 0;
+              if (++kw == p.ksize) { kw = 0; ++kh; }
+            }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // =============================== weight producer ==============================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t parity = 1;
+      uint8_t *sb = smem + kABytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.ntiles_n) * N_TILE;
+        int kcoord = 0;
+        for (int ks = 0; ks < total_k; ++ks) {
+          mbar_wait(&empty_bar[s], parity);
+          mbar_expect_tx(&full_bar[s], kBBytes);
+          tma_load_2d(sb, &b_map, &full_bar[s], kcoord, n0);
+          kcoord += kChunkK;
+          sb += kStageBytes;
+          if (++s == STAGES) { s = 0; parity ^= 1; sb = smem + kABytes; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem)), b_desc0 = umma_desc_sw128(smem_u32(smem) + kABytes);
+      int s = 0;
+      uint32_t parity = 0, stage_off = 0;
+      uint32_t buf = 0, buf_parity = 1;  // first use of either accumulator buffer: it is free
+      bool first = true;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[buf], buf_parity);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + buf * N_TILE;
+        for (int ks = 0; ks < total_k; ++ks) {
+          mbar_wait(&full_bar[s], parity);
+          if (first) { trace_mark(p, 2); first = false; }
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < kChunkK / 16; ++k)
+            umma_f16_ss(acc, a_desc0 + stage_off + 2 * k, b_desc0 + stage_off + 2 * k, idesc, (uint32_t)((ks | k) != 0));
+          umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+          stage_off += kStageBytes >> 4;
+          if (++s == STAGES) { s = 0; parity ^= 1; stage_off = 0; }
+        }
+        umma_commit(&acc_full[buf]);  // accumulator of this tile complete
+        if (buf == 1) buf_parity ^= 1;
+        buf ^= 1;
+      }
+      trace_mark(p, 3);
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // =============================== epilogue =====================================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int t128 = threadIdx.x - 64;
+    uint8_t *stage = staging + (size_t)q * 32 * kRowB;
+    constexpr int kTPR = N_TILE / 8, kRPI = 32 / kTPR;
+    const int c8 = (lane % kTPR) * 8;
+    uint32_t buf = 0, buf_parity = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = tile_coord<N_TILE>(p, tile);
+      // this tile's slice of the bias + this warp's 32 plane-row offsets, while the MMAs of the tile run
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
+      for (int c = t128; c < N_TILE; c += 128) bias_s[c] = p.bias ? __half2float(__ldg(p.bias + t.n0 + c)) : 0.f;
+      {
+        const int m = q * 32 + lane;
+        int blk, y, x;
+        pixel_of_row(p, m, t.r0, blk, y, x);
+        row_pl_s[m] = (blk < t.nvalid && p.plane_out) ? (long long)(plane_row(p, t.b0 + blk, y, x) - p.plane_out) + t.n0 : -1ll;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const size_t out_base = ((size_t)t.b0 * p.BS_out * p.BS_out + (size_t)t.r0 * p.BS_out) * p.Cout + t.n0;
+      const int m_valid = p.blocks_per_tile == 1 ? kTileM : t.nvalid * p.BS_out * p.BS_out;
+
+      mbar_wait(&acc_full[buf], buf_parity);
+      tc_fence_after_sync();
+      // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's staging rows
+      const uint32_t acc = tmem_base + buf * N_TILE + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t v32[32];
+        tmem_ld_32x32(acc + (uint32_t)c0, v32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            oh[u] = __floats2half2_rn(__uint_as_float(v32[j + 2 * u]) + bias_s[c0 + j + 2 * u],
+                                      __uint_as_float(v32[j + 2 * u + 1]) + bias_s[c0 + j + 2 * u + 1]);
+          *reinterpret_cast<uint4 *>(stage + (size_t)lane * kRowB + (c0 + j) * 2) = o;
+        }
+      }
+      // the accumulator buffer is read out: hand it back to the MMA warp before the stores
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);
+      __syncwarp();
+      // ---- phase B: kTPR lanes cover one pixel's N_TILE channels (16 B each): (+ residual) -> ReLU ->
+      //      whole 32-byte sectors to the tile batch and to the next op's plane
+      constexpr int kBatch = 4;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += kRPI * kBatch) {
+        size_t off[kBatch];
+        __half *pl[kBatch];
+        uint4 res[kBatch];
+        bool ok[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {  // addresses + residual loads of the whole batch first
+          const int m = q * 32 + i0 + u * kRPI + lane / kTPR;
+          const long long rp = row_pl_s[m];
+          ok[u] = m < m_valid;
+          off[u] = out_base + (size_t)m * p.Cout + c8;
+          pl[u] = rp >= 0 ? p.plane_out + rp + c8 : nullptr;
+          res[u] = make_uint4(0, 0, 0, 0);
+          if (p.residual && ok[u]) res[u] = __ldg(reinterpret_cast<const uint4 *>(p.residual + off[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (!ok[u]) continue;
+          const int r = i0 + u * kRPI + lane / kTPR;
+          uint4 o = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kRowB + c8 * 2);
+          __half2 *oh = reinterpret_cast<__half2 *>(&o);
+          const __half2 *rh = reinterpret_cast<const __half2 *>(&res[u]);
+          if (p.residual) {  // fp16-rounded conv output + identity, rounded once more (HADD2 == float add + round)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __hadd2(oh[k], rh[k]);
+          }
+          if (p.relu) {
+            const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
+          }
+          *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
+          if (pl[u]) *reinterpret_cast<uint4 *>(pl[u]) = o;
+        }
+      }
+      __syncwarp();  // staging rows are rewritten by the next tile's phase A
+      if (buf == 1) buf_parity ^= 1;
+      buf ^= 1;
+    }
+    if (threadIdx.x == 64) trace_mark(p, 5);
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (threadIdx.x == 0) { trace_mark(p, 6); trace_wall(p, 10); }
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * N_TILE);
+  }
+}
+
+template <int N_TILE, int STAGES>
+static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 4 * 32 * (N_TILE * 2 + 16) + 1024;
+  static_assert(smem <= 227 * 1024 - 4096, "operand ring + staging must fit one SM");
+  static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_persistent_kernel<N_TILE, STAGES>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_persistent_kernel): %s",
+             cudaGetErrorString(attr));
+  const int total = p.tiles_m * p.ntiles_n;
+  const cudaError_t e = launch_kernel(conv_igemm_persistent_kernel<N_TILE, STAGES>,
+                                      dim3((unsigned)(total < kNumSMs ? total : kNumSMs)), dim3(kPersistThreads), smem, s,
+                                      1, a_map, b_map, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+  }
+  return check_launch("bc_conv_igemm");
+}
+
+int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int n_tile,
+                           cudaStream_t s) {
+  return n_tile == 128 ? launch_persistent<128, 5>(a_map, b_map, p, s) : launch_persistent<64, 8>(a_map, b_map, p, s);
+}
+
+}  // namespace bc
