@@ -99,8 +99,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 bool pdl_enabled();  // BC_PDL=0 disables the launch attribute (bc_api.cu)
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                 unsigned cluster_z, Args &&...args) {
+inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         dim3 cluster, Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -113,16 +113,23 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
   }
-  if (cluster_z > 1) {
+  if (cluster.x * cluster.y * cluster.z > 1) {
     at[n].id = cudaLaunchAttributeClusterDimension;
-    at[n].val.clusterDim.x = 1;
-    at[n].val.clusterDim.y = 1;
-    at[n].val.clusterDim.z = cluster_z;
+    at[n].val.clusterDim.x = cluster.x;
+    at[n].val.clusterDim.y = cluster.y;
+    at[n].val.clusterDim.z = cluster.z;
     ++n;
   }
   cfg.attrs = at;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 unsigned cluster_z, Args &&...args) {
+  return launch_kernel_cluster(kernel, grid, block, smem, stream, dim3(1, 1, cluster_z ? cluster_z : 1),
+                               static_cast<Args &&>(args)...);
 }
 
 inline int gcd_pow2_bytes(uint64_t a) {  // largest power of two <= 16 dividing a (a > 0)

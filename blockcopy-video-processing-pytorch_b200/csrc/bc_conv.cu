@@ -582,6 +582,23 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     p.work = nullptr;
     return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
   }
+  if (use_split && env_persist != 0 && p.work != nullptr) {
+    // split-K on the persistent kernel: one (tile, k-range) unit per CTA, the S CTAs of a cluster (S,1,1)
+    // share a tile.  S fills ~132 SMs (clusters are GPC-local: 148 cannot be reached with every cluster
+    // size) with at least 4 k-steps per CTA; the whole grid is one wave of one CTA per SM.
+    static const int target = getenv("BC_SPLIT_TARGET") ? atoi(getenv("BC_SPLIT_TARGET")) : 132;  // experiments
+    const int ctas = tiles * (Cout / n_tile);
+    int S = target / ctas;
+    if (S > 8) S = 8;
+    if (S > total_k_steps / 4) S = total_k_steps / 4;
+    if (S >= 2 && (long long)ctas * S * kTileM * n_tile * (long long)sizeof(float) <= p.work_bytes) {
+      p.tiles_m = tiles;
+      p.ntiles_n = Cout / n_tile;
+      p.splits = S;
+      p.ksteps_per_split = (total_k_steps + S - 1) / S;
+      return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
+    }
+  }
   // Variant selection (B200 sweep, profiles/r01b_conv_experiments.md): what counts is how many CTAs an SM can
   // keep in flight -- one CTA's operand stream tops out near 35 B/clk whatever the pipeline depth -- so
   // big grids trade stages for co-residency (2 stages -> 3-4 CTAs/SM, single wave), mid-size grids

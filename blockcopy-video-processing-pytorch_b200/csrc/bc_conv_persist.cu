@@ -24,6 +24,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int kAProd = 2;                              // activation producer warps
+constexpr int kPersistThreads = 224 + 32 * (kAProd - 1);  // warps 0..6 as in conv_igemm_kernel + producers 7..
+
 struct TileCoord {
   int b0, r0, nvalid, n0;
 };
@@ -47,8 +50,77 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams &p, int tile) {
   return t;
 }
 
-constexpr int kAProd = 2;                              // activation producer warps
-constexpr int kPersistThreads = 224 + 32 * (kAProd - 1);  // warps 0..6 as in conv_igemm_kernel + producers 7..
+// ---------------------------------------------------------------------------------------------------
+// split-K (cluster (S,1,1), one (tile, k-range) unit per CTA): phase 2.  The S partial accumulators of the
+// tile are in the L2 scratch ([tile][z][128][N_TILE] fp32); CTA `rank` sums its share of the tile's
+// 128 x N_TILE/8 units of 8 channels over the S partials IN RANK ORDER (bit-reproducible) and runs the
+// epilogue for them.  All 2*S partial loads and the residual load of up to 8/S units are issued before
+// the first use: the reduction costs a couple of L2 round trips.
+template <int N_TILE, int S>
+__device__ __forceinline__ void splitk_reduce(const ConvParams &p, int rank, int tile, int n0, size_t out_base,
+                                              int m_valid, const long long *row_pl_s, const float *bias_s) {
+  constexpr int kTPRow = N_TILE / 8, kUnits = kTileM * kTPRow;
+  constexpr int UPB = 8 / S > 0 ? 8 / S : 1;
+  const int lo_u = rank * kUnits / S, hi_u = (rank + 1) * kUnits / S;
+  const int t = threadIdx.x;  // every warp of the CTA takes part: the producers and the MMA warp are idle by now
+  const float *ws = p.work + (size_t)tile * S * kTileM * N_TILE;
+#pragma unroll 1
+  for (int u0 = lo_u + t; u0 < hi_u; u0 += kPersistThreads * UPB) {
+    float4 lo[UPB][S], hi[UPB][S];
+    uint4 res[UPB];
+    int mm[UPB], cc[UPB];
+    bool on[UPB];
+#pragma unroll
+    for (int i = 0; i < UPB; ++i) {
+      const int unit = u0 + i * kPersistThreads;
+      on[i] = unit < hi_u;
+      const int uu = on[i] ? unit : lo_u;
+      mm[i] = uu / kTPRow;
+      cc[i] = (uu % kTPRow) * 8;
+      const float4 *src = reinterpret_cast<const float4 *>(ws + (size_t)mm[i] * N_TILE + cc[i]);
+#pragma unroll
+      for (int z = 0; z < S; ++z) {  // L2 only: the peers' stores were released by the cluster barrier
+        lo[i][z] = __ldcg(src + (size_t)z * (kTileM * N_TILE / 4));
+        hi[i][z] = __ldcg(src + (size_t)z * (kTileM * N_TILE / 4) + 1);
+      }
+      on[i] = on[i] && mm[i] < m_valid;
+      res[i] = make_uint4(0, 0, 0, 0);
+      if (p.residual && on[i])
+        res[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + out_base + (size_t)mm[i] * p.Cout + cc[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < UPB; ++i) {
+      if (!on[i]) continue;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int z = 0; z < S; ++z) {
+        v[0] += lo[i][z].x; v[1] += lo[i][z].y; v[2] += lo[i][z].z; v[3] += lo[i][z].w;
+        v[4] += hi[i][z].x; v[5] += hi[i][z].y; v[6] += hi[i][z].z; v[7] += hi[i][z].w;
+      }
+      uint4 o;
+      __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        oh[k] = __floats2half2_rn(v[2 * k] + bias_s[cc[i] + 2 * k], v[2 * k + 1] + bias_s[cc[i] + 2 * k + 1]);
+      if (p.residual) {  // fp16-rounded conv output + identity, rounded once more
+        const __half2 *rh = reinterpret_cast<const __half2 *>(&res[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __hadd2(oh[k], rh[k]);
+      }
+      if (p.relu) {
+        const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
+      }
+      *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
+      const long long rp = row_pl_s[mm[i]];
+      if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + cc[i]) = o;
+    }
+  }
+}
+
 
 template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(kPersistThreads, 1)
@@ -72,6 +144,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.ntiles_n;
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
+  // work units: (tile, k-range).  S = 1: a unit is a tile and a CTA loops over its tiles.  S > 1 (split-K):
+  // the S CTAs of a cluster own the S k-ranges of one tile; grid = units, one unit per CTA.
+  const int S = p.splits;
+  const int total_units = total_tiles * S;
   if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
   if (warp == 0 && lane == 0) {
@@ -103,13 +179,21 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     if (lane == 0) {
       const int j = warp == 0 ? 0 : warp - 6;
       int g = j;  // global k-step (over all tiles of this CTA) this producer issues next
-      int g_tile0 = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, g_tile0 += total_k) {
+      int g_unit0 = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / S, z = unit - tile * S;
+        const int k0 = z * total_k / S, nk = (z + 1) * total_k / S - k0;
         const TileCoord t = tile_coord<N_TILE>(p, tile);
         int cx0 = 0, cy0 = 0, cn0 = 0;
         int4 *coords = blk_coord_s + 8 * j;
-        for (int i = 0; i < t.nvalid; ++i) {
-          const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + t.b0 + i) : (uint32_t)(t.b0 + i);
+        uint32_t cells[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // all mapping lookups in flight at once
+          cells[i] = (p.mapping && i < t.nvalid) ? (uint32_t)__ldg(p.mapping + t.b0 + i) : (uint32_t)(t.b0 + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i >= t.nvalid) break;
+          const uint32_t cell = cells[i];
           uint32_t n, gh, gw;
           p.cell(cell, n, gh, gw);
           const int4 c = make_int4((int)gw * p.BS_in - p.pad, (int)gh * p.BS_in + t.r0 * p.stride - p.pad, (int)n, 0);
@@ -118,10 +202,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
         }
         const uint32_t tx_bytes = (uint32_t)t.nvalid * p.box_bytes;
         // (tap, channel chunk) of this producer's first k-step in the tile
-        int ks = g - g_tile0;
-        int tap = ks / p.kc_per_tap, cc = ks - tap * p.kc_per_tap, kh = tap / p.ksize;
+        int ks = g - g_unit0;
+        int tap = (k0 + ks) / p.kc_per_tap, cc = (k0 + ks) - tap * p.kc_per_tap, kh = tap / p.ksize;
         int kw = tap - kh * p.ksize;
-        for (; ks < total_k; ks += kAProd, g += kAProd) {
+        g_unit0 += nk;
+        for (; ks < nk; ks += kAProd, g += kAProd) {
           const int s = g % STAGES;
           const uint32_t parity = (uint32_t)(((g / STAGES) & 1) ^ 1);
           uint8_t *sa = smem + (size_t)s * kStageBytes;
@@ -150,10 +235,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       int s = 0;
       uint32_t parity = 1;
       uint8_t *sb = smem + kABytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / S, z = unit - tile * S;
+        const int k0 = z * total_k / S, nk = (z + 1) * total_k / S - k0;
         const int n0 = (tile % p.ntiles_n) * N_TILE;
-        int kcoord = 0;
-        for (int ks = 0; ks < total_k; ++ks) {
+        int kcoord = k0 * kChunkK;
+        for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&empty_bar[s], parity);
           mbar_expect_tx(&full_bar[s], kBBytes);
           tma_load_2d(sb, &b_map, &full_bar[s], kcoord, n0);
@@ -172,11 +259,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       uint32_t parity = 0, stage_off = 0;
       uint32_t buf = 0, buf_parity = 1;  // first use of either accumulator buffer: it is free
       bool first = true;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int z = unit % S;
+        const int nk = (z + 1) * total_k / S - z * total_k / S;
         mbar_wait(&acc_empty[buf], buf_parity);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + buf * N_TILE;
-        for (int ks = 0; ks < total_k; ++ks) {
+        for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&full_bar[s], parity);
           if (first) { trace_mark(p, 2); first = false; }
           tc_fence_after_sync();
@@ -201,7 +290,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     constexpr int kTPR = N_TILE / 8, kRPI = 32 / kTPR;
     const int c8 = (lane % kTPR) * 8;
     uint32_t buf = 0, buf_parity = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / S;
       const TileCoord t = tile_coord<N_TILE>(p, tile);
       // this tile's slice of the bias + this warp's 32 plane-row offsets, while the MMAs of the tile run
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
@@ -218,6 +308,35 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
 
       mbar_wait(&acc_full[buf], buf_parity);
       tc_fence_after_sync();
+      if (S > 1) {
+        // ---- split-K, phase 1: this CTA's fp32 partial -> L2 scratch, whole rows per access (half of the
+        //      tile's columns at a time through the staging rows)
+        constexpr int kCP = N_TILE / 2;                      // columns per pass
+        constexpr int kLPR = kCP / 4, kRowsPI = 32 / kLPR;   // lanes per row (float4 each), rows per access
+        float *ws = p.work + ((size_t)unit * kTileM + q * 32) * N_TILE;
+        if (threadIdx.x == 64) trace_mark(p, 4);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCP; c0 += 32) {
+            uint32_t v32[32];
+            tmem_ld_32x32(tmem_base + buf * N_TILE + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * kCP + c0), v32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4 *>(stage + (size_t)lane * kRowB + (c0 + j) * 4) =
+                  make_uint4(v32[j], v32[j + 1], v32[j + 2], v32[j + 3]);
+          }
+          __syncwarp();
+#pragma unroll 4
+          for (int r = lane / kLPR; r < 32; r += kRowsPI) {
+            const float4 v = *reinterpret_cast<const float4 *>(stage + (size_t)r * kRowB + (lane % kLPR) * 16);
+            *reinterpret_cast<float4 *>(ws + (size_t)r * N_TILE + h * kCP + (lane % kLPR) * 4) = v;
+          }
+          __syncwarp();
+        }
+        continue;  // one unit per CTA in split mode; phase 2 follows the cluster barrier below
+      }
       // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's staging rows
       const uint32_t acc = tmem_base + buf * N_TILE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -287,6 +406,25 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     tc_fence_before_sync();
   }
 
+  if (S > 1) {
+    cluster_sync_all();  // every CTA's partial is in L2 and visible cluster-wide (release / acquire)
+    {
+      const int tile = blockIdx.x / S, rank = blockIdx.x - tile * S;  // cluster (S,1,1): rank = blockIdx.x % S
+      const TileCoord t = tile_coord<N_TILE>(p, tile);
+      const size_t out_base = ((size_t)t.b0 * p.BS_out * p.BS_out + (size_t)t.r0 * p.BS_out) * p.Cout + t.n0;
+      const int m_valid = p.blocks_per_tile == 1 ? kTileM : t.nvalid * p.BS_out * p.BS_out;
+      switch (S) {
+        case 2: splitk_reduce<N_TILE, 2>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        case 3: splitk_reduce<N_TILE, 3>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        case 4: splitk_reduce<N_TILE, 4>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        case 5: splitk_reduce<N_TILE, 5>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        case 6: splitk_reduce<N_TILE, 6>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        case 7: splitk_reduce<N_TILE, 7>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+        default: splitk_reduce<N_TILE, 8>(p, rank, tile, t.n0, out_base, m_valid, row_pl_s, bias_s); break;
+      }
+    }
+  }
+
   __syncthreads();
   if (threadIdx.x == 0) { trace_mark(p, 6); trace_wall(p, 10); }
   if (warp == 1) {
@@ -304,9 +442,9 @@ static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map,
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_persistent_kernel): %s",
              cudaGetErrorString(attr));
   const int total = p.tiles_m * p.ntiles_n;
-  const cudaError_t e = launch_kernel(conv_igemm_persistent_kernel<N_TILE, STAGES>,
-                                      dim3((unsigned)(total < kNumSMs ? total : kNumSMs)), dim3(kPersistThreads), smem, s,
-                                      1, a_map, b_map, p);
+  const unsigned grid = p.splits > 1 ? (unsigned)(total * p.splits) : (unsigned)(total < kNumSMs ? total : kNumSMs);
+  const cudaError_t e = launch_kernel_cluster(conv_igemm_persistent_kernel<N_TILE, STAGES>, dim3(grid), dim3(kPersistThreads),
+                                              smem, s, dim3((unsigned)p.splits, 1, 1), a_map, b_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
