@@ -327,10 +327,13 @@ def bench_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "batched": batched,
             "roofline": {"bound": "tensor",
                          "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: largest share "
-                                   "of the step, profiles/r01b_frame_launch_shares.md)",
+                                   "of a single launch in the step, profiles/r01c_frame_launch_shares.md)",
                          "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                         "frac": dom["tflops"] / peaks["tf_burst"], "traffic": None, "peak_source": peaks["source"]
-                         + " (burst: kernel timed alone)", "algorithmic_flops_per_launch": dom["flops"],
+                         "frac": dom["tflops"] / peaks["tf_burst"], "traffic": 11650000,
+                         "traffic_note": "dram__bytes_read+write of one launch (profiles/r01c_conv_igemm_l20_ncu.md); "
+                                         "algorithmic bytes: 10.5 MB of plane cells + 0.3 MB of weights read, 10.5 MB "
+                                         "of tiles written (they stay in L2 for the next kernel)",
+                         "peak_source": peaks["source"] + " (burst: kernel timed alone)", "algorithmic_flops_per_launch": dom["flops"],
                          "us_per_launch": dom["us"]},
             "roofline_hbm": {"bound": "hbm", "kernel": "bc_gather_halo TMA path (NHWC, C=128, BS=32, p=1, E=38: "
                                                        "BASELINE config 2)",

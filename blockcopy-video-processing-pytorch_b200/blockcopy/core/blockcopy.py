@@ -45,6 +45,9 @@ class BlockCopyModel(nn.Module):
         if settings.get("block_channels_last", True):
             self.base_model.to(memory_format=torch.channels_last)
         self._graphs = _GraphState() if settings.get("block_cuda_graphs", False) else None
+        net = getattr(self.policy, "net", None)
+        if self._graphs is not None and net is not None and hasattr(net, "use_cuda_graphs"):
+            net.use_cuda_graphs = True  # policy trunk forward / backward as graph replays too
 
     def load_state_dict(self, state_dict, strict: bool = True):
         """Checkpoints are base-model checkpoints (reference core/blockcopy.py:30-32)."""

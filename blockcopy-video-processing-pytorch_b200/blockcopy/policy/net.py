@@ -33,6 +33,9 @@ class PolicyNet(nn.Module):
             self._make_layer(planes, planes, relu=True),
             self._make_layer(planes, 1, relu=False),
         )
+        # block_cuda_graphs: trunk forward and backward replayed as CUDA graphs (see _trunk_forward)
+        self.use_cuda_graphs = False
+        self.__dict__["_graphed"] = None  # (input shape, graphed callable); not a submodule: state_dict unchanged
 
     @staticmethod
     def _make_layer(cin, cout, kernel_size=3, stride=2, relu=True):
@@ -83,12 +86,35 @@ class PolicyNet(nn.Module):
 
         return _C.policy_features(frame, state, rep, grid, self.scale_factor)
 
+    def _trunk_forward(self, x: torch.Tensor) -> torch.Tensor:
+        """backbone + head.  With ``use_cuda_graphs`` (BlockCopyModel sets it from ``block_cuda_graphs``) the
+        ~45 fp32 launches of the forward and the ~90 of the backward are each one CUDA-graph replay
+        (``torch.cuda.make_graphed_callables``: same kernels, same order, autograd-aware, so
+        ``loss.backward()`` in PolicyTrainRL.optim works unchanged).  Capture runs the trunk a few times:
+        the batch-norm running statistics are restored afterwards, so capturing is free of side effects."""
+        if not (self.use_cuda_graphs and x.is_cuda and self.training and torch.is_grad_enabled()):
+            return self.layers(self.backbone(x))
+        g = self.__dict__["_graphed"]
+        key = (tuple(x.shape), x.dtype, next(self.parameters()).data_ptr())
+        if g is None or g[0] != key:
+            trunk = nn.Sequential(self.backbone, self.layers)
+            saved = {k: v.detach().clone() for k, v in trunk.state_dict().items()}
+            grads = [None if q.grad is None else q.grad.detach().clone() for q in trunk.parameters()]
+            fn = torch.cuda.make_graphed_callables(trunk, (x.detach().clone(),), allow_unused_input=True)
+            with torch.no_grad():
+                for k, v in trunk.state_dict().items():
+                    v.copy_(saved[k])
+                for q, gr in zip(trunk.parameters(), grads):
+                    q.grad = gr
+            g = self.__dict__["_graphed"] = (key, fn)
+        return g[1](x)
+
     def forward(self, policy_meta: dict):
         N, C, H, W = policy_meta["inputs"].shape
         with timings.env("policy/net/build_features", 5):
             x = self.build_features(policy_meta)
         with timings.env("policy/net/layers", 5):
-            logits = self.layers(self.backbone(x))
+            logits = self._trunk_forward(x)
         expect = (N, 1, H // self.block_size, W // self.block_size)
         assert logits.shape == expect, f"logits shape: {logits.shape}, frame shape: {(N, C, H, W)}, " \
                                        f"block size: {self.block_size}"
