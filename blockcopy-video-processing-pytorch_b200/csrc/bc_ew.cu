@@ -39,81 +39,145 @@ __device__ __forceinline__ void load8(const __half *p, float (&v)[8]) {
 
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
+// Everything one unit (8 channels of one output pixel) needs from memory, loaded before any of it is used:
+// the kernel is a pure stream, so what counts is bytes in flight per thread (two units = up to 160 B).
+struct EwUnit {
+  uint4 a00, a01, a10, a11, res;  // a00 only unless up2x
+  float ly1, lx1;
+  uint32_t pix, b, y, x;
+  int c0;
+};
+
+__device__ __forceinline__ void ew_load(const EwParams &p, uint32_t i, EwUnit &u) {
+  uint32_t ch, rem;
+  p.chunks_per_pixel.divmod(i, u.pix, ch);
+  p.px_per_tile.divmod(u.pix, u.b, rem);
+  p.bs_div.divmod(rem, u.y, u.x);
+  u.c0 = (int)ch * 8;
+  if (p.up2x) {
+    // PyTorch upsample_bilinear2d, align_corners = False, scale 0.5: src = 0.5 * (dst + 0.5) - 0.5, clamped at 0
+    const int hs = p.BS >> 1;
+    const float sy = fmaxf(0.5f * ((float)u.y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * ((float)u.x + 0.5f) - 0.5f, 0.f);
+    const int y1 = (int)sy, x1 = (int)sx;
+    const int yp = y1 < hs - 1 ? 1 : 0, xp = x1 < hs - 1 ? 1 : 0;
+    u.ly1 = sy - (float)y1;
+    u.lx1 = sx - (float)x1;
+    const __half *base = p.a + (((size_t)u.b * hs + y1) * hs + x1) * p.C + u.c0;
+    u.a00 = __ldg(reinterpret_cast<const uint4 *>(base));
+    u.a01 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)xp * p.C));
+    u.a10 = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)yp * hs * p.C));
+    u.a11 = __ldg(reinterpret_cast<const uint4 *>(base + ((size_t)yp * hs + xp) * p.C));
+  } else {
+    u.a00 = __ldg(reinterpret_cast<const uint4 *>(p.a + (size_t)u.pix * p.C + u.c0));
+  }
+  if (p.residual) u.res = __ldg(reinterpret_cast<const uint4 *>(p.residual + (size_t)u.pix * p.C + u.c0));
+}
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&v)[8]) {
+  const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+
+// per-channel batch-norm parameters of 8 consecutive channels
+struct EwAffine {
+  float mean[8], istd[8], w[8], sh[8];
+};
+__device__ __forceinline__ void ew_load_affine(const EwParams &p, int c0, EwAffine &f) {
+  *reinterpret_cast<float4 *>(f.mean) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0));
+  *reinterpret_cast<float4 *>(f.mean + 4) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0 + 4));
+  *reinterpret_cast<float4 *>(f.istd) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0));
+  *reinterpret_cast<float4 *>(f.istd + 4) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0 + 4));
+  if (p.weight) {
+    *reinterpret_cast<float4 *>(f.w) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0));
+    *reinterpret_cast<float4 *>(f.w + 4) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0 + 4));
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f.w[t] = 1.f;
+  }
+  if (p.shift) {
+    *reinterpret_cast<float4 *>(f.sh) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0));
+    *reinterpret_cast<float4 *>(f.sh + 4) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0 + 4));
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f.sh[t] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void ew_finish(const EwParams &p, const EwUnit &u, const EwAffine &f) {
+  float v[8];
+  if (p.up2x) {
+    float v00[8], v01[8], v10[8], v11[8];
+    unpack8(u.a00, v00);
+    unpack8(u.a01, v01);
+    unpack8(u.a10, v10);
+    unpack8(u.a11, v11);
+    const float ly0 = 1.f - u.ly1, lx0 = 1.f - u.lx1;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      v[t] = round_h(ly0 * (lx0 * v00[t] + u.lx1 * v01[t]) + u.ly1 * (lx0 * v10[t] + u.lx1 * v11[t]));
+  } else {
+    unpack8(u.a00, v);
+  }
+  if (p.residual) {
+    float r[8];
+    unpack8(u.res, r);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = round_h(v[t] + r[t]);
+  }
+  if (p.has_affine) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = round_h(f.w[t] * (v[t] - f.mean[t]) * f.istd[t] + f.sh[t]);  // ATen's eval-BN expression
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+  }
+  uint4 o;
+  __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  if (p.out) *reinterpret_cast<uint4 *>(p.out + (size_t)u.pix * p.C + u.c0) = o;
+  if (p.plane) {
+    uint32_t n, gh, gw;
+    p.cell((uint32_t)__ldg(p.mapping + u.b), n, gh, gw);
+    const size_t off = (((size_t)n * p.H + gh * p.BS + u.y) * p.W + gw * p.BS + u.x) * p.C + u.c0;
+    *reinterpret_cast<uint4 *>(p.plane + off) = o;
+  }
+}
+
+// FIXED_CH: the grid stride is a multiple of the chunks per pixel, so a thread always works on the same 8
+// channels and loads their batch-norm parameters once.
+template <bool FIXED_CH>
 __global__ void __launch_bounds__(256) ew_fused_kernel(const EwParams p) {
   pdl_trigger();
   pdl_wait();
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
-    uint32_t pix, ch, b, rem, y, x;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  EwAffine f;
+  if (FIXED_CH && p.has_affine && i < p.total) {
+    uint32_t pix, ch;
     p.chunks_per_pixel.divmod(i, pix, ch);
-    p.px_per_tile.divmod(pix, b, rem);
-    p.bs_div.divmod(rem, y, x);
-    const int c0 = (int)ch * 8;
-    float v[8];
-    if (p.up2x) {
-      // PyTorch upsample_bilinear2d, align_corners = False, scale 0.5: src = 0.5 * (dst + 0.5) - 0.5, clamped at 0
-      const int hs = p.BS >> 1;
-      const float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.f);
-      const int y1 = (int)sy, x1 = (int)sx;
-      const int yp = y1 < hs - 1 ? 1 : 0, xp = x1 < hs - 1 ? 1 : 0;
-      const float ly1 = sy - (float)y1, ly0 = 1.f - ly1, lx1 = sx - (float)x1, lx0 = 1.f - lx1;
-      const __half *base = p.a + (((size_t)b * hs + y1) * hs + x1) * p.C + c0;
-      float v00[8], v01[8], v10[8], v11[8];
-      load8(base, v00);
-      load8(base + (size_t)xp * p.C, v01);
-      load8(base + (size_t)yp * hs * p.C, v10);
-      load8(base + ((size_t)yp * hs + xp) * p.C, v11);
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        v[t] = round_h(ly0 * (lx0 * v00[t] + lx1 * v01[t]) + ly1 * (lx0 * v10[t] + lx1 * v11[t]));
-    } else {
-      load8(p.a + (size_t)pix * p.C + c0, v);
-    }
-    if (p.residual) {
-      float r[8];
-      load8(p.residual + (size_t)pix * p.C + c0, r);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = round_h(v[t] + r[t]);
-    }
-    if (p.has_affine) {
-      // per-channel parameters as 2 x float4 per array (8 vector loads instead of 32 scalar ones)
-      float mean[8], istd[8], w[8], sh[8];
-      *reinterpret_cast<float4 *>(mean) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0));
-      *reinterpret_cast<float4 *>(mean + 4) = __ldg(reinterpret_cast<const float4 *>(p.mean + c0 + 4));
-      *reinterpret_cast<float4 *>(istd) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0));
-      *reinterpret_cast<float4 *>(istd + 4) = __ldg(reinterpret_cast<const float4 *>(p.invstd + c0 + 4));
-      if (p.weight) {
-        *reinterpret_cast<float4 *>(w) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0));
-        *reinterpret_cast<float4 *>(w + 4) = __ldg(reinterpret_cast<const float4 *>(p.weight + c0 + 4));
-      } else {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) w[t] = 1.f;
-      }
-      if (p.shift) {
-        *reinterpret_cast<float4 *>(sh) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0));
-        *reinterpret_cast<float4 *>(sh + 4) = __ldg(reinterpret_cast<const float4 *>(p.shift + c0 + 4));
-      } else {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) sh[t] = 0.f;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = round_h(w[t] * (v[t] - mean[t]) * istd[t] + sh[t]);  // ATen's eval-BN expression
-    }
-    if (p.relu) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
-    }
-    uint4 o;
-    __half2 *oh = reinterpret_cast<__half2 *>(&o);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-    if (p.out) *reinterpret_cast<uint4 *>(p.out + (size_t)pix * p.C + c0) = o;
-    if (p.plane) {
-      uint32_t n, gh, gw;
-      p.cell((uint32_t)__ldg(p.mapping + b), n, gh, gw);
-      const size_t off = (((size_t)n * p.H + gh * p.BS + y) * p.W + gw * p.BS + x) * p.C + c0;
-      *reinterpret_cast<uint4 *>(p.plane + off) = o;
-    }
+    ew_load_affine(p, (int)ch * 8, f);
+  }
+  for (; i + stride < p.total; i += 2 * stride) {  // two units in flight
+    EwUnit u0, u1;
+    ew_load(p, i, u0);
+    ew_load(p, i + stride, u1);
+    if (!FIXED_CH && p.has_affine) ew_load_affine(p, u0.c0, f);
+    ew_finish(p, u0, f);
+    if (!FIXED_CH && p.has_affine) ew_load_affine(p, u1.c0, f);
+    ew_finish(p, u1, f);
+  }
+  if (i < p.total) {
+    EwUnit u0;
+    ew_load(p, i, u0);
+    if (!FIXED_CH && p.has_affine) ew_load_affine(p, u0.c0, f);
+    ew_finish(p, u0, f);
   }
 }
 
@@ -144,10 +208,15 @@ int ew_fused(void *out, void *plane, const void *a, const void *residual, const 
   const int64_t total = (int64_t)E * BS * BS * (C / 8);
   BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_ew_fused: problem too large");
   p.total = (uint32_t)total;
-  int64_t grid = (total + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 16;
+  // two units per thread and iteration; at most 8 CTAs per SM (whole waves)
+  int64_t grid = (total + 511) / 512;
+  const int64_t cap = (int64_t)kNumSMs * 8;
   if (grid > cap) grid = cap;
-  launch_kernel(ew_fused_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  const bool fixed_ch = (grid * 256) % (C / 8) == 0;
+  if (fixed_ch)
+    launch_kernel(ew_fused_kernel<true>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  else
+    launch_kernel(ew_fused_kernel<false>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_ew_fused");
 }
 
