@@ -238,3 +238,54 @@ def test_stem_conv_7x7_s2(N, GH, GW, BS, Cout, frac):
     want = nxt_base.clone()
     O.combine_(out.cpu().contiguous(), want, me)
     assert torch.equal(nxt.cpu().contiguous(), want)
+
+
+_FORMS_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
+from blockcopy import _C
+g = torch.Generator().manual_seed(3)
+Cin = Cout = 128; BS = 32; GH, GW = 8, 16
+plane = torch.randn(1, Cin, GH * BS, GW * BS, generator=g).half().cuda().contiguous(memory_format=torch.channels_last)
+w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).half().cuda().contiguous(memory_format=torch.channels_last)
+b = (0.1 * torch.randn(Cout, generator=g)).half().cuda()
+me = torch.randperm(GH * GW, generator=g)[:40].sort().values.to(torch.int32).cuda()
+res = torch.randn(40, Cout, BS, BS, generator=g).half().cuda().contiguous(memory_format=torch.channels_last)
+nxt = torch.zeros(1, Cout, GH * BS, GW * BS, dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+out = torch.full((40, Cout, BS, BS), float("nan"), dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+_C.conv_igemm(out, plane, w, b, res, me, 40, BS, 1, 1, relu=True, plane_out=nxt)
+torch.cuda.synchronize()
+torch.save({"out": out.cpu(), "nxt": nxt.cpu(), "plane": plane.cpu(), "w": w.cpu(), "b": b.cpu(), "res": res.cpu(), "me": me.cpu()}, sys.argv[1])
+'''
+
+
+def test_large_grid_all_launch_forms_agree(tmp_path):
+    """320 tiles (layer #20 at 1024x2048, E = 40): the one-tile-per-CTA kernel (default for this grid), the
+    persistent kernel looping over 2-3 tiles per CTA with the double-buffered TMEM accumulator
+    (BC_CONV_PERSIST=2) and the build without the persistent kernel (=0) issue the same MMA sequence per tile:
+    identical bits, and within tolerance of the fp32 torch conv + residual + ReLU."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "blockcopy-video-processing-pytorch_b200")
+    outs = {}
+    for form in ("1", "2", "0"):
+        path = str(tmp_path / f"form{form}.pt")
+        env = dict(os.environ, BC_CONV_PERSIST=form)
+        subprocess.run([sys.executable, "-c", _FORMS_SCRIPT, path, root, pkg], check=True, env=env, timeout=300)
+        outs[form] = torch.load(path)
+    a = outs["1"]
+    for form in ("2", "0"):
+        assert torch.equal(a["out"], outs[form]["out"]), form
+        assert torch.equal(a["nxt"], outs[form]["nxt"]), form
+    ref_full = F.conv2d(a["plane"].float(), a["w"].float(), a["b"].float(), padding=1)
+    ref = O.split(ref_full.contiguous(), a["me"], 32).half().float() + a["res"].float()
+    ref = ref.relu()
+    got = a["out"].float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 2 ** -9 * float(ref.abs().max()) + 2e-3
+    want = torch.zeros_like(a["nxt"]).contiguous()
+    O.combine_(a["out"].contiguous(), want, a["me"])
+    assert torch.equal(a["nxt"].contiguous(), want)
