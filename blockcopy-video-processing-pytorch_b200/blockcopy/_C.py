@@ -41,6 +41,7 @@ _SIGNATURES = {
     "bc_ew_fused": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip] + [_i] * 8 + [_vp], _i),
     "bc_maxpool_halo": ([_vp, _vp, _vp, _ip] + [_i] * 9 + [_vp], _i),
     "bc_debug_trace": ([_vp], _i),
+    "bc_head_1x1": ([_vp] * 10 + [_i, _ip, _ip] + [_i] * 9 + [_vp], _i),
     "bc_stem_pack": ([_vp, _vp, _ip] + [_i] * 5 + [_vp], _i),
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
@@ -437,6 +438,50 @@ def conv_stem(out: torch.Tensor, s2d_plane: torch.Tensor, weight_packed: torch.T
                               Cout, int(relu), plane_out.data_ptr() if plane_out is not None else None, _stream()),
            "bc_conv_stem")
     return out
+
+
+# ------------------------------------------------------------------------------------------- output head
+HEAD_MAX_COUT = 32
+
+
+def head_supported(dtype, weight: torch.Tensor, stride, padding, dilation=1, groups=1) -> bool:
+    """1x1 conv with few output channels (class logits) on fp16 CUDA blocks: bc_head_1x1."""
+    if weight.dim() != 4:
+        return False
+    Cout, Cin, kh, kw = weight.shape
+    return (dtype == torch.float16 and weight.dtype == torch.float16 and weight.is_cuda and kh == kw == 1
+            and stride == 1 and padding == 0 and dilation == 1 and groups == 1 and Cout <= HEAD_MAX_COUT
+            and Cin % 8 == 0 and Cin <= 1024)
+
+
+def head_1x1(tiles_in: torch.Tensor, weight2d: torch.Tensor, bias: Optional[torch.Tensor], bn, relu_in: bool,
+             tiles_out: Optional[torch.Tensor] = None, dense_out: Optional[torch.Tensor] = None,
+             dense_prev: Optional[torch.Tensor] = None, grid_idx: Optional[torch.Tensor] = None,
+             mapping_exec: Optional[torch.Tensor] = None):
+    """y = conv1x1(relu?(bn?(tiles_in))) + bias on channels_last tiles (E,Cin,BS,BS); y goes to `tiles_out`
+    (E,Cout,BS,BS) and/or, combined with `dense_prev`, to `dense_out` (N,Cout,GH*BS,GW*BS).  bn = (mean, invstd,
+    weight|None, shift|None) fp32 or None; weight2d fp16 (Cout,Cin) contiguous."""
+    _dev(tiles_in, weight2d, bias, tiles_out, dense_out, dense_prev, grid_idx, mapping_exec)
+    E, Cin, BS, _ = tiles_in.shape
+    Cout = weight2d.shape[0]
+    assert tiles_in.is_contiguous(memory_format=torch.channels_last) and weight2d.is_contiguous()
+    assert weight2d.shape == (Cout, Cin)
+    N = GH = GW = 1
+    dl = BC_NCHW
+    if dense_out is not None:
+        N, _, GH, GW = grid_idx.shape
+        assert tuple(dense_out.shape) == (N, Cout, GH * BS, GW * BS)
+        dl = layout_of(dense_out)
+        if dense_prev is not None:
+            assert dense_prev.shape == dense_out.shape and layout_of(dense_prev) == dl \
+                and dense_prev.data_ptr() != dense_out.data_ptr()
+    tl = layout_of(tiles_out) if tiles_out is not None else BC_NCHW
+    mean, invstd, w, sh = bn if bn is not None else (None, None, None, None)
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    _check(lib().bc_head_1x1(ptr(tiles_out), ptr(dense_out), ptr(dense_prev), tiles_in.data_ptr(), weight2d.data_ptr(),
+                             ptr(bias), ptr(mean), ptr(invstd), ptr(w), ptr(sh), int(relu_in), ptr(grid_idx),
+                             ptr(mapping_exec), E, N, GH, GW, BS, Cin, Cout, tl, dl, _stream()), "bc_head_1x1")
+    return dense_out if dense_out is not None else tiles_out
 
 
 # ------------------------------------------------------------------------------------------- policy features

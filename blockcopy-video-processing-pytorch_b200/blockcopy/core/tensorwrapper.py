@@ -32,6 +32,7 @@ from ..utils.profiler import timings
 FUSED_CONV = os.environ.get("BLOCKCOPY_FUSED_CONV", "1") != "0"  # route eligible convs on blocks to the tcgen05 implicit-GEMM kernel (bc_conv_igemm)
 # defer convs / elementwise ops on blocks and fuse them into epilogues (see _Pending); "0" = op-by-op execution
 LAZY_FUSION = os.environ.get("BLOCKCOPY_LAZY", "1") != "0"
+FUSED_HEAD = os.environ.get("BLOCKCOPY_FUSED_HEAD", "1") != "0"  # few-channel 1x1 output conv + combine as one kernel (bc_head_1x1)
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
 
@@ -233,6 +234,10 @@ class _Pending:
         return False
 
 
+def _is_dense4(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and (t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last))
+
+
 _META_METHODS = {"dim", "size", "stride", "numel", "is_contiguous", "element_size", "storage_offset",
                  "is_floating_point", "is_complex", "ndimension", "nelement", "get_device", "__len__"}
 _META_PROPS = {"shape", "dtype", "device", "ndim", "is_cuda", "requires_grad", "layout", "names", "is_leaf",
@@ -390,7 +395,23 @@ class TensorWrapper(torch.Tensor):
             N, _, GH, GW = grid_idx.shape
             shape = (N, C, GH * BS, GW * BS)
             slot, prev = feats._next_full()
-            if (self._pending is not None and inplace and prev is not None and tuple(prev.shape) == shape
+            head = self._pending if self._pending is not None and self._pending.kind == "head" else None
+            if head is not None and (prev is None or (tuple(prev.shape) == shape and _is_dense4(prev))):
+                # output head + combine in one kernel: tiles and the dense output from the same pass
+                c = head.conv
+                self._pending = None
+                _LIVE_PENDING.pop(id(self), None)
+                if prev is None:
+                    assert E == grid_idx.numel(), "first frame must execute every block"
+                    out, src_prev = torch.empty(shape, dtype=self.dtype, device=self.device), None
+                elif inplace:
+                    out, src_prev = prev, None          # cells that are not executed simply keep their content
+                else:
+                    out, src_prev = torch.empty_like(prev), prev
+                _C.head_1x1(c["src"], c["w"], c["bias"], c["bn"], c["relu"], tiles_out=_raw(self), dense_out=out,
+                            dense_prev=src_prev, grid_idx=grid_idx, mapping_exec=mapping)
+                tiles, done = None, True
+            elif (self._pending is not None and inplace and prev is not None and tuple(prev.shape) == shape
                     and prev.is_contiguous(memory_format=torch.channels_last) and not prev.is_contiguous()):
                 self._materialize(plane_out=prev)  # producer epilogue writes the plane: no scatter kernel
                 tiles, out, done = None, prev, True
@@ -518,6 +539,10 @@ class TensorWrapper(torch.Tensor):
         elif p.kind == "stem":
             c = p.conv
             _C.conv_stem(out, c["src"], c["w"], c["bias"], c["mapping"], c["E"], relu=p.relu, plane_out=plane_out)
+        elif p.kind == "head":
+            c = p.conv
+            _C.head_1x1(c["src"], c["w"], c["bias"], c["bn"], c["relu"], tiles_out=out)
+            return False  # never writes a consumer's plane: the caller scatters
         elif p.kind == "pool":
             c = p.conv
             _C.maxpool_halo(out, c["src"], c["mapping"], c["E"], c["BS_in"], c["k"], c["stride"], c["pad"],
@@ -658,6 +683,21 @@ class TensorWrapper(torch.Tensor):
         if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
             return None
         feats = self._features
+        if LAZY_FUSION and FUSED_HEAD and _C.head_supported(x.dtype, weight, stride, padding, dilation, a["groups"]) \
+                and _C.lazy_supported(x):
+            # output head (few-channel 1x1 conv): one streaming kernel that also absorbs a preceding eval
+            # batch_norm + ReLU and, when the consumer is combine(), writes the dense output directly
+            q = x._pending
+            if q is not None and q.kind == "ew" and not q.up2x and q.residual is None and q.src is not None:
+                src, bn, relu = q.src, q.bn, q.relu  # x itself is only launched if someone else needs it
+            else:
+                src, bn, relu = x._tiles_nhwc(), None, False
+            if src is not None:
+                w2d = weight.detach().reshape(weight.shape[0], Cin)
+                if not w2d.is_contiguous():
+                    w2d = w2d.contiguous()
+                pend = _Pending("head", conv=dict(src=src, w=w2d, bias=bias, E=E, bn=bn, relu=relu))
+                return x._new_pending((E, weight.shape[0], BS, BS), pend)
         if _C.stem_supported(x.dtype, weight, BS, stride, padding, dilation, a["groups"]):
             # ResNet stem: 7x7/s2 on 3 channels as a 4x4/s1 implicit GEMM over a space-to-depth plane
             N, _, GH, GW = feats._grid_idx.shape

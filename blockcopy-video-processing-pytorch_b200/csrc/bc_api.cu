@@ -67,6 +67,11 @@ int spp_levels(void *out, const void *pooled, const float *bn, const void *w, in
 int spp_prep(void *y, const void *x0, const void *lev, const float *bn, int N, int C, int H, int W, int L, const int *gh,
              const int *gw, int Lc, int Cp, cudaStream_t s);
 
+int head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const void *tiles_in, const void *weight,
+             const void *bias, const float *bn_mean, const float *bn_invstd, const float *bn_weight,
+             const float *bn_shift, int relu_in, const int32_t *grid_idx, const int32_t *mapping, int E, int N, int GH,
+             int GW, int BS, int Cin, int Cout, int tiles_layout, int dense_layout, cudaStream_t stream);
+
 bool pdl_enabled() {
   // programmatic dependent launch: the next kernel's prologue (barrier init, TMEM alloc, descriptor prefetch)
   // overlaps this one's tail; ~1.3 % of a SwiftNet frame inside a CUDA graph.  BC_PDL=0 switches it off.
@@ -222,6 +227,18 @@ BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const
   return conv_igemm(out, plane, weight, bias, residual, mapping_exec, E, N, Cin, H, W, BS_in, Cout, ksize, stride,
                     pad, relu, plane_out, out_mapping, out_N, out_GH, out_GW, allow_split_k, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+
+BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const void *tiles_in,
+                       const void *weight, const void *bias, const float *bn_mean, const float *bn_invstd,
+                       const float *bn_weight, const float *bn_shift, int relu_in, const int32_t *grid_idx,
+                       const int32_t *mapping_exec, int E, int N, int GH, int GW, int BS, int Cin, int Cout,
+                       bc_layout_t tiles_layout, bc_layout_t dense_layout, bc_stream_t stream) {
+  BC_REQUIRE(E >= 0, BC_ERR_SHAPE, "bc_head_1x1: E=%d", E);
+  if (E == 0) return BC_OK;
+  return head_1x1(tiles_out, dense_out, dense_prev, tiles_in, weight, bias, bn_mean, bn_invstd, bn_weight, bn_shift,
+                  relu_in, grid_idx, mapping_exec, E, N, GH, GW, BS, Cin, Cout, (int)tiles_layout, (int)dense_layout,
+                  (cudaStream_t)stream);
 }
 
 BC_API int bc_ew_fused(void *out, void *plane_out, const void *a, const void *residual, const float *bn_mean,

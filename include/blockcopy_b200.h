@@ -222,6 +222,23 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
                               int Wo, const int64_t *repr_strides, float inv_scale_y, float inv_scale_x,
                               bc_dtype_t dtype, bc_stream_t stream);
 
+/* ---- output head fused with the final combine ------------------------------------------------------
+ * Replaces, at the end of every frame, eval batch_norm + ReLU on the tile batch, the few-channel 1x1 conv
+ * (class logits; cuDNN in the reference path, core/tensorwrapper.py:519-520), its bias add, and
+ * out.combine() = clone of the previous output + combine_kernel (core/blockcopy.py:79-86,
+ * core/tensorwrapper.py:421-434):
+ *   y = conv1x1(relu?(bn?(tiles_in))) + bias;  tiles_out <- y;  dense_out <- dense_prev with executed cells = y
+ * tiles_in (E,BS,BS,Cin) NHWC fp16, Cin % 8 == 0; weight fp16 [Cout][Cin], Cout <= 32; bn_*: fp32 [Cin] or NULL;
+ * tiles_out (E,Cout,BS,BS) / dense_out, dense_prev (N,Cout,GH*BS,GW*BS) in the given layouts, each optional
+ * (dense_prev NULL: only executed cells are written).  Rounding as op by op: BN -> fp16, conv (fp32 sum) ->
+ * fp16, + bias -> fp16.
+ */
+BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const void *tiles_in,
+                       const void *weight, const void *bias, const float *bn_mean, const float *bn_invstd,
+                       const float *bn_weight, const float *bn_shift, int relu_in, const int32_t *grid_idx,
+                       const int32_t *mapping_exec, int E, int N, int GH, int GW, int BS, int Cin, int Cout,
+                       bc_layout_t tiles_layout, bc_layout_t dense_layout, bc_stream_t stream);
+
 /* ---- information gain of semantic segmentation (policy/information_gain.py:32-41) ------------------
  * out (N,1,h/4,w/4) fp16 = mean_c[ p_prev * (log p_prev - log p_cur) ] of the bilinearly 1/4-resized
  * logits (align_corners False); outputs / outputs_prev: fp16 (N,K,h,w) with element strides[4];

@@ -26,7 +26,8 @@ def cpu_backend():
 
     saved = {k: getattr(_C, k) for k in ("compact_mask", "gather", "scatter", "copy_blocks", "transfer",
                                          "gather_halo_tiles", "gather_halo", "conv_igemm", "ew_fused", "maxpool_halo",
-                                         "conv_supported", "lazy_supported", "stem_supported", "stem_pack", "conv_stem")}
+                                         "conv_supported", "lazy_supported", "stem_supported", "stem_pack", "conv_stem",
+                                         "head_supported", "head_1x1")}
     saved_tw = tw.to_tensorwrapper
 
     def compact_mask(grid_u8, grid_idx, mapping_exec, counts, prev_grid_idx=None, transfer_idx=None):
@@ -170,9 +171,38 @@ def cpu_backend():
     def lazy_supported(x):
         return x.dim() == 4 and x.shape[1] % 8 == 0
 
+    def head_supported(dtype, weight, stride, padding, dilation=1, groups=1):
+        if weight.dim() != 4:
+            return False
+        Cout, Cin, kh, kw = weight.shape
+        return kh == kw == 1 and stride == 1 and padding == 0 and dilation == 1 and groups == 1 and Cout <= 32 and Cin % 8 == 0
+
+    def head_1x1(tiles_in, weight2d, bias, bn, relu_in, tiles_out=None, dense_out=None, dense_prev=None, grid_idx=None,
+                 mapping_exec=None):
+        y = _nchw(tiles_in)
+        if bn is not None:
+            mean, invstd, w, s = bn
+            v = lambda t: t.view(1, -1, 1, 1).to(y.dtype)  # noqa: E731
+            y = (y - v(mean)) * v(invstd)
+            if w is not None:
+                y = y * v(w)
+            if s is not None:
+                y = y + v(s)
+        if relu_in:
+            y = y.relu()
+        y = F.conv2d(y, weight2d.view(*weight2d.shape, 1, 1), bias)
+        if tiles_out is not None:
+            _store(tiles_out, y)
+        if dense_out is not None:
+            tmp = _nchw(dense_prev if dense_prev is not None else dense_out).clone()
+            O.combine_(y.contiguous(), tmp, mapping_exec[: y.shape[0]].contiguous())
+            _store(dense_out, tmp)
+        return dense_out if dense_out is not None else tiles_out
+
     for k, v in dict(conv_igemm=conv_igemm, ew_fused=ew_fused, conv_supported=conv_supported,
                      lazy_supported=lazy_supported, maxpool_halo=maxpool_halo, stem_supported=stem_supported,
-                     stem_pack=stem_pack, conv_stem=conv_stem).items():
+                     stem_pack=stem_pack, conv_stem=conv_stem, head_supported=head_supported,
+                     head_1x1=head_1x1).items():
         setattr(_C, k, v)
     for k, v in dict(compact_mask=compact_mask, gather=gather, scatter=scatter, copy_blocks=copy_blocks,
                      transfer=transfer, gather_halo_tiles=gather_halo_tiles, gather_halo=gather_halo).items():

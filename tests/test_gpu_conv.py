@@ -289,3 +289,46 @@ def test_large_grid_all_launch_forms_agree(tmp_path):
     want = torch.zeros_like(a["nxt"]).contiguous()
     O.combine_(a["out"].contiguous(), want, a["me"])
     assert torch.equal(a["nxt"].contiguous(), want)
+
+
+@pytest.mark.parametrize("bn,relu,dense_cl,with_prev", [(True, True, False, True), (True, True, True, True),
+                                                          (False, False, False, True), (True, False, False, False)])
+def test_head_1x1_matches_op_by_op(bn, relu, dense_cl, with_prev):
+    """bc_head_1x1 == eval batch_norm -> ReLU -> 19-channel 1x1 conv (+bias) of torch on the tile batch, and the dense
+    output == previous output with the executed cells replaced by exactly those tiles."""
+    from blockcopy import _C
+
+    dev = "cuda"
+    g = torch.Generator().manual_seed(11)
+    N, Cin, Cout, GH, GW, BS = 2, 128, 19, 3, 4, 16
+    grid = torch.rand(N, 1, GH, GW, generator=g) < 0.4 if with_prev else torch.ones(N, 1, GH, GW, dtype=torch.bool)
+    gi, me = O.grid_mappings(grid)
+    E = me.numel()
+    x = torch.randn(E, Cin, BS, BS, generator=g).half().to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) * (2.0 / Cin) ** 0.5).half().to(dev)
+    b = (0.1 * torch.randn(Cout, generator=g)).half().to(dev)
+    mean, var = torch.randn(Cin, generator=g).half().to(dev), (torch.rand(Cin, generator=g) + 0.5).half().to(dev)
+    gamma, beta = (torch.rand(Cin, generator=g) + 0.5).half().to(dev), (0.1 * torch.randn(Cin, generator=g)).half().to(dev)
+    y = x
+    params = None
+    if bn:
+        y = F.batch_norm(y, mean, var, gamma, beta, False, 0.1, 1e-5)
+        params = (mean.float(), torch.rsqrt(var.float() + 1e-5), gamma.float(), beta.float())
+    if relu:
+        y = y.relu()
+    ref = F.conv2d(y.float(), w.float()).half().float() + b.float().view(1, -1, 1, 1)  # conv rounded, then the bias add
+    prev = torch.randn(N, Cout, GH * BS, GW * BS, generator=g).half().to(dev)
+    if dense_cl:
+        prev = prev.contiguous(memory_format=torch.channels_last)
+    dense = torch.full_like(prev, float("nan"))
+    tiles = torch.full((E, Cout, BS, BS), float("nan"), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
+    _C.head_1x1(x, w.reshape(Cout, Cin).contiguous(), b, params, relu, tiles_out=tiles, dense_out=dense,
+                dense_prev=prev if with_prev else None, grid_idx=gi.to(dev), mapping_exec=me.to(dev))
+    torch.cuda.synchronize()
+    got = tiles.float()
+    assert torch.isfinite(got).all()
+    # fp32 accumulation in another order than cuDNN's, BN rounded to fp16 in both: a few fp16 ulps of the result
+    assert (got - ref).abs().max().item() <= 2 ** -8 * float(ref.abs().max()) + 2e-3
+    want = prev.cpu().contiguous().clone()
+    O.combine_(tiles.cpu().contiguous(), want, me)
+    assert torch.equal(dense.cpu().contiguous(), want)
