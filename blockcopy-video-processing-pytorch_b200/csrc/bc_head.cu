@@ -35,7 +35,7 @@ struct HeadParams {
   CellDecode cell;
   FastDiv bs_div, px_per_tile, w_div, hw_div;
   int E, Cin, Cout, BS, H, W, GW, cells_per_image, relu_in, has_bn, tiles_nhwc, dense_nhwc;
-  int staged;  // tiles NHWC (or none), dense NCHW (or none), 16 | BS, even Cout*8: outputs leave through a staging tile
+  int staged;  // tiles NHWC (or none), dense none or (NCHW and 16 | BS): outputs leave through a staging tile
   int rows;  // shared-memory rows: Cin rounded up to a multiple of 64 (head_row permutes within 64)
   uint32_t exec_px, total_px;  // E*BS*BS, N*H*W
 };
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_mma_kernel(const HeadParams
   __half *w_s = reinterpret_cast<__half *>(head_smem);  // [NT*8][Cin + kHeadWPad] fp16, zero rows beyond Cout
   const int wrow = p.Cin + kHeadWPad;
   float4 *bn_s = reinterpret_cast<float4 *>(w_s + (size_t)NT * 8 * wrow);  // permuted, see head_prep8
-  __half *stage_s = reinterpret_cast<__half *>(bn_s + p.Cin);                 // [warps][16][kHeadMaxCout]
+  __half *stage_s = reinterpret_cast<__half *>(bn_s + p.Cin);                 // [warps][16][NT * 8]
   pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < NT * 8 * (p.Cin >> 3); i += kHeadThreads) {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_mma_kernel(const HeadParams
       // tiles NHWC + dense NCHW + 16 | BS: the 16 pixels are consecutive in a block row.  Through a per-warp
       // staging tile [16][Cout] so that the tile batch gets one contiguous run of 16*Cout halfs and every
       // channel plane of the dense output 32 contiguous bytes (scattered 2-byte stores cost ~10 us per frame)
-      __half *st = stage_s + (size_t)(threadIdx.x >> 5) * (16 * kHeadMaxCout);
+      __half *st = stage_s + (size_t)(threadIdx.x >> 5) * (16 * NT * 8);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_mma_kernel(const HeadParams
 template <int NT>
 static int launch_head_mma(const HeadParams &p, cudaStream_t stream) {
   const size_t smem = (size_t)NT * 8 * (p.Cin + kHeadWPad) * sizeof(__half) + (size_t)p.Cin * sizeof(float4) +
-                      (size_t)(kHeadThreads / 32) * 16 * kHeadMaxCout * sizeof(__half);
+                      (size_t)(kHeadThreads / 32) * 16 * NT * 8 * sizeof(__half);
   static cudaError_t attr = cudaFuncSetAttribute(head_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(head_mma_kernel): %s", cudaGetErrorString(attr));
   int64_t grid = ((int64_t)(p.exec_px >> 4) * 32 + kHeadThreads - 1) / kHeadThreads;
@@ -334,6 +334,10 @@ int head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const voi
   BC_REQUIRE(tiles_in && weight && (tiles_out || dense_out), BC_ERR_NULL, "bc_head_1x1: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0 && GH > 0 && GW > 0 && BS > 0, BC_ERR_SHAPE, "bc_head_1x1: empty problem");
   BC_REQUIRE(Cin % 8 == 0 && Cin <= 1024, BC_ERR_UNSUPPORTED, "bc_head_1x1: Cin=%d (multiple of 8, <= 1024)", Cin);
+  const bool mma_ok = Cin % 32 == 0 && ((int64_t)E * BS * BS) % 16 == 0;
+  // (A 128-output-channel instantiation for the BN -> ReLU -> 1x1 skip bottlenecks was tried and measured slower
+  //  than bc_ew_fused + bc_conv_igemm: 15.7 / 10.6 / 20.3 us against ~12 us per pair; every CTA re-stages 16-64 KB
+  //  of weights for 128 pixels.  Those convs stay on the tcgen05 kernel.)
   BC_REQUIRE(Cout >= 1 && Cout <= kHeadMaxCout, BC_ERR_UNSUPPORTED, "bc_head_1x1: Cout=%d (1..%d)", Cout, kHeadMaxCout);
   BC_REQUIRE((bn_mean == nullptr) == (bn_invstd == nullptr), BC_ERR_NULL, "bc_head_1x1: mean and invstd come together");
   BC_REQUIRE((((uintptr_t)tiles_in | (uintptr_t)weight) & 15) == 0, BC_ERR_ALIGN, "bc_head_1x1: tiles_in / weight must be 16-byte aligned");
@@ -356,16 +360,15 @@ int head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const voi
   BC_REQUIRE(exec_px < (1ll << 31) && total_px < (1ll << 31), BC_ERR_RANGE, "bc_head_1x1: problem too large");
   p.exec_px = (uint32_t)exec_px; p.total_px = (uint32_t)total_px;
   p.rows = (Cin + 63) / 64 * 64;
-  p.staged = (!tiles_out || p.tiles_nhwc) && (!dense_out || !p.dense_nhwc) && BS % 16 == 0 &&
+  p.staged = (!tiles_out || p.tiles_nhwc) && (!dense_out || (!p.dense_nhwc && BS % 16 == 0)) &&
              (((uintptr_t)tiles_out | (uintptr_t)dense_out) & 7) == 0;
   const size_t smem = (size_t)p.rows * kHeadWStride * sizeof(float) + (size_t)p.rows * sizeof(float4);
-  if (Cin % 32 == 0 && exec_px % 16 == 0) {  // tensor-core form
-    switch ((Cout + 7) / 8) {
-      case 1: return launch_head_mma<1>(p, stream);
-      case 2: return launch_head_mma<2>(p, stream);
-      case 3: return launch_head_mma<3>(p, stream);
-      default: return launch_head_mma<4>(p, stream);
-    }
+  if (mma_ok) {  // tensor-core form
+    const int nt = (Cout + 7) / 8;
+    if (nt <= 1) return launch_head_mma<1>(p, stream);
+    if (nt <= 2) return launch_head_mma<2>(p, stream);
+    if (nt <= 3) return launch_head_mma<3>(p, stream);
+    return launch_head_mma<4>(p, stream);
   }
   return Cout <= 20 ? launch_head<1, 5>(p, smem, stream) : launch_head<1, 8>(p, smem, stream);
 }
