@@ -214,6 +214,8 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
   if (tma_on() && tma_move_eligible(out, plane, E, C, W, BS, BS + 2 * pad, es, layout))
     return launch_tma_move(out, const_cast<void *>(plane), mapping_exec, E, N, C, H, W, BS, pad, BS + 2 * pad, es,
                            layout, false, (cudaStream_t)stream);
+  if (layout == BC_NCHW && pad > 0 && gather_halo_nchw_eligible(out, plane, BS, pad, W, es))
+    return launch_gather_halo_nchw(out, plane, mapping_exec, g, E, es, (cudaStream_t)stream);
   return launch_gather_simt(out, plane, mapping_exec, g, true, (cudaStream_t)stream);
 }
 

@@ -235,6 +235,125 @@ halo_tiles_kernel(char *__restrict__ out, const char *__restrict__ exec, const c
 }
 
 // ---------------------------------------------------------------------------------------------
+// gather-with-halo from an NCHW plane (the reference's layout; BASELINE config 2 as stated).
+// A padded NCHW tile row is (BS + 2p) elements = 68 bytes for BS 32, p 1, fp16: nothing in it is 16-byte
+// aligned, and the generic kernel above degenerates to one thread per 2-byte element with a full
+// div/mod chain each (24.9 us for config 2, 0.9 TB/s).  Here one WARP owns one (tile, channel): the
+// (BS+2p)^2 elements of that pair are CONTIGUOUS in the output.  Rows are read with 4-byte loads over the
+// aligned interior plus element loads for the 2p halo columns (zeros outside the frame), staged in shared
+// memory in output order, and written back as one contiguous run of 4-byte words.
+// ---------------------------------------------------------------------------------------------
+template <typename E>  // element type: uint16_t (fp16) or uint32_t (fp32)
+__global__ void __launch_bounds__(kThreads)
+gather_halo_nchw_kernel(E *__restrict__ out, const E *__restrict__ plane, const int32_t *__restrict__ mapping,
+                        const MoveGeo g, const uint32_t pairs, const int words_per_pair, const FastDiv wpr) {
+  extern __shared__ uint32_t halo_smem[];
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int BS = g.BS, P = g.pad, TE = BS + 2 * P;
+  E *st = reinterpret_cast<E *>(halo_smem + (size_t)warp * words_per_pair);
+  constexpr int kPerWord = 4 / (int)sizeof(E);  // elements per 4-byte word
+  const uint32_t wstride = gridDim.x * (kThreads / 32);
+  for (uint32_t pr = blockIdx.x * (kThreads / 32) + warp; pr < pairs; pr += wstride) {
+    uint32_t b, c, n, gh, gw;
+    g.chan.divmod(pr, b, c);
+    g.cell((uint32_t)__ldg(mapping + b), n, gh, gw);
+    const int y0 = (int)gh * BS - P, x0 = (int)gw * BS;
+    const E *src_c = plane + ((size_t)n * g.C + c) * g.H * g.W;
+    // interior: TE rows x (BS elements starting at x0 = wpr 4-byte words, aligned on the plane side); kU words
+    // per lane are in flight before the first one is staged (a row-by-row loop would serialise TE round trips)
+    constexpr int kU = 17;
+    const int total_w = TE * wpr.d;
+    for (int base = 0; base < total_w; base += 32 * kU) {
+      uint32_t v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = base + u * 32 + lane;
+        uint32_t r, j;
+        wpr.divmod((uint32_t)min(i, total_w - 1), r, j);
+        const int y = y0 + (int)r;
+        v[u] = (i < total_w && y >= 0 && y < g.H)
+                   ? __ldg(reinterpret_cast<const uint32_t *>(src_c + (size_t)y * g.W + x0) + j) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = base + u * 32 + lane;
+        if (i >= total_w) continue;
+        uint32_t r, j;
+        wpr.divmod((uint32_t)i, r, j);
+        E *row = st + r * TE;
+        if (kPerWord == 2) {
+          row[P + 2 * j] = (E)(v[u] & 0xffffu);
+          row[P + 2 * j + 1] = (E)(v[u] >> 16);
+        } else {
+          row[P + j] = (E)v[u];
+        }
+      }
+    }
+    // halo columns: p on either side of every row, zeros outside the frame
+    constexpr int kH = 4;
+    const int total_h = TE * 2 * P;
+    for (int base = 0; base < total_h; base += 32 * kH) {
+      E v[kH];
+#pragma unroll
+      for (int u = 0; u < kH; ++u) {
+        const int i = base + u * 32 + lane;
+        const int ii = min(i, total_h - 1);
+        const int r = ii / (2 * P), k = ii - r * 2 * P;
+        const int e = k < P ? k : BS + k;
+        const int y = y0 + r, x = x0 - P + e;
+        v[u] = (i < total_h && y >= 0 && y < g.H && x >= 0 && x < g.W) ? __ldg(src_c + (size_t)y * g.W + x) : (E)0;
+      }
+#pragma unroll
+      for (int u = 0; u < kH; ++u) {
+        const int i = base + u * 32 + lane;
+        if (i >= total_h) continue;
+        const int r = i / (2 * P), k = i - r * 2 * P;
+        st[r * TE + (k < P ? k : BS + k)] = v[u];
+      }
+    }
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)pr * TE * TE);
+    const uint32_t *sst = reinterpret_cast<const uint32_t *>(st);
+    for (int w = lane; w < words_per_pair; w += 32) dst[w] = sst[w];
+    __syncwarp();
+  }
+}
+
+// eligible: 4-byte words work on both sides and the staging tile is small
+bool gather_halo_nchw_eligible(const void *out, const void *plane, int BS, int pad, int W, int es) {
+  const int TE = BS + 2 * pad;
+  const long long pair_bytes = (long long)TE * TE * es;
+  return (BS * es) % 4 == 0 && (W * es) % 4 == 0 && pair_bytes % 4 == 0 && pair_bytes <= 12 * 1024 && 2 * pad <= 32 &&
+         (((uintptr_t)out | (uintptr_t)plane) & 3) == 0;
+}
+
+int launch_gather_halo_nchw(void *out, const void *plane, const int32_t *mapping, const MoveGeo &g, int E, int es,
+                            cudaStream_t s) {
+  const int TE = g.BS + 2 * g.pad;
+  const int words = TE * TE * es / 4;
+  const long long pairs = (long long)E * g.C;
+  BC_REQUIRE(pairs < (1ll << 31), BC_ERR_RANGE, "bc_gather_halo: problem too large");
+  const size_t smem = (size_t)(kThreads / 32) * words * 4;
+  long long grid = (pairs + kThreads / 32 - 1) / (kThreads / 32);
+  const long long cap = (long long)kNumSMs * 8;
+  if (grid > cap) grid = cap;
+  if (es == 2) {
+    static cudaError_t attr = cudaFuncSetAttribute(gather_halo_nchw_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(gather_halo_nchw_kernel): %s", cudaGetErrorString(attr));
+    launch_kernel(gather_halo_nchw_kernel<uint16_t>, dim3((unsigned)grid), dim3(kThreads), smem, s, 1, (uint16_t *)out,
+                  (const uint16_t *)plane, mapping, g, (uint32_t)pairs, words, FastDiv((uint32_t)(g.BS * 2 / 4)));
+  } else {
+    static cudaError_t attr = cudaFuncSetAttribute(gather_halo_nchw_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(gather_halo_nchw_kernel): %s", cudaGetErrorString(attr));
+    launch_kernel(gather_halo_nchw_kernel<uint32_t>, dim3((unsigned)grid), dim3(kThreads), smem, s, 1, (uint32_t *)out,
+                  (const uint32_t *)plane, mapping, g, (uint32_t)pairs, words, FastDiv((uint32_t)g.BS));
+  }
+  return check_launch("bc_gather_halo");
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int make_geo(MoveGeo &g, int ntiles, int N, int C, int H, int W, int BS, int tile_edge, int pad, int es,

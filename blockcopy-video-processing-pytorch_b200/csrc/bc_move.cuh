@@ -26,6 +26,9 @@ int make_geo(MoveGeo &g, int ntiles, int N, int C, int H, int W, int BS, int til
 
 int launch_gather_simt(void *tiles, const void *plane, const int32_t *mapping, const MoveGeo &g, bool halo,
                        cudaStream_t s);
+bool gather_halo_nchw_eligible(const void *out, const void *plane, int BS, int pad, int W, int es);
+int launch_gather_halo_nchw(void *out, const void *plane, const int32_t *mapping, const MoveGeo &g, int E, int es,
+                            cudaStream_t s);
 int launch_scatter_simt(const void *tiles, void *plane, const int32_t *mapping, const MoveGeo &g, cudaStream_t s);
 int launch_copy_blocks_simt(void *out, const void *prev, const void *tiles, const int32_t *grid_idx,
                             const MoveGeo &g, cudaStream_t s);
