@@ -29,7 +29,9 @@ for r in frame:
     a = agg.setdefault(short(r["Kernel Name"]), [0.0, 0])
     a[0] += us(r)
     a[1] += 1
-ours = sum(v[0] for n, v in agg.items() if n.startswith("bc::"))
+OURS = ("bc::", "conv_igemm", "conv_stem", "ew_fused", "head_", "tma_move", "maxpool_halo", "spp_", "stem_pack", "compact_mask",
+        "scatter_kernel", "gather_kernel", "copy_blocks", "policy_features", "info_gain")
+ours = sum(v[0] for n, v in agg.items() if any(n.startswith(o) or ("bc::" + o) in n for o in OURS))
 print(f"frame total {tot:.0f} us over {len(frame)} kernels (ncu, serialised, cold cache); "
       f"this repo's kernels (`bc::*`) = {100 * ours / tot:.0f} % of it\n")
 print("| share | us/frame | launches | kernel |\n|---:|---:|---:|---|")
