@@ -184,8 +184,49 @@ def time_reference(H=1024, W=2048, clips=3, T=30, fraction=0.3):
     print("reference timing:", json.dumps(res))
 
 
+def time_reference_sweep(out_path=None):
+    """BASELINE config 5: the reference BlockCopy path (same shim, same settings as time_reference) over the
+    active-fraction sweep at 1024x2048 and 2048x4096; one warm-up clip + five timed 30-frame clips per point
+    (median clip reported: the path is host-bound and noisy)."""
+    torch.backends.cudnn.benchmark = True
+    rows = []
+    for H, W in ((1024, 2048), (2048, 4096)):
+        clip = synthetic_clip(30, H, W, seed=0, dtype=torch.float16, device=dev)
+        for fraction in (0.05, 0.10, 0.20, 0.30, 0.50, 0.75, 1.00):
+            model = build_reference_swiftnet(0, 0.8, 128)
+            model.policy = PolicyFixedFraction(128, fraction=fraction, quantize=8, seed=0)
+
+            def run_clip():
+                model.reset_temporal()
+                with torch.no_grad():
+                    for f in clip:
+                        model(f)
+
+            run_clip()  # warm-up: NVRTC compiles, cudnn.benchmark picks algorithms
+            torch.cuda.synchronize()
+            per_clip = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                run_clip()
+                torch.cuda.synchronize()
+                per_clip.append(30 / (time.perf_counter() - t0))
+            per_clip.sort()
+            G = (H // 128) * (W // 128)
+            rows.append(dict(H=H, W=W, fraction=fraction, num_exec=model.policy.num_exec_for(G), total=G,
+                             reference_blockcopy_fps=per_clip[2], best_clip_fps=per_clip[-1], worst_clip_fps=per_clip[0]))
+            print("reference sweep:", json.dumps(rows[-1]), flush=True)
+            del model
+            torch.cuda.empty_cache()
+    out_path = out_path or os.path.join(OUT, "reference_sweep.json")
+    with open(out_path, "w") as f:
+        json.dump(dict(gpu=torch.cuda.get_device_name(0), rows=rows,
+                       note="reference package unmodified; cupy -> NVRTC shim; timings level 0"), f, indent=1)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["kernels", "clip", "time"]
+    if "sweep" in what:
+        time_reference_sweep(os.environ.get("BC_SWEEP_OUT"))
     if "kernels" in what:
         kernel_goldens()
     if "clip" in what:
