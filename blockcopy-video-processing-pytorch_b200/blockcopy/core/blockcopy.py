@@ -48,6 +48,9 @@ class BlockCopyModel(nn.Module):
         net = getattr(self.policy, "net", None)
         if self._graphs is not None and net is not None and hasattr(net, "use_cuda_graphs"):
             net.use_cuda_graphs = True  # policy trunk forward / backward as graph replays too
+        if net is not None and hasattr(net, "channels_last") and settings.get("block_channels_last", True):
+            net.channels_last = True  # fp32 policy trunk on cuDNN's NHWC kernels: forward 0.75 -> 0.57 ms, backward 1.6 -> 0.96 ms
+            net.to(memory_format=torch.channels_last)
 
     def load_state_dict(self, state_dict, strict: bool = True):
         """Checkpoints are base-model checkpoints (reference core/blockcopy.py:30-32)."""

@@ -35,6 +35,9 @@ class PolicyNet(nn.Module):
         )
         # block_cuda_graphs: trunk forward and backward replayed as CUDA graphs (see _trunk_forward)
         self.use_cuda_graphs = False
+        # NHWC activations / weights for the fp32 trunk (same math; cuDNN's NHWC TF32 kernels): set by
+        # BlockCopyModel together with block_channels_last
+        self.channels_last = False
         self.__dict__["_graphed"] = None  # (input shape, graphed callable); not a submodule: state_dict unchanged
 
     @staticmethod
@@ -92,6 +95,8 @@ class PolicyNet(nn.Module):
         (``torch.cuda.make_graphed_callables``: same kernels, same order, autograd-aware, so
         ``loss.backward()`` in PolicyTrainRL.optim works unchanged).  Capture runs the trunk a few times:
         the batch-norm running statistics are restored afterwards, so capturing is free of side effects."""
+        if self.channels_last and x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
         if not (self.use_cuda_graphs and x.is_cuda and self.training and torch.is_grad_enabled()):
             return self.layers(self.backbone(x))
         g = self.__dict__["_graphed"]
