@@ -319,30 +319,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         }
       }
     } else {
-      // ---- split-K, phase 1: park this CTA's partial accumulator in its own shared memory ----------
-      // (the pipeline stages are free: acc_bar says every MMA, hence every TMA load, has completed)
-      float *part = reinterpret_cast<float *>(smem);
-      const int m = q * 32 + lane;
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4 *>(part + (size_t)m * kPartStride<N_TILE> + c0 + j) =
-              make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-      }
+      // ---- split-K, phase 1 (the pipeline stages are free: acc_bar says every MMA, hence every TMA load, has
+      //      completed)
       if (p.work) {
-        // this warp's 32 parked rows -> global scratch, whole rows per access
-        __syncwarp();
-        constexpr int kLPR = N_TILE / 4, kRows = 32 / kLPR;  // lanes per row (float4 each), rows per access
+        // through the L2 scratch: half of the tile's columns at a time via per-warp staging rows (35 KB in all,
+        // so the 2-stage variants can split too), whole rows per global access
+        constexpr int kCP = N_TILE / 2;                      // columns per pass
+        constexpr int kRowB = kCP * 4 + 16;
+        constexpr int kLPR = kCP / 4, kRowsPI = 32 / kLPR;   // lanes per row (float4 each), rows per access
+        uint8_t *stage = smem + (size_t)q * 32 * kRowB;
         const unsigned tile_lin = blockIdx.x + gridDim.x * blockIdx.y;
         float *ws = p.work + ((size_t)(tile_lin * p.splits + blockIdx.z) * kTileM + q * 32) * N_TILE;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCP; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * kCP + c0), acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4 *>(stage + (size_t)lane * kRowB + (c0 + j) * 4) =
+                  make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          }
+          __syncwarp();
 #pragma unroll 4
-        for (int r = lane / kLPR; r < 32; r += kRows) {
-          const float4 v = *reinterpret_cast<const float4 *>(part + (size_t)(q * 32 + r) * kPartStride<N_TILE> + (lane % kLPR) * 4);
-          *reinterpret_cast<float4 *>(ws + (size_t)r * N_TILE + (lane % kLPR) * 4) = v;
+          for (int r = lane / kLPR; r < 32; r += kRowsPI) {
+            const float4 v = *reinterpret_cast<const float4 *>(stage + (size_t)r * kRowB + (lane % kLPR) * 16);
+            *reinterpret_cast<float4 *>(ws + (size_t)r * N_TILE + h * kCP + (lane % kLPR) * 4) = v;
+          }
+          __syncwarp();
+        }
+      } else {
+        // no scratch: park the partial in this CTA's own shared memory for the DSMEM reduction
+        float *part = reinterpret_cast<float *>(smem);
+        const int m = q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4 *>(part + (size_t)m * kPartStride<N_TILE> + c0 + j) =
+                make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
       }
     }
@@ -429,7 +449,7 @@ EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
 
 template <int N_TILE, int STAGES>
 static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvParams &p, int tiles, int ntiles_n,
-                       bool allow_split, cudaStream_t s) {
+                       bool allow_split, cudaStream_t s, int force_splits = 0) {
   // split-K over a cluster when the output tiles alone cannot fill the GPU (deep layers: 4..8-px blocks)
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
   const int ctas = tiles * ntiles_n;
@@ -439,7 +459,10 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
   // grid covers less than a third of the GPU; keep the split grid within ~one wave of 2 CTAs per SM.
   static const int max_ctas = getenv("BC_SPLIT_MAX_CTAS") ? atoi(getenv("BC_SPLIT_MAX_CTAS")) : 48;   // experiments
   static const int target = getenv("BC_SPLIT_TARGET") ? atoi(getenv("BC_SPLIT_TARGET")) : 240;
-  if (allow_split && ctas <= max_ctas && total_k >= 8) {
+  if (force_splits > 1) {
+    p.splits = force_splits;
+    p.ksteps_per_split = (total_k + force_splits - 1) / force_splits;
+  } else if (allow_split && ctas <= max_ctas && total_k >= 8) {
     const int want = target / ctas;
     int splits = 8;                              // portable cluster size limit
     while (splits > 1 && (splits > want || splits * 2 > total_k)) splits >>= 1;
@@ -454,8 +477,10 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
     }
   }
   constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 1024;
-  if ((size_t)kTileM * kPartStride<N_TILE> * sizeof(float) > (size_t)STAGES * (kABytes + N_TILE * 128)) {
-    p.splits = 1;  // the parked accumulator of the split-K path would not fit in this variant's pipeline stages
+  if (p.splits > 1 && (long long)ctas * p.splits * kTileM * N_TILE * (long long)sizeof(float) > p.work_bytes) p.work = nullptr;
+  if (p.work == nullptr &&
+      (size_t)kTileM * kPartStride<N_TILE> * sizeof(float) > (size_t)STAGES * (kABytes + N_TILE * 128)) {
+    p.splits = 1;  // DSMEM path: the parked accumulator would not fit in this variant's pipeline stages
     p.ksteps_per_split = total_k;
   }
   if (p.splits == 1 || (long long)ctas * p.splits * kTileM * N_TILE * (long long)sizeof(float) > p.work_bytes)
@@ -614,6 +639,9 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   }
   if (n_tile == 128) {
     const int ctas = tiles * (Cout / 128);
+    // (Tried for the 4-px layers with 8 streams batched -- 160 tiles x 72 k-steps: two k-halves per tile on the
+    //  2-stage variant.  The split variant's 100 registers allow only 2 CTAs per SM, 320 CTAs need a second wave:
+    //  72 us against 60 us unsplit.  Not used.)
     if (ctas > 2 * kNumSMs) return launch_conv<128, 2>(a_map, b_map, p, tiles, Cout / 128, split, stream);
     if (ctas >= kNumSMs || (split && ctas <= 48))
       return launch_conv<128, 3>(a_map, b_map, p, tiles, Cout / 128, split, stream);

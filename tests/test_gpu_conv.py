@@ -332,3 +332,4 @@ def test_head_1x1_matches_op_by_op(bn, relu, dense_cl, with_prev):
     want = prev.cpu().contiguous().clone()
     O.combine_(tiles.cpu().contiguous(), want, me)
     assert torch.equal(dense.cpu().contiguous(), want)
+
