@@ -241,6 +241,9 @@ struct PoolParams {
   uint32_t total;
 };
 
+// K > 0: window size known at compile time: all K*K taps are loaded before the first max (a runtime-k loop keeps
+// one load in flight at a time: nine serialised L2 round trips per output).  K == 0: any window, runtime loop.
+template <int K>
 __global__ void __launch_bounds__(256) maxpool_halo_kernel(const PoolParams p) {
   pdl_trigger();
   pdl_wait();
@@ -253,19 +256,39 @@ __global__ void __launch_bounds__(256) maxpool_halo_kernel(const PoolParams p) {
     p.cell((uint32_t)__ldg(p.mapping + b), n, gh, gw);
     const int c0 = (int)ch * 8;
     const int y0 = (int)(gh * p.BS_in + oy * p.stride) - p.pad, x0 = (int)(gw * p.BS_in + ox * p.stride) - p.pad;
+    const __half *base = p.plane + (size_t)n * p.H * p.W * p.C + c0;
     __half2 m[4];
-    bool first = true;
-    for (int dy = 0; dy < p.k; ++dy)
-      for (int dx = 0; dx < p.k; ++dx) {
-        const int yy = y0 + dy, xx = x0 + dx;
-        uint4 u = make_uint4(0, 0, 0, 0);  // zero padding outside the frame
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-          u = __ldg(reinterpret_cast<const uint4 *>(p.plane + (((size_t)n * p.H + yy) * p.W + xx) * p.C + c0));
-        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+    if (K > 0) {
+      uint4 u[K > 0 ? K * K : 1];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) m[t] = first ? h[t] : __hmax2_nan(m[t], h[t]);
-        first = false;
-      }
+      for (int dy = 0; dy < K; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const int yy = y0 + dy, xx = x0 + dx;
+          u[dy * K + dx] = make_uint4(0, 0, 0, 0);  // zero padding outside the frame
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+            u[dy * K + dx] = __ldg(reinterpret_cast<const uint4 *>(base + ((size_t)yy * p.W + xx) * p.C));
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) m[t] = reinterpret_cast<const __half2 *>(&u[0])[t];
+#pragma unroll
+      for (int j = 1; j < K * K; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) m[t] = __hmax2_nan(m[t], reinterpret_cast<const __half2 *>(&u[j])[t]);
+    } else {
+      bool first = true;
+      for (int dy = 0; dy < p.k; ++dy)
+        for (int dx = 0; dx < p.k; ++dx) {
+          const int yy = y0 + dy, xx = x0 + dx;
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+            u = __ldg(reinterpret_cast<const uint4 *>(base + ((size_t)yy * p.W + xx) * p.C));
+          const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) m[t] = first ? h[t] : __hmax2_nan(m[t], h[t]);
+          first = false;
+        }
+    }
     const uint4 o = *reinterpret_cast<uint4 *>(m);
     *reinterpret_cast<uint4 *>(p.out + (size_t)pix * p.C + c0) = o;
     if (p.plane_out) {
@@ -300,7 +323,12 @@ int maxpool_halo(void *out, void *plane_out, const void *plane, const int32_t *m
   int64_t grid = (total + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (grid > cap) grid = cap;
-  launch_kernel(maxpool_halo_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  if (k == 3)
+    launch_kernel(maxpool_halo_kernel<3>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  else if (k == 2)
+    launch_kernel(maxpool_halo_kernel<2>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  else
+    launch_kernel(maxpool_halo_kernel<0>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
   return check_launch("bc_maxpool_halo");
 }
 
