@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--microbench", action="store_true", help="only the block-kernel microbenchmarks")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--shared-policy", action="store_true",
+                    help="rl_semseg only: one policy for all ranks (all-reduce of the policy gradients over NCCL)")
     ap.add_argument("--skip-batched", action="store_true", help="skip the extra batch-8 throughput measurement")
     return ap.parse_args()
 
@@ -147,6 +149,8 @@ def build_model(args, device):
                                 block_target=args.fraction, block_train_interval=3)
     if not args.no_graphs:
         settings["block_cuda_graphs"] = True
+    if getattr(args, "shared_policy", False):
+        settings["block_policy_shared"] = True
     model = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), settings).eval().to(device).half()
     if args.policy == "fixed":
         model.policy = PolicyFixedFraction(128, fraction=args.fraction, quantize=8, seed=0)

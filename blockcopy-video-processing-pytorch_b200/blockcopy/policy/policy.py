@@ -48,7 +48,8 @@ def build_policy_from_settings(settings: dict):
             raise AttributeError(f'Policy with name "{name}" not defined!')
         return PolicyTrainRL(block_target=settings["block_target"], cost_momentum=settings["block_cost_momentum"],
                              optimizer=optimizer, complexity_weight=settings["block_complexity_weight"],
-                             quantize_number_exec=quantize, policy_net=net, information_gain=ig, **common)
+                             quantize_number_exec=quantize, policy_net=net, information_gain=ig,
+                             shared_across_ranks=bool(settings.get("block_policy_shared", False)), **common)
     raise NotImplementedError(f"Policy {name} not implemented")
 
 
@@ -184,8 +185,14 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
     def __init__(self, block_size: int, block_target: float, optimizer: torch.optim.Optimizer,
                  complexity_weight: float, policy_net: PolicyNet, information_gain: InformationGain,
                  cost_momentum: float = 0.9, at_least_one: bool = False, quantize_number_exec: float = 0,
-                 verbose: bool = False):
+                 verbose: bool = False, shared_across_ranks: bool = False):
         super().__init__(block_size, verbose, quantize_number_exec)
+        # One policy shared by the streams of all ranks (settings key block_policy_shared, not in the reference):
+        # the only collective of the whole path -- a sum of the flat policy-gradient buffer (2.4 MB fp32) every
+        # block_train_interval frames; with equal initial weights (broadcast from rank 0) and equal gradients the
+        # replicas stay identical by construction.  Every rank must train on the same frames.
+        self.shared_across_ranks = shared_across_ranks
+        self._shared_synced = False
         assert 0 <= block_target <= 1
         self.block_target = block_target
         self.information_gain = information_gain
@@ -204,6 +211,8 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
             grid._bc_num_exec = grid.numel()
             policy_meta["grid"] = grid
         else:
+            if self.shared_across_ranks and not self._shared_synced:
+                self.sync_shared_policy()
             with torch.enable_grad():
                 with timings.env("policy/net", 3):
                     assert self.net.training
@@ -225,6 +234,41 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     grid._bc_num_exec = hint
                 policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
+
+    def _shared_world(self):
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return None
+        return dist
+
+    def sync_shared_policy(self):
+        """Shared policy: every rank starts from rank 0's weights and buffers (called lazily before the first
+        forward; call it explicitly after loading a checkpoint on rank 0)."""
+        dist = self._shared_world()
+        self._shared_synced = True
+        if dist is None:
+            return
+        with torch.no_grad():
+            for t in list(self.net.parameters()) + list(self.net.buffers()):
+                dist.broadcast(t.data, src=0)
+
+    def _allreduce_gradients(self):
+        """Average of the policy gradients over all ranks, one flat buffer, in place."""
+        dist = self._shared_world()
+        if dist is None:
+            return
+        grads = [q.grad for q in self.net.parameters() if q.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
 
     def _get_information_gain(self, policy_meta: dict) -> torch.Tensor:
         with timings.env("policy/information_gain", 3):
@@ -260,6 +304,9 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                 assert not torch.isnan(loss_policy)
                 with timings.env("policy/optimizer_backward", 3):
                     loss_policy.backward()
+                if self.shared_across_ranks:
+                    with timings.env("policy/allreduce", 3):
+                        self._allreduce_gradients()
                 with timings.env("policy/optimizer_step", 3):
                     self.optimizer.step()
                     self.optimizer.zero_grad(set_to_none=True)
