@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--microbench", action="store_true", help="only the block-kernel microbenchmarks")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--concurrent-streams", action="store_true",
+                    help="with --streams-per-gpu > 1: one CUDA stream per video stream (frames overlap on the GPU)")
     ap.add_argument("--shared-policy", action="store_true",
                     help="rl_semseg only: one policy for all ranks (all-reduce of the policy gradients over NCCL)")
     ap.add_argument("--skip-batched", action="store_true", help="skip the extra batch-8 throughput measurement")
@@ -169,14 +171,32 @@ def _advance(models, t, clip_len):
     return k
 
 
-def run_frames(models, clips, start, count, clip_len):
-    """Device-resident inputs: advance every stream by `count` frames from global frame `start`."""
+_SIDE_STREAMS = {}
+
+
+def run_frames(models, clips, start, count, clip_len, concurrent=False):
+    """Device-resident inputs: advance every stream by `count` frames from global frame `start`.
+    concurrent: every video stream issues on its own CUDA stream (forked from / joined to the current one), so
+    frames of different video streams overlap on the GPU."""
     out = None
+    main = torch.cuda.current_stream()
+    side = None
+    if concurrent and len(models) > 1:
+        side = [_SIDE_STREAMS.setdefault((main.device, s), torch.cuda.Stream(device=main.device)) for s in range(len(models))]
+        for st in side:
+            st.wait_stream(main)
     with torch.no_grad():
         for t in range(start, start + count):
             k = _advance(models, t, clip_len)
             for s, model in enumerate(models):
-                out = model(clips[s][k])
+                if side is None:
+                    out = model(clips[s][k])
+                else:
+                    with torch.cuda.stream(side[s]):
+                        out = model(clips[s][k])
+    if side is not None:
+        for st in side:
+            main.wait_stream(st)
     return out
 
 
@@ -249,9 +269,10 @@ def bench_ours(args):
 
     # ---- setup (not steps): two full clips so that every CUDA graph (one per block count) is captured,
     #      cuDNN has picked its algorithms and all planes exist; then the W warm-up steps
-    run_frames(models, clips, 0, 2 * L, L)
+    conc = bool(args.concurrent_streams)
+    run_frames(models, clips, 0, 2 * L, L, conc)
     # ---- device-resident throughput ("value") --------------------------------------------------------
-    run_frames(models, clips, 0, args.warmup, L)
+    run_frames(models, clips, 0, args.warmup, L, conc)
     torch.cuda.synchronize()
     barrier(world)
     n0 = _C.launch_count()
@@ -259,7 +280,7 @@ def bench_ours(args):
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
         ev0.record()
-        run_frames(models, clips, args.warmup, args.steps, L)
+        run_frames(models, clips, args.warmup, args.steps, L, conc)
         ev1.record()
         torch.cuda.synchronize()
     launches = _C.launch_count() - n0

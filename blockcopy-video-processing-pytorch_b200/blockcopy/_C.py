@@ -259,16 +259,39 @@ def lazy_supported(x: torch.Tensor) -> bool:
 
 _SPLITK_WS = {}
 SPLITK_WS_BYTES = 32 << 20
+_SPLITK_OWNER = None  # tensor handed over by splitk_workspace_scope, or None
 
 
 def _splitk_workspace(device: torch.device, stream: int) -> torch.Tensor:
-    """Scratch for the split-K partial sums of bc_conv_igemm, one per (device, stream): launches on one
-    stream are ordered, so they may share it; concurrent streams must not."""
+    """Scratch for the split-K partial sums of bc_conv_igemm.  Launches on one stream are ordered, so they may
+    share one scratch per (device, stream); concurrent streams must not.  A captured CUDA graph bakes the
+    scratch address in and may later be replayed on ANY stream, next to other graphs captured on the same
+    capture stream: graph owners therefore bring their own scratch (splitk_workspace_scope)."""
+    if _SPLITK_OWNER is not None and _SPLITK_OWNER.device == device:
+        return _SPLITK_OWNER
     key = (device.index, stream)
     ws = _SPLITK_WS.get(key)
     if ws is None:
         ws = _SPLITK_WS[key] = torch.empty(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
     return ws
+
+
+class splitk_workspace_scope:
+    """`with splitk_workspace_scope(ws):` -- every bc_conv_igemm issued inside uses the uint8 tensor `ws` as its
+    split-K scratch instead of the per-stream one (BlockCopyModel in CUDA-graph mode: one scratch per model)."""
+
+    def __init__(self, ws: Optional[torch.Tensor]):
+        self.ws, self.prev = ws, None
+
+    def __enter__(self):
+        global _SPLITK_OWNER
+        self.prev, _SPLITK_OWNER = _SPLITK_OWNER, self.ws
+        return self.ws
+
+    def __exit__(self, *exc):
+        global _SPLITK_OWNER
+        _SPLITK_OWNER = self.prev
+        return False
 
 
 def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],

@@ -109,13 +109,21 @@ class BlockCopyModel(nn.Module):
     def _block_frame_inplace(self, inputs, grid):
         """One block-sparse frame with every combine IN PLACE into persistent planes (what a graph
         can replay): returns (frame_state plane, output plane), both persistent tensors."""
-        x = to_tensorwrapper(inputs)
-        self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
-        self.block_temporal_features.track_transfer_idx = False
-        blocks = x.to_blocks(grid)
-        frame_state = blocks.combine_().to_tensor()
-        out = self.base_model(blocks)
-        return frame_state, out.combine_().to_tensor()
+        from .. import _C
+
+        gs = self._graphs
+        if gs.splitk_ws is None or gs.splitk_ws.device != inputs.device:
+            # graph replays of different models may overlap on different CUDA streams: the split-K scratch whose
+            # address the graph bakes in belongs to this model, not to the (shared) capture stream
+            gs.splitk_ws = torch.empty(_C.SPLITK_WS_BYTES, dtype=torch.uint8, device=inputs.device)
+        with _C.splitk_workspace_scope(gs.splitk_ws):
+            x = to_tensorwrapper(inputs)
+            self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
+            self.block_temporal_features.track_transfer_idx = False
+            blocks = x.to_blocks(grid)
+            frame_state = blocks.combine_().to_tensor()
+            out = self.base_model(blocks)
+            return frame_state, out.combine_().to_tensor()
 
     def _forward_graphed(self, inputs, grid, num_exec):
         from .. import _C
@@ -170,6 +178,7 @@ class _GraphState:
         self.pool = None
         self.out_bufs = None
         self.flip = 0
+        self.splitk_ws = None  # this model's split-K scratch (see _block_frame_inplace)
 
 
 def _try_fused_dense(module, x):

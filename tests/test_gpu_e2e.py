@@ -175,3 +175,54 @@ def test_cuda_graph_mode_is_bit_identical_to_eager():
     for t, ((a, fa), (b, fb)) in enumerate(zip(eager, graphed)):
         assert torch.equal(a, b), f"frame {t}: outputs differ between eager and graph mode"
         assert torch.equal(fa, fb), f"frame {t}: frame_state differs"
+
+
+def test_concurrent_cuda_streams_equal_sequential():
+    """Independent video streams on their own CUDA streams (bench.py --concurrent-streams): all state is per
+    wrapper object (planes, graphs, and in graph mode the split-K scratch whose address the graphs bake in) or
+    per CUDA stream (eager split-K scratch), so the outputs must equal the one-after-the-other run bit for bit."""
+    import blockcopy
+    from consumers.clips import PolicyFixedFraction, synthetic_clip
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    BS, H, W, S, T = 64, 256, 512, 3, 5
+    clips = [synthetic_clip(T, H, W, seed=10 + s, device="cuda") for s in range(S)]
+
+    def build():
+        models = []
+        for s in range(S):
+            m = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), _settings(block_policy="all", block_size=BS,
+                                                                              block_cuda_graphs=True)).eval().cuda().half()
+            m.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=2, seed=s)
+            models.append(m)
+        return models
+
+    def run(models, streams):
+        outs = [[] for _ in range(S)]
+        with torch.no_grad():
+            for rep in range(3):  # clip 0: eager, clip 1: capture, clip 2: replay
+                for s, m in enumerate(models):
+                    m.reset_temporal()
+                    m.policy.reseed(s)
+                for t in range(T):
+                    for s, m in enumerate(models):
+                        if streams is None:
+                            o = m(clips[s][t])
+                        else:
+                            with torch.cuda.stream(streams[s]):
+                                o = m(clips[s][t])
+                        if rep == 2:
+                            outs[s].append(o.clone() if streams is None else o)
+        torch.cuda.synchronize()
+        return [[o.clone() for o in per] for per in outs] if streams is not None else outs
+
+    seq = run(build(), None)
+    models = build()  # parameters are uploaded / converted on the current stream ...
+    side = [torch.cuda.Stream() for _ in range(S)]
+    for st in side:
+        st.wait_stream(torch.cuda.current_stream())  # ... which the side streams wait for
+    # outputs of concurrent replays live in ping-pong buffers: compare the last two frames per stream
+    conc = run(models, side)
+    for s in range(S):
+        for k in (-1, -2):
+            assert torch.equal(seq[s][k], conc[s][k]), (s, k)
