@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from ..utils.profiler import timings
-from .tensorwrapper import TensorWrapper, to_tensorwrapper
+from .tensorwrapper import TensorWrapper, side_stream_scope, to_tensorwrapper
 
 
 class BlockCopyModel(nn.Module):
@@ -116,7 +116,9 @@ class BlockCopyModel(nn.Module):
             # graph replays of different models may overlap on different CUDA streams: the split-K scratch whose
             # address the graph bakes in belongs to this model, not to the (shared) capture stream
             gs.splitk_ws = torch.empty(_C.SPLITK_WS_BYTES, dtype=torch.uint8, device=inputs.device)
-        with _C.splitk_workspace_scope(gs.splitk_ws):
+            gs.splitk_ws_side = torch.empty(_C.SPLITK_WS_BYTES // 2, dtype=torch.uint8, device=inputs.device)
+        # side branches of the model (skip bottlenecks) go to a second stream: parallel nodes of the captured graph
+        with _C.splitk_workspace_scope(gs.splitk_ws), side_stream_scope(gs.splitk_ws_side):
             x = to_tensorwrapper(inputs)
             self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
             self.block_temporal_features.track_transfer_idx = False
@@ -179,6 +181,7 @@ class _GraphState:
         self.out_bufs = None
         self.flip = 0
         self.splitk_ws = None  # this model's split-K scratch (see _block_frame_inplace)
+        self.splitk_ws_side = None  # ... and the one of convs issued on the side stream
 
 
 def _try_fused_dense(module, x):

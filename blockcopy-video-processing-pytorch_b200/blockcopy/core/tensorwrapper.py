@@ -33,6 +33,9 @@ FUSED_CONV = os.environ.get("BLOCKCOPY_FUSED_CONV", "1") != "0"  # route eligibl
 # defer convs / elementwise ops on blocks and fuse them into epilogues (see _Pending); "0" = op-by-op execution
 LAZY_FUSION = os.environ.get("BLOCKCOPY_LAZY", "1") != "0"
 FUSED_HEAD = os.environ.get("BLOCKCOPY_FUSED_HEAD", "1") != "0"  # few-channel 1x1 output conv + combine as one kernel (bc_head_1x1)
+# side branches (a pre-activation BN+ReLU on materialised tiles feeding a 1x1 conv: the skip bottlenecks of a
+# ladder decoder) are issued on a second CUDA stream inside a side_stream_scope, see _SideState
+SIDE_STREAM = os.environ.get("BLOCKCOPY_SIDE_STREAM", "1") != "0"
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
 
@@ -114,11 +117,14 @@ class BlockFeatures:
         # persistent planes; slot = call order within a frame
         self._planes: List[torch.Tensor] = prev._planes if prev is not None else []
         self._full: List[torch.Tensor] = prev._full if prev is not None else []
+        # persistent tile-batch buffers of side-stream ops, sized for ALL blocks; slot = call order
+        self._side_bufs: List[torch.Tensor] = prev._side_bufs if prev is not None else []
         self._plane_cursor = 0
         self._full_cursor = 0
+        self._side_cursor = 0
         self._prev_grid_idx = prev._grid_idx if (prev is not None and self.has_history) else None
         if prev is not None:
-            prev._planes, prev._full = [], []  # ownership moved
+            prev._planes, prev._full, prev._side_bufs = [], [], []  # ownership moved
 
     # ------------------------------------------------------------------ grid
     def _process_grid(self, grid: torch.Tensor, meta_prev: Optional["BlockFeatures"] = None) -> None:
@@ -171,6 +177,24 @@ class BlockFeatures:
         self._planes.append(plane)
         return plane
 
+    def _next_side_buf(self, shape, dtype, device) -> torch.Tensor:
+        """(E,C,BS,BS) channels_last view of the next side-stream buffer in call order.  These outputs must not
+        come from the caching allocator: a block recycled there may still be read by kernels the main stream
+        has queued, which a side-stream kernel does not wait for."""
+        i = self._side_cursor
+        self._side_cursor += 1
+        E, tail = shape[0], tuple(shape[1:])
+        if i < len(self._side_bufs):
+            buf = self._side_bufs[i]
+            if tuple(buf.shape[1:]) != tail or buf.dtype != dtype or buf.shape[0] < E:
+                raise AssertionError(f"side op #{i}: buffer {tuple(buf.shape)}/{buf.dtype} does not match this "
+                                     f"frame's {tuple(shape)}/{dtype}; the model must issue the same ops every frame")
+        else:
+            buf = torch.empty((max(self.num_total, E),) + tail, dtype=dtype, device=device,
+                              memory_format=torch.channels_last)
+            self._side_bufs.append(buf)
+        return buf[:E]
+
     def _next_full(self) -> Tuple[int, Optional[torch.Tensor]]:
         i = self._full_cursor
         self._full_cursor += 1
@@ -192,10 +216,11 @@ class BlockFeatures:
         """Drop all stored features."""
         self._planes.clear()
         self._full.clear()
+        self._side_bufs.clear()
         self._prev_grid_idx = None
 
     def state_bytes(self) -> int:
-        return sum(p.numel() * p.element_size() for p in self._planes + self._full)
+        return sum(p.numel() * p.element_size() for p in self._planes + self._full + self._side_bufs)
 
 
 def _raw(t: torch.Tensor) -> torch.Tensor:
@@ -215,15 +240,20 @@ class _Pending:
     padded op, the same launch also writes the result into that op's persistent plane (the scatter
     of the north-star design, fused into the producer's epilogue)."""
 
-    __slots__ = ("kind", "conv", "src", "up2x", "residual", "bn", "relu", "stage", "__weakref__")
+    __slots__ = ("kind", "conv", "src", "up2x", "residual", "bn", "relu", "stage", "side", "deps", "__weakref__")
 
     def __init__(self, kind, conv=None, src=None, up2x=False):
         self.kind, self.conv, self.src, self.up2x = kind, conv, src, up2x
         self.residual, self.bn, self.relu, self.stage = None, None, False, 0
+        # side: launch on the side stream (its output then lives in a BlockFeatures side buffer).  deps: the
+        # "ready" events of ALL tensors the kernel reads, or None when one of them is unknown (the side stream
+        # then waits for everything the main stream has queued so far)
+        self.side, self.deps = False, None
 
     def clone(self):
         q = _Pending(self.kind, self.conv, self.src, self.up2x)
         q.residual, q.bn, q.relu, q.stage = self.residual, self.bn, self.relu, self.stage
+        q.deps = None if self.deps is None else list(self.deps)
         return q
 
     def reads(self, t: torch.Tensor) -> bool:
@@ -231,6 +261,70 @@ class _Pending:
         for u in (self.src, self.residual, self.conv["src"] if self.conv else None):
             if u is not None and u.data_ptr() == ptr:
                 return True
+        return False
+
+
+class _SideState:
+    """Second CUDA stream for side branches of the wrapped CNN (active inside a side_stream_scope only).
+
+    In a ladder decoder the skip bottlenecks (BN -> ReLU -> 1x1 conv on an encoder feature) depend on nothing
+    but that encoder feature, yet the model's call order puts them between decoder kernels that are each too
+    small to fill the GPU.  Inside a scope such a unit is launched on the side stream, waiting only for the
+    "ready" event of the feature it reads, so that -- eagerly, and as parallel branches of a captured CUDA
+    graph -- it runs next to the deeper encoder layers / the pyramid pooling / the decoder.  Rules that keep
+    this race-free:
+      * outputs of side kernels live in persistent BlockFeatures side buffers, never in freshly recycled
+        allocator blocks (see BlockFeatures._next_side_buf);
+      * everything a side kernel reads is kept alive until the scope's join;
+      * a main-stream launch that reads a side output first waits for its event (`sync_main`);
+      * in-place torch ops on blocks and the end of the scope join the side stream completely.
+    """
+    active = False
+    streams: Dict[int, "torch.cuda.Stream"] = {}
+    done: Dict[int, "torch.cuda.Event"] = {}   # data_ptr of a side output -> event recorded after its kernel
+    keep: List[Any] = []                       # tensors read / written by side kernels that were not joined yet
+    last: Optional["torch.cuda.Event"] = None
+    splitk_ws: Optional[torch.Tensor] = None   # split-K scratch of side-stream convs (None: the per-stream one)
+
+    @classmethod
+    def stream(cls, device) -> "torch.cuda.Stream":
+        st = cls.streams.get(device.index)
+        if st is None:
+            st = cls.streams[device.index] = torch.cuda.Stream(device=device)
+        return st
+
+    @classmethod
+    def sync_main(cls, t: Optional[torch.Tensor]) -> None:
+        """The current (main) stream is about to read `t`: wait for its side-stream producer, if any."""
+        if t is not None and cls.done:
+            ev = cls.done.pop(t.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    @classmethod
+    def join(cls) -> None:
+        if cls.last is not None:
+            torch.cuda.current_stream().wait_event(cls.last)
+        cls.last = None
+        cls.done.clear()
+        cls.keep.clear()
+
+
+class side_stream_scope:
+    """`with side_stream_scope():` -- side branches issued inside run on the side stream; the exit joins it.
+    Used by BlockCopyModel around a whole frame in CUDA-graph mode (the branches become parallel graph nodes)."""
+
+    def __init__(self, splitk_ws: Optional[torch.Tensor] = None):
+        self.ws = splitk_ws  # scratch for split-K convs on the side stream (must not be the main stream's)
+
+    def __enter__(self):
+        self.prev = (_SideState.active, _SideState.splitk_ws)
+        _SideState.active, _SideState.splitk_ws = SIDE_STREAM, self.ws
+        return self
+
+    def __exit__(self, *exc):
+        _SideState.join()
+        _SideState.active, _SideState.splitk_ws = self.prev
         return False
 
 
@@ -265,6 +359,7 @@ def _dense(t: torch.Tensor) -> torch.Tensor:
     if isinstance(t, TensorWrapper) and t._pending is not None:
         t._materialize()
     t = t.as_subclass(torch.Tensor)
+    _SideState.sync_main(t)
     if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
         return t
     return t.contiguous()
@@ -290,6 +385,7 @@ class TensorWrapper(torch.Tensor):
     _features: Optional[BlockFeatures] = None
     _features_prev: Optional[BlockFeatures] = None
     _pending: Optional[_Pending] = None  # deferred producer, see _Pending
+    _ready = None  # CUDA event recorded after the kernel that wrote this tensor (inside a side_stream_scope)
 
     # ------------------------------------------------------------------ metadata
     @property
@@ -408,6 +504,7 @@ class TensorWrapper(torch.Tensor):
                     out, src_prev = prev, None          # cells that are not executed simply keep their content
                 else:
                     out, src_prev = torch.empty_like(prev), prev
+                _SideState.sync_main(c["src"])
                 _C.head_1x1(c["src"], c["w"], c["bias"], c["bn"], c["relu"], tiles_out=_raw(self), dense_out=out,
                             dense_prev=src_prev, grid_idx=grid_idx, mapping_exec=mapping)
                 tiles, done = None, True
@@ -531,6 +628,30 @@ class TensorWrapper(torch.Tensor):
         self._pending = None
         _LIVE_PENDING.pop(id(self), None)
         out = _raw(self)
+        reads = (p.src, p.residual, p.conv["src"] if p.conv else None)
+        if p.side and _SideState.active and plane_out is None:
+            side, main = _SideState.stream(out.device), torch.cuda.current_stream()
+            if p.deps is None:
+                side.wait_stream(main)
+            else:
+                for ev in p.deps:
+                    side.wait_event(ev)
+            with torch.cuda.stream(side), _C.splitk_workspace_scope(_SideState.splitk_ws):
+                ran = self._launch(p, out, None)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            _SideState.done[out.data_ptr()] = _SideState.last = self._ready = ev
+            _SideState.keep.append((out,) + reads)
+            return ran
+        for u in reads:
+            _SideState.sync_main(u)
+        ran = self._launch(p, out, plane_out)
+        if _SideState.active:
+            self._ready = torch.cuda.Event()
+            self._ready.record()
+        return ran
+
+    def _launch(self, p: _Pending, out: torch.Tensor, plane_out: Optional[torch.Tensor]) -> bool:
         feats = self._features
         if p.kind == "conv":
             c = p.conv
@@ -552,8 +673,9 @@ class TensorWrapper(torch.Tensor):
                         feats._mapping_exec if plane_out is not None else None)
         return True
 
-    def _new_pending(self, shape, pending: _Pending) -> "TensorWrapper":
-        t = torch.empty(shape, dtype=self.dtype, device=self.device, memory_format=torch.channels_last)
+    def _new_pending(self, shape, pending: _Pending, storage: Optional[torch.Tensor] = None) -> "TensorWrapper":
+        t = storage if storage is not None else \
+            torch.empty(shape, dtype=self.dtype, device=self.device, memory_format=torch.channels_last)
         t = t.as_subclass(TensorWrapper)._inherit(self)
         t._pending = pending
         _LIVE_PENDING[id(t)] = __import__("weakref").ref(t, lambda _r, k=id(t): _LIVE_PENDING.pop(k, None))
@@ -630,12 +752,15 @@ class TensorWrapper(torch.Tensor):
                 if a is None:
                     return NotImplemented
                 q = _Pending("ew", src=a)
+                q.deps = _deps_of(self, a)
             target = self._new_pending(tuple(self.shape), q)
         if what == "add":
             r = operand._tiles_nhwc()
             if r is None:
                 return NotImplemented
             q.residual = r
+            more = _deps_of(operand, r)
+            q.deps = None if (q.deps is None or more is None) else q.deps + more
         elif what == "bn":
             q.bn = operand
         else:
@@ -726,12 +851,28 @@ class TensorWrapper(torch.Tensor):
             plane = feats._next_plane(None, (N, Cin, GH * BS, GW * BS), x.dtype, x.device, True)
             with timings.env("tensorwrapper/transfer", 10):
                 if not x._materialize(plane_out=plane):  # producer epilogue wrote the plane, else scatter now
+                    _SideState.sync_main(_raw(x))
                     _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
             conv = dict(src=plane, w=w, bias=bias, mapping=feats._mapping_exec, E=E, BS_in=BS, stride=stride,
                         pad=padding)
+            pend, storage = _Pending("conv", conv=conv), None
         else:
-            conv = dict(src=x._tiles_nhwc(), w=w, bias=bias, mapping=None, E=E, BS_in=BS, stride=stride, pad=0)
-        out = x._new_pending((E, Cout, BSo, BSo), _Pending("conv", conv=conv))
+            q = x._pending
+            side = _SideState.active and LAZY_FUSION and q is not None and q.kind == "ew" and not q.up2x \
+                and q.residual is None
+            if side:
+                # pre-activation unit on materialised tiles feeding a 1x1 conv (skip bottleneck): a side branch.
+                # x is re-pointed at a persistent side buffer before its kernel is launched on the side stream
+                with torch._C.DisableTorchFunctionSubclass():
+                    x.set_(feats._next_side_buf(tuple(x.shape), x.dtype, x.device))
+                q.side = True
+            src = x._tiles_nhwc()
+            conv = dict(src=src, w=w, bias=bias, mapping=None, E=E, BS_in=BS, stride=stride, pad=0)
+            pend, storage = _Pending("conv", conv=conv), None
+            if side:
+                pend.side, pend.deps = True, _deps_of(x, src)
+                storage = feats._next_side_buf((E, Cout, BSo, BSo), x.dtype, x.device)
+        out = x._new_pending((E, Cout, BSo, BSo), pend, storage)
         if not LAZY_FUSION:
             out._materialize()
         return out
@@ -759,6 +900,7 @@ class TensorWrapper(torch.Tensor):
         N, _, GH, GW = feats._grid_idx.shape
         plane = feats._next_plane(None, (N, C, GH * BS, GW * BS), x.dtype, x.device, True)
         if not x._materialize(plane_out=plane):
+            _SideState.sync_main(_raw(x))
             _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
         pend = _Pending("pool", conv=dict(src=plane, mapping=feats._mapping_exec, E=E, BS_in=BS, k=k, stride=stride,
                                           pad=padding))
@@ -853,14 +995,27 @@ def _materialize_all(args, kwargs=None):
         if isinstance(a, TensorWrapper):
             if a._pending is not None:
                 a._materialize()
+            if _SideState.done:
+                _SideState.sync_main(_raw(a))
         elif isinstance(a, (list, tuple)):
             _materialize_all(a)
     if kwargs:
         _materialize_all(tuple(kwargs.values()))
 
 
+def _deps_of(t: "TensorWrapper", raw: torch.Tensor):
+    """[ready event] of the materialised block tensor `t` whose tiles `raw` a descriptor is about to read, or
+    None when there is none (materialised outside a side_stream_scope, or `raw` is a re-laid-out copy)."""
+    ev = t._ready
+    if ev is None or raw.data_ptr() != _raw(t).data_ptr():
+        return None
+    return [ev]
+
+
 def _flush_readers_of(t):
     """An in-place op is about to change `t`: deferred tensors that still have to READ it go first."""
+    if _SideState.last is not None:
+        _SideState.join()  # side kernels may still be reading it
     if not isinstance(t, torch.Tensor) or not _LIVE_PENDING:
         return
     raw = _raw(t)
