@@ -36,6 +36,7 @@ FUSED_HEAD = os.environ.get("BLOCKCOPY_FUSED_HEAD", "1") != "0"  # few-channel 1
 # side branches (a pre-activation BN+ReLU on materialised tiles feeding a 1x1 conv: the skip bottlenecks of a
 # ladder decoder) are issued on a second CUDA stream inside a side_stream_scope, see _SideState
 SIDE_STREAM = os.environ.get("BLOCKCOPY_SIDE_STREAM", "1") != "0"
+SIDE_DOWNSAMPLE = os.environ.get("BLOCKCOPY_SIDE_DS", "1") != "0"  # also 1x1 convs on materialised tiles (residual downsamples)
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
 
@@ -858,10 +859,12 @@ class TensorWrapper(torch.Tensor):
             pend, storage = _Pending("conv", conv=conv), None
         else:
             q = x._pending
-            side = _SideState.active and LAZY_FUSION and q is not None and q.kind == "ew" and not q.up2x \
-                and q.residual is None
-            if side:
-                # pre-activation unit on materialised tiles feeding a 1x1 conv (skip bottleneck): a side branch.
+            # side branches: (a) a pre-activation unit on materialised tiles feeding a 1x1 conv (skip bottleneck);
+            # (b) a 1x1 conv on tiles whose producer is known (residual downsample: runs next to the block's
+            # first 3x3 conv).  If the consumer turns out to be a padded op, the conv still runs on the main stream.
+            pre = q is not None and q.kind == "ew" and not q.up2x and q.residual is None
+            side = _SideState.active and LAZY_FUSION and (pre or (SIDE_DOWNSAMPLE and q is None and x._ready is not None))
+            if side and pre:
                 # x is re-pointed at a persistent side buffer before its kernel is launched on the side stream
                 with torch._C.DisableTorchFunctionSubclass():
                     x.set_(feats._next_side_buf(tuple(x.shape), x.dtype, x.device))
