@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from ..utils.profiler import timings
-from .tensorwrapper import TensorWrapper, side_stream_scope, to_tensorwrapper
+from .tensorwrapper import TensorWrapper, run_on_side_stream, side_stream_scope, to_tensorwrapper
 
 
 class BlockCopyModel(nn.Module):
@@ -123,7 +123,8 @@ class BlockCopyModel(nn.Module):
             self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
             self.block_temporal_features.track_transfer_idx = False
             blocks = x.to_blocks(grid)
-            frame_state = blocks.combine_().to_tensor()
+            # frame_state is read by the next frame's policy only: its scatter runs beside the model
+            frame_state = run_on_side_stream(lambda: blocks.combine_().to_tensor(), keep=(blocks,))
             out = self.base_model(blocks)
             return frame_state, out.combine_().to_tensor()
 

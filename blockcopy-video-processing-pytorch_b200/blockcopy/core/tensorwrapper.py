@@ -303,6 +303,23 @@ class _SideState:
                 torch.cuda.current_stream().wait_event(ev)
 
     @classmethod
+    def run(cls, fn: Callable, keep: Tuple = ()):
+        """Run fn() -- kernels whose results the main stream needs only after the scope's join -- on the side
+        stream, after everything the main stream has queued so far.  `keep`: tensors fn reads."""
+        if not cls.active:
+            return fn()
+        main = torch.cuda.current_stream()
+        side = cls.stream(main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = fn()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        cls.last = ev
+        cls.keep.append(tuple(keep) + (out,))
+        return out
+
+    @classmethod
     def join(cls) -> None:
         if cls.last is not None:
             torch.cuda.current_stream().wait_event(cls.last)
@@ -327,6 +344,11 @@ class side_stream_scope:
         _SideState.join()
         _SideState.active, _SideState.splitk_ws = self.prev
         return False
+
+
+def run_on_side_stream(fn: Callable, keep: Tuple = ()):
+    """See _SideState.run (no-op wrapper outside a side_stream_scope)."""
+    return _SideState.run(fn, keep)
 
 
 def _is_dense4(t: torch.Tensor) -> bool:
