@@ -444,6 +444,55 @@ def microbench(device, peaks, reps=200, sets=8):
         del planes, tiles, padded, outs
     res.update(large_gather_microbench(device, peaks))
     res.update(conv_microbench(device, peaks, me_full=None))
+    res.update(io_microbench(device, peaks))
+    return res
+
+
+def io_microbench(device, peaks, reps=100, sets=8):
+    """Driver-side steps at BASELINE size: uint8 1024x2048 frame -> fp16 input
+    (18.9 MB algorithmic: 6.3 read + 12.6 written), and (1,19,256,512) fp16 logits -> 1024x2048 uint8 label map
+    (12.1 MB: 10.0 read + 2.1 written), next to the torch op sequences of the reference's driver.  Rotating
+    `sets` buffer sets (151 / 97 MB), graph-timed."""
+    from consumers.frame_io import FrameNormalizer, predict_labels
+    import torch.nn.functional as F
+
+    g = torch.Generator(device=device).manual_seed(0)
+    H, W = 1024, 2048
+    u8 = [torch.randint(0, 256, (1, H, W, 3), dtype=torch.uint8, device=device, generator=g) for _ in range(sets)]
+    fin = [torch.empty(1, 3, H, W, dtype=torch.float16, device=device) for _ in range(sets)]
+    logits = [torch.randn(1, 19, H // 4, W // 4, device=device, generator=g).half() for _ in range(sets)]
+    lab = [torch.empty(1, H, W, dtype=torch.uint8, device=device) for _ in range(sets)]
+    norm = FrameNormalizer()
+    mean = torch.as_tensor(norm.mean, dtype=torch.float32, device=device).view(1, 3, 1, 1)
+    std = torch.as_tensor(norm.std, dtype=torch.float32, device=device).view(1, 3, 1, 1)
+    ops = {
+        "frame_from_u8": (lambda i: norm(u8[i % sets], out=fin[i % sets]), H * W * 3 + H * W * 3 * 2),
+        "frame_from_u8_torch_ops": (lambda i: u8[i % sets].permute(0, 3, 1, 2).float().div_(255).sub_(mean).div_(std).half(),
+                                    H * W * 3 + H * W * 3 * 2),
+        "upsample4x_argmax": (lambda i: predict_labels(logits[i % sets], out=lab[i % sets]), 19 * H * W // 16 * 2 + H * W),
+        "upsample4x_argmax_torch_ops": (lambda i: F.interpolate(logits[i % sets], size=(H, W), mode="bilinear").max(dim=1)[1],
+                                        19 * H * W // 16 * 2 + H * W),
+    }
+    res = {}
+    for name, (fn, nbytes) in ops.items():
+        r = reps if not name.endswith("torch_ops") else 20
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(r):
+                fn(i)
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / r
+        res[name] = {"us": us, "bytes": nbytes, "gbs": nbytes / us * 1e-3, "frac_of_hbm_peak": nbytes / us * 1e-3 / peaks["hbm_gbs"]}
+        del graph
     return res
 
 

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "bc_upsample_argmax": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp], _i),
     "bc_spp_pool": ([_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp], _i),
     "bc_spp_levels": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _vp], _i),
     "bc_spp_prep": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _i, _vp], _i),
@@ -541,6 +543,44 @@ def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor
     strides = (ctypes.c_int64 * 4)(*outputs.stride())
     _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
                               ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- driver-side steps
+def frame_from_u8(src_u8: torch.Tensor, mean, std, dtype=torch.float16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,H,W,3) or (H,W,3) uint8 CUDA frame -> normalised (N,3,H,W) `dtype` network input:
+    ((x / 255) - mean) / std, bit-identical to to_tensor + normalize + .to(dtype) (see bc_frame_from_u8)."""
+    _dev(src_u8, out)
+    if src_u8.dim() == 3:
+        src_u8 = src_u8.unsqueeze(0)
+    assert src_u8.dtype == torch.uint8 and src_u8.dim() == 4 and src_u8.shape[3] == 3 and src_u8.is_contiguous(), \
+        "frame must be a contiguous (N,H,W,3) uint8 tensor"
+    N, H, W, _ = src_u8.shape
+    if out is None:
+        out = torch.empty((N, 3, H, W), dtype=dtype, device=src_u8.device)
+    assert out.shape == (N, 3, H, W) and out.is_contiguous() and out.dtype in (torch.float16, torch.float32)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _check(lib().bc_frame_from_u8(out.data_ptr(), src_u8.data_ptr(), ctypes.cast(m, _vp), ctypes.cast(sd, _vp), N, H, W,
+                                  BC_F16 if out.dtype == torch.float16 else BC_F32, _stream()), "bc_frame_from_u8")
+    return out
+
+
+def upsample_argmax(logits: torch.Tensor, scale: int = 4, label_dtype=torch.uint8,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,K,h,w) fp16/fp32 logits -> (N, scale*h, scale*w) class map = argmax over classes of the bilinear
+    (align_corners=False) upsampling, without materialising it (see bc_upsample_argmax)."""
+    _dev(logits, out)
+    assert logits.dim() == 4 and logits.dtype in (torch.float16, torch.float32)
+    assert label_dtype in (torch.uint8, torch.int64)
+    N, K, h, w = logits.shape
+    if out is None:
+        out = torch.empty((N, h * scale, w * scale), dtype=label_dtype, device=logits.device)
+    assert out.shape == (N, h * scale, w * scale) and out.is_contiguous() and out.dtype == label_dtype
+    strides = (ctypes.c_int64 * 4)(*logits.stride())
+    _check(lib().bc_upsample_argmax(out.data_ptr(), logits.data_ptr(), N, K, h, w, ctypes.cast(strides, _vp), int(scale),
+                                    BC_F16 if logits.dtype == torch.float16 else BC_F32, out.element_size(), _stream()),
+           "bc_upsample_argmax")
     return out
 
 

@@ -61,6 +61,11 @@ int policy_features(float *out, const void *frame, const void *state, const void
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
 
+int frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W, int dtype,
+                  cudaStream_t stream);
+int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides, int scale,
+                    int dtype, int label_bytes, cudaStream_t stream);
+
 int spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int *gh, const int *gw, cudaStream_t s);
 int spp_levels(void *out, const void *pooled, const float *bn, const void *w, int N, int C, int H, int W, int L,
                const int *gh, const int *gw, int Lc, cudaStream_t s);
@@ -283,6 +288,16 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
                               bc_dtype_t dtype, bc_stream_t stream) {
   return policy_features(out, frame, frame_state, output_repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo, repr_strides,
                          inv_scale_y, inv_scale_x, dtype, (cudaStream_t)stream);
+}
+
+BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W,
+                            bc_dtype_t dtype, bc_stream_t stream) {
+  return frame_from_u8(out, src, mean, std, N, H, W, (int)dtype, (cudaStream_t)stream);
+}
+
+BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
+                              int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream) {
+  return upsample_argmax(labels, logits, N, K, h, w, strides, scale, (int)dtype, label_bytes, (cudaStream_t)stream);
 }
 
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,

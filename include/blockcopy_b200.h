@@ -247,6 +247,23 @@ BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev,
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream);
 
+/* ---- the steps on either side of the path in the reference's driver -----------------
+ * bc_frame_from_u8: decoded frame -> network input.  Replaces ExtToTensor + ExtNormalize + .to(device, half)
+ *   (semantic_segmentation/lib/ext_transforms.py:317-372, test_swiftnet.py:64-65,187):
+ *   out (N,3,H,W) NCHW of dtype F16|F32 = ((src / 255) - mean[c]) / std[c], src (N,H,W,3) uint8 on the device,
+ *   mean / std: HOST arrays of 3 floats.  fp32 IEEE arithmetic in ATen's op order, one rounding to F16 at the end:
+ *   bit-identical to the torch sequence.
+ * bc_upsample_argmax: logits -> label map.  Replaces F.interpolate(out, size=(scale*h, scale*w), mode='bilinear')
+ *   + out.max(dim=1)[1] (test_swiftnet.py:196-197) without materialising the upsampled logits:
+ *   labels (N, scale*h, scale*w) contiguous, uint8 (label_bytes 1, K <= 256) or int64 (label_bytes 8);
+ *   logits (N,K,h,w) F16|F32 with ELEMENT strides[4]; scale in {1,2,4}; align_corners False; the blended value is
+ *   rounded to the logits' dtype before comparing (as the upsampled tensor would be); ties -> lowest class.
+ */
+BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W,
+                            bc_dtype_t dtype, bc_stream_t stream);
+BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
+                              int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream);
+
 /* ---- dense pyramid pooling (the @blockcopy_noblocks module of SwiftNet, swiftnet/util.py:85-138) ----------
  * Everything between the module's first and last 1x1 conv, on dense NHWC fp16 planes; grid_h/grid_w are HOST
  * arrays of L <= 4 pooling grids that must divide (H, W).  "cells" = sum_i N*grid_h[i]*grid_w[i], level-major.

@@ -139,3 +139,54 @@ class RingProtocol:
         out = repad(tiles.contiguous(), data_transfer, grid_idx, mapping, pad)
         self.prev = (tiles.contiguous().clone(), data_transfer, grid_idx)
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Driver-side steps.  numpy restatements, pinned in tests/test_oracle_io.py against the very
+# torchvision / torch CPU calls the reference's driver makes (ExtToTensor + ExtNormalize:
+# semantic_segmentation/lib/ext_transforms.py:317-372; F.interpolate(..., mode='bilinear') + max(dim=1):
+# test_swiftnet.py:196-197).
+def frame_from_u8(src_u8: torch.Tensor, mean, std, dtype=torch.float16) -> torch.Tensor:
+    """(N,H,W,3) uint8 -> (N,3,H,W) `dtype`: ((x / 255) - mean) / std in fp32 (IEEE), one final rounding."""
+    import numpy as np
+
+    x = src_u8.numpy().astype(np.float32) / np.float32(255.0)
+    m = np.asarray(mean, dtype=np.float32).reshape(1, 1, 1, 3)
+    s = np.asarray(std, dtype=np.float32).reshape(1, 1, 1, 3)
+    y = ((x - m) / s).astype(np.float32).transpose(0, 3, 1, 2)
+    return torch.from_numpy(np.ascontiguousarray(y)).to(dtype)
+
+
+def upsample_argmax(logits: torch.Tensor, scale: int) -> torch.Tensor:
+    """(N,K,h,w) fp16/fp32 -> (N, scale*h, scale*w) int64: argmax over K of the bilinear (align_corners=False)
+    upsampling computed in fp32 as ATen does -- src = (dst + 0.5) / scale - 0.5 clamped at 0, taps (i0, min(i0+1,
+    last)), value = h0*(w0*a + w1*b) + h1*(w0*c + w1*d) -- rounded to the logits' dtype; ties -> lowest class."""
+    import numpy as np
+
+    x = logits.float().numpy()
+    N, K, h, w = x.shape
+
+    def taps(n_in):
+        dst = np.arange(n_in * scale, dtype=np.float32)
+        src = np.float32(1.0 / scale) * (dst + np.float32(0.5)) - np.float32(0.5)
+        src = np.maximum(src, np.float32(0.0)).astype(np.float32)
+        i0 = src.astype(np.int64)
+        i1 = np.minimum(i0 + 1, n_in - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        return i0, i1, l1, (np.float32(1.0) - l1).astype(np.float32)
+
+    y0, y1, hy1, hy0 = taps(h)
+    x0, x1, wx1, wx0 = taps(w)
+    best = np.full((N, h * scale, w * scale), -np.inf, dtype=np.float32)
+    arg = np.zeros((N, h * scale, w * scale), dtype=np.int64)
+    for c in range(K):
+        p = x[:, c]
+        top = (wx0 * p[:, y0][:, :, x0] + wx1 * p[:, y0][:, :, x1]).astype(np.float32)
+        bot = (wx0 * p[:, y1][:, :, x0] + wx1 * p[:, y1][:, :, x1]).astype(np.float32)
+        v = (hy0[None, :, None] * top + hy1[None, :, None] * bot).astype(np.float32)
+        if logits.dtype == torch.float16:
+            v = v.astype(np.float16).astype(np.float32)
+        upd = v > best
+        best[upd] = v[upd]
+        arg[upd] = c
+    return torch.from_numpy(arg)

@@ -1,0 +1,93 @@
+"""bc_frame_from_u8 / bc_upsample_argmax against the oracle (bit-exact) and against the torch op sequences of
+the reference's driver on the GPU (lib/ext_transforms.py:317-372, test_swiftnet.py:196-197)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cpu_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("N,H,W", [(1, 64, 128), (2, 24, 40), (1, 7, 9), (1, 1024, 2048)])
+def test_frame_from_u8_bit_exact(dtype, N, H, W):
+    from consumers.frame_io import CITYSCAPES_MEAN as M, CITYSCAPES_STD as S, FrameNormalizer
+
+    g = torch.Generator().manual_seed(H * W + N)
+    u8 = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, generator=g)
+    got = FrameNormalizer(dtype=dtype)(u8.cuda())
+    assert got.shape == (N, 3, H, W) and got.dtype == dtype
+    assert torch.equal(got.cpu(), cpu_oracle.frame_from_u8(u8, M, S, dtype))
+    # and the torch sequence of the driver.  It runs on the CPU there (DataLoader workers): CPU `div(255)` is a
+    # true division, while torch's CUDA kernel multiplies by the reciprocal (1 ulp apart for some bytes)
+    t = u8.permute(0, 3, 1, 2).contiguous().float().div(255)
+    mean = torch.as_tensor(M, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.as_tensor(S, dtype=torch.float32).view(1, 3, 1, 1)
+    assert torch.equal(got.cpu(), t.sub_(mean).div_(std).to(dtype))
+
+
+def test_frame_from_u8_unbatched_and_errors():
+    from blockcopy import _C
+
+    u8 = torch.randint(0, 256, (32, 48, 3), dtype=torch.uint8)
+    got = _C.frame_from_u8(u8.cuda(), (0.5, 0.5, 0.5), (0.25, 0.5, 1.0), torch.float32)
+    assert torch.equal(got.cpu(), cpu_oracle.frame_from_u8(u8[None], (0.5, 0.5, 0.5), (0.25, 0.5, 1.0), torch.float32))
+    with pytest.raises(_C.BlockCopyNativeError):
+        _C.frame_from_u8(u8.cuda(), (0, 0, 0), (1, 0, 1))  # std of zero
+    with pytest.raises(AssertionError):
+        _C.frame_from_u8(u8, (0, 0, 0), (1, 1, 1))  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("label", [torch.uint8, torch.int64])
+@pytest.mark.parametrize("N,K,h,w,s,cl", [(1, 19, 32, 64, 4, False), (2, 19, 16, 24, 4, True), (1, 5, 9, 7, 2, False),
+                                          (1, 3, 6, 5, 1, False), (1, 19, 1, 8, 4, False), (1, 19, 8, 1, 4, True)])
+def test_upsample_argmax_equals_oracle(dtype, label, N, K, h, w, s, cl):
+    from blockcopy import _C
+
+    g = torch.Generator().manual_seed(K * h + w)
+    x = (2 * torch.randn(N, K, h, w, generator=g)).to(dtype)
+    xd = x.cuda()
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    got = _C.upsample_argmax(xd, s, label)
+    want = cpu_oracle.upsample_argmax(x, s)
+    assert got.dtype == label and got.shape == want.shape
+    if dtype == torch.float16:
+        assert torch.equal(got.cpu().long(), want)
+    else:  # fp32: a fused multiply-add may move a blended value by one ulp
+        diff = got.cpu().long() != want
+        assert diff.float().mean() < 1e-3
+
+
+def test_upsample_argmax_full_size_vs_torch_sequence():
+    """BASELINE size: (1,19,256,512) fp16 logits -> 1024x2048 labels vs F.interpolate + max on the GPU."""
+    from consumers.frame_io import predict_labels
+
+    g = torch.Generator().manual_seed(11)
+    x = (3 * torch.randn(1, 19, 256, 512, generator=g)).half().cuda()
+    got = predict_labels(x, size=(1024, 2048), label_dtype=torch.int64)
+    up = F.interpolate(x, size=(1024, 2048), mode="bilinear")
+    vals, want = up.max(dim=1)
+    # the chosen class always holds the maximum value; where the maximum is unique the index is the same
+    assert torch.equal(up.gather(1, got[:, None])[:, 0], vals)
+    unique = (up == vals[:, None]).sum(1) == 1
+    assert torch.equal(got[unique], want[unique])
+    assert unique.float().mean() > 0.99
+    # uint8 labels, default scale
+    assert torch.equal(predict_labels(x).long(), got)
+    # ties -> lowest class
+    assert int(predict_labels(torch.zeros(1, 19, 8, 8, device="cuda").half()).max()) == 0
+
+
+def test_upsample_argmax_errors():
+    from blockcopy import _C
+
+    x = torch.randn(1, 19, 8, 8).half().cuda()
+    with pytest.raises(_C.BlockCopyNativeError):
+        _C.upsample_argmax(x, 3)
+    with pytest.raises(_C.BlockCopyNativeError):
+        _C.upsample_argmax(torch.randn(1, 300, 4, 4).half().cuda(), 4, torch.uint8)
+    with pytest.raises(AssertionError):
+        _C.upsample_argmax(x.cpu(), 4)
