@@ -206,22 +206,39 @@ class HostPipeline:
     are double-buffered so that the upload of frame t+1 overlaps the compute of frame t; all of it
     is inside the timed region."""
 
-    def __init__(self, models, host_clips, device, out_shape):
-        self.models, self.host_clips, self.device = models, host_clips, device
+    def __init__(self, models, host_clips, device, out_shape, u8=False):
+        """u8=False: the frame travels as the fp16 network input, the result as fp16 logits (what the reference's
+        driver moves).  u8=True: the host uploads the decoded uint8 frame (H,W,3), bc_frame_from_u8 normalises it on
+        the device, and bc_upsample_argmax turns the logits into the full-resolution uint8 label map that is
+        downloaded (consumers/frame_io.py)."""
+        self.models, self.host_clips, self.device, self.u8 = models, host_clips, device, u8
         S = len(models)
         self.copy_stream = torch.cuda.Stream(device=device)
         shape = host_clips[0][0].shape
-        self.dev_in = [[torch.empty(shape, dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
-        self.host_out = [[torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(S)]
+        if u8:
+            from consumers.frame_io import FrameNormalizer, predict_labels
+            self.norm, self.labels = FrameNormalizer(), predict_labels
+            N, H, W, _ = shape
+            self.dev_u8 = [[torch.empty(shape, dtype=torch.uint8, device=device) for _ in range(2)] for _ in range(S)]
+            self.dev_in = [[torch.empty((N, 3, H, W), dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
+            self.dev_lab = [[torch.empty((N, H, W), dtype=torch.uint8, device=device) for _ in range(2)] for _ in range(S)]
+            self.host_out = [[torch.empty((N, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(S)]
+            self.h2d_bytes, self.d2h_bytes = S * N * H * W * 3, S * N * H * W
+        else:
+            self.dev_in = [[torch.empty(shape, dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
+            self.host_out = [[torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(S)]
+            self.h2d_bytes = S * host_clips[0][0].numel() * 2
+            self.d2h_bytes = S * self.host_out[0][0].numel() * 2
         self.in_ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
         self.in_free = [[None, None] for _ in range(S)]
+        self.out_free = [[None, None] for _ in range(S)]
 
     def _upload(self, s, t, clip_len):
         slot = t % 2
         with torch.cuda.stream(self.copy_stream):
             if self.in_free[s][slot] is not None:
                 self.copy_stream.wait_event(self.in_free[s][slot])
-            self.dev_in[s][slot].copy_(self.host_clips[s][t % clip_len], non_blocking=True)
+            (self.dev_u8 if self.u8 else self.dev_in)[s][slot].copy_(self.host_clips[s][t % clip_len], non_blocking=True)
             self.in_ready[s][slot].record(self.copy_stream)
 
     def run(self, start, count, clip_len):
@@ -237,14 +254,35 @@ class HostPipeline:
                     if t + 1 < start + count:
                         self._upload(s, t + 1, clip_len)
                     main.wait_event(self.in_ready[s][slot])
+                    if self.u8:
+                        self.norm(self.dev_u8[s][slot], out=self.dev_in[s][slot])
                     out = model(self.dev_in[s][slot])
+                    if self.u8:
+                        if self.out_free[s][slot] is not None:
+                            main.wait_event(self.out_free[s][slot])  # the label buffer's previous download is done
+                        out = self.labels(out, out=self.dev_lab[s][slot])
                     done = torch.cuda.Event()
                     done.record(main)
                     self.in_free[s][slot] = done
                     with torch.cuda.stream(self.copy_stream):
                         self.copy_stream.wait_event(done)
                         self.host_out[s][slot].copy_(out, non_blocking=True)
+                        if self.u8:
+                            self.out_free[s][slot] = torch.cuda.Event()
+                            self.out_free[s][slot].record(self.copy_stream)
         main.wait_stream(self.copy_stream)
+
+
+def u8_host_clips(host_clips):
+    """The synthetic fp16 clips as decoded uint8 frames (N,H,W,3): what a video decoder would hand over."""
+    from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD
+    mean = torch.tensor(CITYSCAPES_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CITYSCAPES_STD).view(1, 3, 1, 1)
+    out = []
+    for clip in host_clips:
+        out.append([((f.float() * std + mean) * 255).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+                    .contiguous().pin_memory() for f in clip])
+    return out
 
 
 def bench_ours(args):
@@ -288,7 +326,7 @@ def bench_ours(args):
     barrier(world)
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
-    e2e, pipe = None, None
+    e2e, e2e_u8, pipe = None, None, None
     if not args.skip_e2e:
         pipe = HostPipeline(models, host_clips, device, (B, 19, H // 4, W // 4))
         pipe.run(0, min(args.warmup, L), L)
@@ -303,6 +341,23 @@ def bench_ours(args):
         e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": S * B * 3 * H * W * 2,
                "d2h_bytes_per_step": S * B * 19 * (H // 4) * (W // 4) * 2,
                "note": "pinned host frame -> H2D -> model() -> D2H of the logits, copies double-buffered on a side stream"}
+        # the same through the driver-side kernels: uint8 frame up, full-resolution uint8 label map down
+        pipe = None
+        pipe8 = HostPipeline(models, u8_host_clips(host_clips), device, None, u8=True)
+        pipe8.run(0, min(args.warmup, L), L)
+        torch.cuda.synchronize()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe8.run(args.warmup, args.steps, L)
+        e1.record()
+        torch.cuda.synchronize()
+        _, _, u8_fps = aggregate_throughput(float(args.steps * S * B), e0.elapsed_time(e1), device)
+        e2e_u8 = {"value": u8_fps, "unit": "frames/s", "h2d_bytes_per_step": pipe8.h2d_bytes,
+                  "d2h_bytes_per_step": pipe8.d2h_bytes,
+                  "note": "pinned uint8 (H,W,3) frame -> H2D -> bc_frame_from_u8 -> model() -> bc_upsample_argmax -> "
+                          "D2H of the 1024x2048 uint8 label map"}
+        del pipe8
 
     # ---- same path with 8 streams batched along N (secondary number; config 4 packs 64/ngpu streams per GPU) ---
     batched = None
@@ -349,7 +404,7 @@ def bench_ours(args):
                        "cuda_graphs": not args.no_graphs,
                        "l2_note": "kernel microbenchmarks rotate 8 plane sets (268 MB > 126 MB L2); the frame loop "
                                   "cycles 30 distinct 12.6 MB frames over 0.27 GB of planes per stream"},
-            "e2e": e2e, "gpu_launches": int(launches), "batched": batched,
+            "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "batched": batched,
             "roofline": {"bound": "tensor",
                          "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: largest share "
                                    "of a single launch in the step, profiles/r01c_frame_launch_shares.md)",
@@ -451,7 +506,7 @@ def microbench(device, peaks, reps=200, sets=8):
 def io_microbench(device, peaks, reps=100, sets=8):
     """Driver-side steps at BASELINE size: uint8 1024x2048 frame -> fp16 input
     (18.9 MB algorithmic: 6.3 read + 12.6 written), and (1,19,256,512) fp16 logits -> 1024x2048 uint8 label map
-    (12.1 MB: 10.0 read + 2.1 written), next to the torch op sequences of the reference's driver.  Rotating
+    (7.1 MB: 5.0 read + 2.1 written), next to the torch op sequences of the reference's driver.  Rotating
     `sets` buffer sets (151 / 97 MB), graph-timed."""
     from consumers.frame_io import FrameNormalizer, predict_labels
     import torch.nn.functional as F
