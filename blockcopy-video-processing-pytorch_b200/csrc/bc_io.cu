@@ -158,7 +158,7 @@ template <> __device__ __forceinline__ float round_to<float>(float v) { return v
 // Per class: 9 loads, 3 x S horizontal blends shared by the S output rows, S x S vertical blends; for fp16 logits
 // the rounded values are compared as packed half2 (2 outputs per instruction, class indices in 16-bit lanes).
 template <typename T, typename L, int S>
-__global__ void __launch_bounds__(128) upsample_argmax_kernel(const ArgmaxParams p) {
+__global__ void __launch_bounds__(128, 7) upsample_argmax_kernel(const ArgmaxParams p) {
   pdl_trigger();
   pdl_wait();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,11 +185,11 @@ __global__ void __launch_bounds__(128) upsample_argmax_kernel(const ArgmaxParams
     }
   }
   const int ys[3] = {max(i - 1, 0), i, min(i + 1, p.h - 1)}, xs[3] = {max(j - 1, 0), j, min(j + 1, p.w - 1)};
-  int64_t off[3][3];
+  int off[3][3];  // element offsets within one (n, class) slice: < 2^31, checked on the host
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) off[a][b] = ys[a] * p.sh + xs[b] * p.sw;
+    for (int b = 0; b < 3; ++b) off[a][b] = (int)(ys[a] * p.sh + xs[b] * p.sw);
   const T *pc = reinterpret_cast<const T *>(p.logits) + n * p.sn;
 
   constexpr bool kPacked = sizeof(T) == 2 && S % 2 == 0;
@@ -281,6 +281,8 @@ int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w
   BC_REQUIRE(((uintptr_t)labels & 7) == 0, BC_ERR_ALIGN, "bc_upsample_argmax: labels must be 8-byte aligned");
   const int64_t total = (int64_t)N * h * w;
   BC_REQUIRE(total * scale * scale < (1ll << 31), BC_ERR_RANGE, "bc_upsample_argmax: problem too large");
+  BC_REQUIRE((h - 1) * strides[2] + (w - 1) * strides[3] < (1ll << 31) && strides[2] >= 0 && strides[3] >= 0, BC_ERR_RANGE,
+             "bc_upsample_argmax: slice strides out of range");
   ArgmaxParams p;
   p.logits = logits; p.labels = labels;
   p.N = N; p.K = K; p.h = h; p.w = w;
