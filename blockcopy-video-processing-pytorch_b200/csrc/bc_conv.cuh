@@ -43,7 +43,7 @@ struct ConvParams {
   float *work;
   long long work_bytes;
   unsigned long long *trace;  // bc_debug_trace buffer (16 words per CTA) or nullptr
-  int debug;  // BC_CONV_DEBUG (timing experiments only): bit 0 one k-step, bit 1 no epilogue stores
+  int debug;  // BC_CONV_DEBUG (timing experiments only): bit 0 one k-step, bit 1 no epilogue stores, bit 2 weight producer waits for the previous kernel too
 };
 
 // in-kernel timeline for profiles/ (bc_debug_trace): slot k of this CTA's 16-word record <- SM clock

@@ -169,7 +169,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
   pdl_trigger();
-  pdl_wait();
+  // barrier init, TMEM alloc and descriptor prefetch above overlapped the previous kernel's tail.  The weight
+  // producer (warp 6) does not wait: weights are never written by a kernel of the frame, so its first ring of
+  // tiles is in flight while the previous kernel drains (BC_CONV_DEBUG=4 restores the common wait)
+  if (warp != 6 || (p.debug & 4)) pdl_wait();
   if (threadIdx.x == 0) trace_mark(p, 1);
 
   if (warp == 0 || warp >= 7) {
