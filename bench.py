@@ -153,6 +153,8 @@ def build_model(args, device):
         settings["block_cuda_graphs"] = True
     if getattr(args, "shared_policy", False):
         settings["block_policy_shared"] = True
+    if os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") == "0":  # A/B: policy trunk always through torch/cuDNN
+        settings["block_policy_fused"] = False
     model = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), settings).eval().to(device).half()
     if args.policy == "fixed":
         model.policy = PolicyFixedFraction(128, fraction=args.fraction, quantize=8, seed=0)

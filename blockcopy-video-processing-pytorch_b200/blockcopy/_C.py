@@ -46,6 +46,9 @@ _SIGNATURES = {
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
+    "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
+    "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
     "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_upsample_argmax": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp], _i),
     "bc_spp_pool": ([_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp], _i),
@@ -543,6 +546,46 @@ def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor
     strides = (ctypes.c_int64 * 4)(*outputs.stride())
     _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
                               ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- train-mode BN statistics
+BN_STATS_WORKSPACE = 16 + 2 * 148 * 2 * 128 * 4
+
+
+def bn_stats(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, eps: float, workspace: torch.Tensor):
+    """mean / invstd (fp32 [C]) of a train-mode BatchNorm2d over all pixels of the dense channels_last fp16
+    tensor x (N,C,H,W); workspace: uint8, >= BN_STATS_WORKSPACE bytes, zeroed once by the caller."""
+    _dev(x, mean, invstd, workspace)
+    assert x.dtype == torch.float16 and x.dim() == 4 and (x.is_contiguous(memory_format=torch.channels_last))
+    N, C, H, W = x.shape
+    assert mean.dtype == torch.float32 and invstd.dtype == torch.float32 and mean.numel() >= C and invstd.numel() >= C
+    _check(lib().bc_bn_stats(mean.data_ptr(), invstd.data_ptr(), x.data_ptr(), N * H * W, C, float(eps),
+                             workspace.data_ptr(), workspace.numel(), _stream()), "bc_bn_stats")
+
+
+def pack_params(table: torch.Tensor, total: int):
+    """table: int64 CUDA tensor (n, 12), see bc_pack_params."""
+    _dev(table)
+    assert table.dtype == torch.int64 and table.dim() == 2 and table.shape[1] == 12 and table.is_contiguous()
+    _check(lib().bc_pack_params(table.data_ptr(), table.shape[0], int(total), _stream()), "bc_pack_params")
+
+
+def conv_fewout(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, padding: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv2d with <= 16 output channels: x (N,Cx,H,W) channels_last fp16 (the first weight.shape[1] channels are
+    used), weight fp32 (Cout,C,k,k) any strides, bias fp32 -> (N,Cout,Ho,Wo) fp32."""
+    _dev(x, weight, bias, out)
+    assert x.dtype == torch.float16 and x.is_contiguous(memory_format=torch.channels_last) and weight.dtype == torch.float32
+    N, Cx, H, W = x.shape
+    Cout, C, k, _ = weight.shape
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    if out is None:
+        out = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    ws = (ctypes.c_int64 * 4)(*weight.stride())
+    _check(lib().bc_conv_fewout(out.data_ptr(), x.data_ptr(), weight.data_ptr(),
+                                bias.data_ptr() if bias is not None else None, N, H, W, C, Cx, Cout, k, stride, padding,
+                                ctypes.cast(ws, _vp), _stream()), "bc_conv_fewout")
     return out
 
 

@@ -77,6 +77,8 @@ class BlockCopyModel(nn.Module):
         meta["inputs"] = inputs
 
         with timings.env("blockcopy/policy_forward", 3):
+            # hint for trainable policies: will optim() below be a training step?  (same test as there)
+            meta["policy_will_train"] = self.clip_length % self.train_interval == 0
             meta = self.policy(meta)  # sets grid, num_exec, num_total, perc_exec
             self.policy_meta = meta
 

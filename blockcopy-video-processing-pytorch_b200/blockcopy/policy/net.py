@@ -39,6 +39,10 @@ class PolicyNet(nn.Module):
         # BlockCopyModel together with block_channels_last
         self.channels_last = False
         self.__dict__["_graphed"] = None  # (input shape, graphed callable); not a submodule: state_dict unchanged
+        # frames that are not followed by a policy update need no autograd graph: their trunk forward runs on this
+        # repo's kernels (policy/fused_net.py; fp16 operands, train-mode batch statistics).  False: always torch
+        self.fused_inference = True
+        self.__dict__["_fused"] = None
 
     @staticmethod
     def _make_layer(cin, cout, kernel_size=3, stride=2, relu=True):
@@ -114,12 +118,26 @@ class PolicyNet(nn.Module):
             g = self.__dict__["_graphed"] = (key, fn)
         return g[1](x)
 
-    def forward(self, policy_meta: dict):
+    def _fused_trunk(self):
+        t = self.__dict__["_fused"]
+        if t is None:
+            from blockcopy.policy.fused_net import FusedPolicyTrunk
+
+            t = self.__dict__["_fused"] = FusedPolicyTrunk(self)
+        return t
+
+    def forward(self, policy_meta: dict, no_grad: bool = False):
+        """no_grad: the caller will not back-propagate through this call (a frame without policy update): the
+        trunk may run on the inference kernels."""
         N, C, H, W = policy_meta["inputs"].shape
         with timings.env("policy/net/build_features", 5):
             x = self.build_features(policy_meta)
         with timings.env("policy/net/layers", 5):
-            logits = self._trunk_forward(x)
+            fused = self._fused_trunk() if (no_grad and self.fused_inference and self.training and x.is_cuda) else None
+            if fused is not None and fused.supports(x):
+                logits = fused(x, use_cuda_graph=self.use_cuda_graphs)
+            else:
+                logits = self._trunk_forward(x)
         expect = (N, 1, H // self.block_size, W // self.block_size)
         assert logits.shape == expect, f"logits shape: {logits.shape}, frame shape: {(N, C, H, W)}, " \
                                        f"block size: {self.block_size}"

@@ -39,6 +39,7 @@ def build_policy_from_settings(settings: dict):
         return PolicyRandom(quantize_number_exec=quantize, **common)
     if name.startswith("rl_"):
         net = build_policy_net_from_settings(settings)
+        net.fused_inference = bool(settings.get("block_policy_fused", True))  # policy/fused_net.py (not in the reference)
         optimizer = build_policy_optimizer_from_settings(settings, net)
         if name == "rl_semseg":
             ig = InformationGainSemSeg(num_classes=settings["block_num_classes"])
@@ -216,7 +217,11 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
             with torch.enable_grad():
                 with timings.env("policy/net", 3):
                     assert self.net.training
-                    grid_logits = self.net(policy_meta)
+                    # BlockCopyModel announces whether optim() will train on this frame; if not, nothing is
+                    # back-propagated through this forward (grid_log_probs is only read by the training step)
+                    no_grad = policy_meta.get("policy_will_train", True) is False and \
+                        getattr(self.net, "fused_inference", False)
+                    grid_logits = self.net(policy_meta, no_grad=no_grad) if no_grad else self.net(policy_meta)
                     assert torch.all(~torch.isnan(grid_logits)), \
                         "Policy net returned NaN's, maybe optimization problem?"
                 with timings.env("policy/sample", 3):

@@ -61,6 +61,11 @@ int policy_features(float *out, const void *frame, const void *state, const void
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
 
+int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
+             long long workspace_bytes, cudaStream_t stream);
+int pack_params(const long long *table, int n, long long total, cudaStream_t stream);
+int conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx, int Cout,
+                int k, int stride, int pad, const int64_t *w_strides, cudaStream_t stream);
 int frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W, int dtype,
                   cudaStream_t stream);
 int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides, int scale,
@@ -288,6 +293,20 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
                               bc_dtype_t dtype, bc_stream_t stream) {
   return policy_features(out, frame, frame_state, output_repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo, repr_strides,
                          inv_scale_y, inv_scale_x, dtype, (cudaStream_t)stream);
+}
+
+BC_API int bc_bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
+                       long long workspace_bytes, bc_stream_t stream) {
+  return bn_stats(mean, invstd, x, P, C, eps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_pack_params(const long long *table, int n, long long total, bc_stream_t stream) {
+  return pack_params(table, n, total, (cudaStream_t)stream);
+}
+
+BC_API int bc_conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx,
+                          int Cout, int k, int stride, int pad, const int64_t *w_strides, bc_stream_t stream) {
+  return conv_fewout(out, x, w, bias, N, H, W, C, Cx, Cout, k, stride, pad, w_strides, (cudaStream_t)stream);
 }
 
 BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W,

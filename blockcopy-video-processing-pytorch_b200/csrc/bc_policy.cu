@@ -150,4 +150,218 @@ int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h,
   return check_launch("bc_info_gain");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Batch statistics of a train-mode BatchNorm2d (the policy net runs in train mode, policy/policy.py:240-250 and
+// policy/net.py:115-125): per channel mean and 1/sqrt(biased variance + eps) over all P = N*H*W pixels of a dense
+// NHWC fp16 tensor.  One pass: every CTA sums its pixel slice (fp32 per thread, 8 channels x 16-byte loads),
+// reduces over its threads in shared memory (fixed order) and writes one partial per channel; the CTA that arrives last
+// (atomic ticket) adds the partials IN CTA ORDER in double precision -- run-to-run reproducible -- and resets the
+// ticket for the next launch.
+struct StatsParams {
+  const __half *x;
+  float *mean, *invstd;
+  float *partial;        // [gridDim.x][2][C]
+  unsigned int *ticket;  // zero before the first launch; left at zero
+  uint32_t P;
+  int C;
+  float eps;
+};
+
+constexpr int kStatsThreads = 512;
+
+__global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsParams p) {
+  __shared__ float red[kStatsThreads][17];
+  __shared__ double comb[kStatsThreads];
+  __shared__ bool last;
+  pdl_trigger();
+  pdl_wait();
+  const int lanes = p.C >> 3;                 // threads per pixel (8 channels each); C <= 128 -> <= 16
+  const int sub = threadIdx.x % lanes, row = threadIdx.x / lanes, rows = kStatsThreads / lanes;
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+  const uint32_t step = gridDim.x * rows;
+  const __half *base = p.x + sub * 8;
+  uint32_t px = blockIdx.x * rows + row;
+  // eight independent 16-byte loads in flight per thread, the tail included (the kernel is a pure stream)
+  for (; px < p.P; px += 8 * step) {
+    uint4 u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t pj = px + j * step;
+      u[j] = pj < p.P ? __ldg(reinterpret_cast<const uint4 *>(base + (size_t)pj * p.C)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        s[2 * k] += f.x; s[2 * k + 1] += f.y;
+        q[2 * k] = fmaf(f.x, f.x, q[2 * k]); q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[threadIdx.x][k] = s[k]; red[threadIdx.x][8 + k] = q[k]; }
+  __syncthreads();
+  const int items = 2 * p.C;  // (sum | sumsq, channel)
+  {
+    // item -> `slices` threads, each adds every slices-th pixel row of the CTA in order; then the slices in order
+    const int slices = kStatsThreads / items, item = threadIdx.x % items, slice = threadIdx.x / items;
+    const int which = item / p.C, c = item - which * p.C;
+    float acc = 0.f;
+    for (int r = slice; r < rows; r += slices) acc += red[r * lanes + (c >> 3)][which * 8 + (c & 7)];
+    comb[threadIdx.x] = (double)acc;
+    __syncthreads();
+    if (threadIdx.x < items) {
+      double t = 0.0;
+      for (int z = 0; z < slices; ++z) t += comb[z * items + threadIdx.x];
+      p.partial[(size_t)blockIdx.x * items + threadIdx.x] = (float)t;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  {
+    // the last CTA: item -> `slices` threads, each adds every slices-th CTA partial (8 loads in flight) in order
+    const int slices = kStatsThreads / items, item = threadIdx.x % items, slice = threadIdx.x / items;
+    double t = 0.0;
+    unsigned b = (unsigned)slice;
+    for (; b + 7 * slices < gridDim.x; b += 8 * slices) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(p.partial + (size_t)(b + j * slices) * items + item);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += (double)v[j];
+    }
+    for (; b < gridDim.x; b += slices) t += (double)__ldcg(p.partial + (size_t)b * items + item);
+    comb[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x < p.C) {
+      double sum = 0.0, sq = 0.0;
+      for (int z = 0; z < slices; ++z) { sum += comb[z * items + threadIdx.x]; sq += comb[z * items + p.C + threadIdx.x]; }
+      const double m = sum / (double)p.P;
+      double var = sq / (double)p.P - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      p.mean[threadIdx.x] = (float)m;
+      p.invstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+  }
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
+             long long workspace_bytes, cudaStream_t stream) {
+  BC_REQUIRE(mean && invstd && x && workspace, BC_ERR_NULL, "bc_bn_stats: NULL pointer");
+  BC_REQUIRE(P > 0 && P < (1ll << 31), BC_ERR_SHAPE, "bc_bn_stats: %lld pixels", P);
+  BC_REQUIRE(C >= 8 && C <= 128 && C % 8 == 0 && kStatsThreads % (2 * C) == 0, BC_ERR_UNSUPPORTED,
+             "bc_bn_stats: C=%d (8, 16, 32, 64 or 128 channels)", C);
+  BC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, BC_ERR_ALIGN, "bc_bn_stats: 16-byte alignment");
+  const int rows = kStatsThreads / (C / 8);
+  // one CTA per SM at most, and up to eight pixel rows per thread and round: few partials for the last CTA to add
+  long long grid = (P + 8 * rows - 1) / (8 * rows);
+  if (grid > kNumSMs) grid = kNumSMs;
+  const long long need = 16 + grid * 2 * C * (long long)sizeof(float);
+  BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_bn_stats: workspace of %lld bytes, %lld needed", workspace_bytes, need);
+  StatsParams p;
+  p.x = (const __half *)x; p.mean = mean; p.invstd = invstd;
+  p.ticket = (unsigned int *)workspace;
+  p.partial = (float *)((char *)workspace + 16);
+  p.P = (uint32_t)P; p.C = C; p.eps = eps;
+  launch_kernel(bn_stats_kernel, dim3((unsigned)grid), dim3(kStatsThreads), 0, stream, 1, p);
+  return check_launch("bc_bn_stats");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Parameter re-packing for the fused policy trunk: the live fp32 parameters change with every online optimiser
+// step, the kernels want fp16 channels_last conv weights with channel counts padded to 64 (and fp32 affine
+// vectors padded likewise).  One launch converts them all from a device-side table (built once: the addresses of
+// parameters updated in place never change); padded positions are left as initialised by the caller.
+//   entry e = 12 int64: src ptr | dst ptr | first flat element | Cout | Cin | k | padded Cin | src element strides
+//   (co, ci, kh, kw) | dst is fp16 (1) or fp32 (0).   dst layout: [Cout][k][k][padded Cin].
+__global__ void __launch_bounds__(256) pack_params_kernel(const long long *table, int n, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int e = 0;
+    while (e + 1 < n && table[(e + 1) * 12 + 2] <= i) ++e;
+    const long long *t = table + e * 12;
+    const long long j = i - t[2], cin = t[4], k = t[5];
+    const long long ci = j % cin, kw = (j / cin) % k, kh = (j / (cin * k)) % k, co = j / (cin * k * k);
+    const float v = reinterpret_cast<const float *>(t[0])[co * t[7] + ci * t[8] + kh * t[9] + kw * t[10]];
+    const long long d = ((co * k + kh) * k + kw) * t[6] + ci;
+    if (t[11]) reinterpret_cast<__half *>(t[1])[d] = __float2half_rn(v);
+    else reinterpret_cast<float *>(t[1])[d] = v;
+  }
+}
+
+int pack_params(const long long *table, int n, long long total, cudaStream_t stream) {
+  BC_REQUIRE(table && n > 0 && total > 0, BC_ERR_NULL, "bc_pack_params: empty table");
+  long long grid = (total + 255) / 256;
+  if (grid > (long long)kNumSMs * 8) grid = (long long)kNumSMs * 8;
+  launch_kernel(pack_params_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, table, n, total);
+  return check_launch("bc_pack_params");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Convolution with very few output channels on a dense NHWC fp16 tensor, fp32 weights and result: the policy
+// net's last layer (128 -> 1, 3x3, stride 2: one logit per block, policy/net.py:46-50).  One CTA per output
+// pixel, one thread per input channel, k*k taps each, block reduction per output channel.
+struct FewOutParams {
+  const __half *x;   // (N, H, W, Cx): the first C of Cx channels are used
+  const float *w;    // (Cout, C, k, k) with element strides ws[4]
+  const float *bias; // [Cout] or nullptr
+  float *out;        // (N, Cout, Ho, Wo) contiguous
+  int N, H, W, C, Cx, Cout, k, stride, pad, Ho, Wo;
+  long long ws[4];
+};
+
+__global__ void __launch_bounds__(128) conv_fewout_kernel(const FewOutParams p) {
+  __shared__ float red[4];
+  pdl_trigger();
+  pdl_wait();
+  const int ox = blockIdx.x % p.Wo, oy = (blockIdx.x / p.Wo) % p.Ho, n = blockIdx.x / (p.Wo * p.Ho);
+  for (int co = 0; co < p.Cout; ++co) {
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < p.C; c += 128)
+      for (int kh = 0; kh < p.k; ++kh) {
+        const int y = oy * p.stride + kh - p.pad;
+        if (y < 0 || y >= p.H) continue;
+        for (int kw = 0; kw < p.k; ++kw) {
+          const int x = ox * p.stride + kw - p.pad;
+          if (x < 0 || x >= p.W) continue;
+          acc = fmaf(__half2float(p.x[(((size_t)n * p.H + y) * p.W + x) * p.Cx + c]),
+                     __ldg(p.w + co * p.ws[0] + c * p.ws[1] + kh * p.ws[2] + kw * p.ws[3]), acc);
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      p.out[(((size_t)n * p.Cout + co) * p.Ho + oy) * p.Wo + ox] = red[0] + red[1] + red[2] + red[3] + (p.bias ? p.bias[co] : 0.f);
+    __syncthreads();
+  }
+}
+
+int conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx, int Cout,
+                int k, int stride, int pad, const int64_t *w_strides, cudaStream_t stream) {
+  BC_REQUIRE(out && x && w && w_strides, BC_ERR_NULL, "bc_conv_fewout: NULL pointer");
+  BC_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && Cx >= C && Cout > 0 && Cout <= 16 && k > 0 && stride > 0 && pad >= 0,
+             BC_ERR_SHAPE, "bc_conv_fewout: bad sizes (Cout <= 16)");
+  FewOutParams p;
+  p.x = (const __half *)x; p.w = w; p.bias = bias; p.out = out;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.Cx = Cx; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - k) / stride + 1;
+  p.Wo = (W + 2 * pad - k) / stride + 1;
+  BC_REQUIRE(p.Ho > 0 && p.Wo > 0 && (long long)N * p.Ho * p.Wo < (1ll << 31), BC_ERR_SHAPE, "bc_conv_fewout: output size");
+  for (int i = 0; i < 4; ++i) p.ws[i] = w_strides[i];
+  launch_kernel(conv_fewout_kernel, dim3((unsigned)(N * p.Ho * p.Wo)), dim3(128), 0, stream, 1, p);
+  return check_launch("bc_conv_fewout");
+}
+
 }  // namespace bc

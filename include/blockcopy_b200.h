@@ -247,6 +247,31 @@ BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev,
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream);
 
+/* ---- batch statistics of a train-mode BatchNorm2d (the policy net, policy/net.py:115-125 in train mode) -----
+ * mean[c], invstd[c] = 1/sqrt(biased var + eps) over the P = N*H*W pixels of a dense NHWC fp16 tensor x (P, C),
+ * C in {8,16,32,64,128}.  workspace: caller-owned, >= BC_BN_STATS_WORKSPACE bytes, 16-byte aligned, its first 4
+ * bytes ZERO before the first call (the kernel leaves them zero); private to the stream.  Reproducible run to run.
+ * The pair feeds bc_ew_fused's (mean, invstd, weight, shift) directly: no host round trip.
+ */
+#define BC_BN_STATS_WORKSPACE (16 + 2 * 148 * 2 * 128 * 4)
+BC_API int bc_bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
+                       long long workspace_bytes, bc_stream_t stream);
+
+/* ---- parameter re-packing for the fused policy trunk (policy/fused_net.py): fp32 parameters -> fp16 channels_last
+ * conv weights / fp32 vectors with padded channel counts, all tensors in ONE launch.  table: DEVICE array of n
+ * entries x 12 int64 = { src ptr, dst ptr, first flat element, Cout, Cin, k, padded Cin, src element strides
+ * (co, ci, kh, kw), dst is fp16 }; entries ordered by first flat element; total = elements of all sources;
+ * dst layout [Cout][k][k][padded Cin] (padding left untouched).
+ */
+BC_API int bc_pack_params(const long long *table, int n, long long total, bc_stream_t stream);
+
+/* ---- convolution with <= 16 output channels on a dense NHWC fp16 tensor (the policy net's 128 -> 1 logit layer,
+ * policy/net.py:46-50): out (N,Cout,Ho,Wo) fp32 contiguous = conv(x[..., :C], w) + bias; x (N,H,W,Cx) fp16 of which
+ * the first C channels are used; w fp32 (Cout,C,k,k) with ELEMENT strides w_strides[4]; zero padding `pad`.
+ */
+BC_API int bc_conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx,
+                          int Cout, int k, int stride, int pad, const int64_t *w_strides, bc_stream_t stream);
+
 /* ---- the steps on either side of the path in the reference's driver -----------------
  * bc_frame_from_u8: decoded frame -> network input.  Replaces ExtToTensor + ExtNormalize + .to(device, half)
  *   (semantic_segmentation/lib/ext_transforms.py:317-372, test_swiftnet.py:64-65,187):

@@ -91,3 +91,134 @@ def test_graphed_policy_trunk_matches_eager():
         for (n, a), b in zip(eager.named_buffers(), graphed.buffers()):
             assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=1e-6), (step, n)
     assert list(eager.state_dict().keys()) == list(graphed.state_dict().keys())
+
+
+@pytest.mark.parametrize("N,C,H,W", [(1, 64, 64, 128), (2, 128, 16, 32), (1, 64, 256, 512), (1, 8, 5, 7)])
+def test_bn_stats_matches_float64_and_is_reproducible(N, C, H, W):
+    from blockcopy import _C
+
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = (1.5 * torch.randn(N, C, H, W, device="cuda", generator=g) + 0.7).half().contiguous(memory_format=torch.channels_last)
+    ws = torch.zeros(_C.BN_STATS_WORKSPACE, dtype=torch.uint8, device="cuda")
+    outs = []
+    for _ in range(3):
+        mean = torch.empty(C, device="cuda")
+        invstd = torch.empty(C, device="cuda")
+        _C.bn_stats(x, mean, invstd, 1e-5, ws)
+        outs.append((mean, invstd))
+    x64 = x.double()
+    want_mean = x64.mean(dim=(0, 2, 3))
+    want_inv = 1.0 / torch.sqrt(x64.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    assert torch.allclose(outs[0][0].double(), want_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(outs[0][1].double(), want_inv, rtol=1e-5, atol=1e-6)
+    for m, s in outs[1:]:
+        assert torch.equal(m, outs[0][0]) and torch.equal(s, outs[0][1])
+    assert int(ws[:4].view(torch.int32)) == 0  # the ticket is left at zero
+
+
+def _policy_net(seed=0):
+    from blockcopy.policy.net import PolicyNet
+
+    torch.manual_seed(seed)
+    net = PolicyNet(block_size=128, task_num_classes=19).cuda().train()
+    with torch.no_grad():  # non-trivial affine parameters
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    return net
+
+
+def test_fused_policy_trunk_matches_fp32_torch():
+    """policy/fused_net.py (bc_conv_igemm + bc_bn_stats + bc_ew_fused, fp16 operands) against the torch trunk in
+    strict fp32: logits within 2 % of their range + 0.02, i.e. execute probabilities within ~0.01."""
+    from blockcopy.policy.fused_net import FusedPolicyTrunk
+
+    net = _policy_net()
+    fused = FusedPolicyTrunk(net)
+    assert fused.ok
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for (N, H, W) in [(1, 256, 512), (2, 128, 256)]:
+            x = torch.randn(N, 26, H, W, device="cuda", generator=g)
+            assert fused.supports(x)
+            with torch.no_grad():
+                want = net.layers(net.backbone(x))
+            got = fused(x)
+            assert got.shape == want.shape == (N, 1, H // 32, W // 32) and got.dtype == torch.float32
+            tol = 0.02 * float(want.abs().max()) + 0.02
+            assert float((got - want).abs().max()) <= tol, (float((got - want).abs().max()), tol)
+            assert float((torch.sigmoid(got) - torch.sigmoid(want)).abs().max()) <= 0.02
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert not fused.supports(torch.randn(1, 26, 100, 200, device="cuda"))  # not divisible: torch path
+
+
+def test_fused_policy_trunk_graph_equals_eager_and_follows_parameter_updates():
+    from blockcopy.policy.fused_net import FusedPolicyTrunk
+
+    net = _policy_net(1)
+    a, b = FusedPolicyTrunk(net), FusedPolicyTrunk(net)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(1, 26, 256, 512, device="cuda", generator=g)
+    first = a(x).clone()
+    assert torch.equal(b(x, use_cuda_graph=True), first)
+    assert torch.equal(b(x, use_cuda_graph=True), first)  # replay
+    with torch.no_grad():  # an optimiser step changes the parameters in place
+        for q in net.parameters():
+            q.add_(0.05 * torch.randn(q.shape, device="cuda", generator=g))
+    second = a(x).clone()
+    assert not torch.equal(second, first)
+    assert torch.equal(b(x, use_cuda_graph=True), second)  # the graph re-packs the live weights
+
+
+def test_rl_policy_uses_fused_trunk_on_frames_without_update():
+    """BlockCopyModel tells the policy whether optim() will train; frames that will not run the inference trunk."""
+    import blockcopy
+    from blockcopy.core.argparser import default_settings
+    from blockcopy.policy import fused_net
+    from consumers.clips import synthetic_clip
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    calls = []
+    orig = fused_net.FusedPolicyTrunk.__call__
+
+    def spy(self, x, use_cuda_graph=False):
+        calls.append(tuple(x.shape))
+        return orig(self, x, use_cuda_graph)
+
+    fused_net.FusedPolicyTrunk.__call__ = spy
+    try:
+        model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), default_settings(block_policy="rl_semseg", block_size=128,
+                                                                               block_train_interval=3)).eval().cuda().half()
+        model.policy.net = model.policy.net.float().train()  # the reference driver's configuration
+        clip = synthetic_clip(7, 1024, 2048, seed=0, device="cuda")
+        with torch.no_grad():
+            model.reset_temporal()
+            outs = [model(f) for f in clip]
+        torch.cuda.synchronize()
+    finally:
+        fused_net.FusedPolicyTrunk.__call__ = orig
+    assert all(torch.isfinite(o).all() for o in outs)
+    # frames 2..7 run the policy net (frame 1 has no history); frames 3 and 6 train (clip_length % 3 == 0)
+    assert len(calls) == 4, calls
+    assert model.policy.stats.count_images == 7
+
+
+@pytest.mark.parametrize("N,C,Cx,Cout,H,W,k,s,p,cl", [(1, 128, 128, 1, 16, 32, 3, 2, 1, True), (2, 20, 64, 3, 9, 7, 3, 1, 1, False),
+                                                     (1, 130, 136, 2, 8, 8, 1, 1, 0, False)])
+def test_conv_fewout_matches_torch(N, C, Cx, Cout, H, W, k, s, p, cl):
+    from blockcopy import _C
+
+    g = torch.Generator(device="cuda").manual_seed(C + Cout)
+    x = torch.randn(N, Cx, H, W, device="cuda", generator=g).half().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(Cout, C, k, k, device="cuda", generator=g)
+    if cl:
+        w = w.contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    got = _C.conv_fewout(x, w, b, s, p)
+    want = torch.nn.functional.conv2d(x[:, :C].double(), w.double(), b.double(), stride=s, padding=p)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert torch.allclose(got.double(), want, rtol=1e-4, atol=1e-4)
