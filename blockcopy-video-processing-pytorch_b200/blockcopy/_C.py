@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
+    "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
     "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
     "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_upsample_argmax": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp], _i),
@@ -569,6 +570,17 @@ def pack_params(table: torch.Tensor, total: int):
     _dev(table)
     assert table.dtype == torch.int64 and table.dim() == 2 and table.shape[1] == 12 and table.is_contiguous()
     _check(lib().bc_pack_params(table.data_ptr(), table.shape[0], int(total), _stream()), "bc_pack_params")
+
+
+def rmsprop_step(rows, device: torch.device, lr: float, alpha: float, eps: float, weight_decay: float, momentum: float):
+    """rows: list of (param ptr, grad ptr, square_avg ptr, momentum buffer ptr | 0, cumulative offset, numel) -- a HOST
+    table, see bc_rmsprop_step."""
+    n = len(rows)
+    flat = (ctypes.c_longlong * (6 * n))(*[int(v) for r in rows for v in r])
+    total = rows[-1][4] + rows[-1][5]
+    with torch.cuda.device(device):
+        _check(lib().bc_rmsprop_step(ctypes.cast(flat, _vp), n, int(total), float(lr), float(alpha), float(eps),
+                                     float(weight_decay), float(momentum), _stream()), "bc_rmsprop_step")
 
 
 def conv_fewout(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride: int, padding: int,

@@ -55,9 +55,12 @@ def build_policy_from_settings(settings: dict):
 
 
 def build_policy_optimizer_from_settings(settings: dict, net: PolicyNet) -> torch.optim.Optimizer:
-    return torch.optim.RMSprop(net.parameters(), lr=settings["block_optim_lr"],
-                               weight_decay=settings["block_optim_wd"], centered=False,
-                               momentum=settings["block_optim_momentum"])
+    # torch.optim.RMSprop with a one-kernel step (policy/fused_optim.py): same interface, hyper-parameters and state
+    from blockcopy.policy.fused_optim import FusedRMSprop
+
+    return FusedRMSprop(net.parameters(), lr=settings["block_optim_lr"],
+                        weight_decay=settings["block_optim_wd"], centered=False,
+                        momentum=settings["block_optim_momentum"])
 
 
 class PolicyStats:
@@ -225,14 +228,21 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     assert torch.all(~torch.isnan(grid_logits)), \
                         "Policy net returned NaN's, maybe optimization problem?"
                 with timings.env("policy/sample", 3):
-                    dist = Bernoulli(logits=grid_logits)
-                    grid = dist.sample()
+                    if no_grad:
+                        # same draw as Bernoulli(logits=...).sample() (= torch.bernoulli(sigmoid(logits))) without
+                        # building the distribution object; log-probabilities are only read by a training step
+                        dist, probs = None, torch.sigmoid(grid_logits)
+                        grid = torch.bernoulli(probs)
+                    else:
+                        dist = Bernoulli(logits=grid_logits)
+                        grid = dist.sample()
+                        probs = dist.probs
                 if self.at_least_one and grid.sum() == 0:
                     grid[0, 0, 0, 0] = 1
                 grid = self.quantize_number_exec_grid(grid)
-                policy_meta["grid_log_probs"] = dist.log_prob(grid)
-                policy_meta["grid_probs"] = dist.probs
-                assert grid.dim() == 4 and dist.probs.shape == grid.shape
+                policy_meta["grid_log_probs"] = dist.log_prob(grid) if dist is not None else None
+                policy_meta["grid_probs"] = probs
+                assert grid.dim() == 4 and probs.shape == grid.shape
                 hint = getattr(grid, "_bc_num_exec", None)
                 grid = grid.bool()
                 if hint is not None:

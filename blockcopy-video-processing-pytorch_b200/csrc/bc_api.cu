@@ -64,6 +64,8 @@ int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h,
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
              long long workspace_bytes, cudaStream_t stream);
 int pack_params(const long long *table, int n, long long total, cudaStream_t stream);
+int rmsprop_step(const long long *table, int n, long long total, float lr, float alpha, float eps, float wd, float momentum,
+                 cudaStream_t stream);
 int conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx, int Cout,
                 int k, int stride, int pad, const int64_t *w_strides, cudaStream_t stream);
 int frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W, int dtype,
@@ -302,6 +304,11 @@ BC_API int bc_bn_stats(float *mean, float *invstd, const void *x, long long P, i
 
 BC_API int bc_pack_params(const long long *table, int n, long long total, bc_stream_t stream) {
   return pack_params(table, n, total, (cudaStream_t)stream);
+}
+
+BC_API int bc_rmsprop_step(const long long *table, int n, long long total, float lr, float alpha, float eps,
+                           float weight_decay, float momentum, bc_stream_t stream) {
+  return rmsprop_step(table, n, total, lr, alpha, eps, weight_decay, momentum, (cudaStream_t)stream);
 }
 
 BC_API int bc_conv_fewout(float *out, const void *x, const float *w, const float *bias, int N, int H, int W, int C, int Cx,

@@ -308,6 +308,72 @@ int pack_params(const long long *table, int n, long long total, cudaStream_t str
 }
 
 // ---------------------------------------------------------------------------------------------------
+// RMSprop step of the online policy update (policy/policy.py:56-59 builds torch.optim.RMSprop; the reference steps
+// it every block_train_interval frames, policy.py:361-362) for ALL parameter tensors in one launch:
+//   g  = grad + weight_decay * p
+//   sq = alpha * sq + (1 - alpha) * g * g;   avg = sqrt(sq) + eps
+//   momentum > 0:  buf = momentum * buf + g / avg;  p -= lr * buf      else:  p -= lr * g / avg
+// (torch's _single_tensor_rmsprop, centered = False).  table: n entries x 6 int64 = { param, grad, square_avg,
+// momentum buffer (0 if unused), first flat element (cumulative), numel }; all tensors fp32 and dense.
+constexpr int kRmsMaxEntries = 80;
+struct RmsTable {
+  long long e[kRmsMaxEntries][6];
+};
+
+__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ RmsTable table, int n, long long total, float lr,
+                                                      float alpha, float eps, float wd, float momentum) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {  // last entry whose first element <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (table.e[mid][4] <= i) lo = mid; else hi = mid - 1;
+    }
+    const long long *t = table.e[lo];
+    const long long j = i - t[4];
+    float *p = reinterpret_cast<float *>(t[0]) + j, *sq = reinterpret_cast<float *>(t[2]) + j;
+    float g = reinterpret_cast<const float *>(t[1])[j];
+    if (wd != 0.f) g = __fadd_rn(g, __fmul_rn(wd, *p));
+    const float s = __fadd_rn(__fmul_rn(alpha, *sq), __fmul_rn(__fmul_rn(1.f - alpha, g), g));
+    *sq = s;
+    const float avg = __fadd_rn(__fsqrt_rn(s), eps);
+    if (momentum > 0.f) {
+      float *buf = reinterpret_cast<float *>(t[3]) + j;
+      const float b = __fadd_rn(__fmul_rn(momentum, *buf), __fdiv_rn(g, avg));
+      *buf = b;
+      *p = __fsub_rn(*p, __fmul_rn(lr, b));
+    } else {
+      *p = __fsub_rn(*p, __fmul_rn(lr, __fdiv_rn(g, avg)));
+    }
+  }
+}
+
+// table: HOST array; it travels as a kernel parameter (<= 80 entries per launch, more are chunked), so a step needs
+// no host-to-device copy and no synchronisation
+int rmsprop_step(const long long *table, int n, long long total, float lr, float alpha, float eps, float wd, float momentum,
+                 cudaStream_t stream) {
+  BC_REQUIRE(table && n > 0 && total > 0, BC_ERR_NULL, "bc_rmsprop_step: empty table");
+  for (int e0 = 0; e0 < n; e0 += kRmsMaxEntries) {
+    const int m = n - e0 < kRmsMaxEntries ? n - e0 : kRmsMaxEntries;
+    RmsTable t;
+    const long long base = table[(size_t)e0 * 6 + 4];
+    long long count = 0;
+    for (int i = 0; i < m; ++i) {
+      for (int k = 0; k < 6; ++k) t.e[i][k] = table[(size_t)(e0 + i) * 6 + k];
+      t.e[i][4] -= base;
+      BC_REQUIRE(t.e[i][4] == count && t.e[i][5] > 0, BC_ERR_RANGE, "bc_rmsprop_step: entry %d: offsets must be cumulative", e0 + i);
+      count += t.e[i][5];
+    }
+    long long grid = (count + 255) / 256;
+    if (grid > (long long)kNumSMs * 8) grid = (long long)kNumSMs * 8;
+    launch_kernel(rmsprop_kernel, dim3((unsigned)grid), dim3(256), 0, stream, 1, t, m, count, lr, alpha, eps, wd, momentum);
+  }
+  (void)total;
+  return check_launch("bc_rmsprop_step");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Convolution with very few output channels on a dense NHWC fp16 tensor, fp32 weights and result: the policy
 // net's last layer (128 -> 1, 3x3, stride 2: one logit per block, policy/net.py:46-50).  One CTA per output
 // pixel, one thread per input channel, k*k taps each, block reduction per output channel.

@@ -265,6 +265,16 @@ BC_API int bc_bn_stats(float *mean, float *invstd, const void *x, long long P, i
  */
 BC_API int bc_pack_params(const long long *table, int n, long long total, bc_stream_t stream);
 
+/* ---- RMSprop step of the online policy update (policy/policy.py:56-59, :361-362) for all parameter tensors in one
+ * launch; torch.optim.RMSprop semantics (centered = False):  g = grad + weight_decay * p;  sq = alpha * sq +
+ * (1 - alpha) * g * g;  avg = sqrt(sq) + eps;  momentum > 0: buf = momentum * buf + g / avg, p -= lr * buf;
+ * else p -= lr * g / avg.  table: HOST array of n entries x 6 int64 = { param, grad, square_avg, momentum buffer
+ * (0 if momentum == 0), first flat element (cumulative numel), numel }; all tensors fp32 and dense.  The table
+ * travels as a kernel parameter: no host-to-device copy, no synchronisation.
+ */
+BC_API int bc_rmsprop_step(const long long *table, int n, long long total, float lr, float alpha, float eps,
+                           float weight_decay, float momentum, bc_stream_t stream);
+
 /* ---- convolution with <= 16 output channels on a dense NHWC fp16 tensor (the policy net's 128 -> 1 logit layer,
  * policy/net.py:46-50): out (N,Cout,Ho,Wo) fp32 contiguous = conv(x[..., :C], w) + bias; x (N,H,W,Cx) fp16 of which
  * the first C channels are used; w fp32 (Cout,C,k,k) with ELEMENT strides w_strides[4]; zero padding `pad`.

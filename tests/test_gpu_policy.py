@@ -222,3 +222,38 @@ def test_conv_fewout_matches_torch(N, C, Cx, Cout, H, W, k, s, p, cl):
     want = torch.nn.functional.conv2d(x[:, :C].double(), w.double(), b.double(), stride=s, padding=p)
     assert got.shape == want.shape and got.dtype == torch.float32
     assert torch.allclose(got.double(), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("momentum,wd", [(0.0, 0.0), (0.9, 0.0), (0.9, 1e-3)])
+def test_fused_rmsprop_matches_torch(momentum, wd):
+    """bc_rmsprop_step (one launch for all tensors) against torch.optim.RMSprop, parameter by parameter, over
+    several steps; state_dict layouts agree."""
+    import copy
+
+    from blockcopy.policy.fused_optim import FusedRMSprop
+    from blockcopy.policy.net import PolicyNet
+
+    torch.manual_seed(0)
+    a = PolicyNet(block_size=128, task_num_classes=19).cuda().train().to(memory_format=torch.channels_last)
+    b = copy.deepcopy(a)
+    oa = torch.optim.RMSprop(a.parameters(), lr=1e-3, weight_decay=wd, momentum=momentum, centered=False)
+    ob = FusedRMSprop(b.parameters(), lr=1e-3, weight_decay=wd, momentum=momentum, centered=False)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(4):
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            if pa.dim() == 2 and step % 2:  # some parameters without gradient on some steps (the unused resnet fc)
+                pa.grad = pb.grad = None
+                continue
+            gr = torch.randn(pa.shape, device="cuda", generator=g).contiguous(
+                memory_format=torch.channels_last if pa.dim() == 4 else torch.contiguous_format)
+            pa.grad, pb.grad = gr.clone(memory_format=torch.preserve_format), gr.clone(memory_format=torch.preserve_format)
+        oa.step()
+        ob.step()
+        for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+            assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-8), (step, n, float((pa - pb).abs().max()))
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0].keys() == sb["param_groups"][0].keys()
+    for k in sa["state"]:
+        assert sa["state"][k].keys() == sb["state"][k].keys()
+        assert torch.allclose(sa["state"][k]["square_avg"], sb["state"][k]["square_avg"], rtol=1e-6, atol=1e-10)
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])

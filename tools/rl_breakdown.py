@@ -17,7 +17,7 @@ if settings is None:
     from blockcopy.core.argparser import default_settings
     settings = default_settings()
 settings.update(block_policy="rl_semseg", block_target=0.3, block_train_interval=3, block_size=128, block_num_classes=19,
-                block_cuda_graphs=True)
+                block_cuda_graphs=True, block_policy_fused=os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") != "0")
 model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), settings).eval().cuda().half()
 model.policy.net = model.policy.net.float().train()
 clip = synthetic_clip(30, 1024, 2048, seed=2, dtype=torch.float16, device="cuda")
