@@ -108,9 +108,14 @@ class BlockCopyModel(nn.Module):
 
 
     # ------------------------------------------------------------------ CUDA-graph mode
-    def _block_frame_inplace(self, inputs, grid):
+    def _block_frame_inplace(self, inputs, grid, graph=None):
         """One block-sparse frame with every combine IN PLACE into persistent planes (what a graph
-        can replay): returns (frame_state plane, output plane), both persistent tensors."""
+        can replay): returns (frame_state plane, output plane, prefix), both persistent tensors.
+
+        With `graph` (a torch.cuda.CUDAGraph) only the part AFTER the split is captured: index compaction and
+        the gather of the executed input blocks run eagerly, straight from the caller's tensors, into buffers
+        the captured part reads (`prefix`: what a replay has to refill).  A replay therefore needs no staging
+        copy of the 12.6 MB frame."""
         from .. import _C
 
         gs = self._graphs
@@ -119,28 +124,51 @@ class BlockCopyModel(nn.Module):
             # address the graph bakes in belongs to this model, not to the (shared) capture stream
             gs.splitk_ws = torch.empty(_C.SPLITK_WS_BYTES, dtype=torch.uint8, device=inputs.device)
             gs.splitk_ws_side = torch.empty(_C.SPLITK_WS_BYTES // 2, dtype=torch.uint8, device=inputs.device)
-        # side branches of the model (skip bottlenecks) go to a second stream: parallel nodes of the captured graph
-        with _C.splitk_workspace_scope(gs.splitk_ws), side_stream_scope(gs.splitk_ws_side):
-            x = to_tensorwrapper(inputs)
-            self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
-            self.block_temporal_features.track_transfer_idx = False
-            blocks = x.to_blocks(grid)
-            # frame_state is read by the next frame's policy only: its scatter runs beside the model
-            frame_state = run_on_side_stream(lambda: blocks.combine_().to_tensor(), keep=(blocks,))
-            out = self.base_model(blocks)
-            return frame_state, out.combine_().to_tensor()
+        x = to_tensorwrapper(inputs)
+        self.block_temporal_features = feats = x.process_temporal_features(self.block_temporal_features)
+        feats.track_transfer_idx = False
+        blocks = x.to_blocks(grid)  # bc_compact_mask + bc_gather
+        tiles = blocks.as_subclass(torch.Tensor)
+        prefix = (feats._grid_idx, feats._index_buf, tiles, tuple(inputs.shape), inputs.dtype, _C.layout_of(tiles))
+
+        def body():
+            # side branches of the model (skip bottlenecks) go to a second stream: parallel nodes of the captured graph
+            with _C.splitk_workspace_scope(gs.splitk_ws), side_stream_scope(gs.splitk_ws_side):
+                # frame_state is read by the next frame's policy only: its scatter runs beside the model
+                frame_state = run_on_side_stream(lambda: blocks.combine_().to_tensor(), keep=(blocks,))
+                out = self.base_model(blocks)
+                return frame_state, out.combine_().to_tensor()
+
+        if graph is None:
+            return body() + (prefix,)
+        with torch.cuda.graph(graph, pool=gs.pool):
+            res = body()
+        return res + (prefix,)
+
+    @staticmethod
+    def _refill_prefix(prefix, inputs, grid, num_exec):
+        """What a replay runs eagerly before the graph: this frame's index tensors and executed input blocks."""
+        from .. import _C
+
+        grid_idx, buf, tiles, shape, dtype, layout = prefix
+        assert tuple(inputs.shape) == shape and inputs.dtype == dtype, \
+            "input shape / dtype changed after CUDA graphs were captured"
+        g = grid if (grid.dtype == torch.bool and grid.is_contiguous() and grid.device == tiles.device) else \
+            grid.to(tiles.device, dtype=torch.bool).contiguous()
+        G = g.numel()
+        _C.compact_mask(g.view(torch.uint8), grid_idx, buf[:G], buf[2 * G:])
+        image = inputs.as_subclass(torch.Tensor)
+        fmt = torch.channels_last if layout == _C.BC_NHWC else torch.contiguous_format
+        if not image.is_contiguous(memory_format=fmt):
+            image = image.contiguous(memory_format=fmt)
+        _C.gather(tiles, image, buf[:num_exec], num_exec)
 
     def _forward_graphed(self, inputs, grid, num_exec):
         from .. import _C
 
         gs = self._graphs
-        if gs.static_in is None or gs.static_in.shape != inputs.shape or gs.static_in.dtype != inputs.dtype:
-            assert not gs.graphs, "input shape / dtype changed after CUDA graphs were captured"
-            gs.static_in = torch.empty_like(inputs)
-            gs.static_grid = torch.empty(grid.shape, dtype=torch.bool, device=inputs.device)
-        gs.static_in.copy_(inputs)
-        gs.static_grid.copy_(grid)
-        gs.static_grid._bc_num_exec = num_exec
+        if not hasattr(grid, "_bc_num_exec"):
+            grid._bc_num_exec = num_exec  # spares _process_grid the device round trip
         entry = gs.graphs.get(num_exec)
         if entry is None:
             seen = gs.seen.get(num_exec, 0)
@@ -148,20 +176,24 @@ class BlockCopyModel(nn.Module):
             if seen == 0:
                 # first time this block count shows up: run eagerly (allocates planes on the first
                 # frame of the first clip, lets cuDNN pick its algorithms)
-                frame_state, dense = self._block_frame_inplace(gs.static_in, gs.static_grid)
+                frame_state, dense, _ = self._block_frame_inplace(inputs, grid)
             else:
                 graph = torch.cuda.CUDAGraph()
                 n0 = _C.launch_count()
-                with torch.cuda.graph(graph, pool=gs.pool):
-                    frame_state, dense = self._block_frame_inplace(gs.static_in, gs.static_grid)
+                frame_state, dense, prefix = self._block_frame_inplace(inputs, grid, graph=graph)
                 if gs.pool is None:
                     gs.pool = graph.pool()
-                entry = gs.graphs[num_exec] = (graph, frame_state, dense, _C.launch_count() - n0)
-                _C.add_launches(-entry[3])  # counted again at every replay
-        if entry is not None:
-            graph, frame_state, dense, launches = entry
+                # kernels of ours inside the graph (the eager prefix = 2 launches counts itself)
+                entry = gs.graphs[num_exec] = (graph, frame_state, dense, _C.launch_count() - n0 - 2, prefix)
+                graph.replay()  # capturing does not execute; the prefix of THIS frame has just run eagerly
+                _C.add_launches(0)
+        else:
+            graph, frame_state, dense, launches, prefix = entry
+            self._refill_prefix(prefix, inputs, grid, num_exec)
             graph.replay()
             _C.add_launches(launches)
+        if entry is not None:
+            frame_state, dense = entry[1], entry[2]
             # a replayed frame creates no new BlockFeatures: the kept one now holds this frame's history
             self.block_temporal_features._was_reset = False
         if gs.out_bufs is None or gs.out_bufs[0].shape != dense.shape:
@@ -176,8 +208,6 @@ class _GraphState:
     """Static buffers and captured graphs of one BlockCopyModel (block_cuda_graphs=True)."""
 
     def __init__(self):
-        self.static_in = None
-        self.static_grid = None
         self.graphs = {}   # executed-block count -> (graph, frame_state plane, output plane, kernels of ours)
         self.seen = {}
         self.pool = None

@@ -110,6 +110,7 @@ class BlockFeatures:
         self._grid_idx: Optional[torch.Tensor] = None      # int32 (N,1,GH,GW)
         self._mapping_exec: Optional[torch.Tensor] = None  # int32 (E,)
         self._transfer_idx: Optional[torch.Tensor] = None  # int32 (T,) reference-protocol compat
+        self._index_buf: Optional[torch.Tensor] = None
         self.num_exec = 0
         self.num_total = 0
         self.has_history = prev is not None and not prev._was_reset
@@ -147,6 +148,7 @@ class BlockFeatures:
             if not self.has_history:
                 assert n_exec == G, "No previous features known, first run should execute all blocks!"
             self._grid, self._grid_idx = g, grid_idx
+            self._index_buf = buf  # [mapping_exec (G) | transfer_idx (G) | counts (2)]: re-filled in place by graph replays
             self._mapping_exec = mapping[:n_exec]
             self._transfer_idx = transfer[: G - n_exec] if prev_idx is not None else None
             self.num_exec, self.num_total = n_exec, G
