@@ -288,6 +288,7 @@ class _SideState:
     keep: List[Any] = []                       # tensors read / written by side kernels that were not joined yet
     last: Optional["torch.cuda.Event"] = None
     splitk_ws: Optional[torch.Tensor] = None   # split-K scratch of side-stream convs (None: the per-stream one)
+    launches = 0                               # kernels issued on the side stream so far (diagnostics / tests)
 
     @classmethod
     def stream(cls, device) -> "torch.cuda.Stream":
@@ -666,6 +667,7 @@ class TensorWrapper(torch.Tensor):
                 ev = torch.cuda.Event()
                 ev.record(side)
             _SideState.done[out.data_ptr()] = _SideState.last = self._ready = ev
+            _SideState.launches += 1
             _SideState.keep.append((out,) + reads)
             return ran
         for u in reads:
