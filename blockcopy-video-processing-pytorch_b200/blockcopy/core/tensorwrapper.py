@@ -36,6 +36,9 @@ FUSED_HEAD = os.environ.get("BLOCKCOPY_FUSED_HEAD", "1") != "0"  # few-channel 1
 # side branches (a pre-activation BN+ReLU on materialised tiles feeding a 1x1 conv: the skip bottlenecks of a
 # ladder decoder) are issued on a second CUDA stream inside a side_stream_scope, see _SideState
 SIDE_STREAM = os.environ.get("BLOCKCOPY_SIDE_STREAM", "1") != "0"
+# a deferred elementwise result whose consumer is a padded op is written into that op's plane ONLY; the packed tile
+# batch is gathered from the plane if (and when) somebody else reads it
+TILELESS = os.environ.get("BLOCKCOPY_TILELESS", "1") != "0"
 SIDE_DOWNSAMPLE = os.environ.get("BLOCKCOPY_SIDE_DS", "1") != "0"  # also 1x1 convs on materialised tiles (residual downsamples)
 VERBOSE = False  # print a line per split / combine / grid
 BLOCKPAD_WITH_ZEROES = False  # debugging: keep the op's own zero padding (wrong at block borders)
@@ -382,8 +385,10 @@ def _bn_params(running_mean, running_var, weight, bias, eps):
 def _dense(t: torch.Tensor) -> torch.Tensor:
     """Plain, dense (NCHW or channels_last) view/copy of t for the kernels (launches a deferred
     producer first: Tensor.as_subclass is not routed through __torch_function__)."""
-    if isinstance(t, TensorWrapper) and t._pending is not None:
-        t._materialize()
+    if isinstance(t, TensorWrapper):
+        if t._pending is not None:
+            t._materialize()
+        t._ensure_tiles()
     t = t.as_subclass(torch.Tensor)
     _SideState.sync_main(t)
     if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
@@ -412,6 +417,7 @@ class TensorWrapper(torch.Tensor):
     _features_prev: Optional[BlockFeatures] = None
     _pending: Optional[_Pending] = None  # deferred producer, see _Pending
     _ready = None  # CUDA event recorded after the kernel that wrote this tensor (inside a side_stream_scope)
+    _in_plane = None  # the plane whose executed cells hold this tensor while its own tile batch is unwritten
 
     # ------------------------------------------------------------------ metadata
     @property
@@ -672,11 +678,25 @@ class TensorWrapper(torch.Tensor):
             return ran
         for u in reads:
             _SideState.sync_main(u)
-        ran = self._launch(p, out, plane_out)
+        tileless = TILELESS and plane_out is not None and p.kind == "ew"
+        ran = self._launch(p, None if tileless else out, plane_out)
+        if tileless:
+            self._in_plane = plane_out
         if _SideState.active:
             self._ready = torch.cuda.Event()
             self._ready.record()
         return ran
+
+    def _ensure_tiles(self) -> None:
+        """The packed tile batch is about to be read: if its producer wrote only the consumer's plane, gather it."""
+        plane = self._in_plane
+        if plane is None:
+            return
+        self._in_plane = None
+        _C.gather(_raw(self), plane, self._features._mapping_exec, self.shape[0])
+        if _SideState.active:  # side-stream readers must wait for the gather, not for the producer
+            self._ready = torch.cuda.Event()
+            self._ready.record()
 
     def _launch(self, p: _Pending, out: torch.Tensor, plane_out: Optional[torch.Tensor]) -> bool:
         feats = self._features
@@ -711,6 +731,7 @@ class TensorWrapper(torch.Tensor):
     def _tiles_nhwc(self) -> Optional[torch.Tensor]:
         """Materialised channels_last tiles of this block tensor (copy only if the layout differs)."""
         self._materialize()
+        self._ensure_tiles()
         t = _raw(self)
         if t.dim() != 4:
             return None
@@ -878,6 +899,7 @@ class TensorWrapper(torch.Tensor):
             plane = feats._next_plane(None, (N, Cin, GH * BS, GW * BS), x.dtype, x.device, True)
             with timings.env("tensorwrapper/transfer", 10):
                 if not x._materialize(plane_out=plane):  # producer epilogue wrote the plane, else scatter now
+                    x._ensure_tiles()
                     _SideState.sync_main(_raw(x))
                     _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
             conv = dict(src=plane, w=w, bias=bias, mapping=feats._mapping_exec, E=E, BS_in=BS, stride=stride,
@@ -929,6 +951,7 @@ class TensorWrapper(torch.Tensor):
         N, _, GH, GW = feats._grid_idx.shape
         plane = feats._next_plane(None, (N, C, GH * BS, GW * BS), x.dtype, x.device, True)
         if not x._materialize(plane_out=plane):
+            x._ensure_tiles()
             _SideState.sync_main(_raw(x))
             _C.scatter(_raw(x).contiguous(memory_format=torch.channels_last), plane, feats._mapping_exec, E)
         pend = _Pending("pool", conv=dict(src=plane, mapping=feats._mapping_exec, E=E, BS_in=BS, k=k, stride=stride,
@@ -1024,6 +1047,7 @@ def _materialize_all(args, kwargs=None):
         if isinstance(a, TensorWrapper):
             if a._pending is not None:
                 a._materialize()
+            a._ensure_tiles()
             if _SideState.done:
                 _SideState.sync_main(_raw(a))
         elif isinstance(a, (list, tuple)):

@@ -244,6 +244,9 @@ class _SideTopologies(torch.nn.Module):
         self.bn_p, self.pre = nn.BatchNorm2d(128), nn.Conv2d(128, 64, 1, bias=False)
         self.after_pre = nn.Conv2d(64, 64, 3, 1, 1, bias=False)
         self.out = nn.Conv2d(64, 64, 3, 1, 1, bias=False)
+        self.down = nn.Conv2d(64, 64, 3, 2, 1, bias=False)
+        self.blend = nn.Conv2d(64, 64, 3, 1, 1, bias=False)
+        self.blend2 = nn.Conv2d(64, 64, 3, 1, 1, bias=False)
         for m in self.modules():
             if isinstance(m, nn.BatchNorm2d):
                 torch.nn.init.uniform_(m.weight, 0.5, 1.5)
@@ -266,7 +269,11 @@ class _SideTopologies(torch.nn.Module):
         z = p + s
         z = z * 0.5                         # generic torch op on blocks (materialises, reads side results)
         s.mul_(2.0)                         # in-place op on a side result
-        return self.out(z + s)
+        o = self.out(z + s)
+        # upsample + add written into the consumer's plane only; a second padded consumer and a plain reader follow
+        u = F.interpolate(self.down(o), scale_factor=2, mode="bilinear", align_corners=False)
+        u += o
+        return self.blend(u) + self.blend2(u) + u
 
 
 def test_side_stream_other_topologies_graph_equals_eager():
