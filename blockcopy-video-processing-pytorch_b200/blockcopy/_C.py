@@ -303,10 +303,11 @@ class splitk_workspace_scope:
 def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, bias: Optional[torch.Tensor],
                residual: Optional[torch.Tensor], mapping_exec: Optional[torch.Tensor], E: int, BS_in: int,
                stride: int, padding: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None,
-               out_mapping: Optional[torch.Tensor] = None, split_k: bool = True):
+               out_mapping: Optional[torch.Tensor] = None, split_k: bool = True, write_tiles: bool = True):
     """out (E,Cout,BS_out,BS_out) channels_last <- conv(plane (N,Cin,H,W) channels_last) on the E executed
     blocks (+bias, +residual, ReLU).  weight_cl: channels_last (Cout,Cin,k,k) fp16.  plane_out: the next padded
-    op's persistent plane (N,Cout,GH*BS_out,GW*BS_out) channels_last, written in the same epilogue."""
+    op's persistent plane (N,Cout,GH*BS_out,GW*BS_out) channels_last, written in the same epilogue.
+    write_tiles=False (needs plane_out): `out` only describes the shape, the tile batch is not written."""
     _dev(out, plane, weight_cl, bias, residual, mapping_exec, plane_out, out_mapping)
     N, Cin, H, W = plane.shape
     Cout, _, k, _ = weight_cl.shape
@@ -321,7 +322,8 @@ def conv_igemm(out: torch.Tensor, plane: torch.Tensor, weight_cl: torch.Tensor, 
             out_mapping = mapping_exec
     stream = _stream()
     ws = _splitk_workspace(out.device, int(stream)) if split_k and split_k != "dsmem" else None
-    _check(lib().bc_conv_igemm(out.data_ptr(), plane.data_ptr(), weight_cl.data_ptr(),
+    assert write_tiles or plane_out is not None
+    _check(lib().bc_conv_igemm(out.data_ptr() if write_tiles else None, plane.data_ptr(), weight_cl.data_ptr(),
                                bias.data_ptr() if bias is not None else None,
                                residual.data_ptr() if residual is not None else None,
                                mapping_exec.data_ptr() if mapping_exec is not None else None,
@@ -456,13 +458,15 @@ def stem_pack(s2d_plane: torch.Tensor, tiles: torch.Tensor, mapping_exec: torch.
 
 
 def conv_stem(out: torch.Tensor, s2d_plane: torch.Tensor, weight_packed: torch.Tensor, bias: Optional[torch.Tensor],
-              mapping_exec: torch.Tensor, E: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None):
+              mapping_exec: torch.Tensor, E: int, relu: bool = False, plane_out: Optional[torch.Tensor] = None,
+              write_tiles: bool = True):
     _dev(out, s2d_plane, weight_packed, bias, mapping_exec, plane_out)
+    assert write_tiles or plane_out is not None
     N, _, Hs, Ws = s2d_plane.shape
     Ws -= 2 * STEM_XPAD
     Cout, BSo = out.shape[1], out.shape[-1]
     assert out.is_contiguous(memory_format=torch.channels_last) and weight_packed.shape == (Cout, 256)
-    _check(lib().bc_conv_stem(out.data_ptr(), s2d_plane.data_ptr(), weight_packed.data_ptr(),
+    _check(lib().bc_conv_stem(out.data_ptr() if write_tiles else None, s2d_plane.data_ptr(), weight_packed.data_ptr(),
                               bias.data_ptr() if bias is not None else None, mapping_exec.data_ptr(), E, N, Hs, Ws, BSo,
                               Cout, int(relu), plane_out.data_ptr() if plane_out is not None else None, _stream()),
            "bc_conv_stem")

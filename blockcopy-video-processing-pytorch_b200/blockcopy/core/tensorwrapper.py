@@ -669,7 +669,7 @@ class TensorWrapper(torch.Tensor):
                 for ev in p.deps:
                     side.wait_event(ev)
             with torch.cuda.stream(side), _C.splitk_workspace_scope(_SideState.splitk_ws):
-                ran = self._launch(p, out, None)
+                ran = self._launch(p, out, None, True)
                 ev = torch.cuda.Event()
                 ev.record(side)
             _SideState.done[out.data_ptr()] = _SideState.last = self._ready = ev
@@ -678,8 +678,12 @@ class TensorWrapper(torch.Tensor):
             return ran
         for u in reads:
             _SideState.sync_main(u)
-        tileless = TILELESS and plane_out is not None and p.kind == "ew"
-        ran = self._launch(p, None if tileless else out, plane_out)
+        # Tile-less when the consumer is a padded op (it reads the plane).  For convs only without an absorbed
+        # residual: a block output is also read as the next block's identity, and gathering it back from the plane
+        # would cost more than the epilogue's second store stream; conv -> ReLU -> conv chains and the stem are not.
+        tileless = TILELESS and plane_out is not None and \
+            (p.kind == "ew" or (p.kind in ("conv", "stem") and p.residual is None))
+        ran = self._launch(p, out, plane_out, write_tiles=not tileless)
         if tileless:
             self._in_plane = plane_out
         if _SideState.active:
@@ -698,15 +702,17 @@ class TensorWrapper(torch.Tensor):
             self._ready = torch.cuda.Event()
             self._ready.record()
 
-    def _launch(self, p: _Pending, out: torch.Tensor, plane_out: Optional[torch.Tensor]) -> bool:
+    def _launch(self, p: _Pending, out: torch.Tensor, plane_out: Optional[torch.Tensor], write_tiles: bool = True) -> bool:
         feats = self._features
         if p.kind == "conv":
             c = p.conv
             _C.conv_igemm(out, c["src"], c["w"], c["bias"], p.residual, c["mapping"], c["E"], c["BS_in"],
-                          c["stride"], c["pad"], relu=p.relu, plane_out=plane_out, out_mapping=feats._mapping_exec)
+                          c["stride"], c["pad"], relu=p.relu, plane_out=plane_out, out_mapping=feats._mapping_exec,
+                          write_tiles=write_tiles)
         elif p.kind == "stem":
             c = p.conv
-            _C.conv_stem(out, c["src"], c["w"], c["bias"], c["mapping"], c["E"], relu=p.relu, plane_out=plane_out)
+            _C.conv_stem(out, c["src"], c["w"], c["bias"], c["mapping"], c["E"], relu=p.relu, plane_out=plane_out,
+                         write_tiles=write_tiles)
         elif p.kind == "head":
             c = p.conv
             _C.head_1x1(c["src"], c["w"], c["bias"], c["bn"], c["relu"], tiles_out=out)
@@ -716,7 +722,7 @@ class TensorWrapper(torch.Tensor):
             _C.maxpool_halo(out, c["src"], c["mapping"], c["E"], c["BS_in"], c["k"], c["stride"], c["pad"],
                             plane_out=plane_out)
         else:
-            _C.ew_fused(out, p.src, p.residual, p.bn, p.relu, p.up2x, plane_out,
+            _C.ew_fused(out if write_tiles else None, p.src, p.residual, p.bn, p.relu, p.up2x, plane_out,
                         feats._mapping_exec if plane_out is not None else None)
         return True
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void splitk_reduce_l2(const ConvParams &p, uint32_t r
 #pragma unroll
         for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
       }
-      *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
+      if (p.out) *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
       const long long rp = row_pl_s[mm[i]];
       if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + cc[i]) = o;
     }
@@ -317,7 +317,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
 #pragma unroll
             for (int t = 0; t < 4; ++t) oh[t] = __hmax2(oh[t], zero);
           }
-          *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
+          if (p.out) *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
           if (pl[u]) *reinterpret_cast<uint4 *>(pl[u]) = o;
         }
       }
@@ -427,7 +427,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         if (m < m_valid_all) {
           const size_t off = out_base_all + (size_t)m * p.Cout + c8;
           epilogue_store8(v, p.bias ? p.bias + n0 + c8 : nullptr, p.residual ? p.residual + off : nullptr, p.relu,
-                          p.out + off, rp >= 0 ? p.plane_out + rp + c8 : nullptr);
+                          p.out ? p.out + off : nullptr, rp >= 0 ? p.plane_out + rp + c8 : nullptr);
         }
       }
     }
@@ -508,7 +508,7 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                const int32_t *mapping, int E, int N, int Cin, int H, int W, int BS_in, int Cout, int ksize, int stride,
                int pad, int relu, void *plane_out, const int32_t *out_mapping, int out_N, int out_GH, int out_GW,
                int allow_split_k, void *workspace, long long workspace_bytes, cudaStream_t stream) {
-  BC_REQUIRE(out && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
+  BC_REQUIRE((out || plane_out) && plane && weight, BC_ERR_NULL, "bc_conv_igemm: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
   BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
   BC_REQUIRE(stride == 1 || stride == 2, BC_ERR_UNSUPPORTED, "bc_conv_igemm: stride %d (1 or 2)", stride);

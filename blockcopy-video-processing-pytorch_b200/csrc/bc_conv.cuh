@@ -19,7 +19,7 @@ struct ConvParams {
   CellDecode cell;          // grid of the INPUT plane
   const __half *bias;       // [Cout] or nullptr
   const __half *residual;   // same layout as out, or nullptr
-  __half *out;              // (E, BS_out, BS_out, Cout) NHWC
+  __half *out;              // (E, BS_out, BS_out, Cout) NHWC, or nullptr when only plane_out is wanted
   int E, BS_out, BS_in, stride, pad, ksize, Cout;
   int kc_per_tap;           // Cin / 64
   int rows_per_tile;        // rows of BS_out pixels of ONE block in a tile (BS_out >= 16) or BS_out
@@ -125,7 +125,7 @@ __device__ __forceinline__ void epilogue_store8(float (&v)[8], const __half *bia
   __half2 *oh = reinterpret_cast<__half2 *>(&o);
 #pragma unroll
   for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-  *reinterpret_cast<uint4 *>(out8) = o;
+  if (out8) *reinterpret_cast<uint4 *>(out8) = o;
   if (plane8) *reinterpret_cast<uint4 *>(plane8) = o;
 }
 

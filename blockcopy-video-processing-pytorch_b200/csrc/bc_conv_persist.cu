@@ -114,7 +114,7 @@ __device__ __forceinline__ void splitk_reduce(const ConvParams &p, int rank, int
 #pragma unroll
         for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
       }
-      *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
+      if (p.out) *reinterpret_cast<uint4 *>(p.out + out_base + (size_t)mm[i] * p.Cout + cc[i]) = o;
       const long long rp = row_pl_s[mm[i]];
       if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + cc[i]) = o;
     }
@@ -397,7 +397,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
 #pragma unroll
             for (int k = 0; k < 4; ++k) oh[k] = __hmax2(oh[k], zero);
           }
-          *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
+          if (p.out) *reinterpret_cast<uint4 *>(p.out + off[u]) = o;
           if (pl[u]) *reinterpret_cast<uint4 *>(pl[u]) = o;
         }
       }

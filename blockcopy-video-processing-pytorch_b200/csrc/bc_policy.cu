@@ -165,10 +165,15 @@ struct StatsParams {
   uint32_t P;
   int C;
   float eps;
+  uint32_t zero;         // always 0 (see the note on load batching below)
 };
 
 constexpr int kStatsThreads = 512;
 
+// Left alone, ptxas sinks every load of an unrolled batch next to its use (SASS: math interleaved after every LDG,
+// ~2 loads in flight per thread) to save registers, which bounded the first versions of this kernel at ~1 TB/s.
+// A data dependency keeps a batch together: every value is XOR-ed with (fold of ALL values of the batch) & zero,
+// `zero` being a kernel parameter the compiler cannot fold -- no use can be scheduled before the last load.
 __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsParams p) {
   __shared__ float red[kStatsThreads][17];
   __shared__ double comb[kStatsThreads];
@@ -183,16 +188,23 @@ __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsPara
   const uint32_t step = gridDim.x * rows;
   const __half *base = p.x + sub * 8;
   uint32_t px = blockIdx.x * rows + row;
-  // eight independent 16-byte loads in flight per thread, the tail included (the kernel is a pure stream)
-  for (; px < p.P; px += 8 * step) {
-    uint4 u[8];
+  // sixteen independent 16-byte loads in flight per thread, the tail included: the largest plane of the policy trunk
+  // (131072 pixels x 64 channels on 148 CTAs) is ONE round of loads
+  for (; px < p.P; px += 16 * step) {
+    uint4 u[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 16; ++j) {  // unconditional loads from a clamped pixel: nothing keeps them from being batched
       const uint32_t pj = px + j * step;
-      u[j] = pj < p.P ? __ldg(reinterpret_cast<const uint4 *>(base + (size_t)pj * p.C)) : make_uint4(0, 0, 0, 0);
+      u[j] = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(pj < p.P ? pj : p.P - 1) * p.C));
     }
+    uint32_t fold = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 16; ++j) fold ^= u[j].x;
+    fold &= p.zero;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      u[j].x ^= fold; u[j].y ^= fold; u[j].z ^= fold; u[j].w ^= fold;
+      if (px + j * step >= p.P) u[j] = make_uint4(0, 0, 0, 0);
       const __half2 *h = reinterpret_cast<const __half2 *>(&u[j]);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -230,15 +242,23 @@ __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsPara
     // the last CTA: item -> `slices` threads, each adds every slices-th CTA partial (8 loads in flight) in order
     const int slices = kStatsThreads / items, item = threadIdx.x % items, slice = threadIdx.x / items;
     double t = 0.0;
-    unsigned b = (unsigned)slice;
-    for (; b + 7 * slices < gridDim.x; b += 8 * slices) {
-      float v[8];
+    // all of this thread's partials in flight at once (<= 148 CTAs / slices, padded to batches of 40)
+    for (unsigned b0 = (unsigned)slice; b0 < gridDim.x; b0 += 40 * slices) {
+      float v[40];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldcg(p.partial + (size_t)(b + j * slices) * items + item);
+      for (int j = 0; j < 40; ++j) {
+        const unsigned b = b0 + j * slices;
+        v[j] = __ldcg(p.partial + (size_t)(b < gridDim.x ? b : gridDim.x - 1) * items + item);
+      }
+      uint32_t fold = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t += (double)v[j];
+      for (int j = 0; j < 40; ++j) fold ^= __float_as_uint(v[j]);
+      fold &= p.zero;
+#pragma unroll
+      for (int j = 0; j < 40; ++j) v[j] = __uint_as_float(__float_as_uint(v[j]) ^ fold);
+#pragma unroll
+      for (int j = 0; j < 40; ++j) t += (b0 + j * slices < gridDim.x) ? (double)v[j] : 0.0;
     }
-    for (; b < gridDim.x; b += slices) t += (double)__ldcg(p.partial + (size_t)b * items + item);
     comb[threadIdx.x] = t;
     __syncthreads();
     if (threadIdx.x < p.C) {
@@ -262,8 +282,8 @@ int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, floa
              "bc_bn_stats: C=%d (8, 16, 32, 64 or 128 channels)", C);
   BC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, BC_ERR_ALIGN, "bc_bn_stats: 16-byte alignment");
   const int rows = kStatsThreads / (C / 8);
-  // one CTA per SM at most, and up to eight pixel rows per thread and round: few partials for the last CTA to add
-  long long grid = (P + 8 * rows - 1) / (8 * rows);
+  // one CTA per SM at most, and up to sixteen pixel rows per thread and round: few partials for the last CTA to add
+  long long grid = (P + 16 * rows - 1) / (16 * rows);
   if (grid > kNumSMs) grid = kNumSMs;
   const long long need = 16 + grid * 2 * C * (long long)sizeof(float);
   BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_bn_stats: workspace of %lld bytes, %lld needed", workspace_bytes, need);
@@ -271,7 +291,7 @@ int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, floa
   p.x = (const __half *)x; p.mean = mean; p.invstd = invstd;
   p.ticket = (unsigned int *)workspace;
   p.partial = (float *)((char *)workspace + 16);
-  p.P = (uint32_t)P; p.C = C; p.eps = eps;
+  p.P = (uint32_t)P; p.C = C; p.eps = eps; p.zero = 0u;
   launch_kernel(bn_stats_kernel, dim3((unsigned)grid), dim3(kStatsThreads), 0, stream, 1, p);
   return check_launch("bc_bn_stats");
 }

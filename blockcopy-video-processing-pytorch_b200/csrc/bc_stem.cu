@@ -216,7 +216,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
         const int r = i0 + lane / kTPR;
         const long long ro = row_off_s[q * 32 + r], rp = row_pl_s[q * 32 + r];
         const uint4 o = *reinterpret_cast<const uint4 *>(stage + (size_t)r * kStemRowB + c8 * 2);
-        *reinterpret_cast<uint4 *>(p.out + ro + dt_out + c8) = o;
+        if (p.out) *reinterpret_cast<uint4 *>(p.out + ro + dt_out + c8) = o;
         if (rp >= 0) *reinterpret_cast<uint4 *>(p.plane_out + rp + dt_pl + c8) = o;
       }
       __syncwarp();
@@ -240,7 +240,7 @@ EncodeTiledFn tensor_map_encoder();  // bc_tma.cu
 // s2d_plane (N, Hs, Ws + 2*kStemXPad, 16) fp16 NHWC, pad columns zero; weight fp16 [Cout][4][4][16] (see blockcopy/_C.py: pack_stem_weight)
 int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *bias, const int32_t *mapping, int E,
               int N, int Hs, int Ws, int BS_out, int Cout, int relu, void *plane_out, cudaStream_t stream) {
-  BC_REQUIRE(out && s2d_plane && weight && mapping, BC_ERR_NULL, "bc_conv_stem: NULL pointer");
+  BC_REQUIRE((out || plane_out) && s2d_plane && weight && mapping, BC_ERR_NULL, "bc_conv_stem: NULL pointer");
   BC_REQUIRE(E > 0 && N > 0, BC_ERR_SHAPE, "bc_conv_stem: empty problem");
   BC_REQUIRE(Cout % kStemN == 0, BC_ERR_UNSUPPORTED, "bc_conv_stem: Cout=%d is not a multiple of 64", Cout);
   const int px = BS_out * BS_out;

@@ -89,7 +89,7 @@ def cpu_backend():
         _store(plane_out, tmp)
 
     def conv_igemm(out, plane, weight_cl, bias, residual, mapping_exec, E, BS_in, stride, padding, relu=False,
-                   plane_out=None, out_mapping=None, split_k=True):
+                   plane_out=None, out_mapping=None, split_k=True, write_tiles=True):
         if mapping_exec is None:
             y = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding)
         else:
@@ -99,7 +99,10 @@ def cpu_backend():
             y = y + _nchw(residual)
         if relu:
             y = y.relu()
-        _store(out, y)
+        if write_tiles:
+            _store(out, y)
+        else:
+            out.fill_(float("nan"))  # tile-less launch: whoever reads the tiles without gathering them first gets NaN
         if plane_out is not None:
             _scatter_plane(plane_out, y, (out_mapping if out_mapping is not None else mapping_exec)[:E])
         return out
@@ -149,14 +152,17 @@ def cpu_backend():
         _scatter_plane(s2d_plane[..., 2:-2], s2d, mapping_exec[:E])  # BC_STEM_XPAD columns stay zero
         return s2d_plane
 
-    def conv_stem(out, s2d_plane, weight_packed, bias, mapping_exec, E, relu=False, plane_out=None):
+    def conv_stem(out, s2d_plane, weight_packed, bias, mapping_exec, E, relu=False, plane_out=None, write_tiles=True):
         Cout = weight_packed.shape[0]
         w = weight_packed.view(Cout, 4, 4, 16).permute(0, 3, 1, 2).contiguous()
         full = F.conv2d(F.pad(_nchw(s2d_plane)[..., 2:-2], (2, 1, 2, 1)), w, bias)  # taps oy-2 .. oy+1
         y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), out.shape[-1])
         if relu:
             y = y.relu()
-        _store(out, y)
+        if write_tiles:
+            _store(out, y)
+        else:
+            out.fill_(float("nan"))
         if plane_out is not None:
             _scatter_plane(plane_out, y, mapping_exec[:E])
         return out

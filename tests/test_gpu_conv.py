@@ -110,6 +110,11 @@ def test_conv_dual_write_and_residual_relu():
     want_plane = nxt.clone()
     O.combine_(out.cpu().contiguous(), want_plane, me)
     assert torch.equal(d_next.cpu().contiguous(), want_plane), "plane != scatter of the tiles / untouched cells changed"
+    # plane only (write_tiles=False): same plane bits, the tile batch is left alone
+    out2, d_next2 = d(torch.full((E, C, BS, BS), 7.0).half()), d(nxt)
+    _C.conv_igemm(out2, d(plane), d(w), b.to(dev), d(res), me.to(dev), E, BS, 1, 1, relu=True, plane_out=d_next2,
+                  write_tiles=False)
+    assert torch.equal(d_next2, d_next) and bool((out2 == 7.0).all())
 
 
 @pytest.mark.parametrize("Cin,Cout,BS", [(256, 256, 8), (512, 512, 4), (128, 128, 8)])
