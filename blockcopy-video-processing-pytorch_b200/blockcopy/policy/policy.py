@@ -313,6 +313,12 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                 assert reward.dim() == 4
                 assert not torch.any(torch.isnan(reward))
                 log_probs = policy_meta["grid_log_probs"]
+                if log_probs is None:
+                    raise RuntimeError(
+                        "PolicyTrainRL.optim(train=True) on a frame whose forward ran without autograd: "
+                        "policy_meta['policy_will_train'] was False for this frame (BlockCopyModel sets it from "
+                        "clip_length % block_train_interval; a custom driver must set it to True, or leave it out, "
+                        "on the frames it trains on)")
                 reward = F.adaptive_max_pool2d(reward, output_size=log_probs.shape[2:])
                 reward = torch.where(grid, reward, -reward)  # skipped blocks: negated reward
                 loss_policy = (-log_probs * reward.detach()).mean()

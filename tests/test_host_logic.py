@@ -313,3 +313,40 @@ def test_lazy_fusion_removes_scatters_and_elementwise_kernels(monkeypatch):
     # absorbed, with the 19-channel conv and the final combine, into one bc_head_1x1 launch per frame
     assert c1["ew_fused"] == 2 * 10 and c1["head_1x1"] == 2 and "head_1x1" not in c0, (c0, c1)
     assert c0["scatter"] - c1["scatter"] >= 2 * 18, (c0, c1)     # planes are written by producer epilogues instead
+
+
+def test_policy_will_train_hint_is_set_and_a_wrong_hint_fails_loudly():
+    """BlockCopyModel announces training frames to the policy (policy_meta['policy_will_train']); a training step
+    on a frame that was announced as inference-only raises instead of silently skipping the update."""
+    import pytest
+    import torch
+
+    import blockcopy
+    from blockcopy.core.argparser import default_settings
+    from blockcopy.policy.policy import Policy
+
+    seen = []
+
+    class Spy(Policy):
+        def forward(self, policy_meta):
+            seen.append(policy_meta.get("policy_will_train"))
+            shape = self._grid_shape(policy_meta)
+            policy_meta["grid"] = torch.ones(shape, dtype=torch.bool)
+            return self.stats.add_policy_meta(policy_meta)
+
+    with cpu_backend():
+        model = blockcopy.BlockCopyModel(torch.nn.Conv2d(3, 4, 1), default_settings(block_policy="all", block_size=8,
+                                                                                  block_train_interval=3)).eval()
+        model.policy = Spy(block_size=8)
+        x = torch.randn(1, 3, 16, 16)
+        with torch.no_grad():
+            for _ in range(6):
+                model(x)
+    assert seen == [False, False, True, False, False, True]
+
+    pol = blockcopy.build_policy_from_settings(default_settings(block_policy="rl_semseg", block_size=8))
+    meta = dict(inputs=x, outputs=torch.randn(1, 19, 4, 4), outputs_prev=torch.randn(1, 19, 4, 4),
+                grid=torch.ones(1, 1, 2, 2, dtype=torch.bool), perc_exec=1.0, grid_log_probs=None,
+                grid_probs=torch.full((1, 1, 2, 2), 0.5))
+    with pytest.raises(RuntimeError, match="policy_will_train"):
+        pol.optim(meta, train=True)
