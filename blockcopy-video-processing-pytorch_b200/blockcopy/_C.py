@@ -45,6 +45,7 @@ _SIGNATURES = {
     "bc_stem_pack": ([_vp, _vp, _ip] + [_i] * 5 + [_vp], _i),
     "bc_conv_stem": ([_vp, _vp, _vp, _vp, _ip] + [_i] * 7 + [_vp, _vp], _i),
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
+    "bc_policy_features_nhwc16": ([_vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
@@ -536,6 +537,33 @@ def policy_features(frame: torch.Tensor, frame_state: torch.Tensor, output_repr:
                                     ctypes.cast(strides, ctypes.c_void_p), 1.0 / scale_factor, 1.0 / scale_factor,
                                     _dtype(frame), _stream()), "bc_policy_features")
     return out
+
+
+def policy_features_shape(frame: torch.Tensor, output_repr: torch.Tensor, scale_factor: float):
+    N, _, H, W = frame.shape
+    return (N, 7 + output_repr.shape[1], int(H * scale_factor), int(W * scale_factor))
+
+
+def policy_features_nhwc16(out16: torch.Tensor, frame: torch.Tensor, frame_state: torch.Tensor, output_repr: torch.Tensor,
+                           grid: torch.Tensor, scale_factor: float) -> torch.Tensor:
+    """The policy net's input features written as fp16 channels_last into out16 (N, Cp, Ho, Wo), Cp >= 7+K padded
+    (see bc_policy_features_nhwc16): the values of policy_features() rounded to fp16."""
+    _dev(out16, frame, frame_state, output_repr, grid)
+    N, _, H, W = frame.shape
+    K, h, w = output_repr.shape[1:]
+    Ho, Wo = int(H * scale_factor), int(W * scale_factor)
+    assert out16.dtype == torch.float16 and out16.is_contiguous(memory_format=torch.channels_last)
+    assert out16.shape[0] == N and tuple(out16.shape[2:]) == (Ho, Wo)
+    assert frame.is_contiguous() and frame_state.is_contiguous() and frame_state.dtype == frame.dtype
+    if output_repr.dtype != frame.dtype:
+        output_repr = output_repr.to(frame.dtype)
+    g = grid.to(torch.bool).contiguous()
+    strides = (ctypes.c_int64 * 4)(*output_repr.stride())
+    _check(lib().bc_policy_features_nhwc16(out16.data_ptr(), out16.shape[1], frame.data_ptr(), frame_state.data_ptr(),
+                                           output_repr.data_ptr(), g.data_ptr(), N, K, H, W, h, w, g.shape[2], g.shape[3],
+                                           Ho, Wo, ctypes.cast(strides, ctypes.c_void_p), 1.0 / scale_factor,
+                                           1.0 / scale_factor, _dtype(frame), _stream()), "bc_policy_features_nhwc16")
+    return out16
 
 
 def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor:

@@ -107,11 +107,15 @@ class FusedPolicyTrunk:
 
     # ------------------------------------------------------------------ shape envelope
     def supports(self, x: torch.Tensor) -> bool:
-        if not (self.ok and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and x.shape[1] == self.in_channels):
+        return x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and self.supports_shape(tuple(x.shape), x.device)
+
+    def supports_shape(self, shape, device) -> bool:
+        """Can the trunk run on features of this (N, C, H, W) shape on `device`?"""
+        if not (self.ok and len(shape) == 4 and shape[1] == self.in_channels and device.type == "cuda"):
             return False
-        if any(b.bn.weight.dtype != torch.float32 or b.bn.weight.device != x.device for b in self._bns()):
+        if any(b.bn.weight.dtype != torch.float32 or b.bn.weight.device != device for b in self._bns()):
             return False  # the affine vectors are handed to the kernels as they are
-        H, W = x.shape[2], x.shape[3]
+        H, W = shape[2], shape[3]
         for conv in [self.stem[0]] + [c for b in self.blocks for c in (b[0], b[2])] + [h[0] for h in self.head]:
             if _block_edge(H, W, conv.stride) is None:
                 return False
@@ -139,10 +143,9 @@ class FusedPolicyTrunk:
         _C.ew_fused(out, x, None, (b.mean, b.invstd, b.weight, b.shift), relu=relu)
         return out
 
-    def _forward(self, x: torch.Tensor) -> torch.Tensor:
-        N, C, H, W = x.shape
+    def _forward(self) -> torch.Tensor:
+        """Everything after the input plane ``self._x16`` has been filled."""
         self._pack()
-        self._x16[:, :C].copy_(x)
         h = self._bn(self._conv(self._x16, self.stem[0]), self.stem[1], relu=True)
         for c1, b1, c2, b2, ds in self.blocks:
             y = self._bn(self._conv(h, c1), b1, relu=True)
@@ -191,32 +194,37 @@ class FusedPolicyTrunk:
             self._pack_total, self._pack_key = off, key
         _C.pack_params(self._pack_table, self._pack_total)
 
-    def _prepare(self, x: torch.Tensor):
-        N, C, H, W = x.shape
-        if self._ws is None or self._ws.device != x.device:
-            self._ws = torch.zeros(_C.BN_STATS_WORKSPACE, dtype=torch.uint8, device=x.device)
-        shape = (N, _pad64(C), H, W)
-        if self._x16 is None or tuple(self._x16.shape) != shape or self._x16.device != x.device:
-            self._x16 = torch.zeros(shape, dtype=torch.float16, device=x.device).contiguous(memory_format=torch.channels_last)
+    def _prepare(self, shape, device):
+        N, C, H, W = shape
+        if self._ws is None or self._ws.device != device:
+            self._ws = torch.zeros(_C.BN_STATS_WORKSPACE, dtype=torch.uint8, device=device)
+        shape16 = (N, _pad64(C), H, W)
+        if self._x16 is None or tuple(self._x16.shape) != shape16 or self._x16.device != device:
+            self._x16 = torch.zeros(shape16, dtype=torch.float16, device=device).contiguous(memory_format=torch.channels_last)
+            self._graph = None  # captured on the old plane
 
-    # ------------------------------------------------------------------ entry point
+    # ------------------------------------------------------------------ entry points
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, use_cuda_graph: bool = False) -> torch.Tensor:
         """x: (N, in_channels, H, W) fp32 CUDA features -> (N, 1, H/32, W/32) fp32 logits."""
-        self._prepare(x)
+        return self.run(lambda x16: x16[:, : x.shape[1]].copy_(x), tuple(x.shape), x.device, use_cuda_graph)
+
+    @torch.no_grad()
+    def run(self, fill, shape, device, use_cuda_graph: bool = False) -> torch.Tensor:
+        """fill(x16) writes the features (fp16, channels 0..C-1 of the padded NHWC plane x16) -- eagerly, every call;
+        everything behind it is one CUDA graph when `use_cuda_graph`."""
+        self._prepare(shape, device)
+        fill(self._x16)
         if not use_cuda_graph:
-            return self._forward(x)
-        key = (tuple(x.shape), x.device, self._param_key())
+            return self._forward()
+        key = (tuple(shape), device, self._param_key())
         g = self._graph
         if g is None or g[0] != key:
-            static_in = torch.empty_like(x)
-            static_in.copy_(x)
-            self._forward(static_in)  # warm-up: persistent buffers, cuDNN plan of the last conv
-            torch.cuda.synchronize(x.device)
+            self._forward()  # warm-up: persistent buffers, the packing table
+            torch.cuda.synchronize(device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self._forward(static_in)
-            g = self._graph = (key, graph, static_in, static_out)
-        g[2].copy_(x)
+                static_out = self._forward()
+            g = self._graph = (key, graph, static_out)
         g[1].replay()
-        return g[3]
+        return g[2]

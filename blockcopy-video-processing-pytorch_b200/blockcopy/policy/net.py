@@ -126,18 +126,45 @@ class PolicyNet(nn.Module):
             t = self.__dict__["_fused"] = FusedPolicyTrunk(self)
         return t
 
+    def _fused_forward(self, policy_meta: dict):
+        """Features written straight into the fused trunk's fp16 NHWC input plane (bc_policy_features_nhwc16) and
+        the trunk behind it; None when the inputs are outside that kernel's envelope (see _fused_features)."""
+        frame, state = policy_meta["inputs"], policy_meta.get("frame_state", None)
+        rep, grid = policy_meta.get("output_repr", None), policy_meta.get("grid", None)
+        if not (self.use_frame_state and self.use_prev_output and self.use_prev_grid) or not frame.is_cuda:
+            return None
+        if state is None or rep is None or grid is None or rep.dim() != 4 or grid.dim() != 4 or frame.dim() != 4:
+            return None
+        if frame.dtype not in (torch.float16, torch.float32) or state.dtype != frame.dtype or state.shape != frame.shape:
+            return None
+        if not frame.is_contiguous() or not state.is_contiguous() or rep.dtype not in (torch.float16, torch.float32):
+            return None
+        from blockcopy import _C
+
+        fused = self._fused_trunk()
+        shape = _C.policy_features_shape(frame, rep, self.scale_factor)
+        if not fused.supports_shape(shape, frame.device):
+            return None
+        with timings.env("policy/net/layers", 5):
+            return fused.run(lambda x16: _C.policy_features_nhwc16(x16, frame, state, rep, grid, self.scale_factor),
+                             shape, frame.device, use_cuda_graph=self.use_cuda_graphs)
+
     def forward(self, policy_meta: dict, no_grad: bool = False):
         """no_grad: the caller will not back-propagate through this call (a frame without policy update): the
         trunk may run on the inference kernels."""
         N, C, H, W = policy_meta["inputs"].shape
-        with timings.env("policy/net/build_features", 5):
-            x = self.build_features(policy_meta)
-        with timings.env("policy/net/layers", 5):
-            fused = self._fused_trunk() if (no_grad and self.fused_inference and self.training and x.is_cuda) else None
-            if fused is not None and fused.supports(x):
-                logits = fused(x, use_cuda_graph=self.use_cuda_graphs)
-            else:
-                logits = self._trunk_forward(x)
+        logits = None
+        if no_grad and self.fused_inference and self.training:
+            logits = self._fused_forward(policy_meta)
+        if logits is None:
+            with timings.env("policy/net/build_features", 5):
+                x = self.build_features(policy_meta)
+            with timings.env("policy/net/layers", 5):
+                fused = self._fused_trunk() if (no_grad and self.fused_inference and self.training and x.is_cuda) else None
+                if fused is not None and fused.supports(x):
+                    logits = fused(x, use_cuda_graph=self.use_cuda_graphs)
+                else:
+                    logits = self._trunk_forward(x)
         expect = (N, 1, H // self.block_size, W // self.block_size)
         assert logits.shape == expect, f"logits shape: {logits.shape}, frame shape: {(N, C, H, W)}, " \
                                        f"block size: {self.block_size}"

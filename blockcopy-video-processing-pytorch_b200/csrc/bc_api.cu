@@ -58,6 +58,9 @@ int conv_stem(void *out, const void *s2d_plane, const void *weight, const void *
 int policy_features(float *out, const void *frame, const void *state, const void *repr, const uint8_t *grid, int N,
                     int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
                     float sy_frame, float sx_frame, int dtype, cudaStream_t stream);
+int policy_features_nhwc16(void *out, int Cp, const void *frame, const void *state, const void *repr, const uint8_t *grid,
+                           int N, int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo,
+                           const int64_t *repr_strides, float sy_frame, float sx_frame, int dtype, cudaStream_t stream);
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
 
@@ -324,6 +327,14 @@ BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, co
 BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
                               int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream) {
   return upsample_argmax(labels, logits, N, K, h, w, strides, scale, (int)dtype, label_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_policy_features_nhwc16(void *out, int Cp, const void *frame, const void *frame_state,
+                                     const void *output_repr, const uint8_t *grid, int N, int K, int H, int W, int h,
+                                     int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
+                                     float inv_scale_y, float inv_scale_x, bc_dtype_t dtype, bc_stream_t stream) {
+  return policy_features_nhwc16(out, Cp, frame, frame_state, output_repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo,
+                                repr_strides, inv_scale_y, inv_scale_x, (int)dtype, (cudaStream_t)stream);
 }
 
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,

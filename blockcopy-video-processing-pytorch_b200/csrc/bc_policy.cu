@@ -30,6 +30,22 @@ __device__ __forceinline__ int nearest_src(float scale, int dst, int in_size) {
 }
 
 template <typename T>
+__device__ __forceinline__ float feat_value(const FeatParams &p, int n, int c, int y, int x) {
+  if (c < 6) {
+    const T *src = reinterpret_cast<const T *>(c < 3 ? p.frame : p.state);
+    const int cc = c < 3 ? c : c - 3;
+    const int yy = nearest_src(p.sy_frame, y, p.H), xx = nearest_src(p.sx_frame, x, p.W);
+    return to_f<T>(src[(((size_t)n * 3 + cc) * p.H + yy) * p.W + xx]);
+  }
+  if (c < 6 + p.K) {
+    const int yy = nearest_src(p.sy_repr, y, p.h), xx = nearest_src(p.sx_repr, x, p.w);
+    return to_f<T>(reinterpret_cast<const T *>(p.repr)[n * p.repr_sn + (c - 6) * p.repr_sc + yy * p.repr_sh + xx * p.repr_sw]) - 0.5f;
+  }
+  const int yy = nearest_src(p.sy_grid, y, p.GH), xx = nearest_src(p.sx_grid, x, p.GW);
+  return (p.grid[((size_t)n * p.GH + yy) * p.GW + xx] ? 1.f : 0.f) - 0.5f;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) policy_features_kernel(const FeatParams p) {
   pdl_trigger();
   pdl_wait();
@@ -40,36 +56,62 @@ __global__ void __launch_bounds__(256) policy_features_kernel(const FeatParams p
     const int y = (int)((i / (uint32_t)p.Wo) % (uint32_t)p.Ho);
     const int c = (int)((i / ((uint32_t)p.Wo * p.Ho)) % (uint32_t)C);
     const int n = (int)(i / ((uint32_t)p.Wo * p.Ho * C));
-    float v;
-    if (c < 6) {
-      const T *src = reinterpret_cast<const T *>(c < 3 ? p.frame : p.state);
-      const int cc = c < 3 ? c : c - 3;
-      const int yy = nearest_src(p.sy_frame, y, p.H), xx = nearest_src(p.sx_frame, x, p.W);
-      v = to_f<T>(src[(((size_t)n * 3 + cc) * p.H + yy) * p.W + xx]);
-    } else if (c < 6 + p.K) {
-      const int yy = nearest_src(p.sy_repr, y, p.h), xx = nearest_src(p.sx_repr, x, p.w);
-      v = to_f<T>(reinterpret_cast<const T *>(p.repr)[n * p.repr_sn + (c - 6) * p.repr_sc + yy * p.repr_sh + xx * p.repr_sw]) - 0.5f;
-    } else {
-      const int yy = nearest_src(p.sy_grid, y, p.GH), xx = nearest_src(p.sx_grid, x, p.GW);
-      v = (p.grid[((size_t)n * p.GH + yy) * p.GW + xx] ? 1.f : 0.f) - 0.5f;
-    }
-    p.out[i] = v;
+    p.out[i] = feat_value<T>(p, n, c, y, x);
   }
 }
 
-int policy_features(float *out, const void *frame, const void *state, const void *repr, const uint8_t *grid, int N,
-                    int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
-                    float sy_frame, float sx_frame, int dtype, cudaStream_t stream) {
-  BC_REQUIRE(out && frame && state && repr && grid && repr_strides, BC_ERR_NULL, "bc_policy_features: NULL pointer");
-  BC_REQUIRE(N > 0 && K > 0 && Ho > 0 && Wo > 0, BC_ERR_SHAPE, "bc_policy_features: empty problem");
-  BC_REQUIRE(dtype == BC_F16 || dtype == BC_F32, BC_ERR_DTYPE, "bc_policy_features: dtype");
-  FeatParams p;
-  p.frame = frame; p.state = state; p.repr = repr; p.grid = grid; p.out = out;
+// The same features as fp16 NHWC with the channel count padded to Cp (the input plane of the fused policy trunk,
+// policy/fused_net.py): one thread per (pixel, 8-channel chunk), 16-byte stores; chunks beyond the last real channel
+// are not touched (the caller zeroes the plane once).  Values = the fp32 features rounded to fp16.
+template <typename T>
+__global__ void __launch_bounds__(256) policy_features_nhwc16_kernel(const FeatParams p, __half *out16, int Cp, int chunks,
+                                                                     uint32_t total) {
+  pdl_trigger();
+  pdl_wait();
+  const int C = 7 + p.K;
+  const uint32_t gstride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+    const int chunk = (int)(i % (uint32_t)chunks);
+    const uint32_t pix = i / (uint32_t)chunks;
+    const int x = (int)(pix % (uint32_t)p.Wo), y = (int)((pix / (uint32_t)p.Wo) % (uint32_t)p.Ho);
+    const int n = (int)(pix / ((uint32_t)p.Wo * p.Ho));
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = chunk * 8 + 2 * k;
+      const float a = c0 < C ? feat_value<T>(p, n, c0, y, x) : 0.f, b = c0 + 1 < C ? feat_value<T>(p, n, c0 + 1, y, x) : 0.f;
+      const __half2 h = __floats2half2_rn(a, b);
+      w[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(out16 + (size_t)pix * Cp + chunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+static int fill_feat_params(FeatParams &p, const void *frame, const void *state, const void *repr, const uint8_t *grid, int N,
+                            int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
+                            float sy_frame, float sx_frame, int dtype, const char *who) {
+  BC_REQUIRE(frame && state && repr && grid && repr_strides, BC_ERR_NULL, "%s: NULL pointer", who);
+  BC_REQUIRE(N > 0 && K > 0 && Ho > 0 && Wo > 0, BC_ERR_SHAPE, "%s: empty problem", who);
+  BC_REQUIRE(dtype == BC_F16 || dtype == BC_F32, BC_ERR_DTYPE, "%s: dtype", who);
+  p.frame = frame; p.state = state; p.repr = repr; p.grid = grid; p.out = nullptr;
   p.N = N; p.K = K; p.H = H; p.W = W; p.h = h; p.w = w; p.GH = GH; p.GW = GW; p.Ho = Ho; p.Wo = Wo;
   p.repr_sn = repr_strides[0]; p.repr_sc = repr_strides[1]; p.repr_sh = repr_strides[2]; p.repr_sw = repr_strides[3];
   p.sy_frame = sy_frame; p.sx_frame = sx_frame;        // = 1 / scale_factor, as ATen uses for scale_factor= calls
   p.sy_repr = (float)h / Ho; p.sx_repr = (float)w / Wo;  // size= calls: in / out
   p.sy_grid = (float)GH / Ho; p.sx_grid = (float)GW / Wo;
+  p.total = 0;
+  return BC_OK;
+}
+
+int policy_features(float *out, const void *frame, const void *state, const void *repr, const uint8_t *grid, int N,
+                    int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
+                    float sy_frame, float sx_frame, int dtype, cudaStream_t stream) {
+  BC_REQUIRE(out, BC_ERR_NULL, "bc_policy_features: NULL pointer");
+  FeatParams p;
+  const int rc = fill_feat_params(p, frame, state, repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo, repr_strides, sy_frame,
+                                  sx_frame, dtype, "bc_policy_features");
+  if (rc != BC_OK) return rc;
+  p.out = out;
   const int64_t total = (int64_t)N * (7 + K) * Ho * Wo;
   BC_REQUIRE(total < (1ll << 31), BC_ERR_RANGE, "bc_policy_features: problem too large");
   p.total = (uint32_t)total;
@@ -80,6 +122,29 @@ int policy_features(float *out, const void *frame, const void *state, const void
   else
     launch_kernel(policy_features_kernel<float>, dim3((unsigned)gridsz), dim3(256), 0, stream, 1, p);
   return check_launch("bc_policy_features");
+}
+
+int policy_features_nhwc16(void *out, int Cp, const void *frame, const void *state, const void *repr, const uint8_t *grid,
+                           int N, int K, int H, int W, int h, int w, int GH, int GW, int Ho, int Wo,
+                           const int64_t *repr_strides, float sy_frame, float sx_frame, int dtype, cudaStream_t stream) {
+  BC_REQUIRE(out && ((uintptr_t)out & 15) == 0, BC_ERR_ALIGN, "bc_policy_features_nhwc16: out must be 16-byte aligned");
+  BC_REQUIRE(Cp % 8 == 0 && Cp >= 7 + K, BC_ERR_SHAPE, "bc_policy_features_nhwc16: padded channel count %d", Cp);
+  FeatParams p;
+  const int rc = fill_feat_params(p, frame, state, repr, grid, N, K, H, W, h, w, GH, GW, Ho, Wo, repr_strides, sy_frame,
+                                  sx_frame, dtype, "bc_policy_features_nhwc16");
+  if (rc != BC_OK) return rc;
+  const int chunks = (7 + K + 7) / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * chunks;
+  BC_REQUIRE((int64_t)N * Ho * Wo * Cp < (1ll << 31), BC_ERR_RANGE, "bc_policy_features_nhwc16: problem too large");
+  int64_t gridsz = (total + 255) / 256;
+  if (gridsz > (int64_t)kNumSMs * 16) gridsz = (int64_t)kNumSMs * 16;
+  if (dtype == BC_F16)
+    launch_kernel(policy_features_nhwc16_kernel<__half>, dim3((unsigned)gridsz), dim3(256), 0, stream, 1, p, (__half *)out, Cp,
+                  chunks, (uint32_t)total);
+  else
+    launch_kernel(policy_features_nhwc16_kernel<float>, dim3((unsigned)gridsz), dim3(256), 0, stream, 1, p, (__half *)out, Cp,
+                  chunks, (uint32_t)total);
+  return check_launch("bc_policy_features_nhwc16");
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -222,6 +222,15 @@ BC_API int bc_policy_features(float *out, const void *frame, const void *frame_s
                               int Wo, const int64_t *repr_strides, float inv_scale_y, float inv_scale_x,
                               bc_dtype_t dtype, bc_stream_t stream);
 
+/* The same features as the input plane of the fused policy trunk (blockcopy/policy/fused_net.py): fp16 NHWC
+ * (N, Ho, Wo, Cp) with the channel count padded to Cp (multiple of 8, >= 7+K); values = the fp32 features rounded to
+ * fp16; channels >= 8*ceil((7+K)/8) are not written (zero the plane once).
+ */
+BC_API int bc_policy_features_nhwc16(void *out, int Cp, const void *frame, const void *frame_state,
+                                     const void *output_repr, const uint8_t *grid, int N, int K, int H, int W, int h,
+                                     int w, int GH, int GW, int Ho, int Wo, const int64_t *repr_strides,
+                                     float inv_scale_y, float inv_scale_x, bc_dtype_t dtype, bc_stream_t stream);
+
 /* ---- output head fused with the final combine ------------------------------------------------------
  * Replaces, at the end of every frame, eval batch_norm + ReLU on the tile batch, the few-channel 1x1 conv
  * (class logits; cuDNN in the reference path, core/tensorwrapper.py:519-520), its bias add, and

@@ -183,13 +183,13 @@ def test_rl_policy_uses_fused_trunk_on_frames_without_update():
     from consumers.swiftnet_rn18 import build_swiftnet_rn18
 
     calls = []
-    orig = fused_net.FusedPolicyTrunk.__call__
+    orig = fused_net.FusedPolicyTrunk.run
 
-    def spy(self, x, use_cuda_graph=False):
-        calls.append(tuple(x.shape))
-        return orig(self, x, use_cuda_graph)
+    def spy(self, fill, shape, device, use_cuda_graph=False):
+        calls.append(tuple(shape))
+        return orig(self, fill, shape, device, use_cuda_graph)
 
-    fused_net.FusedPolicyTrunk.__call__ = spy
+    fused_net.FusedPolicyTrunk.run = spy
     try:
         model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), default_settings(block_policy="rl_semseg", block_size=128,
                                                                                block_train_interval=3)).eval().cuda().half()
@@ -200,7 +200,7 @@ def test_rl_policy_uses_fused_trunk_on_frames_without_update():
             outs = [model(f) for f in clip]
         torch.cuda.synchronize()
     finally:
-        fused_net.FusedPolicyTrunk.__call__ = orig
+        fused_net.FusedPolicyTrunk.run = orig
     assert all(torch.isfinite(o).all() for o in outs)
     # frames 2..7 run the policy net (frame 1 has no history); frames 3 and 6 train (clip_length % 3 == 0)
     assert len(calls) == 4, calls
@@ -257,3 +257,27 @@ def test_fused_rmsprop_matches_torch(momentum, wd):
         assert sa["state"][k].keys() == sb["state"][k].keys()
         assert torch.allclose(sa["state"][k]["square_avg"], sb["state"][k]["square_avg"], rtol=1e-6, atol=1e-10)
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_policy_features_nhwc16_equals_rounded_fp32_features_and_feeds_the_trunk(dtype):
+    """bc_policy_features_nhwc16 writes what `policy_features().half()` holds, into the padded channels_last plane;
+    the trunk run from it gives the same logits as the trunk run from the fp32 features."""
+    from blockcopy import _C
+    from blockcopy.policy.fused_net import FusedPolicyTrunk
+
+    g = torch.Generator().manual_seed(2)
+    N, H, W, BS = 1, 512, 1024, 128
+    rep = torch.randn(N, 19, H // 4, W // 4, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    frame, state = torch.randn(N, 3, H, W, generator=g).to(dtype).cuda(), torch.randn(N, 3, H, W, generator=g).to(dtype).cuda()
+    grid = (torch.rand(N, 1, H // BS, W // BS, generator=g) < 0.4).cuda()
+    x = _C.policy_features(frame, state, rep, grid, 0.25)
+    x16 = torch.full((N, 64, H // 4, W // 4), 7.0, dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+    _C.policy_features_nhwc16(x16, frame, state, rep, grid, 0.25)
+    assert torch.equal(x16[:, :26], x.half())
+    assert bool((x16[:, 26:32] == 0).all()) and bool((x16[:, 32:] == 7.0).all())  # written chunk padding / untouched rest
+    net = _policy_net(3)
+    a, b = FusedPolicyTrunk(net), FusedPolicyTrunk(net)
+    want = a(x).clone()
+    got = b.run(lambda buf: _C.policy_features_nhwc16(buf, frame, state, rep, grid, 0.25), tuple(x.shape), x.device)
+    assert torch.equal(got, want)
