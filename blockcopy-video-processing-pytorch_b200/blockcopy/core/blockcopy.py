@@ -24,12 +24,18 @@ class BlockCopyModel(nn.Module):
     Optional extra keys (absent => reference behaviour):
       block_channels_last (bool, default True): store conv weights channels_last so that packed
           tiles and planes are NHWC, the layout the sm_100a kernels are written for.
-      block_cuda_graphs (bool, default False): capture the whole block-sparse frame (index
-          compaction, gather, every layer, combines) into one CUDA graph per executed-block count and
-          replay it; the Python interception layer then runs only while capturing.  Differences to
-          the eager mode: feature planes persist across ``reset_temporal`` (the first frame of a
-          clip rewrites all of them), and the returned output tensor is one of two alternating
-          buffers -- it stays valid until the next-but-one call (clone it to keep it longer).
+      block_cuda_graphs (bool, default False): capture the block-sparse frame behind the split (every
+          layer, the combines) into one CUDA graph per executed-block count and replay it; index
+          compaction and the gather of the executed input blocks run eagerly, straight from the caller's
+          frame; side branches of the model (skip bottlenecks, residual downsamples, the frame_state
+          scatter) are parallel branches of the graph.  The Python interception layer then runs only while
+          capturing.  Differences to the eager mode: feature planes persist across ``reset_temporal`` (the
+          first frame of a clip rewrites all of them), and the returned output tensor is one of two
+          alternating buffers -- it stays valid until the next-but-one call (clone it to keep it longer).
+      block_policy_fused (bool, default True): ``rl_*`` policies run the policy net's trunk on this repo's
+          kernels on frames that are not followed by a policy update (policy/fused_net.py) and step the
+          optimiser with one kernel (policy/fused_optim.py).  False: torch / cuDNN throughout.
+      block_policy_shared (bool, default False): one policy for all ranks (gradient all-reduce).
     """
 
     def __init__(self, base_model: nn.Module, settings: dict):
