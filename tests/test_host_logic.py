@@ -350,3 +350,29 @@ def test_policy_will_train_hint_is_set_and_a_wrong_hint_fails_loudly():
                 grid_probs=torch.full((1, 1, 2, 2), 0.5))
     with pytest.raises(RuntimeError, match="policy_will_train"):
         pol.optim(meta, train=True)
+
+
+def test_deferred_engine_on_other_topologies_equals_op_by_op(monkeypatch):
+    """Lazy epilogue fusion + tile-less launches (kernels emulated on CPU, unwritten tile batches poisoned with NaN)
+    against op-by-op execution on a model with main-chain 1x1 convs, a pre-activation unit feeding a padded conv,
+    results with two consumers, an in-place op, and an upsampled sum read by two padded convs and a plain add."""
+    import blockcopy
+    from blockcopy.core import tensorwrapper as tw
+    from consumers.clips import PolicyFixedFraction, deterministic_init_, synthetic_clip
+    from side_topologies import SideTopologies
+
+    clip = synthetic_clip(4, 128, 256, seed=3, dtype=torch.float32)
+
+    def run(lazy):
+        monkeypatch.setattr(tw, "LAZY_FUSION", lazy)
+        net = deterministic_init_(SideTopologies().eval(), seed=1)
+        model = blockcopy.BlockCopyModel(net, _settings(block_policy="all", block_size=32)).eval()
+        model.policy = PolicyFixedFraction(32, fraction=0.4, quantize=4, seed=5)
+        with cpu_backend(), torch.no_grad():
+            model.reset_temporal()
+            return [model(f).clone() for f in clip]
+
+    lazy, plain = run(True), run(False)
+    for t, (a, b) in enumerate(zip(lazy, plain)):
+        assert torch.isfinite(a).all(), f"frame {t}: an unwritten tile batch was read"
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-4), (t, float((a - b).abs().max()))
