@@ -91,3 +91,20 @@ def test_upsample_argmax_errors():
         _C.upsample_argmax(torch.randn(1, 300, 4, 4).half().cuda(), 4, torch.uint8)
     with pytest.raises(AssertionError):
         _C.upsample_argmax(x.cpu(), 4)
+
+
+def test_kernels_equal_committed_golden(golden_dir):
+    """The CUDA kernels against tests/golden/io_kat.pt (made by torchvision / torch CPU calls, not by the oracle)."""
+    import os
+
+    from blockcopy import _C
+
+    fix = torch.load(os.path.join(golden_dir, "io_kat.pt"))
+    for dtype, key in ((torch.float32, "frames_fp32"), (torch.float16, "frames_fp16")):
+        got = _C.frame_from_u8(fix["u8"].cuda(), fix["mean"], fix["std"], dtype)
+        assert torch.equal(got.cpu(), fix[key])
+    for lab in (torch.uint8, torch.int64):
+        assert torch.equal(_C.upsample_argmax(fix["logits16"].cuda(), 4, lab).cpu().long(), fix["labels16"])
+    got32 = _C.upsample_argmax(fix["logits32"].cuda(), 4, torch.int64).cpu()
+    diff = got32 != fix["labels32"]
+    assert not diff.any() or float(fix["top2_gap32"][diff].max()) < 1e-6

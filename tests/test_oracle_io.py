@@ -74,3 +74,16 @@ def test_upsample_argmax_fp16_rounding_and_ties():
     assert torch.equal(got[~ties], want[~ties])
     # constant logits: everything ties -> class 0
     assert int(cpu_oracle.upsample_argmax(torch.zeros(1, 4, 3, 3).half(), 4).max()) == 0
+
+
+def test_oracle_equals_committed_golden(golden_dir):
+    """tests/golden/io_kat.pt: outputs of torchvision / torch CPU calls (oracle/make_golden_io.py)."""
+    import os
+
+    fix = torch.load(os.path.join(golden_dir, "io_kat.pt"))
+    for dtype, key in ((torch.float32, "frames_fp32"), (torch.float16, "frames_fp16")):
+        assert torch.equal(cpu_oracle.frame_from_u8(fix["u8"], fix["mean"], fix["std"], dtype), fix[key])
+    assert torch.equal(cpu_oracle.upsample_argmax(fix["logits16"], 4), fix["labels16"])
+    got32 = cpu_oracle.upsample_argmax(fix["logits32"], 4)
+    diff = got32 != fix["labels32"]
+    assert not diff.any() or float(fix["top2_gap32"][diff].max()) < 1e-6  # fp32: only exact near-ties may differ
