@@ -125,15 +125,16 @@ class Policy(torch.nn.Module, metaclass=abc.ABCMeta):
         (policy.py:124-144), so seeding ``random`` reproduces its choice."""
         if self.quantize_number_exec > 0:
             with timings.env("policy/quantize_number_exec", 3):
-                flat = grid.flatten()
-                skipped = torch.nonzero(~flat.bool().cpu()).squeeze(1).tolist()
-                total = flat.numel()
+                host = grid.detach().reshape(-1).bool().cpu().numpy()  # the one device round trip (G bytes)
+                skipped = (~host).nonzero()[0].tolist()                 # ascending, like torch.nonzero
+                total = host.size
                 num_exec = total - len(skipped)
                 multiple = int(total * self.quantize_number_exec)
                 target = multiple * (1 + (num_exec - 1) // multiple)
                 extra = random.sample(skipped, target - num_exec)
                 if extra:
-                    flat[torch.as_tensor(extra, device=grid.device, dtype=torch.long)] = 1
+                    host[extra] = True  # one upload of the whole (G-byte) mask instead of index upload + index_put
+                    grid.copy_(torch.from_numpy(host).view(grid.shape), non_blocking=False)
                 grid._bc_num_exec = target  # counted on the host just now: saves the device round trip
         return grid
 
