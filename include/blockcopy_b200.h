@@ -151,7 +151,8 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
  * Optional fused scatter (north-star item (b)/(c)): when plane_out != NULL the epilogue ALSO writes
  * every output pixel into the NEXT padded op's persistent plane (out_N, out_GH*BS_out, out_GW*BS_out,
  * Cout) at the block's position (out_mapping = mapping_exec of the output grid), so no separate
- * scatter kernel runs and cells that were not executed keep the previous frame's values.
+ * scatter kernel runs and cells that were not executed keep the previous frame's values.  With plane_out given,
+ * out may be NULL: the tile batch is then not written at all (the consumer reads the plane).
  * allow_split_k != 0: layers whose output tiles cannot fill 148 SMs (4..8-px blocks) are split along K
  * over a thread-block cluster (1,1,S<=8) and the partial accumulators are summed in rank order, so
  * results are run-to-run reproducible.  workspace (optional, 16-byte aligned device memory private to the
@@ -203,6 +204,7 @@ BC_API int bc_maxpool_halo(void *out, void *plane_out, const void *plane, const 
  *   weight fp16 [Cout][4][4][16], w'[o,kh',kw',(dy*2+dx)*3+c] = w[o,c,2kh'+dy-1,2kw'+dx-1] (0 outside 0..6)
  *   out    fp16 (E, BS_out, BS_out, Cout) NHWC, BS_out = BS/2;  epilogue: + bias, ReLU
  *   plane_out optional: the next padded op's plane (N, H/2, W/2, Cout) NHWC, written in the same pass.
+ *   (out may be NULL when plane_out is given: tiles are not written.)
  */
 #define BC_STEM_XPAD 2
 BC_API int bc_stem_pack(void *s2d_plane, const void *tiles, const int32_t *mapping_exec, int E, int N, int H, int W,
