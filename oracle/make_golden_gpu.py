@@ -9,6 +9,10 @@ The files it writes are copied to tests/golden/ and committed:
 
   ref_kernels_<case>.npz       inputs + outputs of split / combine / transfer / repad kernels
   swiftnet_gpu_fp16_clip.pt    SwiftNet-RN18 + BlockCopyModel, fp16, 512x1024, grid 4x8, 6 frames
+  swiftnet_gpu_fp16_full.npz   the BENCHMARKED configuration: 1024x2048, grid 8x16, 30 frames, frame 0 all blocks
+                               then 40 of 128 (the masks bench.py uses): argmax of every frame + strided logits
+                               + strided frame_state                                              ("full")
+  swiftnet_gpu_fp16_smoke.pt   256x512, 64-px blocks, 3 frames: what __graft_entry__.smoke() compares with ("full")
   reference_timing.json        fps of the reference BlockCopy path on this B200
 """
 import json
@@ -142,6 +146,50 @@ def swiftnet_fp16_clip():
           [round(v, 2) for v in fix["logits_abs_max"]])
 
 
+def _run_fixed_fraction_clip(H, W, BS, T, gain, quantize, clip_seed, mask_seed=0):
+    torch.manual_seed(0)
+    random.seed(0)
+    model = build_reference_swiftnet(0, gain, BS)
+    model.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=quantize, seed=mask_seed)
+    clip = synthetic_clip(T, H, W, seed=clip_seed, dtype=torch.float16, device=dev)
+    outs, states, grids = [], [], []
+    with torch.no_grad():
+        model.reset_temporal()
+        for t in range(T):
+            out = model(clip[t])
+            assert torch.isfinite(out).all(), "fp16 overflow in the fixture: lower the init gain"
+            outs.append(out.clone().cpu())
+            states.append(model.policy_meta["frame_state"].clone().cpu())
+            grids.append(model.policy_meta["grid"].clone().cpu())
+    return outs, states, grids
+
+
+def swiftnet_fp16_full():
+    """The configuration bench.py times (BASELINE configs[2]): 1024x2048, BS 128, 30 frames, PolicyFixedFraction
+    seed 0 (frame 0 all blocks, then 40 of 128).  Frame t stores the logits / frame_state on a stride-8 / stride-16
+    lattice whose offset moves with t, so that over the clip every residue is looked at."""
+    H, W, BS, T, gain = 1024, 2048, 128, 30, 0.8
+    outs, states, grids = _run_fixed_fraction_clip(H, W, BS, T, gain, quantize=8, clip_seed=0)
+    ls = np.stack([o[0, :, (t % 8)::8, ((3 * t) % 8)::8].numpy() for t, o in enumerate(outs)])
+    fs = np.stack([s[0, :, (t % 16)::16, ((5 * t) % 16)::16].numpy() for t, s in enumerate(states)])
+    np.savez_compressed(
+        os.path.join(OUT, "swiftnet_gpu_fp16_full.npz"), H=H, W=W, BS=BS, T=T, clip_seed=0, init_seed=0, init_gain=gain,
+        mask_seed=0, grids=np.stack([g.numpy() for g in grids]).astype(np.uint8),
+        argmax=np.stack([o.argmax(1)[0].to(torch.uint8).numpy() for o in outs]), logits_strided=ls, frame_state_strided=fs,
+        logits_abs_max=np.array([float(o.float().abs().max()) for o in outs]),
+        logits_abs_mean=np.array([float(o.float().abs().mean()) for o in outs]))
+    print("swiftnet fp16 full clip: exec", [int(g.sum()) for g in grids][:4], "... |logits| max",
+          round(max(float(o.float().abs().max()) for o in outs), 2))
+    # the small clip smoke() runs
+    H, W, BS, T = 256, 512, 64, 3
+    outs, states, grids = _run_fixed_fraction_clip(H, W, BS, T, gain, quantize=2, clip_seed=0)
+    torch.save(dict(H=H, W=W, BS=BS, T=T, clip_seed=0, init_seed=0, init_gain=gain, mask_seed=0, quantize=2,
+                    grids=torch.stack(grids).to(torch.uint8), logits=torch.stack(outs),
+                    argmax=torch.stack([o.argmax(1).to(torch.uint8) for o in outs]),
+                    frame_state_last=states[-1]), os.path.join(OUT, "swiftnet_gpu_fp16_smoke.pt"))
+    print("swiftnet fp16 smoke clip: exec", [int(g.sum()) for g in grids])
+
+
 def time_reference(H=1024, W=2048, clips=3, T=30, fraction=0.3):
     """fps of the reference BlockCopy path (baseline 2): SwiftNet-RN18 fp16,
     random init, seeded ~30 % masks (frame 0 all blocks), cudnn.benchmark on, timings level 0."""
@@ -231,5 +279,7 @@ if __name__ == "__main__":
         kernel_goldens()
     if "clip" in what:
         swiftnet_fp16_clip()
+    if "full" in what:
+        swiftnet_fp16_full()
     if "time" in what:
         time_reference()

@@ -88,6 +88,74 @@ def test_swiftnet_clip_fp16_vs_reference_gpu_fixture(golden_dir):
             assert torch.equal(fs[:, :, ::8, ::8].cpu(), fix["frame_state_strided"][t]), "block movement is bit-exact"
 
 
+def test_benchmarked_config_graph_mode_vs_reference_gpu_fixture(golden_dir):
+    """The configuration bench.py times -- 1024x2048, 128-px blocks, 30 frames, frame 0 all blocks then 40 of 128,
+    `block_cuda_graphs=True` (one-tile 320-CTA conv form, persistent 80/120-CTA forms, split-K clusters with the
+    model-owned scratch, side-stream graph branches, all together) -- against what the UNMODIFIED reference produced
+    for the same clip and masks on a B200 (oracle/make_golden_gpu.py full -> swiftnet_gpu_fp16_full.npz).
+    Stated tolerance: fp16 storage, fp32 accumulate => |d| <= 2^-8 * max|ref| + 1e-3 per logit; argmax equal on
+    >= 99.9 % of the pixels of every frame; frame_state (block movement) bit-exact.  And graph replays == eager
+    launches bit for bit at this size."""
+    import numpy as np
+
+    import blockcopy
+    from consumers.clips import PolicyFixedFraction, deterministic_init_, synthetic_clip
+    from consumers.swiftnet_rn18 import SwiftNetRN18, fuse_conv_bn_
+
+    path = os.path.join(golden_dir, "swiftnet_gpu_fp16_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("swiftnet_gpu_fp16_full.npz not generated yet (oracle/make_golden_gpu.py full)")
+    fix = np.load(path)
+    H, W, BS, T = int(fix["H"]), int(fix["W"]), int(fix["BS"]), int(fix["T"])
+    assert (H, W, BS, T) == (1024, 2048, 128, 30)
+    clip = synthetic_clip(T, H, W, seed=int(fix["clip_seed"]), dtype=torch.float16, device="cuda")
+
+    def build(graphs):
+        net = deterministic_init_(SwiftNetRN18().eval(), seed=int(fix["init_seed"]), gain=float(fix["init_gain"]))
+        model = blockcopy.BlockCopyModel(net, _settings(block_policy="all", block_size=BS, block_cuda_graphs=graphs)).eval()
+        fuse_conv_bn_(model)
+        model = model.cuda().half()
+        model.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=8, seed=int(fix["mask_seed"]))
+        return model
+
+    def run(model):
+        outs = []
+        model.policy.reseed(int(fix["mask_seed"]))
+        with torch.no_grad():
+            model.reset_temporal()
+            for t in range(T):
+                o = model(clip[t])
+                g = model.policy_meta["grid"].cpu().numpy().astype(np.uint8)
+                assert (g == fix["grids"][t]).all(), f"frame {t}: mask differs from the fixture's"
+                outs.append((o.clone(), model.policy_meta["frame_state"].clone()))
+        torch.cuda.synchronize()
+        return outs
+
+    graphed = build(True)
+    run(graphed)          # eager pass: planes are allocated, each block count is seen once
+    run(graphed)          # capture pass
+    replayed = run(graphed)
+    assert set(graphed._graphs.graphs) == {128, 40}, "graphs were not captured"
+    worst_err, worst_agree = 0.0, 1.0
+    for t, (o, fs) in enumerate(replayed):
+        ref = torch.from_numpy(fix["logits_strided"][t]).float()
+        got = o[0, :, (t % 8)::8, ((3 * t) % 8)::8].float().cpu()
+        tol = 2 ** -8 * float(fix["logits_abs_max"][t]) + 1e-3
+        err = (got - ref).abs().max().item()
+        assert err <= tol, (t, err, tol)
+        agree = (o.argmax(1)[0].to(torch.uint8).cpu() == torch.from_numpy(fix["argmax"][t])).float().mean().item()
+        assert agree >= 0.999, (t, agree)
+        want = torch.from_numpy(fix["frame_state_strided"][t])
+        assert torch.equal(fs[0, :, (t % 16)::16, ((5 * t) % 16)::16].cpu(), want), f"frame {t}: block movement differs"
+        worst_err, worst_agree = max(worst_err, err / tol), min(worst_agree, agree)
+    print(f"benchmarked config vs reference fixture: worst err/tol {worst_err:.3f}, worst argmax agreement {worst_agree:.5f}")
+    eager = run(build(False))
+    for t, ((a, fa), (b, fb)) in enumerate(zip(eager, replayed)):
+        assert torch.equal(a, b), (t, float((a.float() - b.float()).abs().max()))
+        assert torch.equal(fa, fb), t
+    assert _loaded_native()
+
+
 def test_rl_semseg_runs_and_trains_fp16():
     """The reference driver's configuration: model in fp16, policy net in fp32 (test_swiftnet.py:118-123)."""
     import blockcopy
