@@ -110,6 +110,7 @@ def main():
         from blockcopy.utils.profiler import timings
         timings.set_level(10)
         timings.reset()
+        timings.add_cnt(args.frames)
         with contextlib.redirect_stdout(io.StringIO()):
             run_clip()
         res["timings_level10"] = repr(timings)
