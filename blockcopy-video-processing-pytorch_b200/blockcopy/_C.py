@@ -47,6 +47,7 @@ _SIGNATURES = {
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_policy_features_nhwc16": ([_vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_raster_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
@@ -579,6 +580,19 @@ def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor
     strides = (ctypes.c_int64 * 4)(*outputs.stride())
     _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
                               ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
+    return out
+
+
+def raster_boxes(out: torch.Tensor, rects: torch.Tensor, values: torch.Tensor, shift: int = 0) -> torch.Tensor:
+    """out (H,W) fp32 CUDA <- per pixel max(0, values of the boxes containing (x >> shift, y >> shift));
+    rects int32 (n,4) = x1,y1,x2,y2 half-open, values fp32 (n,), both on the device (see bc_raster_boxes)."""
+    _dev(out, rects, values)
+    assert out.dtype == torch.float32 and out.dim() == 2 and out.is_contiguous()
+    n = rects.shape[0]
+    assert rects.dtype == torch.int32 and rects.is_contiguous() and (n == 0 or rects.shape[1] == 4)
+    assert values.dtype == torch.float32 and values.is_contiguous() and values.numel() == n
+    _check(lib().bc_raster_boxes(out.data_ptr(), rects.data_ptr() if n else None, values.data_ptr() if n else None, n,
+                                 out.shape[0], out.shape[1], int(shift), _stream()), "bc_raster_boxes")
     return out
 
 

@@ -13,6 +13,7 @@ import functools
 import torch
 import torch.nn as nn
 
+from ..utils.hints import get_num_exec_hint, set_num_exec_hint
 from ..utils.profiler import timings
 from .tensorwrapper import TensorWrapper, run_on_side_stream, side_stream_scope, to_tensorwrapper
 
@@ -173,8 +174,15 @@ class BlockCopyModel(nn.Module):
         from .. import _C
 
         gs = self._graphs
-        if not hasattr(grid, "_bc_num_exec"):
-            grid._bc_num_exec = num_exec  # spares _process_grid the device round trip
+        hint = get_num_exec_hint(grid)
+        if hint is None:
+            # no (or a stale) host-side count on this grid -- e.g. a custom policy edited it after the stats were
+            # taken: count on the device like the reference (tensorwrapper.py:157), the graph is chosen by the truth
+            hint = int(grid.sum())
+            set_num_exec_hint(grid, hint)
+        num_exec = hint
+        if num_exec == 0:
+            raise AssertionError("policy_meta['num_exec'] says blocks execute but the grid is empty")
         entry = gs.graphs.get(num_exec)
         if entry is None:
             seen = gs.seen.get(num_exec, 0)
@@ -195,6 +203,9 @@ class BlockCopyModel(nn.Module):
                 _C.add_launches(0)
         else:
             graph, frame_state, dense, launches, prefix = entry
+            if self.block_temporal_features._was_reset:
+                # same contract as the eager path (tensorwrapper.py:164-165): the planes still hold the previous clip
+                assert num_exec == grid.numel(), "No previous features known, first run should execute all blocks!"
             self._refill_prefix(prefix, inputs, grid, num_exec)
             graph.replay()
             _C.add_launches(launches)

@@ -26,11 +26,16 @@ def _unit(u):
         return None
     if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.groups != 1 or conv.bias is not None:
         return None
+    kinds = []
     for m in u.children():
         if isinstance(m, (nn.Dropout, nn.Dropout2d)) and m.training:
             return None
         if not isinstance(m, (nn.BatchNorm2d, nn.ReLU, nn.Conv2d, nn.Dropout, nn.Dropout2d, nn.Identity)):
             return None
+        if isinstance(m, (nn.BatchNorm2d, nn.ReLU, nn.Conv2d)):
+            kinds.append(type(m))
+    if kinds != [nn.BatchNorm2d, nn.ReLU, nn.Conv2d]:  # the fused kernels compute conv(relu(bn(x))), nothing else
+        return None
     return norm, conv
 
 
@@ -84,6 +89,27 @@ def _same(a, b):
     return a[1] == b[1] and len(a[0]) == len(b[0]) and all(x is y for x, y in zip(a[0], b[0]))
 
 
+def _upsampling_is_bilinear(module) -> bool:
+    """The fused kernels hard-code F.interpolate(level, size, mode='bilinear') (align_corners False): probe the
+    module's own `upsampling_method` once on a tiny CPU tensor instead of trusting the attribute names."""
+    fn = getattr(module, "upsampling_method", None)
+    if fn is None:
+        return True  # the module calls F.interpolate itself (consumers/swiftnet_rn18.py)
+    ok = getattr(fn, "_bc_is_bilinear", None)
+    if ok is None:
+        probe = torch.arange(24, dtype=torch.float32).reshape(1, 2, 3, 4).sin()
+        try:
+            got = fn(probe, (6, 12))
+            ok = bool(torch.equal(got, torch.nn.functional.interpolate(probe, (6, 12), mode="bilinear")))
+        except Exception:
+            ok = False
+        try:
+            fn._bc_is_bilinear = ok
+        except AttributeError:
+            pass
+    return ok
+
+
 def _match(module):
     spp, grids = getattr(module, "spp", None), getattr(module, "grids", None)
     if not isinstance(spp, nn.Sequential) or grids is None or len(spp) < 3 or len(spp) - 2 > 4:
@@ -92,6 +118,8 @@ def _match(module):
         return None
     units = [_unit(u) for u in spp.children()]
     if any(u is None for u in units) or len(grids) < len(units) - 2:
+        return None
+    if not _upsampling_is_bilinear(module):
         return None
     return units
 

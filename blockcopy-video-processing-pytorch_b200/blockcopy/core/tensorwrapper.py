@@ -15,7 +15,7 @@ What is different underneath (B200 design):
   padded tiles (tests/test_oracle.py::test_ring_protocol_equals_plane).
 * All index bookkeeping runs on the device (``bc_compact_mask``); the only host round trip left is
   the executed-block count, which the API exposes as a Python int anyway
-  (policy.py:82-94 ``num_exec``) and which is reused here through ``grid._bc_num_exec``.
+  (policy.py:82-94 ``num_exec``) and which is reused here through the version-checked hint of utils/hints.py.
 * Tiles may be NCHW or channels_last; kernels are layout-aware (``_C.layout_of``).
 """
 from __future__ import annotations
@@ -27,6 +27,7 @@ from typing import Any, Callable, Dict, List, Optional, Tuple
 import torch
 
 from .. import _C
+from ..utils.hints import get_num_exec_hint
 from ..utils.profiler import timings
 
 FUSED_CONV = os.environ.get("BLOCKCOPY_FUSED_CONV", "1") != "0"  # route eligible convs on blocks to the tcgen05 implicit-GEMM kernel (bc_conv_igemm)
@@ -135,7 +136,7 @@ class BlockFeatures:
     def _process_grid(self, grid: torch.Tensor, meta_prev: Optional["BlockFeatures"] = None) -> None:
         with timings.env("tensorwrapper/process_grid", 10):
             assert grid.dim() == 4 and grid.shape[1] == 1, "grid must be (N,1,GH,GW)"
-            hint = getattr(grid, "_bc_num_exec", None)
+            hint = get_num_exec_hint(grid)  # ignored when the grid was edited after the count was taken
             g = grid.to(self.device, dtype=torch.bool).contiguous()
             G = g.numel()
             grid_idx = torch.empty(g.shape, dtype=torch.int32, device=self.device)

@@ -24,6 +24,16 @@ class FusedRMSprop(torch.optim.RMSprop):
         super().__init__(*args, **kwargs)
         self._plans = {}  # group index -> (parameter ids, static rows, step tensors, verified gradient pointers)
 
+    # anything that replaces state tensors or parameters invalidates the cached pointer tables
+    def load_state_dict(self, state_dict):
+        self._plans.clear()
+        return super().load_state_dict(state_dict)
+
+    def add_param_group(self, param_group):
+        if hasattr(self, "_plans"):
+            self._plans.clear()
+        return super().add_param_group(param_group)
+
     @staticmethod
     def _group_ok(group) -> bool:
         return not (group.get("centered") or group.get("maximize") or group.get("differentiable") or group.get("capturable"))
@@ -63,6 +73,17 @@ class FusedRMSprop(torch.optim.RMSprop):
                     off += p.numel()
                 plan = self._plans[gi] = (ids, rows, steps, [0] * len(params))
             _, rows, steps, seen = plan
+            stale = False
+            for i, p in enumerate(params):  # ~40 cheap host comparisons: state replaced behind our back (state.clear(),
+                st = self.state[p]          # manual assignment) or a parameter re-allocated (.data = ...)
+                if rows[i][0] != p.data_ptr() or st.get("square_avg") is None or \
+                        rows[i][2] != st["square_avg"].data_ptr() or steps[i] is not st.get("step") or \
+                        (rows[i][3] and rows[i][3] != st["momentum_buffer"].data_ptr()):
+                    stale = True
+                    break
+            if stale:
+                self._plans.pop(gi, None)
+                return self.step()
             for i, p in enumerate(params):
                 g = p.grad
                 ptr = g.data_ptr()

@@ -21,6 +21,7 @@ from torch.distributions import Bernoulli
 
 from blockcopy.policy.information_gain import InformationGain, InformationGainObjectDetection, InformationGainSemSeg
 from blockcopy.policy.net import PolicyNet, build_policy_net_from_settings
+from blockcopy.utils.hints import get_num_exec_hint, set_num_exec_hint
 from blockcopy.utils.profiler import timings
 
 
@@ -73,13 +74,10 @@ class PolicyStats:
 
     def add_policy_meta(self, policy_meta: dict) -> dict:
         grid = policy_meta["grid"]
-        num_exec = getattr(grid, "_bc_num_exec", None)  # host-generated grids carry their count
+        num_exec = get_num_exec_hint(grid)             # host-generated grids carry their (still valid) count
         if num_exec is None:
             num_exec = int(grid.sum())                 # the one host sync per frame
-            try:
-                grid._bc_num_exec = num_exec           # reused by TensorWrapper.to_blocks
-            except AttributeError:
-                pass
+            set_num_exec_hint(grid, num_exec)          # reused by TensorWrapper.to_blocks while the grid is unchanged
         num_total = int(grid.numel())
         policy_meta["num_exec"] = num_exec
         policy_meta["num_total"] = num_total
@@ -135,7 +133,7 @@ class Policy(torch.nn.Module, metaclass=abc.ABCMeta):
                 if extra:
                     host[extra] = True  # one upload of the whole (G-byte) mask instead of index upload + index_put
                     grid.copy_(torch.from_numpy(host).view(grid.shape), non_blocking=False)
-                grid._bc_num_exec = target  # counted on the host just now: saves the device round trip
+                set_num_exec_hint(grid, target)  # counted on the host just now: saves the device round trip
         return grid
 
     @abstractmethod
@@ -152,7 +150,7 @@ class PolicyAll(Policy):
     def forward(self, policy_meta: dict) -> dict:
         shape = self._grid_shape(policy_meta)
         grid = torch.ones(shape, device=policy_meta["inputs"].device, dtype=torch.bool)
-        grid._bc_num_exec = grid.numel()  # known on the host: no device round trip
+        set_num_exec_hint(grid, grid.numel())  # known on the host: no device round trip
         policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
 
@@ -165,7 +163,7 @@ class PolicyNone(Policy):
         shape = self._grid_shape(policy_meta)
         first = policy_meta.get("outputs_prev", None) is None
         grid = torch.full(shape, bool(first), device=policy_meta["inputs"].device, dtype=torch.bool)
-        grid._bc_num_exec = grid.numel() if first else 0
+        set_num_exec_hint(grid, grid.numel() if first else 0)
         policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
 
@@ -213,7 +211,7 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
         if policy_meta["outputs"] is None:
             # no temporal history yet: execute everything
             grid = torch.ones(shape, device=policy_meta["inputs"].device, dtype=torch.bool)
-            grid._bc_num_exec = grid.numel()
+            set_num_exec_hint(grid, grid.numel())
             policy_meta["grid"] = grid
         else:
             if self.shared_across_ranks and not self._shared_synced:
@@ -244,10 +242,10 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                 policy_meta["grid_log_probs"] = dist.log_prob(grid) if dist is not None else None
                 policy_meta["grid_probs"] = probs
                 assert grid.dim() == 4 and probs.shape == grid.shape
-                hint = getattr(grid, "_bc_num_exec", None)
+                hint = get_num_exec_hint(grid)
                 grid = grid.bool()
                 if hint is not None:
-                    grid._bc_num_exec = hint
+                    set_num_exec_hint(grid, hint)
                 policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
 

@@ -62,7 +62,7 @@ class PolicyFixedFraction(Policy):
             grid = grid.view(shape)
         count = int(grid.sum())
         grid = grid.to(dev, non_blocking=True)
-        grid._bc_num_exec = count
+        grid._bc_num_exec = (count, grid._version)  # blockcopy/utils/hints.py (inline: this file also runs against the reference package)
         policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
 
@@ -84,7 +84,7 @@ class PolicyReplay(Policy):
         self.t += 1
         count = int(g.sum())
         g = g.to(policy_meta["inputs"].device)
-        g._bc_num_exec = count
+        g._bc_num_exec = (count, g._version)
         policy_meta["grid"] = g
         return self.stats.add_policy_meta(policy_meta)
 

@@ -63,6 +63,7 @@ int policy_features_nhwc16(void *out, int Cp, const void *frame, const void *sta
                            const int64_t *repr_strides, float sy_frame, float sx_frame, int dtype, cudaStream_t stream);
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
+int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
              long long workspace_bytes, cudaStream_t stream);
@@ -340,6 +341,11 @@ BC_API int bc_policy_features_nhwc16(void *out, int Cp, const void *frame, const
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream) {
   return info_gain(out, outputs, outputs_prev, N, K, h, w, strides, (cudaStream_t)stream);
+}
+
+BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,
+                           bc_stream_t stream) {
+  return raster_boxes(out, rects, values, n, H, W, shift, (cudaStream_t)stream);
 }
 
 BC_API int bc_spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int32_t *grid_h,

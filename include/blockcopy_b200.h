@@ -258,6 +258,16 @@ BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev,
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream);
 
+/* ---- box rasteriser of the object-detection information gain (policy/information_gain.py:56-108) ----
+ * Replaces the reference's per-box torch slice assignments `mask[y1:y2, x1:x2] = max(mask[...], value)`
+ * (build_instance_mask :56-66, build_instance_mask_iou_gain :68-108): out (H,W) fp32 <- for every pixel the
+ * maximum of 0 and the values of the boxes containing (x >> shift, y >> shift); rects = device int32 [n][4]
+ * (x1, y1, x2, y2), half-open like the Python slices; values = device fp32 [n].  shift = 1 reproduces the
+ * reference's half-resolution raster + nearest x2 upsampling (:72,105).  n = 0 writes zeros.
+ */
+BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,
+                           bc_stream_t stream);
+
 /* ---- batch statistics of a train-mode BatchNorm2d (the policy net, policy/net.py:115-125 in train mode) -----
  * mean[c], invstd[c] = 1/sqrt(biased var + eps) over the P = N*H*W pixels of a dense NHWC fp16 tensor x (P, C),
  * C in {8,16,32,64,128}.  workspace: caller-owned, >= BC_BN_STATS_WORKSPACE bytes, 16-byte aligned, its first 4

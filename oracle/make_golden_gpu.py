@@ -12,6 +12,7 @@ The files it writes are copied to tests/golden/ and committed:
   swiftnet_gpu_fp16_full.npz   the BENCHMARKED configuration: 1024x2048, grid 8x16, 30 frames, frame 0 all blocks
                                then 40 of 128 (the masks bench.py uses): argmax of every frame + strided logits
                                + strided frame_state                                              ("full")
+  det_ig_kat.npz               InformationGainObjectDetection on seeded box lists                          ("det")
   swiftnet_gpu_fp16_smoke.pt   256x512, 64-px blocks, 3 frames: what __graft_entry__.smoke() compares with ("full")
   reference_timing.json        fps of the reference BlockCopy path on this B200
 """
@@ -190,6 +191,51 @@ def swiftnet_fp16_full():
     print("swiftnet fp16 smoke clip: exec", [int(g.sum()) for g in grids])
 
 
+def detection_information_gain():
+    """InformationGainObjectDetection of the UNMODIFIED reference (policy/information_gain.py:43-108; its IoU-gain
+    mask is hard-wired to device 'cuda', so this fixture needs the GPU box) on seeded random box lists shaped like
+    mmdet's bbox_results (one class, batch 1) -> det_ig_kat.npz."""
+    from blockcopy.policy.information_gain import InformationGainObjectDetection
+
+    rng = np.random.RandomState(7)
+    H, W = 256, 512
+
+    def boxes(n, jitter_of=None):
+        if jitter_of is not None and len(jitter_of):
+            b = jitter_of[:n].copy()
+            b[:, :4] += rng.uniform(-6, 6, size=(len(b), 4)).astype(np.float32)
+        else:
+            b = np.zeros((0, 5), np.float32)
+        extra = n - len(b)
+        if extra > 0:
+            x1 = rng.uniform(0, W - 40, extra); y1 = rng.uniform(0, H - 40, extra)
+            w = rng.uniform(8, 120, extra); h = rng.uniform(8, 90, extra)
+            e = np.stack([x1, y1, x1 + w, y1 + h, rng.uniform(0.05, 1.0, extra)], 1).astype(np.float32)
+            b = np.concatenate([b, e], 0)
+        b[:, 4] = rng.uniform(0.05, 1.0, len(b)).astype(np.float32)
+        return b.astype(np.float32)
+
+    ig = InformationGainObjectDetection(num_classes=1)
+    frames = [boxes(12)]
+    frames.append(boxes(14, frames[0]))
+    frames.append(boxes(0))                      # nothing detected
+    frames.append(boxes(9))
+    f4 = boxes(11, frames[3])
+    f4[0, :4] = (W - 30.5, H - 20.5, W + 25.0, H + 9.0)   # sticks out of the frame: slices clip
+    f4[1, :4] = (-9.0, 40.0, 31.0, 90.0)                  # negative start: Python slicing counts from the end
+    frames.append(f4)
+    out = dict(H=H, W=W, n_frames=len(frames))
+    inputs = torch.zeros(1, 3, H, W, device=dev)
+    for t, f in enumerate(frames):
+        out[f"boxes_{t}"] = f
+        meta = dict(inputs=inputs, outputs=[[f]], outputs_prev=[[frames[t - 1]]] if t else None)
+        out[f"repr_{t}"] = ig.get_output_repr(meta).cpu().numpy()
+        if t:
+            out[f"gain_{t}"] = ig(meta).cpu().numpy()
+    np.savez_compressed(os.path.join(OUT, "det_ig_kat.npz"), **out)
+    print("detection information gain fixture:", len(frames), "frames")
+
+
 def time_reference(H=1024, W=2048, clips=3, T=30, fraction=0.3):
     """fps of the reference BlockCopy path (baseline 2): SwiftNet-RN18 fp16,
     random init, seeded ~30 % masks (frame 0 all blocks), cudnn.benchmark on, timings level 0."""
@@ -281,5 +327,7 @@ if __name__ == "__main__":
         swiftnet_fp16_clip()
     if "full" in what:
         swiftnet_fp16_full()
+    if "det" in what:
+        detection_information_gain()
     if "time" in what:
         time_reference()

@@ -1,5 +1,7 @@
 """bc_policy_features / bc_info_gain against the torch op sequences of the reference
 (policy/net.py:84-113, policy/information_gain.py:32-41)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -281,3 +283,63 @@ def test_policy_features_nhwc16_equals_rounded_fp32_features_and_feeds_the_trunk
     want = a(x).clone()
     got = b.run(lambda buf: _C.policy_features_nhwc16(buf, frame, state, rep, grid, 0.25), tuple(x.shape), x.device)
     assert torch.equal(got, want)
+
+
+def test_object_detection_information_gain_equals_reference_fixture(golden_dir):
+    """InformationGainObjectDetection (host IoU matching + bc_raster_boxes) against the masks the UNMODIFIED
+    reference painted box by box on a B200 (oracle/make_golden_gpu.py det): bit-exact, including boxes sticking
+    out of the frame and Python-slice semantics for negative coordinates."""
+    import numpy as np
+
+    from blockcopy.policy.information_gain import InformationGainObjectDetection
+
+    path = os.path.join(golden_dir, "det_ig_kat.npz")
+    if not os.path.exists(path):
+        pytest.skip("det_ig_kat.npz not generated yet (oracle/make_golden_gpu.py det)")
+    fix = np.load(path)
+    H, W, T = int(fix["H"]), int(fix["W"]), int(fix["n_frames"])
+    ig = InformationGainObjectDetection(num_classes=1)
+    inputs = torch.zeros(1, 3, H, W, device="cuda")
+    for t in range(T):
+        f = fix[f"boxes_{t}"]
+        meta = dict(inputs=inputs, outputs=[[f]], outputs_prev=[[fix[f"boxes_{t - 1}"]]] if t else None)
+        got = ig.get_output_repr(meta)
+        assert got.dtype == torch.float32 and tuple(got.shape) == (1, 1, H, W)
+        assert np.array_equal(got.cpu().numpy(), fix[f"repr_{t}"]), f"output_repr of frame {t}"
+        if t:
+            gain = ig(meta)
+            assert np.array_equal(gain.cpu().numpy(), fix[f"gain_{t}"]), f"information gain of frame {t}"
+
+
+def test_rl_objectdetection_policy_builds_and_trains():
+    """`--block-policy rl_objectdetection` (it used to crash in the first optim())."""
+    import numpy as np
+
+    import blockcopy
+    from blockcopy.core.argparser import default_settings
+
+    torch.manual_seed(0)
+    s = default_settings(block_policy="rl_objectdetection", block_num_classes=1, block_target=0.3, block_train_interval=2)
+    policy = blockcopy.build_policy_from_settings(s).cuda()
+    policy.net = policy.net.float().train()
+    H, W = 256, 512
+    rng = np.random.RandomState(0)
+
+    def det(n):
+        x1 = rng.uniform(0, W - 60, n); y1 = rng.uniform(0, H - 60, n)
+        return [[np.stack([x1, y1, x1 + rng.uniform(10, 50, n), y1 + rng.uniform(10, 50, n), rng.uniform(0.1, 1, n)], 1)
+                 .astype(np.float32)]]
+
+    before = [p.detach().clone() for p in policy.net.parameters()]
+    meta = {"inputs": torch.randn(1, 3, H, W, device="cuda"), "outputs": None, "outputs_prev": None}
+    for t in range(4):
+        meta["inputs"] = torch.randn(1, 3, H, W, device="cuda")
+        meta["policy_will_train"] = t % 2 == 1
+        if t == 0:
+            meta["frame_state"] = meta["inputs"].clone()
+        meta = policy(meta)
+        assert meta["grid"].dtype == torch.bool and tuple(meta["grid"].shape) == (1, 1, 2, 4)
+        meta["outputs_prev"], meta["outputs"] = meta["outputs"], det(6)
+        meta = policy.optim(meta, train=t % 2 == 1)
+        assert tuple(meta["output_repr"].shape) == (1, 1, H, W)
+    assert any(not torch.equal(a, b) for a, b in zip(before, policy.net.parameters()))

@@ -376,3 +376,29 @@ def test_deferred_engine_on_other_topologies_equals_op_by_op(monkeypatch):
     for t, (a, b) in enumerate(zip(lazy, plain)):
         assert torch.isfinite(a).all(), f"frame {t}: an unwritten tile batch was read"
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-4), (t, float((a - b).abs().max()))
+
+
+def test_num_exec_hint_is_ignored_after_the_grid_was_edited():
+    """the executed-block count attached to a grid is only honoured while the tensor is unchanged
+    (in-place version counter); an edited grid is counted again like the reference does (tensorwrapper.py:157)."""
+    import blockcopy
+    from blockcopy.utils.hints import get_num_exec_hint, set_num_exec_hint
+
+    grid = torch.ones(1, 1, 2, 4, dtype=torch.bool)
+    set_num_exec_hint(grid, 8)
+    assert get_num_exec_hint(grid) == 8
+    with cpu_backend():
+        x = blockcopy.to_tensorwrapper(torch.randn(1, 4, 8, 16))
+        st = x.process_temporal_features(None)
+        b = x.to_blocks(grid)
+        assert tuple(b.shape) == (8, 4, 4, 4)
+        b.combine_()
+        g2 = torch.ones(1, 1, 2, 4, dtype=torch.bool)
+        set_num_exec_hint(g2, 8)
+        g2[0, 0, 0, 1] = False          # a custom policy edits its grid after the count was taken
+        g2[0, 0, 1, 2] = False
+        assert get_num_exec_hint(g2) is None
+        x2 = blockcopy.to_tensorwrapper(torch.randn(1, 4, 8, 16))
+        x2.process_temporal_features(st)
+        b2 = x2.to_blocks(g2)
+        assert tuple(b2.shape) == (6, 4, 4, 4) and b2.get_mapping_exec().tolist() == [0, 2, 3, 4, 5, 7]
