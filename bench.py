@@ -55,6 +55,11 @@ def parse_args():
     ap.add_argument("--shared-policy", action="store_true",
                     help="rl_semseg only: one policy for all ranks (all-reduce of the policy gradients over NCCL)")
     ap.add_argument("--skip-batched", action="store_true", help="skip the extra batch-8 throughput measurement")
+    ap.add_argument("--repeats", type=int, default=20, help="timed windows of --steps steps each; the median is reported")
+    ap.add_argument("--skip-config4", action="store_true", help="skip the 64-stream (config 4) sub-record")
+    ap.add_argument("--skip-rl", action="store_true", help="skip the rl_semseg sub-record")
+    ap.add_argument("--skip-microbench", action="store_true")
+    ap.add_argument("--skip-reference-gpu", action="store_true", help="do not time the reference's BlockCopy path on the GPU")
     return ap.parse_args()
 
 
@@ -141,13 +146,84 @@ def barrier(world):
 
 
 # =============================================================================================== workload
-def build_model(args, device):
+def pin_to_local_numa(local_rank: int):
+    """Restrict this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated (first touch => the staging buffers live in node-local memory; round 1's 8-GPU end-to-end numbers
+    were limited by every rank's pinned pool sitting on one node).  Returns a dict for the JSON line."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # available on recent torch builds
+    except Exception:
+        bus = None
+    if bus is None:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out.splitlines()[0].strip() if out else None
+        except Exception:
+            bus = None
+    try:
+        if isinstance(bus, int):
+            return info
+        dom, rest = bus.split(":", 1)
+        dev = f"{int(dom, 16):04x}:{rest.lower()}"
+        base = f"/sys/bus/pci/devices/{dev}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = ids & set(os.sched_getaffinity(0))
+        if node >= 0 and allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return info
+
+
+def _reference_swiftnet():
+    """The reference's OWN SwiftNet files (staged unmodified under baseline/_ref) when present, else None."""
+    ref_ss = os.path.join(ROOT, "baseline", "_ref", "semantic_segmentation")
+    if not os.path.isdir(os.path.join(ref_ss, "lib", "models", "swiftnet")) or os.environ.get("BLOCKCOPY_BENCH_OWN_MODEL") == "1":
+        return None
+    import contextlib
+    import io
+
+    import blockcopy  # noqa: F401  (this repo's package: the reference model files import its decorator / timings)
+
+    if ref_ss not in sys.path:
+        sys.path.insert(0, ref_ss)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from lib.models.swiftnet.backbones.resnet import resnet18
+            from lib.models.swiftnet.swiftnet import SwiftNet
+            from lib.utils import bn_fusion
+
+            net = SwiftNet(resnet18(pretrained=False), num_classes=19, num_features=128, use_spp=True).eval()
+        return net, bn_fusion
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write(f"bench: reference SwiftNet files not usable ({e}); using consumers/swiftnet_rn18.py\n")
+        return None
+
+
+MODEL_CODE = {"value": None}
+
+
+def build_model(args, device, policy=None):
+    """SwiftNet-RN18 behind this package's BlockCopyModel, set up like the reference driver does
+    (test_swiftnet.py:107-123): wrap, BN fusion, .half(), policy net in fp32."""
+    import contextlib
+    import io
+
     import blockcopy
     from blockcopy.core.argparser import default_settings
-    from consumers.clips import PolicyFixedFraction
-    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+    from consumers.clips import PolicyFixedFraction, deterministic_init_
+    from consumers.swiftnet_rn18 import SwiftNetRN18, fuse_conv_bn_
 
-    settings = default_settings(block_policy="rl_semseg" if args.policy == "rl_semseg" else "all",
+    policy = policy or args.policy
+    settings = default_settings(block_policy="rl_semseg" if policy == "rl_semseg" else "all",
                                 block_target=args.fraction, block_train_interval=3)
     if not args.no_graphs:
         settings["block_cuda_graphs"] = True
@@ -155,8 +231,21 @@ def build_model(args, device):
         settings["block_policy_shared"] = True
     if os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") == "0":  # A/B: policy trunk always through torch/cuDNN
         settings["block_policy_fused"] = False
-    model = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), settings).eval().to(device).half()
-    if args.policy == "fixed":
+    ref = _reference_swiftnet()
+    if ref is not None:
+        net, bn_fusion = ref
+        deterministic_init_(net, seed=0, gain=0.8)
+        model = blockcopy.BlockCopyModel(net, settings).eval().to(device)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = bn_fusion.fuse_bn_recursively(model)
+        MODEL_CODE["value"] = "reference's own lib/models/swiftnet/*.py + lib/utils/bn_fusion.py (baseline/_ref, unmodified)"
+    else:
+        net = deterministic_init_(SwiftNetRN18().eval(), seed=0, gain=0.8)
+        model = blockcopy.BlockCopyModel(net, settings).eval().to(device)
+        fuse_conv_bn_(model)
+        MODEL_CODE["value"] = "consumers/swiftnet_rn18.py (architecture- and state_dict-identical; baseline/_ref not staged)"
+    model = model.half()
+    if policy == "fixed":
         model.policy = PolicyFixedFraction(128, fraction=args.fraction, quantize=8, seed=0)
     else:
         model.policy.net = model.policy.net.float().train()
@@ -203,106 +292,244 @@ def run_frames(models, clips, start, count, clip_len, concurrent=False):
 
 
 class HostPipeline:
-    """End-to-end loop with HOST buffers: every step uploads that step's frame from pinned host
-    memory and reads the step's logits back to pinned host memory.  Copies run on a side stream and
-    are double-buffered so that the upload of frame t+1 overlaps the compute of frame t; all of it
-    is inside the timed region."""
+    """End-to-end loop with HOST buffers, through the public API: every step uploads that step's frames from pinned
+    host memory and reads the step's results back to pinned host memory, all inside the timed region.
 
-    def __init__(self, models, host_clips, device, out_shape, u8=False):
-        """u8=False: the frame travels as the fp16 network input, the result as fp16 logits (what the reference's
-        driver moves).  u8=True: the host uploads the decoded uint8 frame (H,W,3), bc_frame_from_u8 normalises it on
-        the device, and bc_upsample_argmax turns the logits into the full-resolution uint8 label map that is
-        downloaded (consumers/frame_io.py)."""
-        self.models, self.host_clips, self.device, self.u8 = models, host_clips, device, u8
+    u8=True (the `e2e` number): what a video pipeline moves -- the decoded uint8 frame (H,W,3) goes up,
+    bc_frame_from_u8 normalises it on the device, the model runs, bc_upsample_argmax turns the logits into the
+    full-resolution uint8 label map, which goes down (test_swiftnet.py:187-197 does upload -> model -> interpolate
+    -> max -> .cpu()).  u8=False (`e2e_fp16`): the fp16 network input goes up, the fp16 logits come down.
+
+    All S streams of the rank travel in ONE copy per direction and step (one pinned (S,B,...) buffer per step).
+    Three CUDA streams: upload (+ normalise), compute, download (label map + copy), double-buffered, so the copies
+    and the two driver-side kernels of frame t+1 / t-1 overlap the model of frame t."""
+
+    def __init__(self, models, host_clips, device, u8=True):
+        self.models, self.device, self.u8 = models, device, u8
         S = len(models)
-        self.copy_stream = torch.cuda.Stream(device=device)
-        shape = host_clips[0][0].shape
+        L = len(host_clips[0])
+        B, _, H, W = host_clips[0][0].shape
+        self.S, self.B, self.H, self.W = S, B, H, W
+        self.up, self.down = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
         if u8:
-            from consumers.frame_io import FrameNormalizer, predict_labels
+            from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD, FrameNormalizer, predict_labels
             self.norm, self.labels = FrameNormalizer(), predict_labels
-            N, H, W, _ = shape
-            self.dev_u8 = [[torch.empty(shape, dtype=torch.uint8, device=device) for _ in range(2)] for _ in range(S)]
-            self.dev_in = [[torch.empty((N, 3, H, W), dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
-            self.dev_lab = [[torch.empty((N, H, W), dtype=torch.uint8, device=device) for _ in range(2)] for _ in range(S)]
-            self.host_out = [[torch.empty((N, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(S)]
-            self.h2d_bytes, self.d2h_bytes = S * N * H * W * 3, S * N * H * W
+            mean = torch.tensor(CITYSCAPES_MEAN).view(1, 3, 1, 1)
+            std = torch.tensor(CITYSCAPES_STD).view(1, 3, 1, 1)
+            # the synthetic fp16 clips as decoded uint8 frames (S,B,H,W,3) per step, pinned (allocated by THIS rank's
+            # threads after pin_to_local_numa: node-local)
+            self.host_in = []
+            for k in range(L):
+                buf = torch.empty((S, B, H, W, 3), dtype=torch.uint8).pin_memory()
+                for s in range(S):
+                    f = host_clips[s][k].float()
+                    buf[s] = ((f * std + mean) * 255).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+                self.host_in.append(buf)
+            self.dev_raw = [torch.empty((S, B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+            self.dev_in = [torch.empty((S, B, 3, H, W), dtype=torch.float16, device=device) for _ in range(2)]
+            self.dev_res = [torch.empty((S, B, H, W), dtype=torch.uint8, device=device) for _ in range(2)]
+            self.host_out = [torch.empty((S, B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
         else:
-            self.dev_in = [[torch.empty(shape, dtype=torch.float16, device=device) for _ in range(2)] for _ in range(S)]
-            self.host_out = [[torch.empty(out_shape, dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(S)]
-            self.h2d_bytes = S * host_clips[0][0].numel() * 2
-            self.d2h_bytes = S * self.host_out[0][0].numel() * 2
-        self.in_ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
-        self.in_free = [[None, None] for _ in range(S)]
-        self.out_free = [[None, None] for _ in range(S)]
+            self.host_in = []
+            for k in range(L):
+                buf = torch.empty((S, B, 3, H, W), dtype=torch.float16).pin_memory()
+                for s in range(S):
+                    buf[s] = host_clips[s][k]
+                self.host_in.append(buf)
+            self.dev_in = [torch.empty((S, B, 3, H, W), dtype=torch.float16, device=device) for _ in range(2)]
+            self.dev_res = [torch.empty((S, B, 19, H // 4, W // 4), dtype=torch.float16, device=device) for _ in range(2)]
+            self.host_out = [torch.empty((S, B, 19, H // 4, W // 4), dtype=torch.float16).pin_memory() for _ in range(2)]
+        self.h2d_bytes = self.host_in[0].numel() * self.host_in[0].element_size()
+        self.d2h_bytes = self.host_out[0].numel() * self.host_out[0].element_size()
+        self.in_ready = [torch.cuda.Event() for _ in range(2)]
+        self.in_free = [None, None]     # compute finished reading dev_in[slot]
+        self.res_free = [None, None]    # download of dev_res[slot] finished
+        self.out_read = [[None, None] for _ in range(S)]  # the model's ping-pong output buffer was read out
 
-    def _upload(self, s, t, clip_len):
+    def _upload(self, t, clip_len):
         slot = t % 2
-        with torch.cuda.stream(self.copy_stream):
-            if self.in_free[s][slot] is not None:
-                self.copy_stream.wait_event(self.in_free[s][slot])
-            (self.dev_u8 if self.u8 else self.dev_in)[s][slot].copy_(self.host_clips[s][t % clip_len], non_blocking=True)
-            self.in_ready[s][slot].record(self.copy_stream)
+        with torch.cuda.stream(self.up):
+            if self.in_free[slot] is not None:
+                self.up.wait_event(self.in_free[slot])
+            if self.u8:
+                self.dev_raw[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
+                self.norm(self.dev_raw[slot].view(self.S * self.B, self.H, self.W, 3),
+                          out=self.dev_in[slot].view(self.S * self.B, 3, self.H, self.W))
+            else:
+                self.dev_in[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
+            self.in_ready[slot].record(self.up)
 
     def run(self, start, count, clip_len):
         main = torch.cuda.current_stream()
-        S = len(self.models)
         with torch.no_grad():
-            for s in range(S):
-                self._upload(s, start, clip_len)
+            self._upload(start, clip_len)
             for t in range(start, start + count):
                 _advance(self.models, t, clip_len)
                 slot = t % 2
+                if t + 1 < start + count:
+                    self._upload(t + 1, clip_len)
+                main.wait_event(self.in_ready[slot])
+                outs = []
                 for s, model in enumerate(self.models):
-                    if t + 1 < start + count:
-                        self._upload(s, t + 1, clip_len)
-                    main.wait_event(self.in_ready[s][slot])
-                    if self.u8:
-                        self.norm(self.dev_u8[s][slot], out=self.dev_in[s][slot])
-                    out = model(self.dev_in[s][slot])
-                    if self.u8:
-                        if self.out_free[s][slot] is not None:
-                            main.wait_event(self.out_free[s][slot])  # the label buffer's previous download is done
-                        out = self.labels(out, out=self.dev_lab[s][slot])
-                    done = torch.cuda.Event()
-                    done.record(main)
-                    self.in_free[s][slot] = done
-                    with torch.cuda.stream(self.copy_stream):
-                        self.copy_stream.wait_event(done)
-                        self.host_out[s][slot].copy_(out, non_blocking=True)
+                    if self.out_read[s][slot] is not None:
+                        main.wait_event(self.out_read[s][slot])  # the output buffer this call rewrites was read out
+                    outs.append(model(self.dev_in[slot][s]))
+                done = torch.cuda.Event()
+                done.record(main)
+                self.in_free[slot] = done
+                with torch.cuda.stream(self.down):
+                    self.down.wait_event(done)
+                    if self.res_free[slot] is not None:
+                        self.down.wait_event(self.res_free[slot])
+                    for s, out in enumerate(outs):
                         if self.u8:
-                            self.out_free[s][slot] = torch.cuda.Event()
-                            self.out_free[s][slot].record(self.copy_stream)
-        main.wait_stream(self.copy_stream)
+                            self.labels(out, out=self.dev_res[slot][s])
+                        else:
+                            self.dev_res[slot][s].copy_(out, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self.down)
+                        self.out_read[s][slot] = ev
+                    self.host_out[slot].copy_(self.dev_res[slot], non_blocking=True)
+                    self.res_free[slot] = torch.cuda.Event()
+                    self.res_free[slot].record(self.down)
+        main.wait_stream(self.down)
+        main.wait_stream(self.up)
 
 
-def u8_host_clips(host_clips):
-    """The synthetic fp16 clips as decoded uint8 frames (N,H,W,3): what a video decoder would hand over."""
-    from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD
-    mean = torch.tensor(CITYSCAPES_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(CITYSCAPES_STD).view(1, 3, 1, 1)
-    out = []
-    for clip in host_clips:
-        out.append([((f.float() * std + mean) * 255).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
-                    .contiguous().pin_memory() for f in clip])
-    return out
+def timed_windows(fn, steps, repeats, world, device):
+    """`repeats` back-to-back windows of exactly `steps` steps each; every window is bracketed by a barrier +
+    torch.cuda.synchronize() on both sides and timed with CUDA events on the launching stream.  Returns the list of
+    per-window milliseconds, MAX over ranks per window.  fn(start_step, steps)."""
+    ms = []
+    pos = 0
+    for _ in range(repeats):
+        torch.cuda.synchronize()
+        barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(pos, steps)
+        b.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        ms.append(a.elapsed_time(b))
+        pos += steps
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor(ms, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.tolist()
+    return ms
+
+
+def _device_clip(L, H, W, seed, batch, device):
+    """synthetic_clip's recipe generated on the device (config 4 needs 64 streams x 30 frames: too slow on the CPU)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    frame = torch.randn(batch, 3, H, W, generator=g, device=device)
+    frames = []
+    for _ in range(L):
+        frames.append(frame.half())
+        noise = torch.randn(frame.shape, generator=g, device=device)
+        gate = torch.rand(frame.shape, generator=g, device=device) > 0.7
+        frame = frame + 0.3 * noise * gate
+    return frames
+
+
+def bench_config4(args, device, world, rank, total_streams=64, group=8, steps=30):
+    """BASELINE configs[3]: 64 independent 1024x2048 streams sharded over the ranks (stream_id % world), the
+    64/world streams of a GPU batched along N in wrappers of `group` streams (grid (N,1,GH,GW), mapping_exec spans the
+    batch).  Device-resident frames; whole-job frames/s, max over ranks."""
+    H, W, L = args.height, args.width, args.clip_length
+    per_rank = total_streams // world
+    group = min(group, per_rank)
+    wrappers = per_rank // group
+    models = [build_model(args, device, policy="fixed") for _ in range(wrappers)]
+    clips = [_device_clip(L, H, W, seed=10_000 + 100 * rank + w, batch=group, device=device) for w in range(wrappers)]
+    run_frames(models, clips, 0, 2 * L + 2, L)
+    ms = timed_windows(lambda pos, n: run_frames(models, clips, 2 + pos, n, L), steps, 3, world, device)
+    med = statistics.median(ms)
+    frames = float(steps * per_rank * world)
+    del models, clips
+    torch.cuda.empty_cache()
+    return {"streams_total": per_rank * world, "streams_per_gpu": per_rank, "batched_along_N": group,
+            "wrappers_per_gpu": wrappers, "value": frames / (med * 1e-3), "unit": "frames/s", "steps": steps,
+            "ms_per_step": med / steps, "windows_ms": ms, "data": "synthetic, device-resident"}
+
+
+def bench_rl(args, device, steps=90):
+    """The mode the reference ships (`--block-policy rl_semseg`): policy net fp32, Bernoulli sampling, online
+    REINFORCE step every 3rd frame (block_train_interval 3), target 0.3.  Single stream, device-resident frames."""
+    from consumers.clips import synthetic_clip
+
+    H, W, L = args.height, args.width, args.clip_length
+    import random
+
+    random.seed(0)
+    torch.manual_seed(0)
+    m = build_model(args, device, policy="rl_semseg")
+    clip = [f.to(device) for f in synthetic_clip(L, H, W, seed=3, dtype=torch.float16)]
+    run_frames([m], [clip], 0, 3 * L, L)
+    execd = []
+
+    def fn(pos, n):
+        with torch.no_grad():
+            for t in range(pos, pos + n):
+                k = _advance([m], t, L)
+                m(clip[k])
+                execd.append(m.policy_meta["num_exec"])
+
+    ms = timed_windows(fn, steps, 5, 1, device)
+    med = statistics.median(ms)
+    res = {"policy": "rl_semseg", "value": steps / (med * 1e-3), "unit": "frames/s", "steps": steps, "windows_ms": ms,
+           "mean_exec_blocks": sum(execd) / len(execd), "total_blocks": (H // 128) * (W // 128),
+           "train_interval": 3, "note": "random-init policy net trained online; masks are sampled (not replayed), so "
+                                        "the executed fraction follows the policy, see mean_exec_blocks; the fused "
+                                        "policy trunk runs fp16 operands (reference: fp32), masks are statistically, "
+                                        "not bitwise, equivalent"}
+    del m, clip
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_gpu_live(policy="fixed", clips=5, timeout=600):
+    """BASELINE.md section 3, baseline 2, measured IN THIS RUN: the unmodified reference package + reference
+    SwiftNet on this GPU through the NVRTC cupy shim, `python -O`, in its own interpreter
+    (baseline/time_reference_gpu.py)."""
+    script = os.path.join(ROOT, "baseline", "time_reference_gpu.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "blockcopy")) and not os.path.isdir("/root/reference/blockcopy"):
+        return {"unavailable": "reference not staged (baseline/_ref)"}
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run([sys.executable, "-O", script, "--policy", policy, "--clips", str(clips)], capture_output=True,
+                             text=True, timeout=timeout, env=env, cwd=ROOT)
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not line:
+            return {"unavailable": f"rc {res.returncode}: {res.stderr.strip()[-300:]}"}
+        out = json.loads(line[-1])
+        out["measured_in_this_run"] = True
+        return out
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": repr(e)}
 
 
 def bench_ours(args):
     from blockcopy import _C
     from consumers.clips import synthetic_clip
-    from consumers.streams import aggregate_throughput
 
     world, rank, local = dist_setup(args)
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = pin_to_local_numa(local)
     torch.backends.cudnn.benchmark = True
     peaks = load_peaks()
     H, W, L, S, B = args.height, args.width, args.clip_length, args.streams_per_gpu, args.batch
+    K, R = args.steps, args.repeats
 
     models = [build_model(args, device) for _ in range(S)]
-    host_clips = [[f.pin_memory() for f in synthetic_clip(L, H, W, seed=100 * rank + s, batch=B, dtype=torch.float16)]
-                  for s in range(S)]
+    host_clips = [synthetic_clip(L, H, W, seed=100 * rank + s, batch=B, dtype=torch.float16) for s in range(S)]
     clips = [[f.to(device) for f in hc] for hc in host_clips]
     G = (H // 128) * (W // 128)
     num_exec = models[0].policy.num_exec_for(G) if hasattr(models[0].policy, "num_exec_for") else None
@@ -311,129 +538,153 @@ def bench_ours(args):
     #      cuDNN has picked its algorithms and all planes exist; then the W warm-up steps
     conc = bool(args.concurrent_streams)
     run_frames(models, clips, 0, 2 * L, L, conc)
-    # ---- device-resident throughput ("value") --------------------------------------------------------
+    # ---- device-resident throughput ("value"): R windows of K steps, median window ------------------------------
     run_frames(models, clips, 0, args.warmup, L, conc)
     torch.cuda.synchronize()
-    barrier(world)
+    # enough windows for >= ~2 s of timed work (a 20-step window is only ~7 ms; the clock sampler needs samples)
+    t_est = time.perf_counter()
+    run_frames(models, clips, args.warmup, K, L, conc)
+    torch.cuda.synchronize()
+    t_est = time.perf_counter() - t_est
+    R = int(min(400, max(R, 2.0 / max(t_est, 1e-4))))
+    if world > 1:
+        import torch.distributed as dist
+
+        r_t = torch.tensor([R], device=device)
+        dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+        R = int(r_t.item())
     n0 = _C.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        torch.cuda.synchronize()
-        ev0.record()
-        run_frames(models, clips, args.warmup, args.steps, L, conc)
-        ev1.record()
-        torch.cuda.synchronize()
-    launches = _C.launch_count() - n0
-    frames_total, elapsed_ms, value = aggregate_throughput(float(args.steps * S * B), ev0.elapsed_time(ev1), device)
-    barrier(world)
+        win = timed_windows(lambda pos, n: run_frames(models, clips, args.warmup + pos, n, L, conc), K, R, world, device)
+    launches = (_C.launch_count() - n0) // R
+    med = statistics.median(win)
+    frames_step = float(S * B * world)
+    value = K * frames_step / (med * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e") ---------------------------------
-    e2e, e2e_u8, pipe = None, None, None
+    e2e, e2e_fp16 = None, None
     if not args.skip_e2e:
-        pipe = HostPipeline(models, host_clips, device, (B, 19, H // 4, W // 4))
+        Re = max(5, R // 2)
+        pipe = HostPipeline(models, host_clips, device, u8=True)
         pipe.run(0, min(args.warmup, L), L)
-        torch.cuda.synchronize()
-        barrier(world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe.run(args.warmup, args.steps, L)
-        e1.record()
-        torch.cuda.synchronize()
-        _, e2e_ms, e2e_fps = aggregate_throughput(float(args.steps * S * B), e0.elapsed_time(e1), device)
-        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": S * B * 3 * H * W * 2,
-               "d2h_bytes_per_step": S * B * 19 * (H // 4) * (W // 4) * 2,
-               "note": "pinned host frame -> H2D -> model() -> D2H of the logits, copies double-buffered on a side stream"}
-        # the same through the driver-side kernels: uint8 frame up, full-resolution uint8 label map down
-        pipe = None
-        pipe8 = HostPipeline(models, u8_host_clips(host_clips), device, None, u8=True)
-        pipe8.run(0, min(args.warmup, L), L)
-        torch.cuda.synchronize()
-        barrier(world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe8.run(args.warmup, args.steps, L)
-        e1.record()
-        torch.cuda.synchronize()
-        _, _, u8_fps = aggregate_throughput(float(args.steps * S * B), e0.elapsed_time(e1), device)
-        e2e_u8 = {"value": u8_fps, "unit": "frames/s", "h2d_bytes_per_step": pipe8.h2d_bytes,
-                  "d2h_bytes_per_step": pipe8.d2h_bytes,
-                  "note": "pinned uint8 (H,W,3) frame -> H2D -> bc_frame_from_u8 -> model() -> bc_upsample_argmax -> "
-                          "D2H of the 1024x2048 uint8 label map"}
-        del pipe8
+        w8 = timed_windows(lambda pos, n: pipe.run(args.warmup + pos, n, L), K, Re, world, device)
+        e2e = {"value": K * frames_step / (statistics.median(w8) * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "windows_ms": w8,
+               "note": "pinned uint8 (H,W,3) frames of all the rank's streams -> ONE H2D copy -> bc_frame_from_u8 -> "
+                       "model() -> bc_upsample_argmax -> ONE D2H copy of the full-resolution uint8 label maps; upload, "
+                       "compute and download on three streams, double-buffered; pinned buffers NUMA-local",
+               "numa": numa}
+        del pipe
+        pipe = HostPipeline(models, host_clips, device, u8=False)
+        pipe.run(0, min(args.warmup, L), L)
+        w16 = timed_windows(lambda pos, n: pipe.run(args.warmup + pos, n, L), K, 3, world, device)
+        e2e_fp16 = {"value": K * frames_step / (statistics.median(w16) * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                    "note": "the interface the reference's driver uses on the way up: fp16 network input up, fp16 logits down"}
+        del pipe
+    del clips, host_clips
+    models.clear()
+    torch.cuda.empty_cache()
 
-    # ---- same path with 8 streams batched along N (secondary number; config 4 packs 64/ngpu streams per GPU) ---
+    # ---- secondary records ---------------------------------------------------------------------------------------
     batched = None
     if not args.skip_batched and B == 1 and S == 1 and world == 1:
-        pipe = None
-        models.clear()
-        torch.cuda.empty_cache()
         B8 = 8
         m8 = build_model(args, device)
-        clip8 = [f.to(device) for f in synthetic_clip(L, H, W, seed=7, batch=B8, dtype=torch.float16)]
+        clip8 = _device_clip(L, H, W, seed=7, batch=B8, device=device)
         run_frames([m8], [clip8], 0, 2 * L + 2, L)
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        run_frames([m8], [clip8], 2, L, L)
-        b1.record()
-        torch.cuda.synchronize()
-        batched = {"batch": B8, "value": B8 * L / (b0.elapsed_time(b1) * 1e-3), "unit": "frames/s",
-                   "ms_per_step": b0.elapsed_time(b1) / L, "steps": L}
+        wb = timed_windows(lambda pos, n: run_frames([m8], [clip8], 2 + pos, n, L), L, 3, 1, device)
+        batched = {"batch": B8, "value": B8 * L / (statistics.median(wb) * 1e-3), "unit": "frames/s",
+                   "ms_per_step": statistics.median(wb) / L, "steps": L}
         del m8, clip8
+        torch.cuda.empty_cache()
+    config4 = None
+    if not args.skip_config4 and B == 1 and S == 1 and 64 % world == 0:
+        config4 = bench_config4(args, device, world, rank)
+    rl = None
+    if not args.skip_rl and args.policy == "fixed" and world == 1:
+        rl = bench_rl(args, device)
 
     # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
-    kern = microbench(device, peaks) if rank == 0 else None
+    kern = microbench(device, peaks) if rank == 0 and not args.skip_microbench else None
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         cpu = cpu_dense_baseline(H, W, frames=5)
+    ref_gpu, ref_gpu_rl = None, None
+    if rank == 0 and world == 1 and not args.skip_reference_gpu:
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_live("fixed")
+        if "value" in ref_gpu:
+            ref_gpu["ratio_ours_over_reference"] = value / ref_gpu["value"]
+        if rl is not None:
+            ref_gpu_rl = reference_gpu_live("rl_semseg", clips=3)
+            if "value" in ref_gpu_rl:
+                ref_gpu_rl["ratio_ours_over_reference"] = rl["value"] / ref_gpu_rl["value"]
+                ref_gpu_rl["caveat"] = "each side's own random-init policy decides how many blocks run (mean_exec_blocks)"
 
     if rank == 0:
-        hbm = kern["gather_halo_nhwc"]
-        dom = kern["conv3x3_c128_bs32(#20)"]
-        ref_gpu = None
-        rt = os.path.join(ROOT, "tests", "golden", "reference_timing.json")
-        if os.path.exists(rt):
-            ref_gpu = json.load(open(rt))
         line = {
             "metric": "frames/s @1024x2048, 30% active blocks (SwiftNet-RN18 + BlockCopy)", "value": value,
-            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": med / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "timing": {"windows": R, "window_ms": win, "statistic": "median window of `steps` steps, each window bracketed "
+                       "by barrier + synchronize, CUDA events, max over ranks per window"},
             "config": {"workload": "configs[2]: SwiftNet-RN18 + BlockCopy, synthetic 1024x2048 30-frame clips, "
                                    "random-init weights, seeded masks",
+                       "model_code": MODEL_CODE["value"],
                        "height": H, "width": W, "block_size": 128, "active_blocks": num_exec, "total_blocks": G,
                        "clip_length": L, "streams_per_gpu": S, "batch": B, "policy": args.policy,
                        "cuda_graphs": not args.no_graphs,
                        "l2_note": "kernel microbenchmarks rotate 8 plane sets (268 MB > 126 MB L2); the frame loop "
                                   "cycles 30 distinct 12.6 MB frames over 0.27 GB of planes per stream"},
-            "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "batched": batched,
-            "roofline": {"bound": "tensor",
-                         "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: largest share "
-                                   "of a single launch in the step, profiles/r01c_frame_launch_shares.md)",
-                         "achieved": dom["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                         "frac": dom["tflops"] / peaks["tf_burst"], "traffic": 11650000,
-                         "traffic_note": "dram__bytes_read+write of one launch (profiles/r01c_conv_igemm_l20_ncu.md); "
-                                         "algorithmic bytes: 10.5 MB of plane cells + 0.3 MB of weights read, 10.5 MB "
-                                         "of tiles written (they stay in L2 for the next kernel)",
-                         "peak_source": peaks["source"] + " (burst: kernel timed alone)", "algorithmic_flops_per_launch": dom["flops"],
-                         "us_per_launch": dom["us"]},
-            "roofline_hbm": {"bound": "hbm", "kernel": "bc_gather_halo TMA path (NHWC, C=128, BS=32, p=1, E=38: "
-                                                       "BASELINE config 2)",
-                             "achieved": hbm["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": hbm["gbs"] / peaks["hbm_gbs"], "traffic": 19937792,
-                             "traffic_note": "dram__bytes_read+write of one launch, profiles/r01_tma_move_ncu.md "
-                                             "(writes stay in L2)",
-                             "peak_source": peaks["source"], "algorithmic_bytes_per_launch": hbm["bytes"],
-                             "us_per_launch": hbm["us"],
-                             "at_config5_size": {k: kern[k] for k in ("gather_halo_nhwc_cfg5", "gather_nhwc_cfg5",
-                                                                      "scatter_nhwc_cfg5") if k in kern}},
-            "kernels": kern, "cpu_baseline": cpu, "reference_gpu_path": ref_gpu, "clocks": clk.summary(),
+            "e2e": e2e, "e2e_fp16": e2e_fp16, "gpu_launches": int(launches), "batched": batched, "config4": config4,
+            "rl_semseg": rl, "cpu_baseline": cpu, "reference_gpu_path": ref_gpu, "reference_gpu_path_rl_semseg": ref_gpu_rl,
+            "clocks": clk.summary(),
         }
+        if kern is not None:
+            line.update(roofline_records(kern, peaks))
+            line["kernels"] = kern
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
 
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def roofline_records(kern, peaks):
+    """`roofline`: the kernel with the largest share of the step (conv_igemm_persistent_kernel<128,5>: 16 of the 43
+    launches, ~44 % of the frame's GPU time, profiles/r02_frame_launch_shares.md) over its three characteristic
+    shapes (layer2 / layer3 / layer4 3x3 convs at E = 40: 3.02 GFLOP each), sum of flops / sum of launch times.
+    `roofline_l20` (largest single launch) and `roofline_hbm` (block movement) beside it."""
+    dom_keys = ("conv3x3_c128_bs16(layer2)", "conv3x3_c256_bs8(layer3)", "conv3x3_c512_bs4(layer4)")
+    flops = sum(kern[k]["flops"] for k in dom_keys)
+    us = sum(kern[k]["us"] for k in dom_keys)
+    tf = flops / us * 1e-6
+    l20 = kern["conv3x3_c128_bs32(#20)"]
+    hbm = kern["gather_halo_nhwc"]
+    return {
+        "roofline": {"bound": "tensor",
+                     "kernel": "bc_conv_igemm / conv_igemm_persistent_kernel<128,5> (share-dominant kernel of the step) on the "
+                               "3x3 convs of layer2 (128ch, 16-px blocks), layer3 (256ch, 8-px, split-K) and layer4 "
+                               "(512ch, 4-px, split-K), E=40",
+                     "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
+                     "traffic": None, "per_shape": {k: kern[k] for k in dom_keys},
+                     "peak_source": peaks["source"] + " (burst: kernel timed alone)",
+                     "algorithmic_flops_per_launch": flops / len(dom_keys), "us_per_launch": us / len(dom_keys)},
+        "roofline_l20": {"bound": "tensor", "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: "
+                                                      "the largest single launch of the step)",
+                         "achieved": l20["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                         "frac": l20["tflops"] / peaks["tf_burst"], "algorithmic_flops_per_launch": l20["flops"],
+                         "us_per_launch": l20["us"]},
+        "roofline_hbm": {"bound": "hbm", "kernel": "bc_gather_halo TMA path (NHWC, C=128, BS=32, p=1, E=38: BASELINE config 2)",
+                         "achieved": hbm["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm["gbs"] / peaks["hbm_gbs"],
+                         "peak_source": peaks["source"], "algorithmic_bytes_per_launch": hbm["bytes"], "us_per_launch": hbm["us"],
+                         "nchw": kern.get("gather_halo_nchw"),
+                         "at_config5_size": {k: kern[k] for k in ("gather_halo_nhwc_cfg5", "gather_nhwc_cfg5",
+                                                                  "scatter_nhwc_cfg5") if k in kern}},
+    }
 
 
 # =============================================================================================== microbench

@@ -139,12 +139,14 @@ class InformationGainObjectDetection(InformationGain):
                     if iou > best_iou:
                         best_iou, best_j = iou, j
                 matched.add(best_j)
-                ig = np.float32(1 - best_iou)  # torch.tensor(1 - best_iou): rounded to fp32 before the product
+                # reference: `ig = torch.tensor(1 - best_iou)` is a float64 tensor (best_iou is a numpy double), so
+                # `ig * float(score)` is a double product that torch.max(mask, .) rounds to fp32 ONCE
+                ig = 1.0 - float(best_iou)
                 rects.append(box)
-                values.append(ig * np.float32(score))
+                values.append(np.float32(ig * float(score)))
                 if best_j is not None:
                     rects.append(boxes_prev[best_j])
-                    values.append(ig * np.float32(prev[best_j, 4]))
+                    values.append(np.float32(ig * float(prev[best_j, 4])))
             for j in range(len(boxes_prev)):
                 if j not in matched:
                     rects.append(boxes_prev[j])

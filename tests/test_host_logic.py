@@ -402,3 +402,39 @@ def test_num_exec_hint_is_ignored_after_the_grid_was_edited():
         x2.process_temporal_features(st)
         b2 = x2.to_blocks(g2)
         assert tuple(b2.shape) == (6, 4, 4, 4) and b2.get_mapping_exec().tolist() == [0, 2, 3, 4, 5, 7]
+
+
+def test_object_detection_information_gain_host_logic_vs_reference_fixture(golden_dir):
+    """Host side of InformationGainObjectDetection (IoU matching, value arithmetic, Python-slice box semantics)
+    against the masks of the unmodified reference (tests/golden/det_ig_kat.npz, made on a B200 because the
+    reference hard-wires device 'cuda' there); the device rasteriser is replaced by numpy slice painting."""
+    import numpy as np
+
+    from blockcopy.policy import information_gain as IG
+
+    path = os.path.join(golden_dir, "det_ig_kat.npz")
+    if not os.path.exists(path):
+        pytest.skip("det_ig_kat.npz not generated yet")
+    fix = np.load(path)
+    H, W, T = int(fix["H"]), int(fix["W"]), int(fix["n_frames"])
+
+    def paint(out2d, rects, values, shift):
+        o = np.zeros(tuple(out2d.shape), np.float32)
+        for (x1, y1, x2, y2), v in zip(rects, values):
+            ys, xs = slice(y1 << shift, y2 << shift), slice(x1 << shift, x2 << shift)
+            o[ys, xs] = np.maximum(o[ys, xs], v)
+        out2d.copy_(torch.from_numpy(o))
+
+    saved = IG.InformationGainObjectDetection._paint
+    IG.InformationGainObjectDetection._paint = staticmethod(paint)
+    try:
+        ig = IG.InformationGainObjectDetection(num_classes=1)
+        inputs = torch.zeros(1, 3, H, W)
+        for t in range(T):
+            meta = dict(inputs=inputs, outputs=[[fix[f"boxes_{t}"]]],
+                        outputs_prev=[[fix[f"boxes_{t - 1}"]]] if t else None)
+            assert np.array_equal(ig.get_output_repr(meta).numpy(), fix[f"repr_{t}"]), t
+            if t:
+                assert np.array_equal(ig(meta).numpy(), fix[f"gain_{t}"]), t
+    finally:
+        IG.InformationGainObjectDetection._paint = saved
