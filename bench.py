@@ -146,13 +146,19 @@ def barrier(world):
 
 
 # =============================================================================================== workload
+_ORIG_AFFINITY = {}
+
+
 def pin_to_local_numa(local_rank: int):
     """Restrict this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
     allocated (first touch => the staging buffers live in node-local memory; round 1's 8-GPU end-to-end numbers
     were limited by every rank's pinned pool sitting on one node).  Returns a dict for the JSON line."""
     info = {"numa_node": None, "cpus": None}
+    bus = None
     try:
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # available on recent torch builds
+        pr = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
     except Exception:
         bus = None
     if bus is None:
@@ -163,8 +169,6 @@ def pin_to_local_numa(local_rank: int):
         except Exception:
             bus = None
     try:
-        if isinstance(bus, int):
-            return info
         dom, rest = bus.split(":", 1)
         dev = f"{int(dom, 16):04x}:{rest.lower()}"
         base = f"/sys/bus/pci/devices/{dev}"
@@ -175,9 +179,11 @@ def pin_to_local_numa(local_rank: int):
             a, _, b = part.partition("-")
             ids.update(range(int(a), int(b or a) + 1))
         allowed = ids & set(os.sched_getaffinity(0))
+        info = {"numa_node": node, "cpus": len(allowed), "pci": dev}
         if node >= 0 and allowed:
+            _ORIG_AFFINITY.setdefault("cpus", set(os.sched_getaffinity(0)))
             os.sched_setaffinity(0, allowed)
-            info = {"numa_node": node, "cpus": len(allowed)}
+            info["pinned"] = True
     except Exception:
         pass
     return info
@@ -911,6 +917,11 @@ def cpu_dense_baseline(H, W, frames=5, warm=2):
 
         net = build_swiftnet_rn18(seed=0)
     x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(0))
+    if "cpus" in _ORIG_AFFINITY:  # the CPU baseline uses ALL host cores, not only the GPU's NUMA node
+        try:
+            os.sched_setaffinity(0, _ORIG_AFFINITY["cpus"])
+        except Exception:
+            pass
     try:  # torchrun exports OMP_NUM_THREADS=1: use every core this process may run on
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_policy_features_nhwc16": ([_vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_sample_grid": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "bc_raster_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
@@ -581,6 +582,23 @@ def info_gain(outputs: torch.Tensor, outputs_prev: torch.Tensor) -> torch.Tensor
     _check(lib().bc_info_gain(out.data_ptr(), outputs.data_ptr(), outputs_prev.data_ptr(), N, K, h, w,
                               ctypes.cast(strides, ctypes.c_void_p), _stream()), "bc_info_gain")
     return out
+
+
+SAMPLE_GRID_MAX_CELLS = 8192
+
+
+def sample_grid(probs: torch.Tensor, uniforms: torch.Tensor, multiple: int, at_least_one: bool = False):
+    """Bernoulli draw + executed-count quantisation on the device (see bc_sample_grid): probs fp32 (any shape, G
+    cells), uniforms fp32 (2G,) in [0,1) -> (grid bool like probs, counts int32 (2,) = executed after / before)."""
+    _dev(probs, uniforms)
+    G = probs.numel()
+    assert probs.dtype == torch.float32 and probs.is_contiguous() and uniforms.dtype == torch.float32
+    assert uniforms.is_contiguous() and uniforms.numel() >= 2 * G
+    grid = torch.empty(probs.shape, dtype=torch.bool, device=probs.device)
+    counts = torch.empty(2, dtype=torch.int32, device=probs.device)
+    _check(lib().bc_sample_grid(grid.data_ptr(), counts.data_ptr(), probs.data_ptr(), uniforms.data_ptr(), G, int(multiple),
+                                int(bool(at_least_one)), _stream()), "bc_sample_grid")
+    return grid, counts
 
 
 def raster_boxes(out: torch.Tensor, rects: torch.Tensor, values: torch.Tensor, shift: int = 0) -> torch.Tensor:

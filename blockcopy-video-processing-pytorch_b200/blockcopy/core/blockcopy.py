@@ -37,6 +37,9 @@ class BlockCopyModel(nn.Module):
           kernels on frames that are not followed by a policy update (policy/fused_net.py) and step the
           optimiser with one kernel (policy/fused_optim.py).  False: torch / cuDNN throughout.
       block_policy_shared (bool, default False): one policy for all ranks (gradient all-reduce).
+      block_policy_device_sampling (bool, default True): ``rl_*`` policies draw the grid and round the executed-block
+          count up on the device (bc_sample_grid).  False: the reference's host procedure (``random.sample``), which
+          reproduces the reference's masks under ``random.seed``.
     """
 
     def __init__(self, base_model: nn.Module, settings: dict):

@@ -51,7 +51,8 @@ def build_policy_from_settings(settings: dict):
         return PolicyTrainRL(block_target=settings["block_target"], cost_momentum=settings["block_cost_momentum"],
                              optimizer=optimizer, complexity_weight=settings["block_complexity_weight"],
                              quantize_number_exec=quantize, policy_net=net, information_gain=ig,
-                             shared_across_ranks=bool(settings.get("block_policy_shared", False)), **common)
+                             shared_across_ranks=bool(settings.get("block_policy_shared", False)),
+                             device_sampling=bool(settings.get("block_policy_device_sampling", True)), **common)
     raise NotImplementedError(f"Policy {name} not implemented")
 
 
@@ -62,6 +63,32 @@ def build_policy_optimizer_from_settings(settings: dict, net: PolicyNet) -> torc
     return FusedRMSprop(net.parameters(), lr=settings["block_optim_lr"],
                         weight_decay=settings["block_optim_wd"], centered=False,
                         momentum=settings["block_optim_momentum"])
+
+
+def sample_grid_host(probs, uniforms, multiple: int, at_least_one: bool = False):
+    """Host restatement (numpy) of bc_sample_grid: probs (G,), uniforms (2G,) float32 -> (grid bool (G,), executed
+    after rounding, executed before).  Bernoulli draw ``u < p``; the executed count is rounded up to
+    ``multiple * (1 + (E0 - 1) // multiple)`` exactly like the reference (policy.py:139-140) and the extra cells are
+    the skipped ones with the smallest keys ``uniforms[G + g]`` (ties: lower index) -- a uniform random subset, where
+    the reference uses ``random.sample`` (policy.py:141)."""
+    import numpy as np
+
+    p = np.asarray(probs, dtype=np.float32).reshape(-1)
+    G = p.size
+    u = np.asarray(uniforms, dtype=np.float32).reshape(-1)
+    grid = u[:G] < p
+    if at_least_one and not grid.any():
+        grid[0] = True
+    e0 = int(grid.sum())
+    target = e0
+    if multiple > 0:
+        target = multiple * (1 + (e0 - 1) // multiple)  # Python floor division: e0 == 0 gives 0
+    need = min(target - e0, G - e0)
+    if need > 0:
+        skipped = np.nonzero(~grid)[0]
+        order = np.lexsort((skipped, u[G:2 * G][skipped]))  # by key, then by index
+        grid[skipped[order[:need]]] = True
+    return grid, e0 + max(need, 0), e0
 
 
 class PolicyStats:
@@ -188,8 +215,12 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
     def __init__(self, block_size: int, block_target: float, optimizer: torch.optim.Optimizer,
                  complexity_weight: float, policy_net: PolicyNet, information_gain: InformationGain,
                  cost_momentum: float = 0.9, at_least_one: bool = False, quantize_number_exec: float = 0,
-                 verbose: bool = False, shared_across_ranks: bool = False):
+                 verbose: bool = False, shared_across_ranks: bool = False, device_sampling: bool = True):
         super().__init__(block_size, verbose, quantize_number_exec)
+        # Bernoulli draw + count quantisation in one kernel (bc_sample_grid), the only host round trip of the frame
+        # being the executed-block count the API exposes anyway.  False: the reference's host procedure
+        # (grid download, Python random.sample, mask upload) -- reproduces its masks under random.seed.
+        self.device_sampling = device_sampling
         # One policy shared by the streams of all ranks (settings key block_policy_shared, not in the reference):
         # the only collective of the whole path -- a sum of the flat policy-gradient buffer (2.4 MB fp32) every
         # block_train_interval frames; with equal initial weights (broadcast from rank 0) and equal gradients the
@@ -226,6 +257,16 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     grid_logits = self.net(policy_meta, no_grad=no_grad) if no_grad else self.net(policy_meta)
                     assert torch.all(~torch.isnan(grid_logits)), \
                         "Policy net returned NaN's, maybe optimization problem?"
+                sampled = None
+                if self.device_sampling and grid_logits.is_cuda and grid_logits.numel() <= 8192:
+                    with timings.env("policy/sample", 3):
+                        sampled = self._sample_on_device(grid_logits, no_grad)
+                if sampled is not None:
+                    grid, probs, dist = sampled
+                    policy_meta["grid_log_probs"] = dist.log_prob(grid.to(grid_logits.dtype)) if dist is not None else None
+                    policy_meta["grid_probs"] = probs
+                    policy_meta["grid"] = grid
+                    return self.stats.add_policy_meta(policy_meta)
                 with timings.env("policy/sample", 3):
                     if no_grad:
                         # same draw as Bernoulli(logits=...).sample() (= torch.bernoulli(sigmoid(logits))) without
@@ -248,6 +289,23 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     set_num_exec_hint(grid, hint)
                 policy_meta["grid"] = grid
         return self.stats.add_policy_meta(policy_meta)
+
+    def _sample_on_device(self, grid_logits: torch.Tensor, no_grad: bool):
+        """(bool grid with its count hint, probabilities, Bernoulli distribution | None)."""
+        from blockcopy import _C
+
+        if no_grad:
+            dist, probs = None, torch.sigmoid(grid_logits.detach())
+        else:
+            dist = Bernoulli(logits=grid_logits)
+            probs = dist.probs
+        p32 = probs.detach().float().contiguous()
+        G = p32.numel()
+        uniforms = torch.rand(2 * G, device=p32.device, dtype=torch.float32)  # torch's generator: torch.manual_seed
+        multiple = int(G * self.quantize_number_exec) if self.quantize_number_exec > 0 else 0
+        grid, counts = _C.sample_grid(p32, uniforms, multiple, self.at_least_one)
+        set_num_exec_hint(grid, int(counts[0]))  # the one host sync of the frame (the API's num_exec is a Python int)
+        return grid, probs, dist
 
     def _shared_world(self):
         import torch.distributed as dist

@@ -63,6 +63,8 @@ int policy_features_nhwc16(void *out, int Cp, const void *frame, const void *sta
                            const int64_t *repr_strides, float sy_frame, float sx_frame, int dtype, cudaStream_t stream);
 int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h, int w, const int64_t *strides,
               cudaStream_t stream);
+int sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
+                int at_least_one, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -341,6 +343,11 @@ BC_API int bc_policy_features_nhwc16(void *out, int Cp, const void *frame, const
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream) {
   return info_gain(out, outputs, outputs_prev, N, K, h, w, strides, (cudaStream_t)stream);
+}
+
+BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
+                          int at_least_one, bc_stream_t stream) {
+  return sample_grid(grid, counts, probs, uniforms, G, multiple, at_least_one, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -516,3 +516,83 @@ int conv_fewout(float *out, const void *x, const float *w, const float *bias, in
 }
 
 }  // namespace bc
+
+// =====================================================================================================
+// bc_sample_grid -- Bernoulli draw of the execution grid + rounding of the executed-block count UP to a multiple,
+// on the device (reference policy/policy.py:124-144 does the rounding on the host: D2H of the grid, Python
+// random.sample over the skipped cells, index_put).  One CTA; the grid has 128 .. a few thousand cells.
+//   exec0[g]  = uniforms[g] < probs[g]                      (what torch.bernoulli(probs) computes from its draw)
+//   E0        = sum(exec0);  target = E0 == 0 ? 0 : multiple * (1 + (E0 - 1) / multiple)      (policy.py:139-140)
+//   the (target - E0) skipped cells with the smallest (uniforms[G + g], g) are switched on: a uniformly random
+//   subset of the skipped cells, like random.sample (policy.py:141-142), drawn from the caller's uniforms.
+// =====================================================================================================
+namespace bc {
+
+constexpr int kSampleMaxCells = 8192;
+
+__global__ void __launch_bounds__(1024) sample_grid_kernel(uint8_t *__restrict__ grid, int32_t *__restrict__ counts,
+                                                           const float *__restrict__ probs, const float *__restrict__ uni,
+                                                           int G, int multiple, int at_least_one) {
+  __shared__ float key_s[kSampleMaxCells];   // tie-break key of a skipped cell, +inf for executed cells
+  __shared__ int warp_cnt[32];
+  __shared__ int total_s;
+  pdl_trigger();
+  pdl_wait();
+  const int t = threadIdx.x;
+  int mine = 0;
+  for (int g = t; g < G; g += 1024) {
+    const bool e = __ldg(uni + g) < __ldg(probs + g);
+    key_s[g] = e ? __int_as_float(0x7f800000) : __ldg(uni + G + g);
+    mine += e ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((t & 31) == 0) warp_cnt[t >> 5] = mine;
+  __syncthreads();
+  if (t < 32) {
+    int v = warp_cnt[t];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (t == 0) {
+      if (v == 0 && at_least_one && G > 0) {  // policy.py:262-263: grid[0,0,0,0] = 1
+        key_s[0] = __int_as_float(0x7f800000);
+        v = 1;
+      }
+      total_s = v;
+    }
+  }
+  __syncthreads();
+  const int E0 = total_s;
+  int target = E0;
+  if (multiple > 0) target = E0 == 0 ? 0 : multiple * (1 + (E0 - 1) / multiple);
+  int need = target - E0;
+  if (need > G - E0) need = G - E0;
+  const float inf = __int_as_float(0x7f800000);
+  for (int g = t; g < G; g += 1024) {
+    const float k = key_s[g];
+    bool e = k == inf;
+    if (!e && need > 0) {
+      int rank = 0;
+      for (int j = 0; j < G; ++j) {  // broadcast reads: every thread of a warp reads the same shared word
+        const float kj = key_s[j];
+        rank += (kj < k || (kj == k && j < g)) ? 1 : 0;
+      }
+      e = rank < need;
+    }
+    grid[g] = e ? 1 : 0;
+  }
+  if (t == 0) {
+    counts[0] = E0 + need;
+    counts[1] = E0;
+  }
+}
+
+int sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
+                int at_least_one, cudaStream_t stream) {
+  BC_REQUIRE(grid && counts && probs && uniforms, BC_ERR_NULL, "bc_sample_grid: NULL pointer");
+  BC_REQUIRE(G > 0 && G <= kSampleMaxCells, BC_ERR_UNSUPPORTED, "bc_sample_grid: %d cells (1..%d)", G, kSampleMaxCells);
+  BC_REQUIRE(multiple >= 0, BC_ERR_RANGE, "bc_sample_grid: multiple %d", multiple);
+  launch_kernel(sample_grid_kernel, dim3(1), dim3(1024), 0, stream, 1, grid, counts, probs, uniforms, G, multiple,
+                at_least_one);
+  return check_launch("bc_sample_grid");
+}
+
+}  // namespace bc

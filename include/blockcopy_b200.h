@@ -258,6 +258,18 @@ BC_API int bc_head_1x1(void *tiles_out, void *dense_out, const void *dense_prev,
 BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev, int N, int K, int h, int w,
                         const int64_t *strides, bc_stream_t stream);
 
+/* ---- Bernoulli draw of the execution grid + count quantisation (policy/policy.py:124-144, :255-266) ----------
+ * grid[g] = uniforms[g] < probs[g] (the comparison torch.bernoulli makes with its own draw); if nothing executes
+ * and at_least_one, cell 0 does (policy.py:262-263); then the executed count E0 is rounded UP to
+ * target = multiple * (1 + (E0 - 1) / multiple) (0 stays 0; multiple 0 = no rounding) by switching on the
+ * (target - E0) skipped cells with the smallest (uniforms[G + g], g): a uniformly random subset, the device-side
+ * counterpart of the reference's host round trip + random.sample.  probs fp32 [G], uniforms fp32 [2G] in [0,1),
+ * grid uint8 [G], counts int32 [2] = {executed after rounding, executed before}.  G <= 8192.  Deterministic in its
+ * inputs (blockcopy/policy/policy.py::sample_grid_host is the host restatement the tests compare with).
+ */
+BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
+                          int at_least_one, bc_stream_t stream);
+
 /* ---- box rasteriser of the object-detection information gain (policy/information_gain.py:56-108) ----
  * Replaces the reference's per-box torch slice assignments `mask[y1:y2, x1:x2] = max(mask[...], value)`
  * (build_instance_mask :56-66, build_instance_mask_iou_gain :68-108): out (H,W) fp32 <- for every pixel the

@@ -343,3 +343,54 @@ def test_rl_objectdetection_policy_builds_and_trains():
         meta = policy.optim(meta, train=t % 2 == 1)
         assert tuple(meta["output_repr"].shape) == (1, 1, H, W)
     assert any(not torch.equal(a, b) for a, b in zip(before, policy.net.parameters()))
+
+
+@pytest.mark.parametrize("G,multiple,alo", [(128, 8, False), (128, 8, True), (32, 2, False), (1024, 64, False),
+                                            (8192, 512, False), (100, 6, False), (128, 0, False)])
+def test_sample_grid_equals_host_restatement(G, multiple, alo):
+    """bc_sample_grid (Bernoulli draw + executed-count quantisation on the device) == its numpy restatement, bit for
+    bit, and the count follows the reference's rounding rule (policy/policy.py:139-140)."""
+    from blockcopy import _C
+    from blockcopy.policy.policy import sample_grid_host
+
+    g = torch.Generator(device="cuda").manual_seed(G + multiple)
+    for trial in range(6):
+        scale = (0.02, 0.3, 1.0, 3.0, 0.0, 1.0)[trial]
+        probs = torch.sigmoid(scale * torch.randn(G, device="cuda", generator=g) - (4.0 if trial == 4 else 0.0))
+        if trial == 4:
+            probs.zero_()  # nothing executes before rounding
+        uni = torch.rand(2 * G, device="cuda", generator=g)
+        if trial == 5:
+            uni[G:] = (uni[G:] * 4).floor() / 4  # many equal keys: ties go to the lower index
+        grid, counts = _C.sample_grid(probs, uni, multiple, alo)
+        want, e1, e0 = sample_grid_host(probs.cpu().numpy(), uni.cpu().numpy(), multiple, alo)
+        assert grid.dtype == torch.bool and counts.tolist() == [e1, e0], (counts.tolist(), e1, e0)
+        assert (grid.cpu().numpy() == want).all()
+        assert int(grid.sum()) == e1
+        if multiple > 0 and e0 > 0 and G % multiple == 0:
+            assert e1 % multiple == 0 and 0 <= e1 - e0 < multiple
+            assert e1 == multiple * (1 + (e0 - 1) // multiple)
+        # rounding only switches cells ON
+        assert bool((grid.cpu() | ~(uni[:G] < probs).cpu()).all())
+
+
+def test_sample_grid_extra_cells_are_uniform():
+    """The cells switched on by the rounding are a uniformly random subset of the skipped ones (what the reference's
+    random.sample draws): over many draws every skipped cell is picked about equally often."""
+    from blockcopy import _C
+
+    G, multiple = 64, 16
+    probs = torch.zeros(G, device="cuda")
+    probs[:9] = 1.0  # 9 executed -> rounded to 16: 7 of the 55 skipped cells are added
+    hits = torch.zeros(G, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    trials = 4000
+    for _ in range(trials):
+        uni = torch.rand(2 * G, device="cuda", generator=g)
+        uni[:G].clamp_(max=0.999)
+        grid, counts = _C.sample_grid(probs, uni, multiple, False)
+        hits += grid.float()
+    assert hits[:9].eq(trials).all()
+    freq = hits[9:] / trials
+    assert abs(float(freq.mean()) - 7 / 55) < 1e-6
+    assert float((freq - 7 / 55).abs().max()) < 0.03  # 5 sigma of a binomial(4000, 0.127) is 0.026
