@@ -316,7 +316,10 @@ class HostPipeline:
         L = len(host_clips[0])
         B, _, H, W = host_clips[0][0].shape
         self.S, self.B, self.H, self.W = S, B, H, W
-        self.up, self.down = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        # copies and the two driver-side kernels run at the LOWEST priority, the model on a high-priority stream: the
+        # block scheduler hands SMs to the frame's (latency-bound) kernels first, the I/O kernels fill the gaps
+        self.up, self.down = torch.cuda.Stream(device=device, priority=0), torch.cuda.Stream(device=device, priority=0)
+        self.compute = torch.cuda.Stream(device=device, priority=-1)
         if u8:
             from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD, FrameNormalizer, predict_labels
             self.norm, self.labels = FrameNormalizer(), predict_labels
@@ -366,8 +369,10 @@ class HostPipeline:
             self.in_ready[slot].record(self.up)
 
     def run(self, start, count, clip_len):
-        main = torch.cuda.current_stream()
-        with torch.no_grad():
+        caller = torch.cuda.current_stream()
+        main = self.compute
+        main.wait_stream(caller)
+        with torch.no_grad(), torch.cuda.stream(main):
             self._upload(start, clip_len)
             for t in range(start, start + count):
                 _advance(self.models, t, clip_len)
@@ -398,8 +403,9 @@ class HostPipeline:
                     self.host_out[slot].copy_(self.dev_res[slot], non_blocking=True)
                     self.res_free[slot] = torch.cuda.Event()
                     self.res_free[slot].record(self.down)
-        main.wait_stream(self.down)
-        main.wait_stream(self.up)
+        caller.wait_stream(main)
+        caller.wait_stream(self.down)
+        caller.wait_stream(self.up)
 
 
 def timed_windows(fn, steps, repeats, world, device):

@@ -151,7 +151,11 @@ class BlockCopyModel(nn.Module):
 
         if graph is None:
             return body() + (prefix,)
-        with torch.cuda.graph(graph, pool=gs.pool):
+        if gs.capture_stream is None or gs.capture_stream.device != inputs.device:
+            # kernel nodes inherit the capture stream's priority: the frame's latency-bound kernels get SMs before
+            # lower-priority work that shares the GPU (uploads, driver-side kernels, other processes' streams)
+            gs.capture_stream = torch.cuda.Stream(device=inputs.device, priority=-1)
+        with torch.cuda.graph(graph, pool=gs.pool, stream=gs.capture_stream):
             res = body()
         return res + (prefix,)
 
@@ -235,6 +239,7 @@ class _GraphState:
         self.flip = 0
         self.splitk_ws = None  # this model's split-K scratch (see _block_frame_inplace)
         self.splitk_ws_side = None  # ... and the one of convs issued on the side stream
+        self.capture_stream = None  # high-priority stream the graphs are captured on
 
 
 def _try_fused_dense(module, x):

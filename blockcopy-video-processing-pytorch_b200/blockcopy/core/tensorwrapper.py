@@ -298,7 +298,7 @@ class _SideState:
     def stream(cls, device) -> "torch.cuda.Stream":
         st = cls.streams.get(device.index)
         if st is None:
-            st = cls.streams[device.index] = torch.cuda.Stream(device=device)
+            st = cls.streams[device.index] = torch.cuda.Stream(device=device, priority=-1)
         return st
 
     @classmethod
