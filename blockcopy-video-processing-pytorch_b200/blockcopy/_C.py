@@ -248,12 +248,17 @@ def gather_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Tens
 # ------------------------------------------------------------------------------------------- convolution
 def conv_supported(dtype, weight: torch.Tensor, BS_in: int, stride: int, padding: int, dilation: int = 1,
                    groups: int = 1) -> bool:
-    """True when bc_conv_igemm covers this conv: fp16, k in {1,3} with pad k//2, stride 1/2, dilation 1,
-    groups 1, Cin and Cout multiples of 64, output block edge a power of two in [4,128]."""
+    """True when bc_conv_igemm covers this conv: fp16, 1x1 (pad 0) or 3x3 with pad == dilation in 1..4 (dilation > 1
+    only with stride 1), stride 1/2, groups 1, Cin and Cout multiples of 64, output block edge a power of two in
+    [4,128]."""
     Cout, Cin, kh, kw = weight.shape
     if dtype != torch.float16 or weight.dtype != torch.float16 or not weight.is_cuda:
         return False
-    if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
+    if kh != kw or kh not in (1, 3) or stride not in (1, 2) or groups != 1:
+        return False
+    if kh == 1 and (padding != 0 or dilation != 1):
+        return False
+    if kh == 3 and (padding != dilation or not 1 <= dilation <= 4 or (dilation > 1 and stride != 1)):
         return False
     if Cin % 64 or Cout % 64 or BS_in % stride:
         return False

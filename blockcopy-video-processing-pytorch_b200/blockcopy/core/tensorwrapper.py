@@ -230,6 +230,27 @@ class BlockFeatures:
         return sum(p.numel() * p.element_size() for p in self._planes + self._full + self._side_bufs)
 
 
+REUSE_UNOBSERVED_PLANES = os.environ.get("BLOCKCOPY_REUSE_PLANES", "1") != "0"
+
+
+def _only_the_store_holds(t: torch.Tensor) -> bool:
+    """True when the previous frame's combined tensor `t` is referenced by nothing but the feature store (and
+    this call chain): no Python variable, no view / alias / autograd node shares its storage.  A non-in-place
+    combine may then write into it -- nobody can tell the difference from clone + scatter (reference
+    tensorwrapper.py:421-434), and the copy of the unchanged blocks (a full pass over the plane: 67 MB per call for
+    the 256-channel planes of Pedestron's head, csp_head.py:137,143,150) disappears.
+    Reference counts: the store's list, the caller's local, this function's argument, getrefcount's own = 4; storage
+    use count: the tensor + the temporary storage wrapper = 2."""
+    import sys
+
+    if not REUSE_UNOBSERVED_PLANES:
+        return False
+    try:
+        return sys.getrefcount(t) <= 4 and torch._C._storage_Use_Count(t.untyped_storage()._cdata) <= 2
+    except Exception:
+        return False
+
+
 def _raw(t: torch.Tensor) -> torch.Tensor:
     """Plain-tensor alias of t WITHOUT going through __torch_function__ (so it never materialises)."""
     with torch._C.DisableTorchFunctionSubclass():
@@ -524,6 +545,8 @@ class TensorWrapper(torch.Tensor):
             N, _, GH, GW = grid_idx.shape
             shape = (N, C, GH * BS, GW * BS)
             slot, prev = feats._next_full()
+            if not inplace and prev is not None and tuple(prev.shape) == shape and _only_the_store_holds(prev):
+                inplace = True  # the old tensor is unobservable: update it instead of clone + scatter
             head = self._pending if self._pending is not None and self._pending.kind == "head" else None
             if head is not None and (prev is None or (tuple(prev.shape) == shape and _is_dense4(prev))):
                 # output head + combine in one kernel: tiles and the dense output from the same pass

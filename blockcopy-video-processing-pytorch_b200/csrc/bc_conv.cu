@@ -186,11 +186,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
         mbar_wait(&empty_bar[s], parity);
         mbar_expect_tx(&full_bar[s], tx_bytes);
         if (nvalid == 1) {
-          tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw, cy0 + kh, cn0);
+          tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw * p.dil, cy0 + kh * p.dil, cn0);
         } else {
           for (int i = 0; i < nvalid; ++i) {
             const int4 c = blk_coord_s[i];
-            tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw, c.y + kh, c.z);
+            tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw * p.dil, c.y + kh * p.dil, c.z);
           }
         }
         if (++cc == p.kc_per_tap) {
@@ -512,7 +512,12 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0, BC_ERR_SHAPE, "bc_conv_igemm: empty problem");
   BC_REQUIRE(ksize == 1 || ksize == 3, BC_ERR_UNSUPPORTED, "bc_conv_igemm: kernel size %d (1 or 3)", ksize);
   BC_REQUIRE(stride == 1 || stride == 2, BC_ERR_UNSUPPORTED, "bc_conv_igemm: stride %d (1 or 2)", stride);
-  BC_REQUIRE(pad == ksize / 2, BC_ERR_UNSUPPORTED, "bc_conv_igemm: padding %d for kernel %d", pad, ksize);
+  // a 3x3 conv with padding p is the size-preserving DILATED conv with dilation p (taps at -p, 0, +p): the
+  // Pedestron backbone's dilated stage (padding 2, dilation 2) takes the same operand path, its halo is 2 pixels
+  const int dil = ksize == 3 ? pad : 1;
+  BC_REQUIRE((ksize == 1 && pad == 0) || (ksize == 3 && pad >= 1 && pad <= 4), BC_ERR_UNSUPPORTED,
+             "bc_conv_igemm: padding %d for kernel %d (1x1: 0; 3x3: p = dilation in 1..4)", pad, ksize);
+  BC_REQUIRE(dil == 1 || stride == 1, BC_ERR_UNSUPPORTED, "bc_conv_igemm: dilation %d with stride %d", dil, stride);
   BC_REQUIRE(Cin % kChunkK == 0, BC_ERR_UNSUPPORTED, "bc_conv_igemm: Cin=%d is not a multiple of 64", Cin);
   BC_REQUIRE(Cout % 64 == 0, BC_ERR_UNSUPPORTED, "bc_conv_igemm: Cout=%d is not a multiple of 64", Cout);
   BC_REQUIRE(H % BS_in == 0 && W % BS_in == 0 && BS_in % stride == 0, BC_ERR_SHAPE,
@@ -533,6 +538,7 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   p.residual = (const __half *)residual;
   p.out = (__half *)out;
   p.E = E; p.BS_out = BS_out; p.BS_in = BS_in; p.stride = stride; p.pad = pad; p.ksize = ksize; p.Cout = Cout;
+  p.dil = dil;
   p.kc_per_tap = Cin / kChunkK;
   p.relu = relu;
   {

@@ -21,6 +21,7 @@ struct ConvParams {
   const __half *residual;   // same layout as out, or nullptr
   __half *out;              // (E, BS_out, BS_out, Cout) NHWC, or nullptr when only plane_out is wanted
   int E, BS_out, BS_in, stride, pad, ksize, Cout;
+  int dil;                  // tap spacing (3x3: = pad, the size-preserving dilated conv; 1 otherwise)
   int kc_per_tap;           // Cin / 64
   int rows_per_tile;        // rows of BS_out pixels of ONE block in a tile (BS_out >= 16) or BS_out
   int blocks_per_tile;      // 1, or 128 / BS_out^2 for small blocks

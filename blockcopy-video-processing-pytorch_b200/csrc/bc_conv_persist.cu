@@ -216,11 +216,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
           mbar_wait(&empty_bar[s], parity);
           mbar_expect_tx(&full_bar[s], tx_bytes);
           if (t.nvalid == 1) {
-            tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw, cy0 + kh, cn0);
+            tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw * p.dil, cy0 + kh * p.dil, cn0);
           } else {
             for (int i = 0; i < t.nvalid; ++i) {
               const int4 c = coords[i];
-              tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw, c.y + kh, c.z);
+              tma_load_4d(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw * p.dil, c.y + kh * p.dil, c.z);
             }
           }
 #pragma unroll

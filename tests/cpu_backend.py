@@ -90,10 +90,11 @@ def cpu_backend():
 
     def conv_igemm(out, plane, weight_cl, bias, residual, mapping_exec, E, BS_in, stride, padding, relu=False,
                    plane_out=None, out_mapping=None, split_k=True, write_tiles=True):
+        dil = padding if weight_cl.shape[-1] == 3 else 1  # bc_conv_igemm: a 3x3 conv with padding p has dilation p
         if mapping_exec is None:
-            y = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding)
+            y = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding, dil)
         else:
-            full = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding)
+            full = F.conv2d(_nchw(plane), weight_cl, bias, stride, padding, dil)
             y = O.split(full.contiguous(), mapping_exec[:E].contiguous(), BS_in // stride)
         if residual is not None:
             y = y + _nchw(residual)
@@ -169,7 +170,10 @@ def cpu_backend():
 
     def conv_supported(dtype, weight, BS_in, stride, padding, dilation=1, groups=1):
         Cout, Cin, kh, kw = weight.shape
-        if kh != kw or kh not in (1, 3) or padding != kh // 2 or stride not in (1, 2) or dilation != 1 or groups != 1:
+        if kh != kw or kh not in (1, 3) or stride not in (1, 2) or groups != 1:
+            return False
+        if (kh == 1 and (padding != 0 or dilation != 1)) or (kh == 3 and (padding != dilation or not 1 <= dilation <= 4
+                                                                          or (dilation > 1 and stride != 1))):
             return False
         bo = BS_in // stride
         return Cin % 64 == 0 and Cout % 64 == 0 and BS_in % stride == 0 and bo >= 1

@@ -10,7 +10,7 @@ from oracle import cpu_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _run(N, Cin, Cout, GH, GW, BS_in, k, stride, frac, bias=True, seed=0, relu=False):
+def _run(N, Cin, Cout, GH, GW, BS_in, k, stride, frac, bias=True, seed=0, relu=False, dil=1):
     from blockcopy import _C
 
     dev = "cuda"
@@ -26,14 +26,14 @@ def _run(N, Cin, Cout, GH, GW, BS_in, k, stride, frac, bias=True, seed=0, relu=F
         return
     BSo = BS_in // stride
     ref_full = F.conv2d(plane.to(dev).float(), weight.to(dev).float(), b.to(dev).float() if bias else None,
-                        stride=stride, padding=k // 2)
+                        stride=stride, padding=(k // 2) * dil, dilation=dil)
     if relu:
         ref_full = ref_full.relu()
     ref = O.split(ref_full.cpu().contiguous(), me, BSo)
     out = torch.full((E, Cout, BSo, BSo), float("nan"), dtype=torch.float16, device=dev).contiguous(memory_format=torch.channels_last)
     d_plane = plane.to(dev).contiguous(memory_format=torch.channels_last)
     d_w = weight.to(dev).contiguous(memory_format=torch.channels_last)
-    _C.conv_igemm(out, d_plane, d_w, b.to(dev) if bias else None, None, me.to(dev), E, BS_in, stride, k // 2, relu=relu)
+    _C.conv_igemm(out, d_plane, d_w, b.to(dev) if bias else None, None, me.to(dev), E, BS_in, stride, (k // 2) * dil, relu=relu)
     torch.cuda.synchronize()
     got = out.float().cpu()
     assert torch.isfinite(got).all(), "unwritten or non-finite outputs"
@@ -50,6 +50,22 @@ def _run(N, Cin, Cout, GH, GW, BS_in, k, stride, frac, bias=True, seed=0, relu=F
 ])
 def test_swiftnet_conv_shapes(Cin, Cout, BS_in, k, stride):
     _run(1, Cin, Cout, 3, 4, BS_in, k, stride, 0.4, seed=Cin + Cout + BS_in)
+
+
+@pytest.mark.parametrize("Cin,Cout,BS_in,dil,N,GH,GW,frac", [
+    (64, 64, 16, 2, 1, 3, 4, 0.5), (256, 256, 8, 2, 2, 2, 3, 0.6), (128, 64, 32, 2, 1, 2, 2, 1.0), (64, 128, 4, 2, 1, 3, 3, 0.4),
+    (128, 128, 16, 3, 1, 2, 3, 0.5), (64, 64, 8, 4, 1, 4, 4, 0.3)])
+def test_dilated_3x3_conv(Cin, Cout, BS_in, dil, N, GH, GW, frac):
+    """Pedestron's dilated backbone stage: 3x3, padding = dilation = 2 (reference tensorwrapper.py:539-548 leaves the
+    dilation alone and takes a halo of `padding` pixels from the neighbouring blocks); also dilation 3 and 4, where
+    the halo is wider than half a small block."""
+    from blockcopy import _C
+
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float16, device="cuda")
+    assert _C.conv_supported(torch.float16, w, BS_in, 1, dil, dil)
+    assert not _C.conv_supported(torch.float16, w, BS_in, 1, 1, dil)      # padding != dilation: not size preserving
+    assert not _C.conv_supported(torch.float16, w, BS_in, 2, dil, dil)    # dilated + strided: not supported
+    _run(N, Cin, Cout, GH, GW, BS_in, 3, 1, frac, seed=Cin + dil, dil=dil, relu=True)
 
 
 @pytest.mark.parametrize("N,GH,GW,frac", [(1, 2, 2, 1.0), (2, 2, 3, 0.5), (1, 1, 1, 1.0), (3, 3, 3, 0.2)])

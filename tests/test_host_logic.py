@@ -438,3 +438,41 @@ def test_object_detection_information_gain_host_logic_vs_reference_fixture(golde
                 assert np.array_equal(ig(meta).numpy(), fix[f"gain_{t}"]), t
     finally:
         IG.InformationGainObjectDetection._paint = saved
+
+
+def test_non_inplace_combine_reuses_the_previous_plane_only_when_nobody_can_see_it():
+    """combine() (non in place, reference tensorwrapper.py:421-434: clone + scatter) may update the stored previous
+    tensor when the store is its only owner -- the clone is unobservable then; as soon as anybody holds the old
+    tensor, a view or an alias of it, the copy is made and the old tensor keeps its values."""
+    import blockcopy
+
+    g = torch.Generator().manual_seed(0)
+    full = torch.ones(1, 1, 2, 2, dtype=torch.bool)
+    part = torch.tensor([[[[True, False], [False, True]]]])
+    frames = [torch.randn(1, 8, 8, 8, generator=g) for _ in range(4)]
+    with cpu_backend():
+        def step(frame, grid, state):
+            x = blockcopy.to_tensorwrapper(frame.clone())
+            state = x.process_temporal_features(state)
+            return x.to_blocks(grid).combine().to_tensor(), state
+
+        out0, st = step(frames[0], full, None)
+        ptr0, keep0 = out0.data_ptr(), out0.clone()
+        # (a) the caller still holds frame 0's result: frame 1 must not touch it
+        out1, st = step(frames[1], part, st)
+        assert out1.data_ptr() != ptr0 and torch.equal(out0, keep0)
+        want1 = frames[0].clone()
+        want1[..., :4, :4], want1[..., 4:, 4:] = frames[1][..., :4, :4], frames[1][..., 4:, 4:]
+        assert torch.equal(out1, want1)
+        # (b) a view of the old result is still alive
+        ptr1, view1 = out1.data_ptr(), out1[:, :2]
+        del out1
+        out2, st = step(frames[2], part, st)
+        assert out2.data_ptr() != ptr1 and torch.equal(view1, want1[:, :2])
+        # (c) nothing refers to frame 2's result any more: frame 3 is combined into the same storage
+        ptr2 = out2.data_ptr()
+        want3 = out2.clone()
+        want3[..., :4, :4], want3[..., 4:, 4:] = frames[3][..., :4, :4], frames[3][..., 4:, 4:]
+        del out2, view1
+        out3, st = step(frames[3], part, st)
+        assert out3.data_ptr() == ptr2 and torch.equal(out3, want3)

@@ -54,3 +54,18 @@ steady(n)
 pr.disable()
 torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+
+# ---- the end-to-end pipeline (bench.HostPipeline): host issue cost vs wall clock per frame
+host_clip = synthetic_clip(30, 1024, 2048, seed=0, dtype=torch.float16)
+for u8 in (True, False):
+    pipe = bench.HostPipeline([m], [host_clip], dev, u8=u8)
+    pipe.run(0, 30, 30)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        t0 = time.perf_counter()
+        pipe.run(1, 29, 30)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"pipeline u8={u8}: issue {1e6 * (t1 - t0) / 29:.1f} us/frame   issue+drain {1e6 * (t2 - t0) / 29:.1f} us/frame")
+    del pipe
