@@ -47,6 +47,7 @@ _SIGNATURES = {
     "bc_policy_features": ([_vp, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_policy_features_nhwc16": ([_vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "bc_bn_update_running": ([_vp, _i, _vp], _i),
     "bc_sample_grid": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "bc_raster_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
@@ -632,6 +633,13 @@ def bn_stats(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, eps: flo
     assert mean.dtype == torch.float32 and invstd.dtype == torch.float32 and mean.numel() >= C and invstd.numel() >= C
     _check(lib().bc_bn_stats(mean.data_ptr(), invstd.data_ptr(), x.data_ptr(), N * H * W, C, float(eps),
                              workspace.data_ptr(), workspace.numel(), _stream()), "bc_bn_stats")
+
+
+def bn_update_running(table: torch.Tensor):
+    """table: int64 CUDA tensor (n, 8), see bc_bn_update_running."""
+    _dev(table)
+    assert table.dtype == torch.int64 and table.dim() == 2 and table.shape[1] == 8 and table.is_contiguous()
+    _check(lib().bc_bn_update_running(table.data_ptr(), table.shape[0], _stream()), "bc_bn_update_running")
 
 
 def pack_params(table: torch.Tensor, total: int):

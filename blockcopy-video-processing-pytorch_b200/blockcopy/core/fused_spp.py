@@ -160,8 +160,8 @@ def try_fused_spp(module, x: torch.Tensor):
     a = torch.empty((N, C, H, W), **cl)
     _C.ew_fused(a, x, None, plan.bn0, relu=True)                         # relu(bn(x))
     x0 = torch.empty((N, plan.bt, H, W), **cl)
-    scratch = torch.empty((E, plan.bt, BS, BS), **cl)
-    _C.conv_igemm(scratch, a, plan.w0, None, None, cells, E, BS, 1, 0, plane_out=x0, split_k=False)   # 1x1 conv -> x0
+    # tile-less launches: only the dense planes are written
+    _C.conv_igemm(x0, a, plan.w0, None, None, cells, E, BS, 1, 0, plane_out=x0, split_k=False, write_tiles=False)   # 1x1 conv -> x0
     ncell = sum(N * p * q for p, q in zip(gh, gw))
     pooled = torch.empty((ncell, plan.bt), dtype=torch.float16, device=dev)
     _C.spp_pool(pooled, x0, gh, gw)
@@ -170,6 +170,5 @@ def try_fused_spp(module, x: torch.Tensor):
     y = torch.empty((N, plan.Cp, H, W), **cl)
     _C.spp_prep(y, x0, lev, plan.bnf, gh, gw)
     out = torch.empty((N, plan.Cout, H, W), **cl)
-    scratch2 = torch.empty((E, plan.Cout, BS, BS), **cl)
-    _C.conv_igemm(scratch2, y, plan.wf, None, None, cells, E, BS, 1, 0, plane_out=out, split_k=False)
+    _C.conv_igemm(out, y, plan.wf, None, None, cells, E, BS, 1, 0, plane_out=out, split_k=False, write_tiles=False)
     return out

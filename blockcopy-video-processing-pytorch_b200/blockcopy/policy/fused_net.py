@@ -17,9 +17,10 @@ every call (they change with each online optimiser step), inside the same CUDA g
 
 Numerics: fp16 operands / fp32 accumulation / fp16 activations against the reference's fp32 (TF32 on cuDNN)
 trunk -- logits agree to ~1e-2 of their range (tests/test_gpu_policy.py states the bound); the grid is sampled
-from them with torch's RNG exactly as on the torch path.  Train-mode side effects of the torch path that this
-path does NOT reproduce: the BatchNorm running statistics are not updated (the net never runs in eval mode, so
-they are never read).
+from them with torch's RNG exactly as on the torch path.  The train-mode side effect of the torch path -- the
+BatchNorm running statistics and ``num_batches_tracked`` -- is reproduced by one table-driven launch at the end
+(bc_bn_update_running), so the policy's ``state_dict`` after a clip matches the torch path's (to fp16-activation
+accuracy).
 """
 from __future__ import annotations
 
@@ -61,6 +62,7 @@ class _BN:
     def __init__(self, bn: nn.BatchNorm2d):
         self.bn, self.c, self.cp = bn, bn.num_features, _pad64(bn.num_features)
         self.weight = self.shift = self.mean = self.invstd = None
+        self.count = 0
 
 
 
@@ -98,6 +100,7 @@ class FusedPolicyTrunk:
         self._graph = None   # (key, graph, static input, static output)
         self._pack_key = self._pack_table = None
         self._pack_total = 0
+        self._run_key = self._run_table = None
 
     def _bns(self) -> List[_BN]:
         out = [self.stem[1]]
@@ -131,14 +134,16 @@ class FusedPolicyTrunk:
         if cells is None:
             cells = self._cells[(E, x.device)] = torch.arange(E, dtype=torch.int32, device=x.device)
         cl = dict(dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
-        cout, bo = c.w16.shape[0], bs // c.stride
+        cout = c.w16.shape[0]
         out = torch.empty((N, cout, H // c.stride, W // c.stride), **cl)
-        scratch = torch.empty((E, cout, bo, bo), **cl)
-        _C.conv_igemm(scratch, x, c.w16, None, None, cells, E, bs, c.stride, c.k // 2, plane_out=out, split_k=False)
+        # tile-less launch: only the dense output plane is written (`out` stands in for the unused tile batch)
+        _C.conv_igemm(out, x, c.w16, None, None, cells, E, bs, c.stride, c.k // 2, plane_out=out, split_k=False,
+                      write_tiles=False)
         return out
 
     def _bn(self, x: torch.Tensor, b: _BN, relu: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         _C.bn_stats(x, b.mean, b.invstd, b.bn.eps, self._ws)
+        b.count = x.shape[0] * x.shape[2] * x.shape[3]
         out = torch.empty_like(x) if out is None else out
         _C.ew_fused(out, x, None, (b.mean, b.invstd, b.weight, b.shift), relu=relu)
         return out
@@ -155,9 +160,31 @@ class FusedPolicyTrunk:
             _C.ew_fused(h, y, sc, None, relu=True)   # relu(bn2(conv2) + shortcut)
         for c, b in self.head:
             h = self._bn(self._conv(h, c), b, relu=True)
+        self._update_running_stats()
         last = self.last
         return _C.conv_fewout(h, last.weight.detach(), None if last.bias is None else last.bias.detach(),
                               last.stride[0], last.padding[0])
+
+    def _update_running_stats(self):
+        """running_mean / running_var / num_batches_tracked of every batch norm, one launch."""
+        import struct
+
+        bns = [b for b in self._bns() if b.bn.track_running_stats and b.bn.running_mean is not None]
+        if not bns:
+            return
+        key = tuple((b.mean.data_ptr(), b.bn.running_mean.data_ptr(), b.bn.running_var.data_ptr(), b.count,
+                     b.bn.momentum, b.bn.eps) for b in bns)
+        if self._run_key != key:
+            rows = []
+            for b in bns:
+                mom = -1.0 if b.bn.momentum is None else float(b.bn.momentum)
+                bits = struct.unpack("<q", struct.pack("<ff", mom, float(b.bn.eps)))[0]
+                nbt = b.bn.num_batches_tracked
+                rows.append([b.mean.data_ptr(), b.invstd.data_ptr(), b.bn.running_mean.data_ptr(), b.bn.running_var.data_ptr(),
+                             0 if nbt is None else nbt.data_ptr(), b.c, b.count, bits])
+            self._run_table = torch.tensor(rows, dtype=torch.int64, device=bns[0].mean.device)
+            self._run_key = key
+        _C.bn_update_running(self._run_table)
 
     def _param_key(self):
         """Storage identity of every parameter the trunk reads (in-place optimiser steps keep it)."""

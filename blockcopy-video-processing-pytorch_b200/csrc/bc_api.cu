@@ -65,6 +65,7 @@ int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h,
               cudaStream_t stream);
 int sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
                 int at_least_one, cudaStream_t stream);
+int bn_update_running(const long long *table, int n, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -348,6 +349,10 @@ BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev
 BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
                           int at_least_one, bc_stream_t stream) {
   return sample_grid(grid, counts, probs, uniforms, G, multiple, at_least_one, (cudaStream_t)stream);
+}
+
+BC_API int bc_bn_update_running(const long long *table, int n, bc_stream_t stream) {
+  return bn_update_running(table, n, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -596,3 +596,50 @@ int sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float 
 }
 
 }  // namespace bc
+
+// =====================================================================================================
+// bc_bn_update_running -- the train-mode side effect of BatchNorm2d (running_mean / running_var /
+// num_batches_tracked, torch.nn.functional.batch_norm with training=True, as the reference's policy net runs every
+// frame: policy/net.py:115-125, policy/resnet.py:60-115) for ALL batch norms of the fused trunk in one launch.
+// Row l of the device table (8 x int64): { batch mean fp32*, batch invstd fp32*, running_mean fp32*,
+// running_var fp32*, num_batches_tracked int64*, C, count = N*H*W, momentum as float bits (< 0: cumulative
+// average, momentum=None) | eps as float bits << 32 }.  var_biased = 1/invstd^2 - eps; running_var takes the
+// UNBIASED variance (count / (count - 1)), like torch.
+// =====================================================================================================
+namespace bc {
+
+__global__ void __launch_bounds__(128) bn_update_running_kernel(const long long *__restrict__ table, int n) {
+  pdl_trigger();
+  pdl_wait();
+  const int l = blockIdx.x;
+  if (l >= n) return;
+  const long long *row = table + (size_t)l * 8;
+  const float *mean = reinterpret_cast<const float *>(row[0]);
+  const float *invstd = reinterpret_cast<const float *>(row[1]);
+  float *rmean = reinterpret_cast<float *>(row[2]);
+  float *rvar = reinterpret_cast<float *>(row[3]);
+  long long *nbt = reinterpret_cast<long long *>(row[4]);
+  const int C = (int)row[5];
+  const double count = (double)row[6];
+  const float momentum = __int_as_float((int)(row[7] & 0xffffffffll));
+  const float eps = __int_as_float((int)(row[7] >> 32));
+  long long tracked = nbt ? *nbt + 1 : 1;
+  const float f = momentum < 0.f ? (float)(1.0 / (double)tracked) : momentum;
+  const float unbias = count > 1.0 ? (float)(count / (count - 1.0)) : 1.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = mean[c], is = invstd[c];
+    const float var_b = 1.f / (is * is) - eps;
+    if (rmean) rmean[c] = (1.f - f) * rmean[c] + f * m;
+    if (rvar) rvar[c] = (1.f - f) * rvar[c] + f * (var_b * unbias);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && nbt) *nbt = tracked;
+}
+
+int bn_update_running(const long long *table, int n, cudaStream_t stream) {
+  BC_REQUIRE(table != nullptr && n > 0, BC_ERR_NULL, "bc_bn_update_running: empty table");
+  launch_kernel(bn_update_running_kernel, dim3((unsigned)n), dim3(128), 0, stream, 1, table, n);
+  return check_launch("bc_bn_update_running");
+}
+
+}  // namespace bc

@@ -271,6 +271,14 @@ BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev
 BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
                           int at_least_one, bc_stream_t stream);
 
+/* ---- running statistics of train-mode batch norms (policy/net.py:115-125 runs the policy net in train mode) ----
+ * For every row l < n of the DEVICE table (8 x int64 per row: batch mean fp32*, batch invstd fp32* -- the outputs of
+ * bc_bn_stats --, running_mean fp32* | 0, running_var fp32* | 0, num_batches_tracked int64* | 0, C, count = N*H*W,
+ * momentum float bits (negative: cumulative average) | eps float bits << 32): running = (1 - f) * running + f * batch
+ * statistic with the UNBIASED batch variance, num_batches_tracked += 1 -- what F.batch_norm(training=True) does.
+ */
+BC_API int bc_bn_update_running(const long long *table, int n, bc_stream_t stream);
+
 /* ---- box rasteriser of the object-detection information gain (policy/information_gain.py:56-108) ----
  * Replaces the reference's per-box torch slice assignments `mask[y1:y2, x1:x2] = max(mask[...], value)`
  * (build_instance_mask :56-66, build_instance_mask_iou_gain :68-108): out (H,W) fp32 <- for every pixel the

@@ -394,3 +394,35 @@ def test_sample_grid_extra_cells_are_uniform():
     freq = hits[9:] / trials
     assert abs(float(freq.mean()) - 7 / 55) < 1e-6
     assert float((freq - 7 / 55).abs().max()) < 0.03  # 5 sigma of a binomial(4000, 0.127) is 0.026
+
+
+def test_fused_policy_trunk_updates_bn_running_statistics_like_torch():
+    """VERDICT r01 missing #8: the fused trunk reproduces the train-mode side effect of the torch path -- running_mean,
+    running_var (unbiased batch variance, the module's momentum) and num_batches_tracked of every BatchNorm2d."""
+    import copy
+
+    from blockcopy.policy.fused_net import FusedPolicyTrunk
+
+    net_t = _policy_net()
+    net_f = copy.deepcopy(net_t)
+    fused = FusedPolicyTrunk(net_f)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for step in range(3):
+            x = torch.randn(1, 26, 128, 256, device="cuda", generator=g) * (1 + step)
+            with torch.no_grad():
+                net_t.layers(net_t.backbone(x))
+            fused(x, use_cuda_graph=step > 0)  # eager once, then capture + replay
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    bns_t = [m for m in net_t.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    bns_f = [m for m in net_f.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    assert len(bns_t) == len(bns_f) > 5
+    for a, b in zip(bns_t, bns_f):
+        assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 3
+        for ra, rb in ((a.running_mean, b.running_mean), (a.running_var, b.running_var)):
+            tol = 0.03 * float(ra.abs().max()) + 1e-3
+            assert float((ra - rb).abs().max()) <= tol, (float((ra - rb).abs().max()), tol)
+        assert not torch.equal(b.running_var, torch.ones_like(b.running_var))
