@@ -274,7 +274,11 @@ def lazy_supported(x: torch.Tensor) -> bool:
 
 _SPLITK_WS = {}
 SPLITK_WS_BYTES = 32 << 20
-_SPLITK_OWNER = None  # tensor handed over by splitk_workspace_scope, or None
+class _SplitKOwner(__import__("threading").local):
+    ws = None  # tensor handed over by splitk_workspace_scope on THIS thread, or None
+
+
+_SPLITK = _SplitKOwner()
 
 
 def _splitk_workspace(device: torch.device, stream: int) -> torch.Tensor:
@@ -282,8 +286,8 @@ def _splitk_workspace(device: torch.device, stream: int) -> torch.Tensor:
     share one scratch per (device, stream); concurrent streams must not.  A captured CUDA graph bakes the
     scratch address in and may later be replayed on ANY stream, next to other graphs captured on the same
     capture stream: graph owners therefore bring their own scratch (splitk_workspace_scope)."""
-    if _SPLITK_OWNER is not None and _SPLITK_OWNER.device == device:
-        return _SPLITK_OWNER
+    if _SPLITK.ws is not None and _SPLITK.ws.device == device:
+        return _SPLITK.ws
     key = (device.index, stream)
     ws = _SPLITK_WS.get(key)
     if ws is None:
@@ -299,13 +303,11 @@ class splitk_workspace_scope:
         self.ws, self.prev = ws, None
 
     def __enter__(self):
-        global _SPLITK_OWNER
-        self.prev, _SPLITK_OWNER = _SPLITK_OWNER, self.ws
+        self.prev, _SPLITK.ws = _SPLITK.ws, self.ws
         return self.ws
 
     def __exit__(self, *exc):
-        global _SPLITK_OWNER
-        _SPLITK_OWNER = self.prev
+        _SPLITK.ws = self.prev
         return False
 
 

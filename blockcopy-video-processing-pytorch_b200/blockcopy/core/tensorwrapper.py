@@ -21,6 +21,7 @@ What is different underneath (B200 design):
 from __future__ import annotations
 
 import os
+import threading
 import warnings
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
@@ -292,7 +293,7 @@ class _Pending:
         return False
 
 
-class _SideState:
+class _SideStateT(threading.local):
     """Second CUDA stream for side branches of the wrapped CNN (active inside a side_stream_scope only).
 
     In a ladder decoder the skip bottlenecks (BN -> ReLU -> 1x1 conv on an encoder feature) depend on nothing
@@ -306,54 +307,57 @@ class _SideState:
       * everything a side kernel reads is kept alive until the scope's join;
       * a main-stream launch that reads a side output first waits for its event (`sync_main`);
       * in-place torch ops on blocks and the end of the scope join the side stream completely.
+    All of it is PER PYTHON THREAD (threading.local): wrappers driven from different threads on different CUDA
+    streams do not share scopes, events or side streams (re-entrant w.r.t. distinct streams).
     """
-    active = False
-    streams: Dict[int, "torch.cuda.Stream"] = {}
-    done: Dict[int, "torch.cuda.Event"] = {}   # data_ptr of a side output -> event recorded after its kernel
-    keep: List[Any] = []                       # tensors read / written by side kernels that were not joined yet
-    last: Optional["torch.cuda.Event"] = None
-    splitk_ws: Optional[torch.Tensor] = None   # split-K scratch of side-stream convs (None: the per-stream one)
-    launches = 0                               # kernels issued on the side stream so far (diagnostics / tests)
 
-    @classmethod
-    def stream(cls, device) -> "torch.cuda.Stream":
-        st = cls.streams.get(device.index)
+    def __init__(self):
+        self.active = False
+        self.streams: Dict[int, "torch.cuda.Stream"] = {}
+        self.done: Dict[int, "torch.cuda.Event"] = {}   # data_ptr of a side output -> event recorded after its kernel
+        self.keep: List[Any] = []                       # tensors read / written by side kernels that were not joined yet
+        self.last: Optional["torch.cuda.Event"] = None
+        self.splitk_ws: Optional[torch.Tensor] = None   # split-K scratch of side-stream convs (None: the per-stream one)
+        self.launches = 0                               # kernels issued on the side stream so far (diagnostics / tests)
+
+    def stream(self, device) -> "torch.cuda.Stream":
+        st = self.streams.get(device.index)
         if st is None:
-            st = cls.streams[device.index] = torch.cuda.Stream(device=device, priority=-1)
+            st = self.streams[device.index] = torch.cuda.Stream(device=device, priority=-1)
         return st
 
-    @classmethod
-    def sync_main(cls, t: Optional[torch.Tensor]) -> None:
+    def sync_main(self, t: Optional[torch.Tensor]) -> None:
         """The current (main) stream is about to read `t`: wait for its side-stream producer, if any."""
-        if t is not None and cls.done:
-            ev = cls.done.pop(t.data_ptr(), None)
+        if t is not None and self.done:
+            ev = self.done.pop(t.data_ptr(), None)
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
 
-    @classmethod
-    def run(cls, fn: Callable, keep: Tuple = ()):
+    def run(self, fn: Callable, keep: Tuple = ()):
         """Run fn() -- kernels whose results the main stream needs only after the scope's join -- on the side
         stream, after everything the main stream has queued so far.  `keep`: tensors fn reads."""
-        if not cls.active:
+        if not self.active:
             return fn()
         main = torch.cuda.current_stream()
-        side = cls.stream(main.device)
+        side = self.stream(main.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             out = fn()
             ev = torch.cuda.Event()
             ev.record(side)
-        cls.last = ev
-        cls.keep.append(tuple(keep) + (out,))
+        self.last = ev
+        self.keep.append(tuple(keep) + (out,))
         return out
 
-    @classmethod
-    def join(cls) -> None:
-        if cls.last is not None:
-            torch.cuda.current_stream().wait_event(cls.last)
-        cls.last = None
-        cls.done.clear()
-        cls.keep.clear()
+    def join(self) -> None:
+        if self.last is not None:
+            torch.cuda.current_stream().wait_event(self.last)
+        self.last = None
+        self.done.clear()
+        self.keep.clear()
+
+
+_SideState = _SideStateT()
 
 
 class side_stream_scope:
@@ -1068,7 +1072,26 @@ def _first_wrapper(items) -> Optional[TensorWrapper]:
     return first
 
 
-_LIVE_PENDING: Dict[int, Any] = {}  # id -> weakref of deferred tensors that have not been launched yet
+class _LivePending(threading.local):
+    """id -> weakref of deferred tensors that have not been launched yet; per Python thread."""
+
+    def __init__(self):
+        self.d: Dict[int, Any] = {}
+
+    def pop(self, key, default=None):
+        return self.d.pop(key, default)
+
+    def __setitem__(self, key, value):
+        self.d[key] = value
+
+    def __bool__(self):
+        return bool(self.d)
+
+    def values(self):
+        return self.d.values()
+
+
+_LIVE_PENDING = _LivePending()
 
 
 def _materialize_all(args, kwargs=None):

@@ -247,11 +247,14 @@ class FusedPolicyTrunk:
         key = (tuple(shape), device, self._param_key())
         g = self._graph
         if g is None or g[0] != key:
-            self._forward()  # warm-up: persistent buffers, the packing table
+            # this call runs eagerly (it also creates the persistent buffers and the tables); the graph captured right
+            # after it serves the following calls.  No extra execution: the trunk has a side effect (running statistics)
+            out = self._forward()
             torch.cuda.synchronize(device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self._forward()
-            g = self._graph = (key, graph, static_out)
+            self._graph = (key, graph, static_out)
+            return out
         g[1].replay()
         return g[2]

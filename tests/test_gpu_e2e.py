@@ -296,6 +296,70 @@ def test_concurrent_cuda_streams_equal_sequential():
             assert torch.equal(seq[s][k], conc[s][k]), (s, k)
 
 
+def test_two_python_threads_on_two_cuda_streams_equal_sequential():
+    """re-entrant w.r.t. distinct streams.  The wrapper's bookkeeping that is not per model -- the
+    side-stream scope, the registry of deferred tensors, the split-K scratch owner -- is per Python thread, so two
+    threads driving two models on two CUDA streams (graph replays; captured beforehand, capture is process-wide in
+    torch) produce the same bits as one thread running them one after the other."""
+    import threading
+
+    import blockcopy
+    from consumers.clips import PolicyFixedFraction, synthetic_clip
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    BS, H, W, T = 64, 256, 512, 6
+    clips = [synthetic_clip(T, H, W, seed=20 + s, device="cuda") for s in range(2)]
+
+    def build(s):
+        m = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=0), _settings(block_policy="all", block_size=BS,
+                                                                          block_cuda_graphs=True)).eval().cuda().half()
+        m.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=2, seed=s)
+        return m
+
+    def clip_pass(m, s, keep):
+        m.reset_temporal()
+        m.policy.reseed(s)
+        with torch.no_grad():
+            for f in clips[s]:
+                o = m(f)
+                if keep is not None:
+                    keep.append(o.clone())
+
+    models = [build(0), build(1)]
+    for s, m in enumerate(models):      # eager pass + capture pass, sequentially
+        clip_pass(m, s, None)
+        clip_pass(m, s, None)
+    seq = [[], []]
+    for s, m in enumerate(models):
+        clip_pass(m, s, seq[s])
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    par, errors = [[], []], []
+
+    def worker(s):
+        try:
+            with torch.cuda.stream(streams[s]):
+                for _ in range(3):
+                    del par[s][:]
+                    clip_pass(models[s], s, par[s])
+            streams[s].synchronize()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s in range(2):
+        assert len(par[s]) == T
+        for a, b in zip(seq[s], par[s]):
+            assert torch.equal(a, b)
+
+
 from side_topologies import SideTopologies as _SideTopologies  # noqa: E402
 
 
