@@ -251,7 +251,7 @@ def conv_supported(dtype, weight: torch.Tensor, BS_in: int, stride: int, padding
                    groups: int = 1) -> bool:
     """True when bc_conv_igemm covers this conv: fp16, 1x1 (pad 0) or 3x3 with pad == dilation in 1..4 (dilation > 1
     only with stride 1), stride 1/2, groups 1, Cin and Cout multiples of 64, output block edge a power of two in
-    [4,128]."""
+    [2,128]."""
     Cout, Cin, kh, kw = weight.shape
     if dtype != torch.float16 or weight.dtype != torch.float16 or not weight.is_cuda:
         return False
@@ -264,7 +264,7 @@ def conv_supported(dtype, weight: torch.Tensor, BS_in: int, stride: int, padding
     if Cin % 64 or Cout % 64 or BS_in % stride:
         return False
     bo = BS_in // stride
-    return 4 <= bo <= 128 and (bo & (bo - 1)) == 0
+    return 2 <= bo <= 128 and (bo & (bo - 1)) == 0
 
 
 def lazy_supported(x: torch.Tensor) -> bool:

@@ -133,11 +133,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   const int num_k = (p.debug & 1) ? 1 : min(p.ksteps_per_split, total_k - k_begin);
   if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
-  // Plane coordinates of the (up to 8) blocks of this tile.  The mapping lookup (an L2 round trip) is issued
+  // Plane coordinates of the (up to 32: 2-px blocks) blocks of this tile.  The mapping lookup (an L2 round trip) is issued
   // before the set-up barrier so that it overlaps barrier init and the TMEM allocation.  `mapping` is written
   // once per frame by bc_compact_mask, never by the kernel just before this one, so reading it ahead of
   // griddepcontrol.wait is safe under programmatic dependent launch as well.
-  __shared__ int4 blk_coord_s[8];  // (x0, y0, image, -) per block; private to warp 0 lane 0
+  __shared__ int4 blk_coord_s[kMaxBlocksPerTile];  // (x0, y0, image, -) per block; private to warp 0 lane 0
   int cx0 = 0, cy0 = 0, cn0 = 0;   // block 0 in registers (the only one when BS_out >= 16)
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
@@ -524,8 +524,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
              "bc_conv_igemm: plane %dx%d / block %d / stride %d", H, W, BS_in, stride);
   const int BS_out = BS_in / stride;
   const int px = BS_out * BS_out;
-  BC_REQUIRE(BS_out >= 4 && BS_out <= 128 && (px % kTileM == 0 || kTileM % px == 0) && (BS_out & (BS_out - 1)) == 0,
-             BC_ERR_UNSUPPORTED, "bc_conv_igemm: output block edge %d (power of two, 4..128)", BS_out);
+  BC_REQUIRE(BS_out >= 2 && BS_out <= 128 && (px % kTileM == 0 || kTileM % px == 0) && (BS_out & (BS_out - 1)) == 0,
+             BC_ERR_UNSUPPORTED, "bc_conv_igemm: output block edge %d (power of two, 2..128)", BS_out);
   BC_REQUIRE((((uintptr_t)out | (uintptr_t)plane | (uintptr_t)weight | (uintptr_t)bias | (uintptr_t)residual) & 15) == 0,
              BC_ERR_ALIGN, "bc_conv_igemm: pointers must be 16-byte aligned");
   EncodeTiledFn enc = tensor_map_encoder();

@@ -11,6 +11,7 @@ namespace bc {
 constexpr int kConvThreads = 192;      // stem kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kConvThreadsV1 = 224;    // conv_igemm: + a second TMA producer warp (weights)
 constexpr int kTileM = 128;
+constexpr int kMaxBlocksPerTile = 32;          // 2-px output blocks: 128 / 4 blocks share an accumulator tile
 constexpr int kChunkK = 64;                    // channels per k-step = one 128-byte swizzled row
 constexpr uint32_t kABytes = kTileM * 128;     // 16 KB per stage
 

@@ -137,7 +137,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[N_TILE];
   __shared__ long long row_pl_s[kTileM];  // see conv_igemm_kernel
-  __shared__ int4 blk_coord_s[8 * kAProd];
+  __shared__ int4 blk_coord_s[kMaxBlocksPerTile * kAProd];
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *staging = smem + (size_t)STAGES * kStageBytes;
@@ -188,13 +188,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
         const int k0 = z * total_k / S, nk = (z + 1) * total_k / S - k0;
         const TileCoord t = tile_coord<N_TILE>(p, tile);
         int cx0 = 0, cy0 = 0, cn0 = 0;
-        int4 *coords = blk_coord_s + 8 * j;
-        uint32_t cells[8];
+        int4 *coords = blk_coord_s + kMaxBlocksPerTile * j;
+        uint32_t cells[kMaxBlocksPerTile];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)  // all mapping lookups in flight at once
+        for (int i = 0; i < kMaxBlocksPerTile; ++i)  // all mapping lookups in flight at once
           cells[i] = (p.mapping && i < t.nvalid) ? (uint32_t)__ldg(p.mapping + t.b0 + i) : (uint32_t)(t.b0 + i);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kMaxBlocksPerTile; ++i) {
           if (i >= t.nvalid) break;
           const uint32_t cell = cells[i];
           uint32_t n, gh, gw;

@@ -161,7 +161,7 @@ BC_API int bc_gather_halo(void *out, const void *plane, const int32_t *mapping_e
  * they stay in shared memory and are reduced through distributed shared memory (slower, same result).
  * Supported: k = 1 (pad 0) or k = 3 with pad = dilation = p in 1..4 (the size-preserving dilated conv: taps at
  * -p, 0, +p; p = 1 is the ordinary 3x3; p > 1 needs stride 1), stride in {1,2}, Cin % 64 == 0, Cout % 64 == 0,
- * output block edge a power of two in [4,128]; anything else returns BC_ERR_UNSUPPORTED.
+ * output block edge a power of two in [2,128]; anything else returns BC_ERR_UNSUPPORTED.
  */
 BC_API int bc_conv_igemm(void *out, const void *plane, const void *weight, const void *bias,
                          const void *residual, const int32_t *mapping_exec, int E, int N, int Cin, int H,

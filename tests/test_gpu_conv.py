@@ -68,6 +68,16 @@ def test_dilated_3x3_conv(Cin, Cout, BS_in, dil, N, GH, GW, frac):
     _run(N, Cin, Cout, GH, GW, BS_in, 3, 1, frac, seed=Cin + dil, dil=dil, relu=True)
 
 
+@pytest.mark.parametrize("Cin,Cout,BS_in,k,stride,GH,GW,frac", [
+    (512, 512, 2, 3, 1, 4, 8, 0.3), (256, 512, 4, 3, 2, 4, 8, 0.3), (256, 512, 4, 1, 2, 4, 8, 0.4), (512, 128, 2, 1, 1, 4, 8, 1.0),
+    (64, 64, 2, 3, 1, 8, 16, 0.45), (512, 512, 2, 3, 1, 1, 1, 1.0), (128, 128, 2, 3, 1, 7, 9, 0.8)])
+def test_two_pixel_blocks(Cin, Cout, BS_in, k, stride, GH, GW, frac):
+    """`--block-size 64` (reference core/argparser.py:9) puts SwiftNet's layer4 at 2-px blocks: 32 blocks share one
+    128-row accumulator tile (partly filled tiles, split-K over tiny grids, halo = the whole neighbouring block)."""
+    _run(1, Cin, Cout, GH, GW, BS_in, k, stride, frac, seed=Cin + BS_in + GH, relu=True)
+    _run(2, Cin, Cout, GH, GW, BS_in, k, stride, frac, seed=Cin + BS_in + GW, bias=False)
+
+
 @pytest.mark.parametrize("N,GH,GW,frac", [(1, 2, 2, 1.0), (2, 2, 3, 0.5), (1, 1, 1, 1.0), (3, 3, 3, 0.2)])
 def test_conv_grids_and_batches(N, GH, GW, frac):
     _run(N, 64, 64, GH, GW, 16, 3, 1, frac, seed=N * 10 + GH)

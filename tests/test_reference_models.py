@@ -135,7 +135,8 @@ def test_reference_swiftnet_files_run_on_this_package_gpu(graphs):
 
 
 @pytest.mark.gpu
-def test_reference_swiftnet_steady_frame_has_no_library_conv_kernels():
+@pytest.mark.parametrize("H,W,BS", [(1024, 2048, 128), (256, 512, 64)])
+def test_reference_swiftnet_steady_frame_has_no_library_conv_kernels(H, W, BS):
     """Every kernel of a steady block-sparse frame of the reference's SwiftNet is one of this library's `bc::`
     kernels (plus torch's tiny fill / copy helpers): no cuDNN / cuBLAS / CUTLASS / ATen convolution, pooling,
     batch-norm or interpolation kernel."""
@@ -144,9 +145,9 @@ def test_reference_swiftnet_steady_frame_has_no_library_conv_kernels():
     from blockcopy.core.argparser import default_settings
     from consumers.clips import PolicyFixedFraction, synthetic_clip
 
-    H, W, BS = 1024, 2048, 128
+    # 256x512 with 64-px blocks (the reference's --block-size 64, also what smoke() runs) puts layer4 at 2-px blocks
     m_ref, _ = _pair(default_settings(block_policy="all", block_size=BS), "cuda", half=True)
-    m_ref.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=8, seed=0)
+    m_ref.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=8 if BS == 128 else 2, seed=0)
     clip = synthetic_clip(4, H, W, seed=5, dtype=torch.float16, device="cuda")
     _steady_frames(m_ref, clip, 3)
     with profile(activities=[ProfilerActivity.CUDA]) as prof, torch.no_grad():
