@@ -321,8 +321,8 @@ class HostPipeline:
         self.up, self.down = torch.cuda.Stream(device=device, priority=0), torch.cuda.Stream(device=device, priority=0)
         self.compute = torch.cuda.Stream(device=device, priority=-1)
         if u8:
-            from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD, FrameNormalizer, predict_labels
-            self.norm, self.labels = FrameNormalizer(), predict_labels
+            from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD, BlockLabelMap, FrameNormalizer
+            self.norm = FrameNormalizer()
             mean = torch.tensor(CITYSCAPES_MEAN).view(1, 3, 1, 1)
             std = torch.tensor(CITYSCAPES_STD).view(1, 3, 1, 1)
             # the synthetic fp16 clips as decoded uint8 frames (S,B,H,W,3) per step, pinned (allocated by THIS rank's
@@ -336,7 +336,10 @@ class HostPipeline:
                 self.host_in.append(buf)
             self.dev_raw = [torch.empty((S, B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
             self.dev_in = [torch.empty((S, B, 3, H, W), dtype=torch.float16, device=device) for _ in range(2)]
-            self.dev_res = [torch.empty((S, B, H, W), dtype=torch.uint8, device=device) for _ in range(2)]
+            # ONE persistent device label buffer for all streams, updated in place, block-sparsely, every frame
+            # (consumers/frame_io.BlockLabelMap); downloads are ordered behind the updates on the download stream
+            self.dev_res = [torch.empty((S, B, H, W), dtype=torch.uint8, device=device)] * 2
+            self.label_maps = [BlockLabelMap(out=self.dev_res[0][s]) for s in range(S)]
             self.host_out = [torch.empty((S, B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
         else:
             self.host_in = []
@@ -355,16 +358,20 @@ class HostPipeline:
         self.res_free = [None, None]    # download of dev_res[slot] finished
         self.out_read = [[None, None] for _ in range(S)]  # the model's ping-pong output buffer was read out
 
+    SKIP = set(filter(None, os.environ.get("BC_E2E_SKIP", "").split(",")))  # diagnostics: h2d,d2h,norm,labels
+
     def _upload(self, t, clip_len):
         slot = t % 2
         with torch.cuda.stream(self.up):
             if self.in_free[slot] is not None:
                 self.up.wait_event(self.in_free[slot])
             if self.u8:
-                self.dev_raw[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
-                self.norm(self.dev_raw[slot].view(self.S * self.B, self.H, self.W, 3),
-                          out=self.dev_in[slot].view(self.S * self.B, 3, self.H, self.W))
-            else:
+                if "h2d" not in self.SKIP:
+                    self.dev_raw[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
+                if "norm" not in self.SKIP:
+                    self.norm(self.dev_raw[slot].view(self.S * self.B, self.H, self.W, 3),
+                              out=self.dev_in[slot].view(self.S * self.B, 3, self.H, self.W))
+            elif "h2d" not in self.SKIP:
                 self.dev_in[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
             self.in_ready[slot].record(self.up)
 
@@ -380,11 +387,14 @@ class HostPipeline:
                 if t + 1 < start + count:
                     self._upload(t + 1, clip_len)
                 main.wait_event(self.in_ready[slot])
-                outs = []
+                outs, grids = [], []
                 for s, model in enumerate(self.models):
                     if self.out_read[s][slot] is not None:
                         main.wait_event(self.out_read[s][slot])  # the output buffer this call rewrites was read out
                     outs.append(model(self.dev_in[slot][s]))
+                    g = model.policy_meta["grid"]
+                    g.record_stream(self.down)  # read by the label update on the download stream
+                    grids.append(g)
                 done = torch.cuda.Event()
                 done.record(main)
                 self.in_free[slot] = done
@@ -393,14 +403,17 @@ class HostPipeline:
                     if self.res_free[slot] is not None:
                         self.down.wait_event(self.res_free[slot])
                     for s, out in enumerate(outs):
-                        if self.u8:
-                            self.labels(out, out=self.dev_res[slot][s])
+                        if "labels" in self.SKIP:
+                            pass
+                        elif self.u8:
+                            self.label_maps[s].update(out, grids[s])
                         else:
                             self.dev_res[slot][s].copy_(out, non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(self.down)
                         self.out_read[s][slot] = ev
-                    self.host_out[slot].copy_(self.dev_res[slot], non_blocking=True)
+                    if "d2h" not in self.SKIP:
+                        self.host_out[slot].copy_(self.dev_res[slot], non_blocking=True)
                     self.res_free[slot] = torch.cuda.Event()
                     self.res_free[slot].record(self.down)
         caller.wait_stream(main)

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
     "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_upsample_argmax": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp], _i),
+    "bc_upsample_argmax_blocks": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "bc_spp_pool": ([_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp], _i),
     "bc_spp_levels": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _vp], _i),
     "bc_spp_prep": ([_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp, _vp, _i, _i, _vp], _i),
@@ -716,6 +717,24 @@ def upsample_argmax(logits: torch.Tensor, scale: int = 4, label_dtype=torch.uint
                                     BC_F16 if logits.dtype == torch.float16 else BC_F32, out.element_size(), _stream()),
            "bc_upsample_argmax")
     return out
+
+
+def upsample_argmax_blocks(labels: torch.Tensor, logits: torch.Tensor, grid: torch.Tensor, scale: int = 4) -> torch.Tensor:
+    """In-place block-sparse update of `labels` (the previous frame's label map, (N, scale*h, scale*w) uint8/int64)
+    from this frame's dense `logits` (N,K,h,w): only executed cells of `grid` (bool (N,1,GH,GW)) + a one-logit-pixel
+    ring are recomputed (see bc_upsample_argmax_blocks)."""
+    _dev(labels, logits, grid)
+    N, K, h, w = logits.shape
+    assert logits.dtype in (torch.float16, torch.float32) and labels.dtype in (torch.uint8, torch.int64)
+    assert tuple(labels.shape) == (N, h * scale, w * scale) and labels.is_contiguous()
+    assert grid.dim() == 4 and grid.shape[0] == N and grid.shape[1] == 1 and grid.dtype in (torch.bool, torch.uint8)
+    g = grid if grid.is_contiguous() else grid.contiguous()
+    strides = (ctypes.c_int64 * 4)(*logits.stride())
+    _check(lib().bc_upsample_argmax_blocks(labels.data_ptr(), logits.data_ptr(), g.data_ptr(), N, K, h, w,
+                                           ctypes.cast(strides, _vp), int(scale),
+                                           BC_F16 if logits.dtype == torch.float16 else BC_F32, labels.element_size(),
+                                           g.shape[2], g.shape[3], _stream()), "bc_upsample_argmax_blocks")
+    return labels
 
 
 # ------------------------------------------------------------------------------------------- dense pyramid pooling

@@ -39,3 +39,38 @@ def predict_labels(logits: torch.Tensor, size=None, label_dtype=torch.uint8, out
             raise NotImplementedError(f"predict_labels: {h}x{w} -> {H}x{W} (integer scale 1, 2 or 4)")
         scale = H // h
     return _C.upsample_argmax(logits, scale, label_dtype, out)
+
+
+class BlockLabelMap:
+    """Stateful label map of one video stream: the driver-side counterpart of BlockCopy's own idea.  The dense logits
+    of a frame differ from the previous frame's only inside the executed blocks, so only those blocks (plus a ring of
+    one logit pixel, which the bilinear taps of the neighbours reach) need a new arg-max; the rest of the label map is
+    still right.  ``update`` returns the full label map, equal to ``predict_labels(logits)`` bit for bit.
+
+        labels = BlockLabelMap()
+        for frame in clip:
+            out = model(frame)
+            lab = labels.update(out, model.policy_meta["grid"])      # (N, 4h, 4w) uint8, updated in place
+        labels.reset()                                               # with model.reset_temporal()
+    """
+
+    def __init__(self, scale: int = 4, label_dtype=torch.uint8, out: torch.Tensor = None):
+        """out: optional caller-owned (N, scale*h, scale*w) label buffer to keep updated in place."""
+        self.scale, self.label_dtype, self.labels = scale, label_dtype, out
+        self._valid = False  # does `labels` hold the previous frame's label map?
+
+    def reset(self):
+        self._valid = False
+
+    def update(self, logits: torch.Tensor, grid: torch.Tensor = None) -> torch.Tensor:
+        N, K, h, w = logits.shape
+        shape = (N, h * self.scale, w * self.scale)
+        fits = self.labels is not None and tuple(self.labels.shape) == shape and self.labels.device == logits.device
+        sparse = fits and self._valid and grid is not None and grid.dim() == 4 and grid.shape[0] == N \
+            and h % grid.shape[2] == 0 and w % grid.shape[3] == 0 and h // grid.shape[2] == w // grid.shape[3]
+        if sparse:
+            _C.upsample_argmax_blocks(self.labels, logits, grid, self.scale)
+        else:
+            self.labels = _C.upsample_argmax(logits, self.scale, self.label_dtype, self.labels if fits else None)
+            self._valid = True
+        return self.labels

@@ -78,7 +78,7 @@ int conv_fewout(float *out, const void *x, const float *w, const float *bias, in
 int frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W, int dtype,
                   cudaStream_t stream);
 int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides, int scale,
-                    int dtype, int label_bytes, cudaStream_t stream);
+                    int dtype, int label_bytes, cudaStream_t stream, const uint8_t *grid = nullptr, int GH = 0, int GW = 0);
 
 int spp_pool(void *pooled, const void *x0, int N, int C, int H, int W, int L, const int *gh, const int *gw, cudaStream_t s);
 int spp_levels(void *out, const void *pooled, const float *bn, const void *w, int N, int C, int H, int W, int L,
@@ -331,6 +331,14 @@ BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, co
 BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
                               int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream) {
   return upsample_argmax(labels, logits, N, K, h, w, strides, scale, (int)dtype, label_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_upsample_argmax_blocks(void *labels, const void *logits, const uint8_t *grid, int N, int K, int h, int w,
+                                     const int64_t *strides, int scale, bc_dtype_t dtype, int label_bytes, int GH, int GW,
+                                     bc_stream_t stream) {
+  BC_REQUIRE(grid != nullptr, BC_ERR_NULL, "bc_upsample_argmax_blocks: NULL grid");
+  return upsample_argmax(labels, logits, N, K, h, w, strides, scale, (int)dtype, label_bytes, (cudaStream_t)stream, grid, GH,
+                         GW);
 }
 
 BC_API int bc_policy_features_nhwc16(void *out, int Cp, const void *frame, const void *frame_state,

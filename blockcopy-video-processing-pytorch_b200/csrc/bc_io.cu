@@ -141,6 +141,9 @@ struct ArgmaxParams {
   int N, K, h, w;
   int64_t sn, sc, sh, sw;
   uint32_t total;      // N*h*w
+  // block-sparse update (bc_upsample_argmax_blocks): executed cells of the (N,1,GH,GW) grid, logit block edge BSl
+  const uint8_t *grid;
+  int GH, GW, BSl, chunks;  // chunks = CTAs per cell = ceil((BSl+2)^2 / 128)
 };
 
 template <typename T> __device__ __forceinline__ float ld_f(const T *p);
@@ -158,13 +161,7 @@ template <> __device__ __forceinline__ float round_to<float>(float v) { return v
 // Per class: 9 loads, 3 x S horizontal blends shared by the S output rows, S x S vertical blends; for fp16 logits
 // the rounded values are compared as packed half2 (2 outputs per instruction, class indices in 16-bit lanes).
 template <typename T, typename L, int S>
-__global__ void __launch_bounds__(128, 7) upsample_argmax_kernel(const ArgmaxParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.total) return;
-  const int j = (int)(t % (uint32_t)p.w), i = (int)((t / (uint32_t)p.w) % (uint32_t)p.h);
-  const int n = (int)(t / ((uint32_t)p.w * p.h));
+__device__ __forceinline__ void argmax_pixel(const ArgmaxParams &p, const int n, const int i, const int j) {
   constexpr float rs = 1.f / (float)S;  // ATen: area_pixel_compute_scale = in / out (size= call), exact for S = 2^k
   constexpr int kHalf = S / 2;          // offsets r < kHalf use taps (-1, 0), the others (0, +1)
   float h0[S], h1[S], w0[S], w1[S];
@@ -262,8 +259,44 @@ __global__ void __launch_bounds__(128, 7) upsample_argmax_kernel(const ArgmaxPar
   }
 }
 
+template <typename T, typename L, int S>
+__global__ void __launch_bounds__(128, 7) upsample_argmax_kernel(const ArgmaxParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.total) return;
+  const int j = (int)(t % (uint32_t)p.w), i = (int)((t / (uint32_t)p.w) % (uint32_t)p.h);
+  const int n = (int)(t / ((uint32_t)p.w * p.h));
+  argmax_pixel<T, L, S>(p, n, i, j);
+}
+
+// Block-sparse update of a label map that already holds the previous frame's labels: only the logit pixels of the
+// EXECUTED cells, plus a ring of one logit pixel around each (bilinear taps reach one pixel into the neighbours), are
+// recomputed from the dense logits; every other label is unchanged because every logit it depends on is.
+template <typename T, typename L, int S>
+__global__ void __launch_bounds__(128, 7) upsample_argmax_blocks_kernel(const ArgmaxParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int cell = (int)(blockIdx.x / (uint32_t)p.chunks), chunk = (int)(blockIdx.x - (uint32_t)cell * p.chunks);
+  if (!__ldg(p.grid + cell)) return;
+  const int edge = p.BSl + 2, local = chunk * 128 + (int)threadIdx.x;
+  if (local >= edge * edge) return;
+  const int ly = local / edge, lx = local - ly * edge;
+  const int per = p.GH * p.GW, n = cell / per, rem = cell - n * per, gh = rem / p.GW, gw = rem - gh * p.GW;
+  const int i = gh * p.BSl + ly - 1, j = gw * p.BSl + lx - 1;
+  if (i < 0 || j < 0 || i >= p.h || j >= p.w) return;
+  argmax_pixel<T, L, S>(p, n, i, j);
+}
+
 template <typename T, typename L>
 static void launch_argmax(const ArgmaxParams &p, int scale, cudaStream_t stream) {
+  if (p.grid != nullptr) {
+    const dim3 grid((unsigned)(p.N * p.GH * p.GW * p.chunks)), block(128);
+    if (scale == 1) launch_kernel(upsample_argmax_blocks_kernel<T, L, 1>, grid, block, 0, stream, 1, p);
+    else if (scale == 2) launch_kernel(upsample_argmax_blocks_kernel<T, L, 2>, grid, block, 0, stream, 1, p);
+    else launch_kernel(upsample_argmax_blocks_kernel<T, L, 4>, grid, block, 0, stream, 1, p);
+    return;
+  }
   const dim3 grid((p.total + 127) / 128), block(128);
   if (scale == 1) launch_kernel(upsample_argmax_kernel<T, L, 1>, grid, block, 0, stream, 1, p);
   else if (scale == 2) launch_kernel(upsample_argmax_kernel<T, L, 2>, grid, block, 0, stream, 1, p);
@@ -271,7 +304,7 @@ static void launch_argmax(const ArgmaxParams &p, int scale, cudaStream_t stream)
 }
 
 int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides, int scale,
-                    int dtype, int label_bytes, cudaStream_t stream) {
+                    int dtype, int label_bytes, cudaStream_t stream, const uint8_t *grid, int GH, int GW) {
   BC_REQUIRE(labels && logits && strides, BC_ERR_NULL, "bc_upsample_argmax: NULL pointer");
   BC_REQUIRE(N > 0 && K > 0 && h > 0 && w > 0, BC_ERR_SHAPE, "bc_upsample_argmax: empty problem");
   BC_REQUIRE(scale == 1 || scale == 2 || scale == 4, BC_ERR_UNSUPPORTED, "bc_upsample_argmax: scale %d (1, 2 or 4)", scale);
@@ -288,6 +321,14 @@ int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w
   p.N = N; p.K = K; p.h = h; p.w = w;
   p.sn = strides[0]; p.sc = strides[1]; p.sh = strides[2]; p.sw = strides[3];
   p.total = (uint32_t)total;
+  p.grid = grid;
+  p.GH = GH; p.GW = GW; p.BSl = 0; p.chunks = 0;
+  if (grid != nullptr) {
+    BC_REQUIRE(GH > 0 && GW > 0 && h % GH == 0 && w % GW == 0 && h / GH == w / GW, BC_ERR_SHAPE,
+               "bc_upsample_argmax_blocks: %dx%d logits on a %dx%d grid", h, w, GH, GW);
+    p.BSl = h / GH;
+    p.chunks = ((p.BSl + 2) * (p.BSl + 2) + 127) / 128;
+  }
   if (dtype == BC_F16) {
     if (label_bytes == 1) launch_argmax<__half, uint8_t>(p, scale, stream);
     else launch_argmax<__half, long long>(p, scale, stream);
@@ -295,7 +336,7 @@ int upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w
     if (label_bytes == 1) launch_argmax<float, uint8_t>(p, scale, stream);
     else launch_argmax<float, long long>(p, scale, stream);
   }
-  return check_launch("bc_upsample_argmax");
+  return check_launch(grid ? "bc_upsample_argmax_blocks" : "bc_upsample_argmax");
 }
 
 }  // namespace bc

@@ -340,6 +340,16 @@ BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, co
                             bc_dtype_t dtype, bc_stream_t stream);
 BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
                               int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream);
+/* Block-sparse form of the same step ("x4 bilinear + argmax fused with the logits' block structure"):
+ * `labels` already holds the label map of the PREVIOUS frame and `logits` is the combined dense output of this frame,
+ * which differs from the previous one only inside the executed cells of grid (uint8/bool (N,1,GH,GW), 1 = executed;
+ * h % GH == 0, w % GW == 0, square logit blocks).  Only the logit pixels of executed cells plus a ring of one logit
+ * pixel around each are recomputed (a bilinear tap reaches one pixel into the neighbouring cell); the result equals
+ * bc_upsample_argmax over the whole frame bit for bit, at num_exec / num_total of its cost.
+ */
+BC_API int bc_upsample_argmax_blocks(void *labels, const void *logits, const uint8_t *grid, int N, int K, int h, int w,
+                                     const int64_t *strides, int scale, bc_dtype_t dtype, int label_bytes, int GH, int GW,
+                                     bc_stream_t stream);
 
 /* ---- dense pyramid pooling (the @blockcopy_noblocks module of SwiftNet, swiftnet/util.py:85-138) ----------
  * Everything between the module's first and last 1x1 conv, on dense NHWC fp16 planes; grid_h/grid_w are HOST

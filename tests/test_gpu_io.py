@@ -108,3 +108,30 @@ def test_kernels_equal_committed_golden(golden_dir):
     got32 = _C.upsample_argmax(fix["logits32"].cuda(), 4, torch.int64).cpu()
     diff = got32 != fix["labels32"]
     assert not diff.any() or float(fix["top2_gap32"][diff].max()) < 1e-6
+
+
+@pytest.mark.parametrize("N,K,h,w,GH,GW,scale,frac", [(1, 19, 256, 512, 8, 16, 4, 0.3), (2, 19, 64, 128, 4, 8, 4, 0.5),
+                                                       (1, 7, 32, 32, 4, 4, 2, 0.2), (1, 19, 64, 64, 2, 2, 4, 1.0),
+                                                       (1, 19, 48, 96, 3, 6, 4, 0.0), (1, 3, 8, 8, 8, 8, 4, 0.4)])
+def test_block_sparse_label_update_equals_dense_argmax(N, K, h, w, GH, GW, scale, frac):
+    """bc_upsample_argmax_blocks: the previous frame's label map + this frame's logits (changed only inside executed
+    cells) -> exactly the label map bc_upsample_argmax computes from scratch (1-px logit blocks included)."""
+    from blockcopy import _C
+    from consumers.frame_io import BlockLabelMap
+
+    g = torch.Generator().manual_seed(h + GH)
+    prev = (2 * torch.randn(N, K, h, w, generator=g)).half()
+    grid = torch.rand(N, 1, GH, GW, generator=g) < frac
+    BS = h // GH
+    mask = grid.repeat_interleave(BS, 2).repeat_interleave(BS, 3)
+    cur = torch.where(mask, (2 * torch.randn(N, K, h, w, generator=g)).half(), prev)
+    lm = BlockLabelMap(scale=scale)
+    first = lm.update(prev.cuda(), None)
+    assert torch.equal(first, _C.upsample_argmax(prev.cuda(), scale))
+    ptr = first.data_ptr()
+    got = lm.update(cur.cuda(), grid.cuda())
+    assert got.data_ptr() == ptr  # updated in place
+    want = _C.upsample_argmax(cur.cuda(), scale)
+    assert torch.equal(got, want), int((got != want).sum())
+    if 0 < frac < 1:
+        assert not torch.equal(want, _C.upsample_argmax(prev.cuda(), scale))  # the update was needed
