@@ -387,14 +387,16 @@ class HostPipeline:
                 if t + 1 < start + count:
                     self._upload(t + 1, clip_len)
                 main.wait_event(self.in_ready[slot])
-                outs, grids = [], []
+                outs = []
                 for s, model in enumerate(self.models):
                     if self.out_read[s][slot] is not None:
                         main.wait_event(self.out_read[s][slot])  # the output buffer this call rewrites was read out
                     outs.append(model(self.dev_in[slot][s]))
-                    g = model.policy_meta["grid"]
-                    g.record_stream(self.down)  # read by the label update on the download stream
-                    grids.append(g)
+                    if self.u8 and "labels" not in self.SKIP:
+                        # block-sparse label update right behind the frame, on the compute stream: ~1/3 of the label
+                        # map per frame; run concurrently (download stream) its 1000+ small CTAs took the SMs' register
+                        # files away from the next frame's first kernels and cost more than they do in line
+                        self.label_maps[s].update(outs[-1], model.policy_meta["grid"])
                 done = torch.cuda.Event()
                 done.record(main)
                 self.in_free[slot] = done
@@ -406,7 +408,7 @@ class HostPipeline:
                         if "labels" in self.SKIP:
                             pass
                         elif self.u8:
-                            self.label_maps[s].update(out, grids[s])
+                            pass  # done on the compute stream (see above)
                         else:
                             self.dev_res[slot][s].copy_(out, non_blocking=True)
                         ev = torch.cuda.Event()
