@@ -608,6 +608,10 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (weights) failed: CUresult %d", (int)r);
   }
+  p.d_kc_per_tap = FastDiv((uint32_t)p.kc_per_tap);
+  p.d_tiles_per_block = FastDiv((uint32_t)p.tiles_per_block);
+  p.d_ntiles_n = FastDiv((uint32_t)(Cout / n_tile));
+  p.d_splits = FastDiv(1u);
   if (persistent) {
     p.tiles_m = tiles;
     p.ntiles_n = Cout / n_tile;
@@ -629,6 +633,7 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
       p.tiles_m = tiles;
       p.ntiles_n = Cout / n_tile;
       p.splits = S;
+      p.d_splits = FastDiv((uint32_t)S);
       p.ksteps_per_split = (total_k_steps + S - 1) / S;
       return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
     }

@@ -28,6 +28,9 @@ struct ConvParams {
   int blocks_per_tile;      // 1, or 128 / BS_out^2 for small blocks
   int tiles_per_block;      // BS_out^2 / 128 for big blocks, else 1
   int tiles_m, ntiles_n;    // persistent kernel: number of 128-pixel tiles / of N_TILE-channel slices
+  // persistent kernel: exact divisions by these run-time constants as one mul.hi each (the single-thread producer
+  // prologue used to spend ~1000 clk in six 32-bit integer divisions before its first load, profiles/r02_conv_prologue.md)
+  FastDiv d_ntiles_n, d_tiles_per_block, d_splits, d_kc_per_tap;
   int relu;
   uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
   // optional second destination: the next padded op's persistent plane (N, GH*BS_out, GW*BS_out, Cout)

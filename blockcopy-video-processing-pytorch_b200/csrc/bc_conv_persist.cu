@@ -36,10 +36,10 @@ struct TileCoord {
 template <int N_TILE>
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams &p, int tile) {
   TileCoord t;
-  const int m_idx = tile / p.ntiles_n;
+  const int m_idx = (int)p.d_ntiles_n.div((uint32_t)tile);
   t.n0 = (tile - m_idx * p.ntiles_n) * N_TILE;
   if (p.blocks_per_tile == 1) {
-    t.b0 = m_idx / p.tiles_per_block;
+    t.b0 = (int)p.d_tiles_per_block.div((uint32_t)m_idx);
     t.r0 = (m_idx - t.b0 * p.tiles_per_block) * p.rows_per_tile;
     t.nvalid = 1;
   } else {
@@ -163,6 +163,40 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     }
     fence_mbar_init();
   }
+  // The producers decode their FIRST tile here, ahead of the set-up barrier and of griddepcontrol.wait: the mapping
+  // lookup (an L2 round trip) overlaps barrier init / the TMEM allocation / the previous kernel's tail.  `mapping`
+  // is written once per frame by bc_compact_mask, which never triggers its dependents early, so it is complete
+  // before any kernel behind it starts.  Lane i: mapping lookup + cell decode of block i of the tile.
+  const bool is_producer = warp == 0 || warp >= 7;
+  int4 *const my_coords = blk_coord_s + kMaxBlocksPerTile * (warp >= 7 ? warp - 6 : 0);
+  auto decode_blocks = [&](const TileCoord &t) {
+    if (lane < t.nvalid) {
+      const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + t.b0 + lane) : (uint32_t)(t.b0 + lane);
+      uint32_t n, gh, gw;
+      p.cell(cell, n, gh, gw);
+      my_coords[lane] = make_int4((int)gw * p.BS_in - p.pad, (int)gh * p.BS_in + t.r0 * p.stride - p.pad, (int)n, 0);
+    }
+    __syncwarp();
+  };
+  struct UnitInfo { int k0, nk; TileCoord t; };
+  auto unit_info = [&](int unit) {
+    UnitInfo u;
+    const int tile = (int)p.d_splits.div((uint32_t)unit), z = unit - tile * S;
+    u.k0 = (int)p.d_splits.div((uint32_t)(z * total_k));
+    u.nk = (int)p.d_splits.div((uint32_t)((z + 1) * total_k)) - u.k0;
+    u.t = tile_coord<N_TILE>(p, tile);
+    return u;
+  };
+  UnitInfo ui;
+  ui.k0 = ui.nk = 0;
+  ui.t.b0 = ui.t.r0 = ui.t.nvalid = ui.t.n0 = 0;
+  if (is_producer) {
+    __syncwarp();
+    if ((int)blockIdx.x < total_units) {
+      ui = unit_info((int)blockIdx.x);
+      decode_blocks(ui.t);
+    }
+  }
   if (warp == 1) tmem_alloc(&tmem_base_slot, 2 * N_TILE);
   tc_fence_before_sync();
   __syncthreads();
@@ -179,42 +213,36 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     // =============================== activation producers =========================================
     // kAProd warps (0, 7, ...), one elected lane each; producer j issues the k-steps g = j, j + kAProd, ...
     // of the CTA's global k-step sequence (the ring position follows from g alone)
-    if (lane == 0) {
-      const int j = warp == 0 ? 0 : warp - 6;
-      int g = j;  // global k-step (over all tiles of this CTA) this producer issues next
-      int g_unit0 = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int tile = unit / S, z = unit - tile * S;
-        const int k0 = z * total_k / S, nk = (z + 1) * total_k / S - k0;
-        const TileCoord t = tile_coord<N_TILE>(p, tile);
-        int cx0 = 0, cy0 = 0, cn0 = 0;
-        int4 *coords = blk_coord_s + kMaxBlocksPerTile * j;
-        uint32_t cells[kMaxBlocksPerTile];
-#pragma unroll
-        for (int i = 0; i < kMaxBlocksPerTile; ++i)  // all mapping lookups in flight at once
-          cells[i] = (p.mapping && i < t.nvalid) ? (uint32_t)__ldg(p.mapping + t.b0 + i) : (uint32_t)(t.b0 + i);
-#pragma unroll
-        for (int i = 0; i < kMaxBlocksPerTile; ++i) {
-          if (i >= t.nvalid) break;
-          const uint32_t cell = cells[i];
-          uint32_t n, gh, gw;
-          p.cell(cell, n, gh, gw);
-          const int4 c = make_int4((int)gw * p.BS_in - p.pad, (int)gh * p.BS_in + t.r0 * p.stride - p.pad, (int)n, 0);
-          coords[i] = c;
-          if (i == 0) { cx0 = c.x; cy0 = c.y; cn0 = c.z; }
-        }
+    // Per unit the WHOLE warp decodes the tile (lane i: mapping lookup + cell decode of block i, all in flight at
+    // once), then lane 0 alone issues the loads.  The decode used to be a serial single-thread prologue of ~1900-2600 clk
+    // before the first load (profiles/r02_conv_prologue.md).
+    const int j = warp == 0 ? 0 : warp - 6;
+    int g = j;  // global k-step (over all tiles of this CTA) this producer issues next
+    int g_unit0 = 0;
+    int4 *coords = my_coords;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      if (unit != (int)blockIdx.x) {  // (the first unit was decoded ahead of the set-up barrier)
+        ui = unit_info(unit);
+        decode_blocks(ui.t);
+      }
+      const int k0 = ui.k0, nk = ui.nk;
+      const TileCoord t = ui.t;
+      if (lane == 0) {
+        const int4 c0 = coords[0];
+        const int cx0 = c0.x, cy0 = c0.y, cn0 = c0.z;
         const uint32_t tx_bytes = (uint32_t)t.nvalid * p.box_bytes;
         // (tap, channel chunk) of this producer's first k-step in the tile
         int ks = g - g_unit0;
-        int tap = (k0 + ks) / p.kc_per_tap, cc = (k0 + ks) - tap * p.kc_per_tap, kh = tap / p.ksize;
+        int tap = (int)p.d_kc_per_tap.div((uint32_t)(k0 + ks)), cc = (k0 + ks) - tap * p.kc_per_tap;
+        int kh = p.ksize == 1 ? 0 : (tap >= 6 ? 2 : (tap >= 3 ? 1 : 0));
         int kw = tap - kh * p.ksize;
-        g_unit0 += nk;
         for (; ks < nk; ks += kAProd, g += kAProd) {
           const int s = g % STAGES;
           const uint32_t parity = (uint32_t)(((g / STAGES) & 1) ^ 1);
           uint8_t *sa = smem + (size_t)s * kStageBytes;
           mbar_wait(&empty_bar[s], parity);
           mbar_expect_tx(&full_bar[s], tx_bytes);
+          if (g == 0) trace_mark(p, 12);  // about to issue the first activation load
           if (t.nvalid == 1) {
             tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw * p.dil, cy0 + kh * p.dil, cn0);
           } else {
@@ -231,6 +259,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
             }
         }
       }
+      g_unit0 += nk;  // (g and g_unit0 matter to lane 0 only; it advanced g inside its loop)
+      __syncwarp();  // lane 0 is done with coords[] before the next unit's decode overwrites it
     }
   } else if (warp == 6) {
     // =============================== weight producer ==============================================
@@ -239,9 +269,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       uint32_t parity = 1;
       uint8_t *sb = smem + kABytes;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int tile = unit / S, z = unit - tile * S;
-        const int k0 = z * total_k / S, nk = (z + 1) * total_k / S - k0;
-        const int n0 = (tile % p.ntiles_n) * N_TILE;
+        const int tile = (int)p.d_splits.div((uint32_t)unit), z = unit - tile * S;
+        const int k0 = (int)p.d_splits.div((uint32_t)(z * total_k)), nk = (int)p.d_splits.div((uint32_t)((z + 1) * total_k)) - k0;
+        const int n0 = (tile - (int)p.d_ntiles_n.div((uint32_t)tile) * p.ntiles_n) * N_TILE;
         int kcoord = k0 * kChunkK;
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&empty_bar[s], parity);
@@ -263,8 +293,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       uint32_t buf = 0, buf_parity = 1;  // first use of either accumulator buffer: it is free
       bool first = true;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int z = unit % S;
-        const int nk = (z + 1) * total_k / S - z * total_k / S;
+        const int z = unit - (int)p.d_splits.div((uint32_t)unit) * S;
+        const int nk = (int)p.d_splits.div((uint32_t)((z + 1) * total_k)) - (int)p.d_splits.div((uint32_t)(z * total_k));
         mbar_wait(&acc_empty[buf], buf_parity);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + buf * N_TILE;
@@ -294,7 +324,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
     const int c8 = (lane % kTPR) * 8;
     uint32_t buf = 0, buf_parity = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const int tile = unit / S;
+      const int tile = (int)p.d_splits.div((uint32_t)unit);
       const TileCoord t = tile_coord<N_TILE>(p, tile);
       // this tile's slice of the bias + this warp's 32 plane-row offsets, while the MMAs of the tile run
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
@@ -412,7 +442,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   if (S > 1) {
     cluster_sync_all();  // every CTA's partial is in L2 and visible cluster-wide (release / acquire)
     {
-      const int tile = blockIdx.x / S, rank = blockIdx.x - tile * S;  // cluster (S,1,1): rank = blockIdx.x % S
+      const int tile = (int)p.d_splits.div(blockIdx.x), rank = (int)blockIdx.x - tile * S;  // cluster (S,1,1): rank = blockIdx.x % S
       const TileCoord t = tile_coord<N_TILE>(p, tile);
       const size_t out_base = ((size_t)t.b0 * p.BS_out * p.BS_out + (size_t)t.r0 * p.BS_out) * p.Cout + t.n0;
       const int m_valid = p.blocks_per_tile == 1 ? kTileM : t.nvalid * p.BS_out * p.BS_out;

@@ -16,7 +16,9 @@ compact_mask_kernel(const uint8_t *__restrict__ grid, int G, int32_t *__restrict
                     const int32_t *__restrict__ prev_grid_idx, int32_t *__restrict__ transfer_idx) {
   __shared__ int warp_sums[kScanThreads / 32];
   __shared__ int total_exec;
-  pdl_trigger();
+  // No early griddepcontrol.launch_dependents here: the conv kernels read `mapping_exec` BEFORE their own
+  // griddepcontrol.wait (the lookup then overlaps their set-up), which is only safe if a kernel launched right
+  // behind this one cannot start before this one has finished (implicit trigger at grid completion).
   pdl_wait();
   const int tid = threadIdx.x;
   const int per = (G + kScanThreads - 1) / kScanThreads;

@@ -31,6 +31,10 @@ def report(name, trace, flops=None):
           + (f" ({flops / (wall1 - wall0) * 1e-3:.0f} TFLOP/s)" if flops else ""))
     print("   phase clocks (mean / p90): " + "; ".join(
         f"{p} {x.mean():.0f}/{x.quantile(0.9):.0f}" for p, x in zip(PH, d)))
+    if (t[:, 11] != 0).any():
+        m = [(t[:, k].double() - c[:, 1]).mean() for k in (11, 13, 14, 12)]
+        print(f"   producer 0 after the PDL wait: tile decoded +{m[0]:.0f} clk, block coordinates (mapping loads) +{m[1]:.0f}, "
+              f"tap decoded +{m[2]:.0f}, first activation load issued +{m[3]:.0f}, first operands landed +{d[1].mean():.0f}")
     print(f"   CTA lifetime clocks mean {life.mean():.0f} p90 {life.quantile(0.9):.0f}; "
           f"CTA start offsets us: p50 {starts.quantile(0.5):.1f} p90 {starts.quantile(0.9):.1f} max {starts.max():.1f}")
 
