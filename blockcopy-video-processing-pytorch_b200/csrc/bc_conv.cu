@@ -571,6 +571,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     tiles = (E + p.blocks_per_tile - 1) / p.blocks_per_tile;
   }
   p.box_bytes = (uint32_t)(p.rows_per_tile * BS_out * 128);
+  p.a3_bytes = 0;
+  p.a3_stages = 0;
 
   // A: the plane (Cin, W, H, N), box = 64 channels x BS_out x rows (sampled every `stride` pixels)
   CUtensorMap a_map, b_map;
@@ -612,6 +614,33 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   p.d_tiles_per_block = FastDiv((uint32_t)p.tiles_per_block);
   p.d_ntiles_n = FastDiv((uint32_t)(Cout / n_tile));
   p.d_splits = FastDiv(1u);
+  // "Shared halo rows" (bc_conv_persist.cu, A3): 3x3 / stride-1 convs on blocks of 16..64 px can take ONE activation
+  // box per (kw, chunk) with the three kh taps as descriptor offsets (-25 % operand bytes on 32-px blocks).  Bit-correct
+  // (tests/test_gpu_conv.py::test_large_grid_all_launch_forms_agree) but MEASURED SLOWER on B200 (k-loop 560 vs 358
+  // clk per k-step on the layer-2 shape, whatever the activation ring depth: profiles/r02_conv_a3.md), so it is an
+  // experiment switch only: BC_CONV_A3=1 enables it.
+  static const int env_a3 = getenv("BC_CONV_A3") ? atoi(getenv("BC_CONV_A3")) : 0;
+  if (env_a3 && env_persist != 0 && !use_split && !env_ntile && ksize == 3 && stride == 1 && dil == 1 && p.blocks_per_tile == 1 &&
+      BS_out >= 16 && BS_out <= 64) {
+    CUtensorMap a3_map;
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kChunkK, (cuuint32_t)BS_out, (cuuint32_t)(p.rows_per_tile + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&a3_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(plane), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (halo-row box) failed: CUresult %d", (int)r);
+    p.a3_bytes = (uint32_t)((p.rows_per_tile + 2) * BS_out * 128);
+    p.a3_stages = p.a3_bytes <= 24 * 1024 ? 3 : 2;
+    if (getenv("BC_A3_STAGES")) p.a3_stages = atoi(getenv("BC_A3_STAGES"));
+    p.tiles_m = tiles;
+    p.ntiles_n = Cout / n_tile;
+    p.splits = 1;
+    p.ksteps_per_split = total_k_steps;
+    p.work = nullptr;
+    return launch_conv_persistent(a3_map, b_map, p, n_tile, stream);
+  }
   if (persistent) {
     p.tiles_m = tiles;
     p.ntiles_n = Cout / n_tile;

@@ -33,6 +33,8 @@ struct ConvParams {
   FastDiv d_ntiles_n, d_tiles_per_block, d_splits, d_kc_per_tap;
   int relu;
   uint32_t box_bytes;       // bytes one A box (one block's share of the tile) occupies in smem
+  uint32_t a3_bytes;        // shared-halo-rows mode: bytes of one (rows_per_tile + 2)-row activation box (0: off)
+  int a3_stages;            // ... and the depth of the activation ring (persistent kernel)
   // optional second destination: the next padded op's persistent plane (N, GH*BS_out, GW*BS_out, Cout)
   __half *plane_out;
   const int32_t *out_mapping;  // cell of packed tile b in the OUTPUT grid (== mapping unless mapping is null)

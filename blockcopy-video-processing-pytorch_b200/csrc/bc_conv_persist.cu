@@ -60,7 +60,9 @@ template <int N_TILE, int S>
 __device__ __forceinline__ void splitk_reduce(const ConvParams &p, int rank, int tile, int n0, size_t out_base,
                                               int m_valid, const long long *row_pl_s, const float *bias_s) {
   constexpr int kTPRow = N_TILE / 8, kUnits = kTileM * kTPRow;
-  constexpr int UPB = 8 / S > 0 ? 8 / S : 1;
+  // units per thread and round: the CTA's whole share in ONE round, so that every partial load of the reduction is in
+  // flight before the first use (a second round cost another L2 round trip: ~1000 clk of a ~4000 clk tail)
+  constexpr int UPB = (kUnits / S + kPersistThreads) / kPersistThreads;
   const int lo_u = rank * kUnits / S, hi_u = (rank + 1) * kUnits / S;
   const int t = threadIdx.x;  // every warp of the CTA takes part: the producers and the MMA warp are idle by now
   const float *ws = p.work + (size_t)tile * S * kTileM * N_TILE;
@@ -122,16 +124,29 @@ __device__ __forceinline__ void splitk_reduce(const ConvParams &p, int rank, int
 }
 
 
-template <int N_TILE, int STAGES>
+// A3 = true: "shared halo rows" (3x3, stride 1, dilation 1, one block per tile, S = 1).  The three taps of a kernel
+// column read the same pixels shifted by one image row, so ONE activation box of rows_per_tile + 2 rows per
+// (kw, 64-channel chunk) feeds three k-steps: the MMA of tap kh starts kh * BS_out rows (a multiple of the 1024-byte
+// swizzle atom) into the box.  Operand bytes per k-step drop from 32 KB to 16 KB + (R + 2) / 3R * 16 KB (32-px blocks:
+// 24 KB), i.e. below what the ring sustains (~110 B/clk against the 128 B/clk a k-step needs at the MMA floor,
+// profiles/r01c_conv_persistent.md), so the k-loop becomes tensor-pipe bound.  Activations and weights run on
+// SEPARATE rings (p.a3_stages boxes of p.a3_bytes, kB3 weight tiles); k-steps are ordered (kw, chunk, kh).
+template <int N_TILE> constexpr int kPersistB3 = N_TILE == 128 ? 6 : 8;
+constexpr int kPersistA3Max = 3;
+
+template <int N_TILE, int STAGES, bool A3 = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                              const ConvParams p) {
   constexpr uint32_t kBBytes = N_TILE * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int kRowB = N_TILE * 2 + 16;  // staged output row (+16 B: rows start in different bank groups)
+  constexpr int kBStages = A3 ? kPersistB3<N_TILE> : STAGES;  // ring depth of full_bar / empty_bar
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[kBStages];   // A3: the weight ring
+  __shared__ __align__(8) uint64_t empty_bar[kBStages];
+  __shared__ __align__(8) uint64_t a_full[kPersistA3Max];   // A3: the activation ring
+  __shared__ __align__(8) uint64_t a_empty[kPersistA3Max];
   __shared__ __align__(8) uint64_t acc_full[2];   // MMA warp -> epilogue: accumulator buffer complete
   __shared__ __align__(8) uint64_t acc_empty[2];  // epilogue -> MMA warp: buffer read out (128 arrivals)
   __shared__ uint32_t tmem_base_slot;
@@ -140,7 +155,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   __shared__ int4 blk_coord_s[kMaxBlocksPerTile * kAProd];
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *staging = smem + (size_t)STAGES * kStageBytes;
+  const uint32_t a3_stride = (p.a3_bytes + 1023u) & ~1023u;
+  const int a3_stages = p.a3_stages;
+  uint8_t *staging = A3 ? smem + (size_t)a3_stages * a3_stride + (size_t)kBStages * kBBytes : smem + (size_t)STAGES * kStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.ntiles_n;
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
@@ -153,10 +170,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&full_bar[s], A3 ? 1 : 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
       mbar_init(&empty_bar[s], 1);
     }
+    if (A3)
+      for (int s = 0; s < kPersistA3Max; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_empty[s], 1);
+      }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 128);
@@ -209,6 +231,98 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   if (warp != 6 || (p.debug & 4)) pdl_wait();
   if (threadIdx.x == 0) trace_mark(p, 1);
 
+  const int a3_groups = p.ksize * p.kc_per_tap;  // (kw, chunk) groups of a tile, three k-steps each
+  if (A3 && (warp == 0 || warp >= 7)) {
+    // =============================== activation producers (shared halo rows) ======================
+    // producer j issues the groups gg = j, j + kAProd, ... of the CTA's global group sequence
+    const int j = warp == 0 ? 0 : warp - 6;
+    int gg = j, gg_unit0 = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      if (unit != (int)blockIdx.x) {
+        ui = unit_info(unit);
+        decode_blocks(ui.t);
+      }
+      if (lane == 0) {
+        const int4 c0 = my_coords[0];
+        int gi = gg - gg_unit0;  // group within the tile
+        int kw = (int)p.d_kc_per_tap.div((uint32_t)gi), cc = gi - kw * p.kc_per_tap;
+        for (; gi < a3_groups; gi += kAProd, gg += kAProd) {
+          const int s = gg % a3_stages;
+          const uint32_t parity = (uint32_t)(((gg / a3_stages) & 1) ^ 1);
+          mbar_wait(&a_empty[s], parity);
+          mbar_expect_tx(&a_full[s], p.a3_bytes);
+          if (gg == 0) trace_mark(p, 12);
+          tma_load_4d(smem + (size_t)s * a3_stride, &a_map, &a_full[s], cc * kChunkK, c0.x + kw, c0.y, c0.z);
+#pragma unroll
+          for (int u = 0; u < kAProd; ++u)
+            if (++cc == p.kc_per_tap) { cc = 0; ++kw; }
+        }
+      }
+      gg_unit0 += a3_groups;
+      __syncwarp();
+    }
+  } else if (A3 && warp == 6) {
+    // =============================== weight producer (k-steps ordered (kw, chunk, kh)) ============
+    if (lane == 0) {
+      int s = 0;
+      uint32_t parity = 1;
+      uint8_t *const sb0 = smem + (size_t)a3_stages * a3_stride;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int n0 = (unit - (int)p.d_ntiles_n.div((uint32_t)unit) * p.ntiles_n) * N_TILE;
+        int kw = 0, cc = 0;
+        for (int gi = 0; gi < a3_groups; ++gi) {
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh) {
+            mbar_wait(&empty_bar[s], parity);
+            mbar_expect_tx(&full_bar[s], kBBytes);
+            tma_load_2d(sb0 + (size_t)s * kBBytes, &b_map, &full_bar[s], ((kh * 3 + kw) * p.kc_per_tap + cc) * kChunkK, n0);
+            if (++s == kBStages) { s = 0; parity ^= 1; }
+          }
+          if (++cc == p.kc_per_tap) { cc = 0; ++kw; }
+        }
+      }
+    }
+  } else if (A3 && warp == 1) {
+    // =============================== MMA issuer (shared halo rows) ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileM, N_TILE);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem) + (uint32_t)a3_stages * a3_stride);
+      const uint32_t tap_off = (uint32_t)(p.BS_out * 128) >> 4;  // one image row of the box, in 16-byte units
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t buf = 0, buf_parity = 1;
+      bool first = true;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        mbar_wait(&acc_empty[buf], buf_parity);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + buf * N_TILE;
+        for (int gi = 0; gi < a3_groups; ++gi) {
+          mbar_wait(&a_full[sa], pa);
+          if (first) { trace_mark(p, 2); first = false; }
+          const uint64_t a_desc = a_desc0 + (uint64_t)sa * (a3_stride >> 4);
+#pragma unroll 1
+          for (int kh = 0; kh < 3; ++kh) {
+            mbar_wait(&full_bar[sb], pb);
+            tc_fence_after_sync();
+            const uint64_t b_desc = b_desc0 + (uint64_t)sb * (kBBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)
+              umma_f16_ss(acc, a_desc + kh * tap_off + 2 * k, b_desc + 2 * k, idesc, (uint32_t)((gi | kh | k) != 0));
+            umma_commit(&empty_bar[sb]);
+            if (++sb == kBStages) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&a_empty[sa]);  // frees the activation box once its three taps have been read
+          if (++sa == a3_stages) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+        if (buf == 1) buf_parity ^= 1;
+        buf ^= 1;
+      }
+      trace_mark(p, 3);
+    }
+  } else if (A3 && (warp < 2 || warp >= 6)) {
+  } else
   if (warp == 0 || warp >= 7) {
     // =============================== activation producers =========================================
     // kAProd warps (0, 7, ...), one elected lane each; producer j issues the k-steps g = j, j + kAProd, ...
@@ -440,7 +554,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   }
 
   if (S > 1) {
+    if (threadIdx.x == 0) trace_mark(p, 13);
     cluster_sync_all();  // every CTA's partial is in L2 and visible cluster-wide (release / acquire)
+    if (threadIdx.x == 0) trace_mark(p, 14);
     {
       const int tile = (int)p.d_splits.div(blockIdx.x), rank = (int)blockIdx.x - tile * S;  // cluster (S,1,1): rank = blockIdx.x % S
       const TileCoord t = tile_coord<N_TILE>(p, tile);
@@ -485,8 +601,31 @@ static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map,
   return check_launch("bc_conv_igemm");
 }
 
+// shared-halo-rows form (p.a3_bytes / p.a3_stages set by the caller; S = 1)
+template <int N_TILE>
+static int launch_persistent_a3(const CUtensorMap &a3_map, const CUtensorMap &b_map, const ConvParams &p, cudaStream_t s) {
+  const size_t a3_stride = ((size_t)p.a3_bytes + 1023) & ~(size_t)1023;
+  const size_t smem = (size_t)p.a3_stages * a3_stride + (size_t)kPersistB3<N_TILE> * N_TILE * 128 + 4 * 32 * (N_TILE * 2 + 16) + 1024;
+  constexpr size_t kMax = 227 * 1024 - 4096;
+  static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_persistent_kernel<N_TILE, 2, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax);
+  BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_persistent_kernel a3): %s", cudaGetErrorString(attr));
+  BC_REQUIRE(smem <= kMax && p.a3_stages >= 1 && p.a3_stages <= kPersistA3Max && p.splits == 1, BC_ERR_UNSUPPORTED,
+             "bc_conv_igemm: halo-row ring of %zu bytes", smem);
+  const int total = p.tiles_m * p.ntiles_n;
+  const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+  const cudaError_t e = launch_kernel_cluster(conv_igemm_persistent_kernel<N_TILE, 2, true>, dim3(grid), dim3(kPersistThreads),
+                                              smem, s, dim3(1, 1, 1), a3_map, b_map, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+  }
+  return check_launch("bc_conv_igemm");
+}
+
 int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int n_tile,
                            cudaStream_t s) {
+  if (p.a3_bytes) return n_tile == 128 ? launch_persistent_a3<128>(a_map, b_map, p, s) : launch_persistent_a3<64>(a_map, b_map, p, s);
   return n_tile == 128 ? launch_persistent<128, 5>(a_map, b_map, p, s) : launch_persistent<64, 8>(a_map, b_map, p, s);
 }
 

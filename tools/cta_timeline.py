@@ -35,6 +35,11 @@ def report(name, trace, flops=None):
         m = [(t[:, k].double() - c[:, 1]).mean() for k in (11, 13, 14, 12)]
         print(f"   producer 0 after the PDL wait: tile decoded +{m[0]:.0f} clk, block coordinates (mapping loads) +{m[1]:.0f}, "
               f"tap decoded +{m[2]:.0f}, first activation load issued +{m[3]:.0f}, first operands landed +{d[1].mean():.0f}")
+    if (t[:, 13] != 0).any():
+        w = (t[:, 14] - t[:, 13]).double()
+        r = c[:, 6] - t[:, 14].double()
+        print(f"   split-K tail: thread 0 reaches the cluster barrier {(t[:, 13].double() - c[:, 3]).mean():.0f} clk after its last MMA issue, "
+              f"waits {w.mean():.0f} (p90 {w.quantile(0.9):.0f}) clk in it, reduce + stores {r.mean():.0f} clk")
     print(f"   CTA lifetime clocks mean {life.mean():.0f} p90 {life.quantile(0.9):.0f}; "
           f"CTA start offsets us: p50 {starts.quantile(0.5):.1f} p90 {starts.quantile(0.9):.1f} max {starts.max():.1f}")
 
