@@ -48,8 +48,10 @@ _SIGNATURES = {
     "bc_policy_features_nhwc16": ([_vp, _i, _vp, _vp, _vp, _vp] + [_i] * 10 + [_vp, ctypes.c_float, ctypes.c_float, _i, _vp], _i),
     "bc_info_gain": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "bc_bn_update_running": ([_vp, _i, _vp], _i),
+    "bc_gn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_sample_grid": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "bc_raster_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "bc_depth_to_space": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
@@ -623,6 +625,64 @@ def raster_boxes(out: torch.Tensor, rects: torch.Tensor, values: torch.Tensor, s
     return out
 
 
+# ------------------------------------------------------------------------------------------- per-block ConvTranspose2d
+_DECONV_W = TensorCache(64)
+
+
+def deconv_supported(dtype, weight: torch.Tensor, BS_in: int, stride, padding, output_padding=0, dilation=1,
+                     groups: int = 1) -> bool:
+    """True when a per-block ConvTranspose2d can run as bc_conv_igemm + bc_depth_to_space: fp16, groups 1, no dilation /
+    output padding, (k, s, p) = (4, 2, 1) [3x3 conv over the zero-bordered tile, four output phases] or k == s in
+    {2, 4}, p = 0 [1x1 conv, s*s phases]; Cin and s*s*Cout multiples of 64, tile edge a power of two in [2, 128]."""
+    Cin, Cout, kh, kw = weight.shape
+    if dtype != torch.float16 or weight.dtype != torch.float16 or not weight.is_cuda or groups != 1:
+        return False
+    if dilation != 1 or output_padding != 0 or kh != kw:
+        return False
+    if not ((kh, stride, padding) == (4, 2, 1) or (kh == stride and padding == 0 and stride in (2, 4))):
+        return False
+    if Cin % 64 or (stride * stride * Cout) % 64 or Cout % 8:
+        return False
+    return 2 <= BS_in <= 128 and (BS_in & (BS_in - 1)) == 0
+
+
+def pack_deconv_weight(w: torch.Tensor, bias: Optional[torch.Tensor], stride: int):
+    """ConvTranspose2d weight (Cin,Cout,k,k) -> (conv weight (s*s*Cout, Cin, k', k') channels_last, bias repeated per
+    phase | None), output channel (a*s + b)*Cout + co = output phase (a, b) of channel co; cached per version.
+    k == s: k' = 1, W'[(a,b,co), ci] = w[ci, co, a, b].  (4, 2, 1): k' = 3 (cross-correlation, pad 1); output row
+    2y + a reads input rows y-1, y (a = 0: taps 3, 1) or y, y+1 (a = 1: taps 2, 0); the other row of the 3x3 is zero."""
+    hit = _DECONV_W.get((w, bias), (stride,))
+    if hit is None:
+        Cin, Cout, k, _ = w.shape
+        s = stride
+        wd = w.detach()
+        if k == s:
+            wp = wd.permute(2, 3, 1, 0).reshape(s * s * Cout, Cin, 1, 1).contiguous()
+        else:
+            taps = {0: {0: 3, 1: 1}, 1: {1: 2, 2: 0}}  # phase -> {3x3 row t: transposed-conv tap}
+            wp = torch.zeros(2, 2, Cout, Cin, 3, 3, dtype=w.dtype, device=w.device)
+            for a in (0, 1):
+                for t, ky in taps[a].items():
+                    for b in (0, 1):
+                        for u, kx in taps[b].items():
+                            wp[a, b, :, :, t, u] = wd[:, :, ky, kx].t()
+            wp = wp.reshape(4 * Cout, Cin, 3, 3).contiguous(memory_format=torch.channels_last)
+        bp = None if bias is None else bias.detach().repeat(s * s).contiguous()
+        hit = _DECONV_W.put((w, bias), (stride,), (wp, bp))
+    return hit
+
+
+def depth_to_space(out: torch.Tensor, x: torch.Tensor, r: int) -> torch.Tensor:
+    """out (E,C,r*h,r*w) channels_last <- x (E,r*r*C,h,w) channels_last, channel (a*r+b)*C + c -> pixel (r*y+a, r*x+b)."""
+    _dev(out, x)
+    E, C, H, W = out.shape
+    h, w = x.shape[2], x.shape[3]
+    assert x.dtype == out.dtype == torch.float16 and x.shape[0] == E and x.shape[1] == r * r * C and (H, W) == (r * h, r * w)
+    assert x.is_contiguous(memory_format=torch.channels_last) and out.is_contiguous(memory_format=torch.channels_last)
+    _check(lib().bc_depth_to_space(out.data_ptr(), x.data_ptr(), E, C, h, w, int(r), _stream()), "bc_depth_to_space")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- train-mode BN statistics
 BN_STATS_WORKSPACE = 16 + 2 * 148 * 2 * 128 * 4
 
@@ -636,6 +696,26 @@ def bn_stats(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, eps: flo
     assert mean.dtype == torch.float32 and invstd.dtype == torch.float32 and mean.numel() >= C and invstd.numel() >= C
     _check(lib().bc_bn_stats(mean.data_ptr(), invstd.data_ptr(), x.data_ptr(), N * H * W, C, float(eps),
                              workspace.data_ptr(), workspace.numel(), _stream()), "bc_bn_stats")
+
+
+GN_STATS_WORKSPACE = 16 + 2 * 148 * 256 * 2 * 8
+
+
+def gn_stats(x: torch.Tensor, groups: int, eps: float, mean: torch.Tensor, invstd: torch.Tensor, workspace: torch.Tensor):
+    """Per-channel (mean, invstd) of each channel's GROUP over all pixels of the packed channels_last fp16 tile
+    batch x (E,C,h,w): GroupNorm statistics with the executed blocks folded into one sample (bc_gn_stats)."""
+    _dev(x, mean, invstd, workspace)
+    assert x.dtype == torch.float16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    E, C, h, w = x.shape
+    assert mean.dtype == torch.float32 and invstd.dtype == torch.float32 and mean.numel() >= C and invstd.numel() >= C
+    _check(lib().bc_gn_stats(mean.data_ptr(), invstd.data_ptr(), x.data_ptr(), E * h * w, C, int(groups), float(eps),
+                             workspace.data_ptr(), workspace.numel(), _stream()), "bc_gn_stats")
+
+
+def gn_supported(x: torch.Tensor, groups: int) -> bool:
+    C = x.shape[1]
+    return (x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and C % 8 == 0 and C <= 2048 and 1 <= groups <= 256
+            and C % groups == 0 and (C // groups) % 8 == 0)
 
 
 def bn_update_running(table: torch.Tensor):

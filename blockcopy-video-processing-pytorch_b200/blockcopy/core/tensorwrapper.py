@@ -408,6 +408,30 @@ def _bn_params(running_mean, running_var, weight, bias, eps):
     return hit
 
 
+_GN_WS: Dict[Tuple[int, int], torch.Tensor] = {}
+_F32_CACHE = _C.TensorCache(1024)
+
+
+def _gn_workspace(device: torch.device) -> torch.Tensor:
+    """bc_gn_stats scratch (zeroed once), private to a (device, CUDA stream) pair."""
+    key = (device.index, int(torch.cuda.current_stream(device).cuda_stream))
+    ws = _GN_WS.get(key)
+    if ws is None:
+        ws = _GN_WS[key] = torch.zeros(_C.GN_STATS_WORKSPACE, dtype=torch.uint8, device=device)
+    return ws
+
+
+def _f32_vector(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """fp32 contiguous copy of a per-channel parameter vector, cached per parameter version."""
+    if t is None:
+        return None
+    hit = _F32_CACHE.get((t,))
+    if hit is None:
+        with torch.no_grad():
+            hit = _F32_CACHE.put((t,), (), _raw(t).detach().float().contiguous())
+    return hit
+
+
 def _dense(t: torch.Tensor) -> torch.Tensor:
     """Plain, dense (NCHW or channels_last) view/copy of t for the kernels (launches a deferred
     producer first: Tensor.as_subclass is not routed through __torch_function__)."""
@@ -671,7 +695,9 @@ class TensorWrapper(torch.Tensor):
                 warnings.warn(f"Operation {op} might behave differently with TensorWrapper!")
                 out = super().__torch_function__(func, types, args, kwargs)
         else:
-            out = super().__torch_function__(func, types, args, kwargs)
+            out = src._try_fused_conv_transpose(args, kwargs) if op == "conv_transpose2d" else None
+            if out is None:
+                out = super().__torch_function__(func, types, args, kwargs)
 
         if isinstance(out, TensorWrapper) and out is not src and out._features is None:
             out._inherit(src)
@@ -962,6 +988,41 @@ class TensorWrapper(torch.Tensor):
             out._materialize()
         return out
 
+    def _try_fused_conv_transpose(self, args, kwargs):
+        """conv_transpose2d on fp16 blocks (a pass-through op in the reference, tensorwrapper.py:519-520: every tile
+        is its own sample, zeros beyond the tile edge): bc_conv_igemm over the tile batch viewed as E one-block
+        frames, with s*s*Cout output channels (one group per output phase), then bc_depth_to_space.  None: outside
+        the envelope (torch runs the op on the tile batch)."""
+        names = ("input", "weight", "bias", "stride", "padding", "output_padding", "groups", "dilation")
+        a = dict(bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1)
+        a.update(zip(names, args))
+        a.update(kwargs)
+        one = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)  # noqa: E731
+        stride, padding, opad, dil = one(a["stride"]), one(a["padding"]), one(a["output_padding"]), one(a["dilation"])
+        x, weight, bias = a["input"], a["weight"], a["bias"]
+        if None in (stride, padding, opad, dil) or not isinstance(x, TensorWrapper) or not x._is_blocks \
+                or isinstance(weight, TensorWrapper):
+            return None
+        if weight.dim() != 4 or x.dim() != 4 or x.shape[0] == 0 or weight.shape[0] != x.shape[1] or x.shape[2] != x.shape[3]:
+            return None
+        if not _C.deconv_supported(x.dtype, weight, x.shape[2], stride, padding, opad, dil, a["groups"]):
+            return None
+        if bias is not None and (bias.dtype != x.dtype or not bias.is_cuda or isinstance(bias, TensorWrapper)):
+            return None
+        tiles = x._tiles_nhwc()
+        if tiles is None:
+            return None
+        E, Cin, h, _ = tiles.shape
+        Cout = weight.shape[1]
+        wp, bp = _C.pack_deconv_weight(weight, bias, stride)
+        _SideState.sync_main(tiles)
+        phases = torch.empty((E, stride * stride * Cout, h, h), dtype=x.dtype, device=x.device,
+                             memory_format=torch.channels_last)
+        _C.conv_igemm(phases, tiles, wp, bp, None, None, E, h, 1, wp.shape[2] // 2)
+        out = torch.empty((E, Cout, stride * h, stride * h), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        _C.depth_to_space(out, phases, stride)
+        return out.as_subclass(TensorWrapper)._inherit(x)
+
     def _try_fused_pool(self, args, kwargs):
         """max_pool2d with padding on fp16 NHWC blocks through bc_maxpool_halo (reads the op's plane,
         halo included); deferred like the convs so that its result lands in the next op's plane."""
@@ -1040,9 +1101,43 @@ class TensorWrapper(torch.Tensor):
         BLOCK border exactly like the reference's trilinear rewrite (tensorwrapper.py:577-598)."""
         return super().__torch_function__(func, types, args, kwargs)
 
+    def _try_fused_group_norm(self, args, kwargs):
+        """group_norm on fp16 blocks: statistics over ALL executed blocks in one kernel (bc_gn_stats, the reference's
+        fold of the tile batch into one sample), normalisation + affine as a deferred elementwise stage (bc_ew_fused)
+        that absorbs a following ReLU and writes the consumer's plane.  None: outside the envelope."""
+        names = ("input", "num_groups", "weight", "bias", "eps")
+        a = dict(weight=None, bias=None, eps=1e-5)
+        a.update(zip(names, args))
+        a.update(kwargs)
+        x, groups = a["input"], a["num_groups"]
+        if not LAZY_FUSION or not isinstance(x, TensorWrapper) or not x._is_blocks or not isinstance(groups, int):
+            return None
+        if not _C.lazy_supported(x) or not _C.gn_supported(x, groups) or x.shape[0] == 0:
+            return None
+        w, b = a["weight"], a["bias"]
+        for t in (w, b):
+            if t is not None and (isinstance(t, TensorWrapper) or t.dim() != 1 or t.shape[0] != x.shape[1] or not t.is_cuda):
+                return None
+        tiles = x._tiles_nhwc()
+        if tiles is None:
+            return None
+        C = x.shape[1]
+        _SideState.sync_main(tiles)
+        stats = torch.empty((2, C), dtype=torch.float32, device=tiles.device)
+        _C.gn_stats(tiles, groups, float(a["eps"]), stats[0], stats[1], _gn_workspace(tiles.device))
+        q = _Pending("ew", src=tiles)
+        q.bn = (stats[0], stats[1], _f32_vector(w), _f32_vector(b))
+        q.stage = 2
+        return x._new_pending(tuple(x.shape), q)
+
     def _func_batched(self, func, types, args, kwargs):
         """Ops with per-sample statistics (group_norm): fold all executed blocks into ONE sample
         (reference tensorwrapper.py:600-633; batch size 1 only)."""
+        if getattr(func, "__name__", "") == "group_norm":
+            fused = self._try_fused_group_norm(args, kwargs)
+            if fused is not None:
+                return fused
+            _materialize_all(args, kwargs)
         args = list(args)
         x = args[0].as_subclass(torch.Tensor)
         E, C, h, w = x.shape

@@ -66,6 +66,9 @@ int info_gain(void *out, const void *cur, const void *prev, int N, int K, int h,
 int sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
                 int at_least_one, cudaStream_t stream);
 int bn_update_running(const long long *table, int n, cudaStream_t stream);
+int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int groups, float eps, void *workspace,
+             long long workspace_bytes, cudaStream_t stream);
+int depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -361,6 +364,15 @@ BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, co
 
 BC_API int bc_bn_update_running(const long long *table, int n, bc_stream_t stream) {
   return bn_update_running(table, n, (cudaStream_t)stream);
+}
+
+BC_API int bc_gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int groups, float eps, void *workspace,
+                       long long workspace_bytes, bc_stream_t stream) {
+  return gn_stats(mean, invstd, x, P, C, groups, eps, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, bc_stream_t stream) {
+  return depth_to_space(out, in, E, C, h, w, r, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -643,3 +643,114 @@ int bn_update_running(const long long *table, int n, cudaStream_t stream) {
 }
 
 }  // namespace bc
+
+// =====================================================================================================
+// bc_gn_stats -- GroupNorm statistics over ALL executed blocks (reference core/tensorwrapper.py:600-633,
+// `_func_batched`: the (E, C, h, w) tile batch is folded into one (1, C, E*h*w, 1) sample, so a group's mean / variance
+// run over the group's channels of every executed block).  x: packed NHWC fp16 tiles = (P pixels, C channels);
+// output: per CHANNEL mean[c] / invstd[c] of the channel's group, which bc_ew_fused applies like a batch norm
+// (y = weight * (x - mean) * invstd + bias).  One pass; per-CTA partials are added in CTA order by the last CTA
+// (atomic ticket) in double precision: run-to-run reproducible.  C % 8 == 0, (C / groups) % 8 == 0, C <= 2048.
+// =====================================================================================================
+namespace bc {
+
+constexpr int kGnThreads = 256;
+
+struct GnParams {
+  const __half *x;
+  float *mean, *invstd;  // [C]
+  double *partial;       // [gridDim.x][groups][2]
+  unsigned int *ticket;
+  uint32_t P;
+  int C, groups;
+  float eps;
+};
+
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
+  __shared__ float red[kGnThreads][2];
+  __shared__ double fin[2 * 256];
+  __shared__ bool last;
+  pdl_trigger();
+  pdl_wait();
+  const int lanes = p.C >> 3;  // threads per pixel (8 channels each), <= 256
+  const int sub = threadIdx.x % lanes, row = threadIdx.x / lanes, rows = kGnThreads / lanes;
+  float s = 0.f, q = 0.f;
+  if (row < rows) {
+    const __half *base = p.x + sub * 8;
+    for (uint32_t px = blockIdx.x * rows + row; px < p.P; px += gridDim.x * rows) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.C));
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        s += f.x + f.y;
+        q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+      }
+    }
+  }
+  red[threadIdx.x][0] = s;
+  red[threadIdx.x][1] = q;
+  __syncthreads();
+  const int lpg = (p.C / p.groups) >> 3;  // lanes (8-channel chunks) per group
+  if (threadIdx.x < p.groups) {           // group g: its lanes of every pixel row of the CTA, in a fixed order
+    double ts = 0.0, tq = 0.0;
+    for (int r = 0; r < rows; ++r)
+      for (int l = 0; l < lpg; ++l) {
+        const int t = r * lanes + threadIdx.x * lpg + l;
+        ts += (double)red[t][0];
+        tq += (double)red[t][1];
+      }
+    p.partial[((size_t)blockIdx.x * p.groups + threadIdx.x) * 2] = ts;
+    p.partial[((size_t)blockIdx.x * p.groups + threadIdx.x) * 2 + 1] = tq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < p.groups) {
+    double ts = 0.0, tq = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      ts += __ldcg(p.partial + ((size_t)b * p.groups + threadIdx.x) * 2);
+      tq += __ldcg(p.partial + ((size_t)b * p.groups + threadIdx.x) * 2 + 1);
+    }
+    const double n = (double)p.P * (double)(p.C / p.groups);
+    const double m = ts / n;
+    double var = tq / n - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    fin[2 * threadIdx.x] = m;
+    fin[2 * threadIdx.x + 1] = 1.0 / sqrt(var + (double)p.eps);
+  }
+  __syncthreads();
+  const int cpg = p.C / p.groups;
+  for (int c = threadIdx.x; c < p.C; c += kGnThreads) {
+    p.mean[c] = (float)fin[2 * (c / cpg)];
+    p.invstd[c] = (float)fin[2 * (c / cpg) + 1];
+  }
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int groups, float eps, void *workspace,
+             long long workspace_bytes, cudaStream_t stream) {
+  BC_REQUIRE(mean && invstd && x && workspace, BC_ERR_NULL, "bc_gn_stats: NULL pointer");
+  BC_REQUIRE(P > 0 && P < (1ll << 31), BC_ERR_SHAPE, "bc_gn_stats: %lld pixels", P);
+  BC_REQUIRE(C >= 8 && C <= 2048 && C % 8 == 0 && groups >= 1 && groups <= 256 && C % groups == 0 && (C / groups) % 8 == 0,
+             BC_ERR_UNSUPPORTED, "bc_gn_stats: C=%d in %d groups (C and C/groups multiples of 8, C <= 2048, <= 256 groups)",
+             C, groups);
+  BC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, BC_ERR_ALIGN, "bc_gn_stats: 16-byte alignment");
+  const int rows = kGnThreads / (C / 8);
+  long long grid = (P + rows - 1) / rows;
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  const long long need = 16 + grid * groups * 2 * (long long)sizeof(double);
+  BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_gn_stats: workspace of %lld bytes, %lld needed", workspace_bytes, need);
+  GnParams p;
+  p.x = (const __half *)x; p.mean = mean; p.invstd = invstd;
+  p.ticket = (unsigned int *)workspace;
+  p.partial = (double *)((char *)workspace + 16);
+  p.P = (uint32_t)P; p.C = C; p.groups = groups; p.eps = eps;
+  launch_kernel(gn_stats_kernel, dim3((unsigned)grid), dim3(kGnThreads), 0, stream, 1, p);
+  return check_launch("bc_gn_stats");
+}
+
+}  // namespace bc

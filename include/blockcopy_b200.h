@@ -271,6 +271,28 @@ BC_API int bc_info_gain(void *out, const void *outputs, const void *outputs_prev
 BC_API int bc_sample_grid(uint8_t *grid, int32_t *counts, const float *probs, const float *uniforms, int G, int multiple,
                           int at_least_one, bc_stream_t stream);
 
+/* ---- GroupNorm statistics over all executed blocks (core/tensorwrapper.py:600-633, `_func_batched`) -------------
+ * The reference folds the (E,C,h,w) tile batch into ONE sample before F.group_norm, so a group's statistics run over
+ * that group's channels of every executed block.  x: packed NHWC fp16 tiles = P = E*h*w pixels x C channels;
+ * mean[c], invstd[c] = 1/sqrt(biased var + eps) of channel c's GROUP (fp32 [C]), ready for bc_ew_fused, which then
+ * computes weight * (x - mean) * invstd + bias.  C and C/groups multiples of 8, C <= 2048, groups <= 256.
+ * workspace: caller-owned, >= BC_GN_STATS_WORKSPACE bytes, 16-byte aligned, first 4 bytes zero before the first call
+ * (left at zero), private to the stream.  Reproducible run to run.
+ */
+#define BC_GN_STATS_WORKSPACE (16 + 2 * 148 * 256 * 2 * 8)
+BC_API int bc_gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int groups, float eps, void *workspace,
+                       long long workspace_bytes, bc_stream_t stream);
+
+/* ---- depth-to-space on packed NHWC fp16 tiles: second half of a per-block ConvTranspose2d ---------------------
+ * The reference runs ConvTranspose2d as a pass-through op on the tile batch (core/tensorwrapper.py:519-520; Pedestron
+ * necks/csp_neck.py:37-83): every tile is its own sample, zeros beyond the TILE edge.  A transposed conv with stride r
+ * is then a plain conv with r*r times the output channels -- bc_conv_igemm over the tile batch viewed as E one-block
+ * frames (mapping 0..E-1), so the frame border of the kernel is the tile border -- followed by
+ *     out[e, r*y + a, r*x + b, c] = in[e, y, x, (a*r + b)*C + c]
+ * in: (E, h, w, r*r*C), out: (E, r*h, r*w, C), fp16, C % 8 == 0, 1 <= r <= 8.
+ */
+BC_API int bc_depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, bc_stream_t stream);
+
 /* ---- running statistics of train-mode batch norms (policy/net.py:115-125 runs the policy net in train mode) ----
  * For every row l < n of the DEVICE table (8 x int64 per row: batch mean fp32*, batch invstd fp32* -- the outputs of
  * bc_bn_stats --, running_mean fp32* | 0, running_var fp32* | 0, num_batches_tracked int64* | 0, C, count = N*H*W,

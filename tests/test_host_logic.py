@@ -135,6 +135,24 @@ def test_group_norm_folds_blocks_into_one_sample():
     assert torch.allclose(out, F.group_norm(img, 2), atol=1e-5)
 
 
+def test_deconv_weight_packing_is_exact_on_cpu_math():
+    """conv2d with the packed weight + depth-to-space == conv_transpose2d (fp64 on the CPU): the phase decomposition
+    behind TensorWrapper._try_fused_conv_transpose."""
+    import torch.nn.functional as F
+    from blockcopy import _C
+
+    g = torch.Generator().manual_seed(0)
+    for (k, s, p) in [(4, 2, 1), (4, 4, 0), (2, 2, 0)]:
+        x = torch.randn(3, 6, 5, 5, generator=g, dtype=torch.float64)
+        w = torch.randn(6, 8, k, k, generator=g, dtype=torch.float64)
+        b = torch.randn(8, generator=g, dtype=torch.float64)
+        wp, bp = _C.pack_deconv_weight(w, b, s)
+        y = F.conv2d(x, wp, bp, padding=wp.shape[2] // 2)
+        y = y.reshape(3, s, s, 8, 5, 5).permute(0, 3, 4, 1, 5, 2).reshape(3, 8, 5 * s, 5 * s)
+        want = F.conv_transpose2d(x, w, b, stride=s, padding=p)
+        assert torch.allclose(y, want, atol=1e-12), (k, s, p)
+
+
 # ------------------------------------------------------------------------------------------- end to end
 def test_swiftnet_clip_matches_reference(golden_dir):
     """SwiftNet-RN18 + BlockCopyModel over a seeded 6-frame clip with replayed masks (incl. an
