@@ -664,8 +664,12 @@ struct GnParams {
   uint32_t P;
   int C, groups;
   float eps;
+  uint32_t zero;  // always 0 (load batching, see bn_stats_kernel)
 };
 
+// Loads are issued in batches of eight per thread and kept together by the data dependency bn_stats_kernel uses (see the
+// note there); the last CTA adds the per-CTA partials of a (group, statistic) pair with one warp: lane l takes CTAs
+// l, l+32, ... in order, then a fixed shuffle tree -- all loads of the final reduction are in flight at once.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
   __shared__ float red[kGnThreads][2];
   __shared__ double fin[2 * 256];
@@ -677,14 +681,29 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
   float s = 0.f, q = 0.f;
   if (row < rows) {
     const __half *base = p.x + sub * 8;
-    for (uint32_t px = blockIdx.x * rows + row; px < p.P; px += gridDim.x * rows) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)px * p.C));
-      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+    const uint32_t step = gridDim.x * rows;
+    for (uint32_t px = blockIdx.x * rows + row; px < p.P; px += 8 * step) {
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(h[k]);
-        s += f.x + f.y;
-        q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t pj = px + j * step;
+        u[j] = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(pj < p.P ? pj : p.P - 1) * p.C));
+      }
+      uint32_t fold = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fold ^= u[j].x;
+      fold &= p.zero;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        u[j].x ^= fold; u[j].y ^= fold; u[j].z ^= fold; u[j].w ^= fold;
+        if (px + j * step >= p.P) u[j] = make_uint4(0, 0, 0, 0);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          s += f.x + f.y;
+          q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+        }
       }
     }
   }
@@ -709,15 +728,26 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (threadIdx.x < p.groups) {
-    double ts = 0.0, tq = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) {
-      ts += __ldcg(p.partial + ((size_t)b * p.groups + threadIdx.x) * 2);
-      tq += __ldcg(p.partial + ((size_t)b * p.groups + threadIdx.x) * 2 + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pair = warp; pair < 2 * p.groups; pair += kGnThreads / 32) {  // pair = 2 * group + (0: sum | 1: sum of squares)
+    double v[10];  // gridDim.x <= 2 * 148 = 296 <= 320
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const unsigned b = (unsigned)lane + 32u * j;
+      v[j] = b < gridDim.x ? __ldcg(p.partial + (size_t)b * 2 * p.groups + pair) : 0.0;
     }
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) t += v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) fin[pair] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < p.groups) {
     const double n = (double)p.P * (double)(p.C / p.groups);
-    const double m = ts / n;
-    double var = tq / n - m * m;
+    const double m = fin[2 * threadIdx.x] / n;
+    double var = fin[2 * threadIdx.x + 1] / n - m * m;
     var = var < 0.0 ? 0.0 : var;
     fin[2 * threadIdx.x] = m;
     fin[2 * threadIdx.x + 1] = 1.0 / sqrt(var + (double)p.eps);
@@ -740,7 +770,7 @@ int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int 
              C, groups);
   BC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, BC_ERR_ALIGN, "bc_gn_stats: 16-byte alignment");
   const int rows = kGnThreads / (C / 8);
-  long long grid = (P + rows - 1) / rows;
+  long long grid = (P + 8 * rows - 1) / (8 * rows);
   if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
   const long long need = 16 + grid * groups * 2 * (long long)sizeof(double);
   BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_gn_stats: workspace of %lld bytes, %lld needed", workspace_bytes, need);
@@ -748,7 +778,7 @@ int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int 
   p.x = (const __half *)x; p.mean = mean; p.invstd = invstd;
   p.ticket = (unsigned int *)workspace;
   p.partial = (double *)((char *)workspace + 16);
-  p.P = (uint32_t)P; p.C = C; p.groups = groups; p.eps = eps;
+  p.P = (uint32_t)P; p.C = C; p.groups = groups; p.eps = eps; p.zero = 0u;
   launch_kernel(gn_stats_kernel, dim3((unsigned)grid), dim3(kGnThreads), 0, stream, 1, p);
   return check_launch("bc_gn_stats");
 }

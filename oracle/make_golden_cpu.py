@@ -152,13 +152,13 @@ def policy_pieces():
 
 
 # ------------------------------------------------------------------------------------------- 4. CSP stand-in
-def csp_standin_clip():
+def csp_standin_clip(wide=False):
     """Second consumer (Pedestron CSPBlockCopy op set, tests/csp_standin.py) on the reference package."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from csp_standin import StandinDetector
 
     H, W, BS = 128, 256, 64
-    det = StandinDetector(settings(block_size=BS)).eval()
+    det = StandinDetector(settings(block_size=BS), wide=wide).eval()
     deterministic_init_(det, seed=4)
     g = torch.Generator().manual_seed(2)
     grids = [torch.ones(1, 1, H // BS, W // BS, dtype=torch.bool)]
@@ -172,12 +172,13 @@ def csp_standin_clip():
     with torch.no_grad():
         outs = [det.simple_test(f).clone() for f in clip]
     torch.save(dict(H=H, W=W, BS=BS, init_seed=4, clip_seed=6, grids=torch.stack(grids).to(torch.uint8),
-                    outs=torch.stack(outs)), os.path.join(GOLD, "csp_standin_cpu.pt"))
-    print("csp_standin_cpu.pt:", tuple(outs[0].shape), [round(float(o.abs().mean()), 4) for o in outs])
+                    outs=torch.stack(outs)), os.path.join(GOLD, "csp_standin_wide_cpu.pt" if wide else "csp_standin_cpu.pt"))
+    print("csp_standin_wide_cpu.pt:" if wide else "csp_standin_cpu.pt:", tuple(outs[0].shape), [round(float(o.abs().mean()), 4) for o in outs])
 
 
 if __name__ == "__main__":
     csp_standin_clip()
+    csp_standin_clip(wide=True)
     index_kats()
     policy_pieces()
     swiftnet_clip()

@@ -23,19 +23,24 @@ class L2Norm(nn.Module):
 
 
 class StandinDetector(nn.Module):
-    def __init__(self, settings):
+    """wide=False: small channel counts (32/64/16, a 3x3 stem).  wide=True: the channel structure of the real CSP
+    (ResNet 7x7 stem, every count a multiple of 64, 192-channel concatenation, GroupNorm(8, 64)), at which this repo
+    runs every block op on its own kernels."""
+
+    def __init__(self, settings, wide=False):
         super().__init__()
         self.is_blockcopy_manager = True
-        self.stem = nn.Conv2d(3, 32, 3, 2, 1)
-        self.layer = nn.Conv2d(32, 64, 3, 2, 1)
+        c1, c2, cu, ch, g = (64, 128, 64, 64, 8) if wide else (32, 64, 16, 32, 4)
+        self.stem = nn.Conv2d(3, c1, 7, 2, 3) if wide else nn.Conv2d(3, c1, 3, 2, 1)
+        self.layer = nn.Conv2d(c1, 64, 3, 2, 1)
         self.dil = nn.Conv2d(64, 64, 3, 1, padding=2, dilation=2)
-        self.down = nn.Conv2d(64, 64, 3, 2, 1)
-        self.p_a = nn.ConvTranspose2d(64, 16, kernel_size=4, stride=2, padding=1)
-        self.p_b = nn.ConvTranspose2d(64, 16, kernel_size=4, stride=4, padding=0)
-        self.l2_a, self.l2_b = L2Norm(16, 10), L2Norm(16, 10)
-        self.head_conv = nn.Conv2d(64, 32, 3, padding=1)
-        self.head_gn = nn.GroupNorm(4, 32)
-        self.cls = nn.Conv2d(32, 8, 3, padding=1)
+        self.down = nn.Conv2d(64, c2, 3, 2, 1)
+        self.p_a = nn.ConvTranspose2d(64, cu, kernel_size=4, stride=2, padding=1)
+        self.p_b = nn.ConvTranspose2d(c2, cu, kernel_size=4, stride=4, padding=0)
+        self.l2_a, self.l2_b = L2Norm(cu, 10), L2Norm(cu, 10)
+        self.head_conv = nn.Conv2d(c1 + 2 * cu, ch, 3, padding=1)
+        self.head_gn = nn.GroupNorm(g, ch)
+        self.cls = nn.Conv2d(ch, 8, 3, padding=1)
         self.relu = nn.ReLU(inplace=True)
         self.policy = blockcopy.build_policy_from_settings(settings)
         self.train_interval = settings["block_train_interval"]
