@@ -237,19 +237,26 @@ def build_model(args, device, policy=None):
         settings["block_policy_shared"] = True
     if os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") == "0":  # A/B: policy trunk always through torch/cuDNN
         settings["block_policy_fused"] = False
+    if os.environ.get("BLOCKCOPY_POLICY_FUSED_TRAINING", "1") == "0":  # A/B: training frames through torch autograd / cuDNN
+        settings["block_policy_fused_training"] = False
+    else:
+        settings["block_policy_fused_training"] = True
+    # the reference driver's order (test_swiftnet.py:104-123): base model in eval mode, THEN wrapped (the policy net
+    # stays in train mode, so the BN fusion below leaves its BatchNorms alone), fused, .half(), policy net back to fp32
     ref = _reference_swiftnet()
     if ref is not None:
         net, bn_fusion = ref
         deterministic_init_(net, seed=0, gain=0.8)
-        model = blockcopy.BlockCopyModel(net, settings).eval().to(device)
+        model = blockcopy.BlockCopyModel(net.eval(), settings).to(device)
         with contextlib.redirect_stdout(io.StringIO()):
             model = bn_fusion.fuse_bn_recursively(model)
         MODEL_CODE["value"] = "reference's own lib/models/swiftnet/*.py + lib/utils/bn_fusion.py (baseline/_ref, unmodified)"
     else:
         net = deterministic_init_(SwiftNetRN18().eval(), seed=0, gain=0.8)
-        model = blockcopy.BlockCopyModel(net, settings).eval().to(device)
+        model = blockcopy.BlockCopyModel(net, settings).to(device)
         fuse_conv_bn_(model)
         MODEL_CODE["value"] = "consumers/swiftnet_rn18.py (architecture- and state_dict-identical; baseline/_ref not staged)"
+    model = model.eval()
     model = model.half()
     if policy == "fixed":
         model.policy = PolicyFixedFraction(128, fraction=args.fraction, quantize=8, seed=0)

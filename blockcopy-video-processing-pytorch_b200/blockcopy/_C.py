@@ -52,6 +52,10 @@ _SIGNATURES = {
     "bc_sample_grid": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "bc_raster_boxes": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "bc_depth_to_space": ([_vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "bc_bwd_mask_add": ([_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp], _i),
+    "bc_bn_bwd_reduce": ([_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _vp, ctypes.c_longlong, _vp], _i),
+    "bc_bn_bwd_apply": ([_vp] * 9 + [_i] * 4 + [_vp], _i),
+    "bc_conv_wgrad": ([_vp] * 4 + [_i] * 9 + [_vp] * 5 + [ctypes.c_longlong, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
@@ -681,6 +685,62 @@ def depth_to_space(out: torch.Tensor, x: torch.Tensor, r: int) -> torch.Tensor:
     assert x.is_contiguous(memory_format=torch.channels_last) and out.is_contiguous(memory_format=torch.channels_last)
     _check(lib().bc_depth_to_space(out.data_ptr(), x.data_ptr(), E, C, h, w, int(r), _stream()), "bc_depth_to_space")
     return out
+
+
+# ------------------------------------------------------------------------------------------- policy CNN backward
+WGRAD_WORKSPACE = 148 * 9 * 64 * 64 * 4
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def bwd_mask_add(dst: torch.Tensor, grad: torch.Tensor, out: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None):
+    """dst = (out > 0 ? grad : 0 when `out` is given, else grad) + (add or 0); dense fp16 tensors of one shape / layout."""
+    _dev(dst, grad, out, add)
+    assert dst.dtype == torch.float16 and all(t is None or (t.dtype == torch.float16 and t.shape == dst.shape) for t in (grad, out, add))
+    _check(lib().bc_bwd_mask_add(dst.data_ptr(), grad.data_ptr(), _p(out), _p(add), dst.numel(), _stream()), "bc_bwd_mask_add")
+    return dst
+
+
+def bn_bwd_reduce(sums: torch.Tensor, g: torch.Tensor, out: Optional[torch.Tensor], z: torch.Tensor, mean: torch.Tensor,
+                  invstd: torch.Tensor, workspace: torch.Tensor):
+    """sums fp32 (2, C) <- [sum g, sum g * xhat] per channel over the NHWC fp16 planes g / z (N,C,H,W channels_last);
+    g is masked by `out > 0` when `out` is given."""
+    _dev(sums, g, out, z, mean, invstd, workspace)
+    N, C, H, W = z.shape
+    assert g.shape == z.shape and z.is_contiguous(memory_format=torch.channels_last) and g.is_contiguous(memory_format=torch.channels_last)
+    assert sums.dtype == torch.float32 and sums.numel() >= 2 * C and sums.is_contiguous()
+    _check(lib().bc_bn_bwd_reduce(sums.data_ptr(), g.data_ptr(), _p(out), z.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                  N * H * W, C, workspace.data_ptr(), workspace.numel(), _stream()), "bc_bn_bwd_reduce")
+
+
+def bn_bwd_apply(dz: Optional[torch.Tensor], dz_up: Optional[torch.Tensor], g: torch.Tensor, out: Optional[torch.Tensor],
+                 z: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor], sums: torch.Tensor):
+    """dz (and / or dz_up: the (N,C,2H,2W) zero-interleaved copy) <- gamma * invstd * (g - sum_g/P - xhat * sum_gx/P)."""
+    _dev(dz, dz_up, g, out, z, mean, invstd, gamma, sums)
+    N, C, H, W = z.shape
+    assert dz is None or dz.shape == z.shape
+    assert dz_up is None or tuple(dz_up.shape) == (N, C, 2 * H, 2 * W)
+    _check(lib().bc_bn_bwd_apply(_p(dz), _p(dz_up), g.data_ptr(), _p(out), z.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                 _p(gamma), sums.data_ptr(), N, H, W, C, _stream()), "bc_bn_bwd_apply")
+
+
+def conv_wgrad(grad_w: torch.Tensor, dz: torch.Tensor, x: torch.Tensor, stride: int, inv_scale: Optional[torch.Tensor],
+               workspace: torch.Tensor, bn_sums: Optional[torch.Tensor] = None, dgamma: Optional[torch.Tensor] = None,
+               dbeta: Optional[torch.Tensor] = None):
+    """grad_w fp32 (Cout,Cin,k,k) <- sum over pixels of dz (N,Cout_p,H/s,W/s) x x (N,Cin_p,H,W) (fp16 channels_last),
+    times *inv_scale; optionally the unit's BatchNorm gradients from bn_sums (see bc_conv_wgrad)."""
+    _dev(grad_w, dz, x, inv_scale, workspace, bn_sums, dgamma, dbeta)
+    N, Cin_p, H, W = x.shape
+    Cout_p = dz.shape[1]
+    Cout, Cin, k, _ = grad_w.shape
+    assert grad_w.dtype == torch.float32 and tuple(dz.shape) == (N, Cout_p, H // stride, W // stride)
+    assert x.is_contiguous(memory_format=torch.channels_last) and dz.is_contiguous(memory_format=torch.channels_last)
+    gs = (ctypes.c_longlong * 4)(*grad_w.stride())
+    _check(lib().bc_conv_wgrad(grad_w.data_ptr(), ctypes.cast(gs, _vp), dz.data_ptr(), x.data_ptr(), N, H, W, Cin_p, Cout_p, Cin,
+                               Cout, k, int(stride), _p(inv_scale), _p(dgamma), _p(dbeta), _p(bn_sums), workspace.data_ptr(),
+                               workspace.numel(), _stream()), "bc_conv_wgrad")
 
 
 # ------------------------------------------------------------------------------------------- train-mode BN statistics

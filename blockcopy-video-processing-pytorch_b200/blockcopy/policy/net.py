@@ -43,6 +43,11 @@ class PolicyNet(nn.Module):
         # repo's kernels (policy/fused_net.py; fp16 operands, train-mode batch statistics).  False: always torch
         self.fused_inference = True
         self.__dict__["_fused"] = None
+        # frames that ARE followed by a policy update: forward with saved activations + backward on this repo's kernels
+        # (policy/fused_train.py) instead of torch autograd over cuDNN.  PolicyTrainRL sets it from
+        # settings['block_policy_fused_training']
+        self.fused_training = False
+        self.__dict__["_trainer"] = None
 
     @staticmethod
     def _make_layer(cin, cout, kernel_size=3, stride=2, relu=True):
@@ -126,7 +131,15 @@ class PolicyNet(nn.Module):
             t = self.__dict__["_fused"] = FusedPolicyTrunk(self)
         return t
 
-    def _fused_forward(self, policy_meta: dict):
+    def _fused_trainer(self):
+        t = self.__dict__["_trainer"]
+        if t is None:
+            from blockcopy.policy.fused_train import FusedPolicyTrainer
+
+            t = self.__dict__["_trainer"] = FusedPolicyTrainer(self)
+        return t
+
+    def _fused_forward(self, policy_meta: dict, train: bool = False):
         """Features written straight into the fused trunk's fp16 NHWC input plane (bc_policy_features_nhwc16) and
         the trunk behind it; None when the inputs are outside that kernel's envelope (see _fused_features)."""
         frame, state = policy_meta["inputs"], policy_meta.get("frame_state", None)
@@ -141,10 +154,15 @@ class PolicyNet(nn.Module):
             return None
         from blockcopy import _C
 
-        fused = self._fused_trunk()
+        fused = self._fused_trainer() if train else self._fused_trunk()
         shape = _C.policy_features_shape(frame, rep, self.scale_factor)
         if not fused.supports_shape(shape, frame.device):
             return None
+        if train:
+            fused.use_cuda_graph = self.use_cuda_graphs
+            with timings.env("policy/net/layers", 5):
+                return fused.run_train(lambda x16: _C.policy_features_nhwc16(x16, frame, state, rep, grid, self.scale_factor),
+                                       shape, frame.device)
         with timings.env("policy/net/layers", 5):
             return fused.run(lambda x16: _C.policy_features_nhwc16(x16, frame, state, rep, grid, self.scale_factor),
                              shape, frame.device, use_cuda_graph=self.use_cuda_graphs)
@@ -156,6 +174,8 @@ class PolicyNet(nn.Module):
         logits = None
         if no_grad and self.fused_inference and self.training:
             logits = self._fused_forward(policy_meta)
+        elif not no_grad and self.fused_training and self.training and torch.is_grad_enabled():
+            logits = self._fused_forward(policy_meta, train=True)
         if logits is None:
             with timings.env("policy/net/build_features", 5):
                 x = self.build_features(policy_meta)

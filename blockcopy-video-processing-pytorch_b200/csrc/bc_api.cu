@@ -69,6 +69,14 @@ int bn_update_running(const long long *table, int n, cudaStream_t stream);
 int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int groups, float eps, void *workspace,
              long long workspace_bytes, cudaStream_t stream);
 int depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, cudaStream_t stream);
+int bwd_mask_add(void *dst, const void *grad, const void *out, const void *add, long long n, cudaStream_t stream);
+int bn_bwd_reduce(float *sums, const void *g, const void *out, const void *z, const float *mean, const float *invstd,
+                  long long P, int C, void *workspace, long long workspace_bytes, cudaStream_t stream);
+int bn_bwd_apply(void *dz, void *dz_up, const void *g, const void *out, const void *z, const float *mean, const float *invstd,
+                 const float *gamma, const float *sums, int N, int H, int W, int C, cudaStream_t stream);
+int conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, const void *x, int N, int H, int W, int Cin_p,
+               int Cout_p, int Cin, int Cout, int ksize, int stride, const float *inv_scale, float *dgamma, float *dbeta,
+               const float *bn_sums, void *workspace, long long workspace_bytes, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -373,6 +381,28 @@ BC_API int bc_gn_stats(float *mean, float *invstd, const void *x, long long P, i
 
 BC_API int bc_depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, bc_stream_t stream) {
   return depth_to_space(out, in, E, C, h, w, r, (cudaStream_t)stream);
+}
+
+BC_API int bc_bwd_mask_add(void *dst, const void *grad, const void *out, const void *add, long long n, bc_stream_t stream) {
+  return bwd_mask_add(dst, grad, out, add, n, (cudaStream_t)stream);
+}
+
+BC_API int bc_bn_bwd_reduce(float *sums, const void *g, const void *out, const void *z, const float *mean, const float *invstd,
+                            long long P, int C, void *workspace, long long workspace_bytes, bc_stream_t stream) {
+  return bn_bwd_reduce(sums, g, out, z, mean, invstd, P, C, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_bn_bwd_apply(void *dz, void *dz_up, const void *g, const void *out, const void *z, const float *mean,
+                           const float *invstd, const float *gamma, const float *sums, int N, int H, int W, int C,
+                           bc_stream_t stream) {
+  return bn_bwd_apply(dz, dz_up, g, out, z, mean, invstd, gamma, sums, N, H, W, C, (cudaStream_t)stream);
+}
+
+BC_API int bc_conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, const void *x, int N, int H, int W,
+                         int Cin_p, int Cout_p, int Cin, int Cout, int ksize, int stride, const float *inv_scale, float *dgamma,
+                         float *dbeta, const float *bn_sums, void *workspace, long long workspace_bytes, bc_stream_t stream) {
+  return conv_wgrad(grad_w, grad_strides, dz, x, N, H, W, Cin_p, Cout_p, Cin, Cout, ksize, stride, inv_scale, dgamma, dbeta,
+                    bn_sums, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -301,6 +301,39 @@ BC_API int bc_depth_to_space(void *out, const void *in, int E, int C, int h, int
  */
 BC_API int bc_bn_update_running(const long long *table, int n, bc_stream_t stream);
 
+/* ---- backward pass of the policy CNN (policy/policy.py:319-370 `loss.backward()` through policy/net.py:78-125 and
+ * policy/resnet.py:60-115; the reference runs it as ~90 fp32 cuDNN / ATen launches every block_train_interval frames) ----
+ * All planes are dense NHWC fp16 with channel counts padded to 64 / 128 (padded channels carry zeros), statistics and
+ * parameter gradients are fp32.  One unit = conv -> BatchNorm(batch statistics) -> [+ shortcut] -> [ReLU]:
+ *   z = conv(x);  out = relu?(gamma * (z - mean) * invstd + beta [+ shortcut])
+ * and, given dOut (scaled by a power-of-two loss scale so that fp16 holds it),
+ *   g     = out > 0 ? dOut : 0                     (when the unit, or the block it ends, has a ReLU)
+ *   sums  = [ sum_p g, sum_p g * xhat ]            bc_bn_bwd_reduce   (xhat = (z - mean) * invstd; reproducible)
+ *   dz    = gamma * invstd * (g - sums[0]/P - xhat * sums[1]/P)        bc_bn_bwd_apply
+ *   dW    = wgrad(dz, x) / scale, dgamma = sums[1] / scale, dbeta = sums[0] / scale      bc_conv_wgrad
+ *   dx    = conv(dz, flipped / transposed W): bc_conv_igemm; for a stride-2 conv over dz_up, the (N,2H,2W,C) plane
+ *           bc_bn_bwd_apply writes dz into at the even positions (all other positions stay zero: zeroed once by the owner)
+ */
+/* dst = (out ? (out > 0 ? grad : 0) : grad) + (add ? add : 0); n fp16 elements (multiple of 8), dst may alias grad / add. */
+BC_API int bc_bwd_mask_add(void *dst, const void *grad, const void *out, const void *add, long long n, bc_stream_t stream);
+/* sums fp32 [2][C]; g, out (NULL: no mask), z: (P, C) fp16; C in {8,16,32,64,128}; workspace >= BC_BN_STATS_WORKSPACE bytes,
+ * first 4 bytes zero before the first call (left at zero), private to the stream. */
+BC_API int bc_bn_bwd_reduce(float *sums, const void *g, const void *out, const void *z, const float *mean, const float *invstd,
+                            long long P, int C, void *workspace, long long workspace_bytes, bc_stream_t stream);
+/* dz (N,H,W,C) and / or dz_up (N,2H,2W,C), either may be NULL (not both); gamma NULL = 1. */
+BC_API int bc_bn_bwd_apply(void *dz, void *dz_up, const void *g, const void *out, const void *z, const float *mean,
+                           const float *invstd, const float *gamma, const float *sums, int N, int H, int W, int C,
+                           bc_stream_t stream);
+/* grad_w: the fp32 parameter gradient (Cout, Cin, k, k) with element strides grad_strides[4]; dz (N, H/s, W/s, Cout_p),
+ * x (N, H, W, Cin_p); k in {1,3} with pad k/2, stride s in {1,2}; Cin_p, Cout_p in {64,128}, Cin_p <= Cout_p.
+ * inv_scale: device scalar (NULL = 1) multiplied into every output.  bn_sums (NULL: none): the unit's bc_bn_bwd_reduce
+ * output, from which dgamma / dbeta (fp32 [Cout], either may be NULL) are written in the same launch.
+ * workspace: >= BC_WGRAD_WORKSPACE bytes, private to the stream.  Reproducible run to run. */
+#define BC_WGRAD_WORKSPACE (148ll * 9 * 64 * 64 * 4)
+BC_API int bc_conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, const void *x, int N, int H, int W,
+                         int Cin_p, int Cout_p, int Cin, int Cout, int ksize, int stride, const float *inv_scale, float *dgamma,
+                         float *dbeta, const float *bn_sums, void *workspace, long long workspace_bytes, bc_stream_t stream);
+
 /* ---- box rasteriser of the object-detection information gain (policy/information_gain.py:56-108) ----
  * Replaces the reference's per-box torch slice assignments `mask[y1:y2, x1:x2] = max(mask[...], value)`
  * (build_instance_mask :56-66, build_instance_mask_iou_gain :68-108): out (H,W) fp32 <- for every pixel the
