@@ -217,7 +217,7 @@ def _reference_swiftnet():
 MODEL_CODE = {"value": None}
 
 
-def build_model(args, device, policy=None):
+def build_model(args, device, policy=None, native_training=False):
     """SwiftNet-RN18 behind this package's BlockCopyModel, set up like the reference driver does
     (test_swiftnet.py:107-123): wrap, BN fusion, .half(), policy net in fp32."""
     import contextlib
@@ -237,10 +237,9 @@ def build_model(args, device, policy=None):
         settings["block_policy_shared"] = True
     if os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") == "0":  # A/B: policy trunk always through torch/cuDNN
         settings["block_policy_fused"] = False
-    if os.environ.get("BLOCKCOPY_POLICY_FUSED_TRAINING", "1") == "0":  # A/B: training frames through torch autograd / cuDNN
-        settings["block_policy_fused_training"] = False
-    else:
-        settings["block_policy_fused_training"] = True
+    # training frames of the policy net on this repo's kernels (policy/fused_train.py) instead of torch autograd over
+    # cuDNN graph replays: measured slightly slower end to end, so it is an opt-in setting
+    settings["block_policy_fused_training"] = bool(native_training) or os.environ.get("BLOCKCOPY_POLICY_FUSED_TRAINING", "0") == "1"
     # the reference driver's order (test_swiftnet.py:104-123): base model in eval mode, THEN wrapped (the policy net
     # stays in train mode, so the BN fusion below leaves its BatchNorms alone), fused, .half(), policy net back to fp32
     ref = _reference_swiftnet()
@@ -430,6 +429,12 @@ class HostPipeline:
         caller.wait_stream(self.up)
 
 
+def _summary(ms):
+    """min / median / p90 / max of a list of window times (the JSON line stays readable)."""
+    v = sorted(ms)
+    return {"n": len(v), "min": v[0], "median": statistics.median(v), "p90": v[min(len(v) - 1, int(0.9 * len(v)))], "max": v[-1]}
+
+
 def timed_windows(fn, steps, repeats, world, device):
     """`repeats` back-to-back windows of exactly `steps` steps each; every window is bracketed by a barrier +
     torch.cuda.synchronize() on both sides and timed with CUDA events on the launching stream.  Returns the list of
@@ -487,10 +492,10 @@ def bench_config4(args, device, world, rank, total_streams=64, group=8, steps=30
     torch.cuda.empty_cache()
     return {"streams_total": per_rank * world, "streams_per_gpu": per_rank, "batched_along_N": group,
             "wrappers_per_gpu": wrappers, "value": frames / (med * 1e-3), "unit": "frames/s", "steps": steps,
-            "ms_per_step": med / steps, "windows_ms": ms, "data": "synthetic, device-resident"}
+            "ms_per_step": med / steps, "windows_ms": _summary(ms), "data": "synthetic, device-resident"}
 
 
-def bench_rl(args, device, steps=90):
+def bench_rl(args, device, steps=90, native_training=False):
     """The mode the reference ships (`--block-policy rl_semseg`): policy net fp32, Bernoulli sampling, online
     REINFORCE step every 3rd frame (block_train_interval 3), target 0.3.  Single stream, device-resident frames."""
     from consumers.clips import synthetic_clip
@@ -500,7 +505,7 @@ def bench_rl(args, device, steps=90):
 
     random.seed(0)
     torch.manual_seed(0)
-    m = build_model(args, device, policy="rl_semseg")
+    m = build_model(args, device, policy="rl_semseg", native_training=native_training)
     clip = [f.to(device) for f in synthetic_clip(L, H, W, seed=3, dtype=torch.float16)]
     run_frames([m], [clip], 0, 3 * L, L)
     execd = []
@@ -514,9 +519,11 @@ def bench_rl(args, device, steps=90):
 
     ms = timed_windows(fn, steps, 5, 1, device)
     med = statistics.median(ms)
-    res = {"policy": "rl_semseg", "value": steps / (med * 1e-3), "unit": "frames/s", "steps": steps, "windows_ms": ms,
+    res = {"policy": "rl_semseg", "value": steps / (med * 1e-3), "unit": "frames/s", "steps": steps, "windows_ms": _summary(ms),
            "mean_exec_blocks": sum(execd) / len(execd), "total_blocks": (H // 128) * (W // 128),
-           "train_interval": 3, "note": "random-init policy net trained online; masks are sampled (not replayed), so "
+           "train_interval": 3, "policy_training_frames": "native kernels (policy/fused_train.py)" if native_training
+           else "torch autograd over cuDNN graph replays",
+           "note": "random-init policy net trained online; masks are sampled (not replayed), so "
                                         "the executed fraction follows the policy, see mean_exec_blocks; the fused "
                                         "policy trunk runs fp16 operands (reference: fp32), masks are statistically, "
                                         "not bitwise, equivalent"}
@@ -603,7 +610,7 @@ def bench_ours(args):
         pipe.run(0, min(args.warmup, L), L)
         w8 = timed_windows(lambda pos, n: pipe.run(args.warmup + pos, n, L), K, Re, world, device)
         e2e = {"value": K * frames_step / (statistics.median(w8) * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "windows_ms": w8,
+               "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "windows_ms": _summary(w8),
                "note": "pinned uint8 (H,W,3) frames of all the rank's streams -> ONE H2D copy -> bc_frame_from_u8 -> "
                        "model() -> bc_upsample_argmax -> ONE D2H copy of the full-resolution uint8 label maps; upload, "
                        "compute and download on three streams, double-buffered; pinned buffers NUMA-local",
@@ -638,6 +645,8 @@ def bench_ours(args):
     rl = None
     if not args.skip_rl and args.policy == "fixed" and world == 1:
         rl = bench_rl(args, device)
+        nat = bench_rl(args, device, native_training=True)
+        rl["native_training"] = {k: nat[k] for k in ("value", "unit", "mean_exec_blocks", "policy_training_frames")}
 
     # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
     kern = microbench(device, peaks) if rank == 0 and not args.skip_microbench else None
@@ -662,7 +671,7 @@ def bench_ours(args):
             "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": med / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "timing": {"windows": R, "window_ms": win, "statistic": "median window of `steps` steps, each window bracketed "
+            "timing": {"windows": R, "window_ms": _summary(win), "statistic": "median window of `steps` steps, each window bracketed "
                        "by barrier + synchronize, CUDA events, max over ranks per window"},
             "config": {"workload": "configs[2]: SwiftNet-RN18 + BlockCopy, synthetic 1024x2048 30-frame clips, "
                                    "random-init weights, seeded masks",
@@ -704,7 +713,9 @@ def roofline_records(kern, peaks):
                                "3x3 convs of layer2 (128ch, 16-px blocks), layer3 (256ch, 8-px, split-K) and layer4 "
                                "(512ch, 4-px, split-K), E=40",
                      "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
-                     "traffic": None, "per_shape": {k: kern[k] for k in dom_keys},
+                     "traffic": 3.42e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the layer2 "
+                     "shape (algorithmic: 6.2 MB; inputs come from L2), ncu --set full: profiles/r02_conv_persist_ncu.md",
+                     "per_shape": {k: kern[k] for k in dom_keys},
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                      "algorithmic_flops_per_launch": flops / len(dom_keys), "us_per_launch": us / len(dom_keys)},
         "roofline_l20": {"bound": "tensor", "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: "

@@ -372,8 +372,11 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const long long *table
   pdl_trigger();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int e = 0;
-    while (e + 1 < n && table[(e + 1) * 12 + 2] <= i) ++e;
+    int e = 0, hi = n - 1;
+    while (e < hi) {  // last entry whose first element <= i
+      const int mid = (e + hi + 1) >> 1;
+      if (table[mid * 12 + 2] <= i) e = mid; else hi = mid - 1;
+    }
     const long long *t = table + e * 12;
     const long long j = i - t[2], cin = t[4], k = t[5];
     const long long ci = j % cin, kw = (j / cin) % k, kh = (j / (cin * k)) % k, co = j / (cin * k * k);

@@ -467,31 +467,48 @@ struct WgradFinishParams {
   int nparts, ksize, CO, CI, Cout, Cin, bn_C, bn_Cp;
 };
 
+// Block = 32 outputs x 8 slices: slice s adds partials s, s+8, ... (all loads independent and in flight), the slices are
+// then added in order through shared memory: the same sum order every run.
 __global__ void __launch_bounds__(256) wgrad_finish_kernel(const WgradFinishParams p) {
+  __shared__ float red[8][33];
   pdl_trigger();
   pdl_wait();
   const float inv = p.inv_scale ? __ldg(p.inv_scale) : 1.f;
   const int taps = p.ksize * p.ksize;
   const int total = taps * p.Cout * p.Cin;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 >= total) {  // trailing block(s): the BatchNorm gradients
+    const int c = (blockIdx.x * 32 - (total + 31) / 32 * 32) + lane;
+    if (slice == 0 && p.bn_sums && c < p.bn_C) {
+      if (p.dbeta) p.dbeta[c] = __ldg(p.bn_sums + c) * inv;
+      if (p.dgamma) p.dgamma[c] = __ldg(p.bn_sums + p.bn_Cp + c) * inv;
+    }
+    return;
+  }
+  float s = 0.f;
+  int ci = 0, co = 0, tap = 0;
   if (i < total) {
-    const int ci = i % p.Cin, co = (i / p.Cin) % p.Cout, tap = i / (p.Cin * p.Cout);
+    ci = i % p.Cin; co = (i / p.Cin) % p.Cout; tap = i / (p.Cin * p.Cout);
     const size_t per = (size_t)taps * p.CO * p.CI;
     const float *src = p.partial + ((size_t)tap * p.CO + co) * p.CI + ci;
-    float s = 0.f;
-    int b = 0;
-    for (; b + 4 <= p.nparts; b += 4) {
-      const float v0 = __ldcg(src + (size_t)b * per), v1 = __ldcg(src + (size_t)(b + 1) * per);
-      const float v2 = __ldcg(src + (size_t)(b + 2) * per), v3 = __ldcg(src + (size_t)(b + 3) * per);
-      s += v0; s += v1; s += v2; s += v3;
+    float v[20];  // nparts <= 148 -> <= 19 per slice
+#pragma unroll
+    for (int k = 0; k < 20; ++k) {
+      const int b = slice + 8 * k;
+      v[k] = b < p.nparts ? __ldcg(src + (size_t)b * per) : 0.f;
     }
-    for (; b < p.nparts; ++b) s += __ldcg(src + (size_t)b * per);
+#pragma unroll
+    for (int k = 0; k < 20; ++k) s += v[k];
+  }
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
     const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-    p.grad[co * p.gs[0] + ci * p.gs[1] + kh * p.gs[2] + kw * p.gs[3]] = s * inv;
-  } else if (p.bn_sums && i - total < p.bn_C) {
-    const int c = i - total;
-    if (p.dbeta) p.dbeta[c] = __ldg(p.bn_sums + c) * inv;
-    if (p.dgamma) p.dgamma[c] = __ldg(p.bn_sums + p.bn_Cp + c) * inv;
+    p.grad[co * p.gs[0] + ci * p.gs[1] + kh * p.gs[2] + kw * p.gs[3]] = t * inv;
   }
 }
 
@@ -551,8 +568,8 @@ int conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, con
   f.inv_scale = inv_scale; f.bn_sums = bn_sums; f.dgamma = dgamma; f.dbeta = dbeta;
   f.nparts = grid_x; f.ksize = ksize; f.CO = Cout_p; f.CI = Cin_p; f.Cout = Cout; f.Cin = Cin;
   f.bn_C = bn_sums ? Cout : 0; f.bn_Cp = Cout_p;
-  const int total = taps * Cout * Cin + f.bn_C;
-  launch_kernel(wgrad_finish_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, 1, f);
+  const int blocks = (taps * Cout * Cin + 31) / 32 + (f.bn_C + 31) / 32;
+  launch_kernel(wgrad_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, f);
   return check_launch("bc_conv_wgrad (finish)");
 }
 
