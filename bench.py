@@ -318,6 +318,12 @@ class HostPipeline:
 
     def __init__(self, models, host_clips, device, u8=True):
         self.models, self.device, self.u8 = models, device, u8
+        # uint8 frames as lazily normalised model inputs (blockcopy.U8Frame: normalisation fused into the first gather,
+        # bc_blocks_from_u8) save 25 MB of HBM traffic per frame but put ~1.5 us more on the frame's critical path than
+        # normalising whole frames on the upload stream: measured +2 % e2e with 8 frames per step, -1.7 % with one
+        # (tools/u8_gather_bench.py) -- so: lazy when a step carries more than one frame
+        env = os.environ.get("BC_E2E_LAZY_U8")
+        self.lazy_u8 = (env == "1") if env is not None else (len(models) * host_clips[0][0].shape[0] > 1)
         S = len(models)
         L = len(host_clips[0])
         B, _, H, W = host_clips[0][0].shape
@@ -328,7 +334,8 @@ class HostPipeline:
         self.compute = torch.cuda.Stream(device=device, priority=-1)
         if u8:
             from consumers.frame_io import CITYSCAPES_MEAN, CITYSCAPES_STD, BlockLabelMap, FrameNormalizer
-            self.norm = FrameNormalizer()
+            from blockcopy.core.frame import U8Frame
+            self.norm, self.U8Frame = FrameNormalizer(), U8Frame
             mean = torch.tensor(CITYSCAPES_MEAN).view(1, 3, 1, 1)
             std = torch.tensor(CITYSCAPES_STD).view(1, 3, 1, 1)
             # the synthetic fp16 clips as decoded uint8 frames (S,B,H,W,3) per step, pinned (allocated by THIS rank's
@@ -374,7 +381,7 @@ class HostPipeline:
             if self.u8:
                 if "h2d" not in self.SKIP:
                     self.dev_raw[slot].copy_(self.host_in[t % clip_len], non_blocking=True)
-                if "norm" not in self.SKIP:
+                if "norm" not in self.SKIP and not self.lazy_u8:
                     self.norm(self.dev_raw[slot].view(self.S * self.B, self.H, self.W, 3),
                               out=self.dev_in[slot].view(self.S * self.B, 3, self.H, self.W))
             elif "h2d" not in self.SKIP:
@@ -397,7 +404,13 @@ class HostPipeline:
                 for s, model in enumerate(self.models):
                     if self.out_read[s][slot] is not None:
                         main.wait_event(self.out_read[s][slot])  # the output buffer this call rewrites was read out
-                    outs.append(model(self.dev_in[slot][s]))
+                    if self.u8 and self.lazy_u8:
+                        # the uint8 frame itself is the model's input: steady frames normalise only the executed blocks,
+                        # inside their first gather (bc_blocks_from_u8); dev_in[slot][s] receives the whole normalised
+                        # frame only when somebody asks for it (first frame of a clip)
+                        outs.append(model(self.U8Frame(self.dev_raw[slot][s], out=self.dev_in[slot][s])))
+                    else:
+                        outs.append(model(self.dev_in[slot][s]))
                     if self.u8 and "labels" not in self.SKIP:
                         # block-sparse label update right behind the frame, on the compute stream: ~1/3 of the label
                         # map per frame; run concurrently (download stream) its 1000+ small CTAs took the SMs' register
@@ -611,8 +624,10 @@ def bench_ours(args):
         w8 = timed_windows(lambda pos, n: pipe.run(args.warmup + pos, n, L), K, Re, world, device)
         e2e = {"value": K * frames_step / (statistics.median(w8) * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes, "windows_ms": _summary(w8),
-               "note": "pinned uint8 (H,W,3) frames of all the rank's streams -> ONE H2D copy -> bc_frame_from_u8 -> "
-                       "model() -> bc_upsample_argmax -> ONE D2H copy of the full-resolution uint8 label maps; upload, "
+               "note": "pinned uint8 (H,W,3) frames of all the rank's streams -> ONE H2D copy -> " + (
+                   "model(U8Frame): normalisation inside the first gather of the executed blocks (bc_blocks_from_u8; whole "
+                   "frames only on a clip's first frame)" if pipe.lazy_u8 else "bc_frame_from_u8 on the upload stream -> model()") +
+                       " -> block-sparse bc_upsample_argmax_blocks -> ONE D2H copy of the full-resolution uint8 label maps; upload, "
                        "compute and download on three streams, double-buffered; pinned buffers NUMA-local",
                "numa": numa}
         del pipe

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
     "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
     "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "bc_blocks_from_u8": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "bc_upsample_argmax": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp], _i),
     "bc_upsample_argmax_blocks": ([_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "bc_spp_pool": ([_vp, _vp] + [_i] * 5 + [_vp, _vp, _vp], _i),
@@ -839,6 +840,23 @@ def frame_from_u8(src_u8: torch.Tensor, mean, std, dtype=torch.float16, out: Opt
     _check(lib().bc_frame_from_u8(out.data_ptr(), src_u8.data_ptr(), ctypes.cast(m, _vp), ctypes.cast(sd, _vp), N, H, W,
                                   BC_F16 if out.dtype == torch.float16 else BC_F32, _stream()), "bc_frame_from_u8")
     return out
+
+
+def blocks_from_u8(tiles: torch.Tensor, src_u8: torch.Tensor, mean, std, mapping_exec: torch.Tensor, E: int) -> torch.Tensor:
+    """tiles (E,3,BS,BS) contiguous fp16/fp32 <- the normalised executed blocks of the (N,H,W,3) uint8 CUDA frame:
+    frame_from_u8 + gather in one pass over the executed blocks only (see bc_blocks_from_u8)."""
+    _dev(tiles, src_u8, mapping_exec)
+    assert src_u8.dtype == torch.uint8 and src_u8.dim() == 4 and src_u8.shape[3] == 3 and src_u8.is_contiguous()
+    N, H, W, _ = src_u8.shape
+    BS = tiles.shape[2]
+    assert tiles.is_contiguous() and tuple(tiles.shape[1:]) == (3, BS, BS) and tiles.shape[0] >= E
+    assert mapping_exec.dtype == torch.int32 and mapping_exec.numel() >= E
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _check(lib().bc_blocks_from_u8(tiles.data_ptr(), src_u8.data_ptr(), ctypes.cast(m, _vp), ctypes.cast(sd, _vp),
+                                   mapping_exec.data_ptr(), E, N, H, W, BS, BC_F16 if tiles.dtype == torch.float16 else BC_F32,
+                                   _stream()), "bc_blocks_from_u8")
+    return tiles
 
 
 def upsample_argmax(logits: torch.Tensor, scale: int = 4, label_dtype=torch.uint8,

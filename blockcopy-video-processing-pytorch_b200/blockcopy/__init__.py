@@ -8,6 +8,7 @@ from blockcopy.core.tensorwrapper import TensorWrapper, is_block, is_tensorwrapp
 from blockcopy.core.blockcopy import BlockCopyModel, blockcopy_noblocks
 from blockcopy.core.argparser import add_argparser_arguments
 from blockcopy.policy.policy import build_policy_from_settings
+from blockcopy.core.frame import U8Frame  # not in the reference: a decoded uint8 frame as lazily normalised input
 
 __all__ = [
     "TensorWrapper", "is_block", "is_tensorwrapper", "to_tensorwrapper", "to_tensor",

@@ -15,6 +15,7 @@ import torch.nn as nn
 
 from ..utils.hints import get_num_exec_hint, set_num_exec_hint
 from ..utils.profiler import timings
+from .frame import U8Frame, as_tensor
 from .tensorwrapper import TensorWrapper, run_on_side_stream, side_stream_scope, to_tensorwrapper
 
 
@@ -93,7 +94,6 @@ class BlockCopyModel(nn.Module):
             self.policy_meta = meta
 
         with timings.env("blockcopy/model", 3):
-            x = to_tensorwrapper(inputs)
             if meta["num_exec"] == 0:
                 # nothing to execute: the previous output object is returned, no state is touched
                 meta = self.policy_meta = meta.copy()
@@ -101,6 +101,7 @@ class BlockCopyModel(nn.Module):
             elif self._graphs is not None and not kwargs:
                 meta["frame_state"], out = self._forward_graphed(inputs, meta["grid"], meta["num_exec"])
             else:
+                x = to_tensorwrapper(as_tensor(inputs))
                 self.block_temporal_features = x.process_temporal_features(self.block_temporal_features)
                 blocks = x.to_blocks(meta["grid"])
                 # frame state: for every block the most recently executed input pixels
@@ -134,7 +135,7 @@ class BlockCopyModel(nn.Module):
             # address the graph bakes in belongs to this model, not to the (shared) capture stream
             gs.splitk_ws = torch.empty(_C.SPLITK_WS_BYTES, dtype=torch.uint8, device=inputs.device)
             gs.splitk_ws_side = torch.empty(_C.SPLITK_WS_BYTES // 2, dtype=torch.uint8, device=inputs.device)
-        x = to_tensorwrapper(inputs)
+        x = to_tensorwrapper(as_tensor(inputs))
         self.block_temporal_features = feats = x.process_temporal_features(self.block_temporal_features)
         feats.track_transfer_idx = False
         blocks = x.to_blocks(grid)  # bc_compact_mask + bc_gather
@@ -171,7 +172,11 @@ class BlockCopyModel(nn.Module):
             grid.to(tiles.device, dtype=torch.bool).contiguous()
         G = g.numel()
         _C.compact_mask(g.view(torch.uint8), grid_idx, buf[:G], buf[2 * G:])
-        image = inputs.as_subclass(torch.Tensor)
+        if isinstance(inputs, U8Frame) and layout == _C.BC_NCHW and tiles.shape[2] % 16 == 0:
+            # decoded uint8 frame: normalisation fused into the gather, executed blocks only (bc_blocks_from_u8)
+            _C.blocks_from_u8(tiles, inputs.u8, inputs.mean, inputs.std, buf[:num_exec], num_exec)
+            return
+        image = as_tensor(inputs).as_subclass(torch.Tensor)
         fmt = torch.channels_last if layout == _C.BC_NHWC else torch.contiguous_format
         if not image.is_contiguous(memory_format=fmt):
             image = image.contiguous(memory_format=fmt)

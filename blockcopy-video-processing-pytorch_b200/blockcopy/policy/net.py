@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from blockcopy.core.frame import as_tensor
 from blockcopy.policy.resnet import resnet8
 from blockcopy.utils.profiler import timings
 
@@ -60,7 +61,7 @@ class PolicyNet(nn.Module):
     def build_features(self, policy_meta: dict) -> torch.Tensor:
         """(N, 3+3+num_classes+1, H*s, W*s) fp32: nearest-resized frame | frame_state |
         previous output - 0.5 | previous grid - 0.5   (reference net.py:84-113)."""
-        frame = policy_meta["inputs"]
+        frame = as_tensor(policy_meta["inputs"])  # a lazily normalised U8Frame: the policy looks at the whole frame
         assert frame.dim() == 4 and frame.size(1) == 3
         fused = self._fused_features(policy_meta)
         if fused is not None:
@@ -84,7 +85,7 @@ class PolicyNet(nn.Module):
     def _fused_features(self, policy_meta: dict):
         """One sm_100a kernel (bc_policy_features) instead of 4 interpolates + casts + cat, when the
         inputs are the usual CUDA tensors; same values bit for bit (pure gathers and `- 0.5` in fp32)."""
-        frame, state = policy_meta["inputs"], policy_meta.get("frame_state", None)
+        frame, state = as_tensor(policy_meta["inputs"]), policy_meta.get("frame_state", None)
         rep, grid = policy_meta.get("output_repr", None), policy_meta.get("grid", None)
         if not (self.use_frame_state and self.use_prev_output and self.use_prev_grid) or not frame.is_cuda:
             return None
@@ -142,7 +143,7 @@ class PolicyNet(nn.Module):
     def _fused_forward(self, policy_meta: dict, train: bool = False):
         """Features written straight into the fused trunk's fp16 NHWC input plane (bc_policy_features_nhwc16) and
         the trunk behind it; None when the inputs are outside that kernel's envelope (see _fused_features)."""
-        frame, state = policy_meta["inputs"], policy_meta.get("frame_state", None)
+        frame, state = as_tensor(policy_meta["inputs"]), policy_meta.get("frame_state", None)
         rep, grid = policy_meta.get("output_repr", None), policy_meta.get("grid", None)
         if not (self.use_frame_state and self.use_prev_output and self.use_prev_grid) or not frame.is_cuda:
             return None

@@ -77,6 +77,8 @@ int bn_bwd_apply(void *dz, void *dz_up, const void *g, const void *out, const vo
 int conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, const void *x, int N, int H, int W, int Cin_p,
                int Cout_p, int Cin, int Cout, int ksize, int stride, const float *inv_scale, float *dgamma, float *dbeta,
                const float *bn_sums, void *workspace, long long workspace_bytes, cudaStream_t stream);
+int blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping, int E, int N,
+                   int H, int W, int BS, int dtype, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -403,6 +405,11 @@ BC_API int bc_conv_wgrad(float *grad_w, const long long *grad_strides, const voi
                          float *dbeta, const float *bn_sums, void *workspace, long long workspace_bytes, bc_stream_t stream) {
   return conv_wgrad(grad_w, grad_strides, dz, x, N, H, W, Cin_p, Cout_p, Cin, Cout, ksize, stride, inv_scale, dgamma, dbeta,
                     bn_sums, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping_exec,
+                             int E, int N, int H, int W, int BS, bc_dtype_t dtype, bc_stream_t stream) {
+  return blocks_from_u8(tiles, src, mean, std, mapping_exec, E, N, H, W, BS, (int)dtype, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -12,6 +12,7 @@
 // is  h0*(w0*a + w1*b) + h1*(w0*c + w1*d)  in fp32 (upsample_bilinear2d's accscalar_t), rounded to the logits'
 // dtype before the comparison, ties -> lowest class index.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "bc_common.cuh"
 
@@ -41,9 +42,9 @@ __device__ __forceinline__ float norm_u8(uint32_t u, float mean, float std) {
 template <typename T>
 __global__ void __launch_bounds__(256) frame_from_u8_kernel(const U8Params p) {
   __shared__ T lut[3][256];
+  pdl_trigger();  // first: the next kernel's launch latency and prologue overlap this whole kernel
   for (int k = threadIdx.x; k < 768; k += 256) lut[k >> 8][k & 255] = cvt_out<T>(norm_u8(k & 255, p.mean[k >> 8], p.std[k >> 8]));
   __syncthreads();
-  pdl_trigger();
   pdl_wait();
   const uint32_t gstride = gridDim.x * blockDim.x;
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < p.total_groups; g += gstride) {
@@ -132,6 +133,101 @@ int frame_from_u8(void *out, const uint8_t *src, const float *mean, const float 
       launch_kernel(frame_from_u8_generic_kernel<float>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p, (uint32_t)total_px);
   }
   return check_launch("bc_frame_from_u8");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bc_blocks_from_u8: the first gather of a frame straight from the decoded uint8 frame (input side):
+// tiles[e] (3, BS, BS) <- normalise(src[n, gh*BS .. , gw*BS .. , :]) for the E executed cells -- bc_frame_from_u8 followed
+// by bc_gather (reference tensorwrapper.py:335-381 on the output of ext_transforms.py:317-372) without ever writing
+// the normalised full frame: 3 bytes per pixel of the executed blocks are read instead of 3 + 2 x 6.  Same table
+// look-up as frame_from_u8_kernel, hence the same bits.  BS and W multiples of 16.
+struct U8BlocksParams {
+  const uint8_t *src;      // (N,H,W,3)
+  void *tiles;             // (E,3,BS,BS)
+  const int32_t *mapping;  // cell of tile e
+  float mean[3], std[3];
+  CellDecode cell;
+  FastDiv groups_per_tile, groups_per_row;  // BS*BS/16, BS/16
+  uint32_t total_groups;                    // E * BS*BS/16
+  int H, W, BS;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) blocks_from_u8_kernel(const U8BlocksParams p) {
+  __shared__ T lut[3][256];
+  pdl_trigger();
+  for (int k = threadIdx.x; k < 768; k += 256) lut[k >> 8][k & 255] = cvt_out<T>(norm_u8(k & 255, p.mean[k >> 8], p.std[k >> 8]));
+  __syncthreads();
+  pdl_wait();
+  const uint32_t gstride = gridDim.x * blockDim.x;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < p.total_groups; g += gstride) {
+    uint32_t e, rem, y, xs, n, gh, gw;
+    p.groups_per_tile.divmod(g, e, rem);
+    p.groups_per_row.divmod(rem, y, xs);
+    p.cell((uint32_t)__ldg(p.mapping + e), n, gh, gw);
+    const size_t px = ((size_t)n * p.H + gh * p.BS + y) * p.W + gw * p.BS + xs * 16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.src + px * 3);
+    uint32_t wd[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 q = __ldg(src + i);
+      wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T f[16];
+#pragma unroll
+      for (int k16 = 0; k16 < 16; ++k16) {
+        const int k = k16 * 3 + c;
+        f[k16] = lut[c][(wd[k >> 2] >> ((k & 3) * 8)) & 0xffu];
+      }
+      T *dst = reinterpret_cast<T *>(p.tiles) + (((size_t)e * 3 + c) * p.BS + y) * p.BS + xs * 16;
+      if constexpr (sizeof(T) == 2) {
+        uint32_t h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          h[k] = (uint32_t)__half_as_ushort(f[2 * k]) | ((uint32_t)__half_as_ushort(f[2 * k + 1]) << 16);
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(h[4], h[5], h[6], h[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          reinterpret_cast<uint4 *>(dst)[k] = make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]),
+                                                         __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3]));
+      }
+    }
+  }
+}
+
+int blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping, int E, int N,
+                   int H, int W, int BS, int dtype, cudaStream_t stream) {
+  BC_REQUIRE(tiles && src && mean && std && mapping, BC_ERR_NULL, "bc_blocks_from_u8: NULL pointer");
+  BC_REQUIRE(E > 0 && N > 0 && H > 0 && W > 0 && BS > 0 && H % BS == 0 && W % BS == 0, BC_ERR_SHAPE,
+             "bc_blocks_from_u8: E=%d N=%d %dx%d block %d", E, N, H, W, BS);
+  BC_REQUIRE(BS % 16 == 0, BC_ERR_UNSUPPORTED, "bc_blocks_from_u8: block edge %d is not a multiple of 16", BS);
+  BC_REQUIRE(dtype == BC_F16 || dtype == BC_F32, BC_ERR_DTYPE, "bc_blocks_from_u8: dtype");
+  BC_REQUIRE((((uintptr_t)tiles | (uintptr_t)src) & 15) == 0, BC_ERR_ALIGN, "bc_blocks_from_u8: 16-byte alignment");
+  const int64_t total = (int64_t)E * BS * BS / 16;
+  BC_REQUIRE(total < (1ll << 31) && (int64_t)N * H * W < (1ll << 31), BC_ERR_RANGE, "bc_blocks_from_u8: problem too large");
+  U8BlocksParams p;
+  p.src = src; p.tiles = tiles; p.mapping = mapping;
+  for (int c = 0; c < 3; ++c) {
+    BC_REQUIRE(std[c] != 0.f, BC_ERR_RANGE, "bc_blocks_from_u8: std[%d] is zero", c);
+    p.mean[c] = mean[c];
+    p.std[c] = std[c];
+  }
+  p.cell = CellDecode(H / BS, W / BS);
+  p.groups_per_tile = FastDiv((uint32_t)(BS * BS / 16));
+  p.groups_per_row = FastDiv((uint32_t)(BS / 16));
+  p.total_groups = (uint32_t)total;
+  p.H = H; p.W = W; p.BS = BS;
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)kNumSMs * 4) grid = (int64_t)kNumSMs * 4;
+  if (dtype == BC_F16)
+    launch_kernel(blocks_from_u8_kernel<__half>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  else
+    launch_kernel(blocks_from_u8_kernel<float>, dim3((unsigned)grid), dim3(256), 0, stream, 1, p);
+  return check_launch("bc_blocks_from_u8");
 }
 
 // ---------------------------------------------------------------------------------------------------

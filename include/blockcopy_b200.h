@@ -393,6 +393,14 @@ BC_API int bc_conv_fewout(float *out, const void *x, const float *w, const float
  */
 BC_API int bc_frame_from_u8(void *out, const uint8_t *src, const float *mean, const float *std, int N, int H, int W,
                             bc_dtype_t dtype, bc_stream_t stream);
+/* bc_blocks_from_u8: the frame's first gather fused with the normalisation (input side) --
+ *   tiles (E,3,BS,BS) NCHW of dtype F16|F32 <- normalised pixels of the E executed cells (mapping_exec[e] = flat cell
+ *   index over (n, gh, gw)) of src (N,H,W,3) uint8: what bc_frame_from_u8 + bc_gather (reference
+ *   core/tensorwrapper.py:335-381 `_split` after ext_transforms.py:317-372) produce, same bits, without writing the
+ *   normalised full frame.  BS a multiple of 16, H and W multiples of BS; mean / std: HOST arrays of 3 floats.
+ */
+BC_API int bc_blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping_exec,
+                             int E, int N, int H, int W, int BS, bc_dtype_t dtype, bc_stream_t stream);
 BC_API int bc_upsample_argmax(void *labels, const void *logits, int N, int K, int h, int w, const int64_t *strides,
                               int scale, bc_dtype_t dtype, int label_bytes, bc_stream_t stream);
 /* Block-sparse form of the same step ("x4 bilinear + argmax fused with the logits' block structure"):

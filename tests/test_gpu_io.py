@@ -135,3 +135,77 @@ def test_block_sparse_label_update_equals_dense_argmax(N, K, h, w, GH, GW, scale
     assert torch.equal(got, want), int((got != want).sum())
     if 0 < frac < 1:
         assert not torch.equal(want, _C.upsample_argmax(prev.cuda(), scale))  # the update was needed
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("N,GH,GW,BS,frac", [(1, 4, 6, 64, 0.4), (2, 3, 2, 128, 0.5), (1, 8, 16, 16, 0.3), (1, 2, 2, 32, 1.0)])
+def test_blocks_from_u8_equals_oracle_normalise_then_split(dtype, N, GH, GW, BS, frac):
+    """bc_blocks_from_u8 == the oracle's frame normalisation followed by the oracle's split (reference
+    ext_transforms.py:317-372 then tensorwrapper.py:335-381), bit for bit; and == bc_frame_from_u8 + bc_gather."""
+    from blockcopy import _C
+
+    g = torch.Generator().manual_seed(BS + GH)
+    H, W = GH * BS, GW * BS
+    u8 = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, generator=g)
+    grid = torch.rand(N, 1, GH, GW, generator=g) < frac
+    grid[0, 0, 0, 0] = True
+    _, me = cpu_oracle.grid_mappings(grid)
+    E = me.numel()
+    M, S = (0.287, 0.325, 0.284), (0.176, 0.181, 0.178)
+    want = cpu_oracle.split(cpu_oracle.frame_from_u8(u8, M, S, dtype).contiguous(), me, BS)
+    tiles = torch.full((E, 3, BS, BS), float("nan"), dtype=dtype, device="cuda")
+    _C.blocks_from_u8(tiles, u8.cuda(), M, S, me.cuda(), E)
+    assert torch.equal(tiles.cpu(), want)
+    dense = _C.frame_from_u8(u8.cuda(), M, S, dtype)
+    two = torch.empty_like(tiles)
+    _C.gather(two, dense, me.cuda(), E)
+    assert torch.equal(two, tiles)
+
+
+def test_model_on_u8_frames_equals_model_on_normalised_frames():
+    """BlockCopyModel(U8Frame) in CUDA-graph mode: the steady frames' first gather reads the uint8 frame
+    (bc_blocks_from_u8, no full-frame normalisation) and every output equals the one for the normalised tensor."""
+    import blockcopy
+    from blockcopy import _C
+    from blockcopy.core.argparser import default_settings
+    from blockcopy.core.frame import U8Frame
+    from consumers.clips import PolicyFixedFraction
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    H, W, BS, T = 256, 512, 64, 7
+    g = torch.Generator().manual_seed(3)
+    base = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, generator=g)
+    clip = [base]
+    for _ in range(T - 1):
+        nxt = clip[-1].clone()
+        m = torch.rand(H, W, 1, generator=g) < 0.2
+        nxt = torch.where(m, torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, generator=g), nxt)
+        clip.append(nxt)
+    clip = [f.cuda() for f in clip]
+    outs, calls = {}, {"fused": 0, "dense": 0}
+    orig_b, orig_f = _C.blocks_from_u8, _C.frame_from_u8
+    _C.blocks_from_u8 = lambda *a, **k: (calls.__setitem__("fused", calls["fused"] + 1), orig_b(*a, **k))[1]
+    _C.frame_from_u8 = lambda *a, **k: (calls.__setitem__("dense", calls["dense"] + 1), orig_f(*a, **k))[1]
+    try:
+        for mode in ("u8", "dense"):
+            settings = default_settings(block_policy="all", block_size=BS)
+            settings["block_cuda_graphs"] = True
+            model = blockcopy.BlockCopyModel(build_swiftnet_rn18(seed=1), settings).eval().cuda().half()
+            model.policy = PolicyFixedFraction(BS, fraction=0.3, quantize=2, seed=0)
+            res = []
+            with torch.no_grad():
+                for rep in range(3):  # eager, capture, replay
+                    model.reset_temporal()
+                    if mode == "u8" and rep == 2:
+                        calls["fused"] = calls["dense"] = 0
+                    for f in clip:
+                        x = U8Frame(f) if mode == "u8" else orig_f(f, U8Frame(f).mean, U8Frame(f).std, torch.float16)
+                        res.append(model(x).clone())
+                    if mode == "u8" and rep == 2:
+                        # replayed clip: only the all-blocks first frame may need the whole normalised frame
+                        assert calls["fused"] >= T - 2 and calls["dense"] <= 1, calls
+            outs[mode] = res
+    finally:
+        _C.blocks_from_u8, _C.frame_from_u8 = orig_b, orig_f
+    for a, b in zip(outs["u8"], outs["dense"]):
+        assert torch.equal(a, b)
