@@ -217,7 +217,7 @@ def _reference_swiftnet():
 MODEL_CODE = {"value": None}
 
 
-def build_model(args, device, policy=None, native_training=False):
+def build_model(args, device, policy=None, native_training=True):
     """SwiftNet-RN18 behind this package's BlockCopyModel, set up like the reference driver does
     (test_swiftnet.py:107-123): wrap, BN fusion, .half(), policy net in fp32."""
     import contextlib
@@ -237,9 +237,9 @@ def build_model(args, device, policy=None, native_training=False):
         settings["block_policy_shared"] = True
     if os.environ.get("BLOCKCOPY_POLICY_FUSED", "1") == "0":  # A/B: policy trunk always through torch/cuDNN
         settings["block_policy_fused"] = False
-    # training frames of the policy net on this repo's kernels (policy/fused_train.py) instead of torch autograd over
-    # cuDNN graph replays: measured slightly slower end to end, so it is an opt-in setting
-    settings["block_policy_fused_training"] = bool(native_training) or os.environ.get("BLOCKCOPY_POLICY_FUSED_TRAINING", "0") == "1"
+    # training frames of the policy net: this repo's kernels (policy/fused_train.py, the default) or torch autograd over
+    # cuDNN graph replays (A/B: native_training=False / BLOCKCOPY_POLICY_FUSED_TRAINING=0)
+    settings["block_policy_fused_training"] = bool(native_training) and os.environ.get("BLOCKCOPY_POLICY_FUSED_TRAINING", "1") == "1"
     # the reference driver's order (test_swiftnet.py:104-123): base model in eval mode, THEN wrapped (the policy net
     # stays in train mode, so the BN fusion below leaves its BatchNorms alone), fused, .half(), policy net back to fp32
     ref = _reference_swiftnet()
@@ -508,7 +508,7 @@ def bench_config4(args, device, world, rank, total_streams=64, group=8, steps=30
             "ms_per_step": med / steps, "windows_ms": _summary(ms), "data": "synthetic, device-resident"}
 
 
-def bench_rl(args, device, steps=90, native_training=False):
+def bench_rl(args, device, steps=90, native_training=True):
     """The mode the reference ships (`--block-policy rl_semseg`): policy net fp32, Bernoulli sampling, online
     REINFORCE step every 3rd frame (block_train_interval 3), target 0.3.  Single stream, device-resident frames."""
     from consumers.clips import synthetic_clip
@@ -660,8 +660,8 @@ def bench_ours(args):
     rl = None
     if not args.skip_rl and args.policy == "fixed" and world == 1:
         rl = bench_rl(args, device)
-        nat = bench_rl(args, device, native_training=True)
-        rl["native_training"] = {k: nat[k] for k in ("value", "unit", "mean_exec_blocks", "policy_training_frames")}
+        alt = bench_rl(args, device, native_training=False)
+        rl["torch_autograd_training"] = {k: alt[k] for k in ("value", "unit", "mean_exec_blocks", "policy_training_frames")}
 
     # ---- kernels: roofline of the dominant block kernel + the others ----------------------------------
     kern = microbench(device, peaks) if rank == 0 and not args.skip_microbench else None

@@ -153,7 +153,7 @@ class FusedPolicyTrainer(FusedPolicyTrunk):
     def _grad_buffer(self, q: torch.Tensor) -> torch.Tensor:
         g = self._grads.get(id(q))
         if g is None or g.shape != q.shape or g.device != q.device:
-            g = self._grads[id(q)] = torch.zeros_like(q, memory_format=torch.contiguous_format)
+            g = self._grads[id(q)] = torch.zeros_like(q)  # the parameter's own strides (channels_last weights): FusedRMSprop's fast path
         return g
 
     def _buf(self, name, shape, zero=False):

@@ -47,7 +47,7 @@ class PolicyNet(nn.Module):
         # frames that ARE followed by a policy update: forward with saved activations + backward on this repo's kernels
         # (policy/fused_train.py) instead of torch autograd over cuDNN.  PolicyTrainRL sets it from
         # settings['block_policy_fused_training']
-        self.fused_training = False
+        self.fused_training = True
         self.__dict__["_trainer"] = None
 
     @staticmethod

@@ -41,7 +41,7 @@ def build_policy_from_settings(settings: dict):
     if name.startswith("rl_"):
         net = build_policy_net_from_settings(settings)
         net.fused_inference = bool(settings.get("block_policy_fused", True))  # policy/fused_net.py (not in the reference)
-        net.fused_training = bool(settings.get("block_policy_fused_training", False))  # policy/fused_train.py
+        net.fused_training = bool(settings.get("block_policy_fused_training", True))  # policy/fused_train.py
         optimizer = build_policy_optimizer_from_settings(settings, net)
         if name == "rl_semseg":
             ig = InformationGainSemSeg(num_classes=settings["block_num_classes"])

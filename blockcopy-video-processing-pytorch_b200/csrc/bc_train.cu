@@ -312,6 +312,7 @@ struct WgradParams {
   int N, H, W, Ho, Wo, ksize, stride, pad;
   int TR, TC, tc_shift, WR, WC;  // tile rows / columns (TR * TC = 64), window rows / columns
   int tiles_y, tiles_x, ntiles, stages;
+  int co_pitch, ci_pitch;  // channels per pixel of the dz / x planes in memory (>= the CO / CI the kernel works on)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
@@ -332,10 +333,12 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int CO, int CI, int TAPS>
+// KSPLIT = 2 (the 32-channel layers: too few output elements for eight warps): warps 4..7 take the second half of the
+// tile's 64 pixels and write a partial of their own.
+template <int CO, int CI, int TAPS, int KSPLIT = 1>
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradParams p) {
   constexpr int WM = CO / 16 < 8 ? CO / 16 : 8;  // warps along the output channels
-  constexpr int WN = 8 / WM;                      // warps along the input channels
+  constexpr int WN = 8 / (WM * KSPLIT);           // warps along the input channels
   constexpr int NEXT = CI / WN;                   // input channels per warp
   constexpr int NT = NEXT / 8;                    // n8 tiles per warp and tap
   constexpr int DZ_PITCH = CO * 2 + 16, X_PITCH = CI * 2 + 16;
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradPa
   pdl_trigger();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp % WM, wn = warp / WM;
+  const int wm = warp % WM, wn = (warp / WM) % WN, kg = warp / (WM * WN);
   const int stage_bytes = 64 * DZ_PITCH + p.WR * p.WC * X_PITCH;
   const uint32_t smem_base = smem_u32(smem);
   const int tap0 = blockIdx.y * TAPS;
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradPa
       const int px = i / DZ_CH, ch = i - px * DZ_CH;
       const int y = ty * p.TR + (px >> p.tc_shift), x = tx * p.TC + (px & (p.TC - 1));
       const bool ok = y < p.Ho && x < p.Wo;
-      const __half *src = p.dz + (ok ? (((size_t)n * p.Ho + y) * p.Wo + x) * CO + ch * 8 : 0);
+      const __half *src = p.dz + (ok ? (((size_t)n * p.Ho + y) * p.Wo + x) * p.co_pitch + ch * 8 : 0);
       cp_async16(base + px * DZ_PITCH + ch * 16, src, ok);
     }
     const int oy = ty * p.TR * p.stride - p.pad, ox = tx * p.TC * p.stride - p.pad;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradPa
       const int wr = px / p.WC, wc = px - wr * p.WC;
       const int y = oy + wr, x = ox + wc;
       const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
-      const __half *src = p.x + (ok ? (((size_t)n * p.H + y) * p.W + x) * CI + ch * 8 : 0);
+      const __half *src = p.x + (ok ? (((size_t)n * p.H + y) * p.W + x) * p.ci_pitch + ch * 8 : 0);
       cp_async16(base + 64 * DZ_PITCH + px * X_PITCH + ch * 16, src, ok);
     }
   };
@@ -418,6 +421,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradPa
     const uint32_t base = smem_base + buf * stage_bytes;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
+      if (KSPLIT == 2 && (ks >> 1) != kg) continue;
       uint32_t a[4];
       ldmatrix_x4_trans(a, base + a_off[ks]);
 #pragma unroll
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const WgradPa
   const int taps_total = p.ksize * p.ksize;
 #pragma unroll
   for (int t = 0; t < TAPS; ++t) {
-    float *dst = p.partial + (((size_t)blockIdx.x * taps_total + tap0 + t) * CO + wm * 16 + g) * CI + wn * NEXT + 2 * t4;
+    float *dst = p.partial + (((size_t)(blockIdx.x * KSPLIT + kg) * taps_total + tap0 + t) * CO + wm * 16 + g) * CI + wn * NEXT + 2 * t4;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       *reinterpret_cast<float2 *>(dst + n * 8) = make_float2(acc[t][n][0], acc[t][n][1]);
@@ -492,14 +496,16 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const WgradFinishPara
     ci = i % p.Cin; co = (i / p.Cin) % p.Cout; tap = i / (p.Cin * p.Cout);
     const size_t per = (size_t)taps * p.CO * p.CI;
     const float *src = p.partial + ((size_t)tap * p.CO + co) * p.CI + ci;
-    float v[20];  // nparts <= 148 -> <= 19 per slice
+    for (int b0 = slice; b0 < p.nparts; b0 += 32) {  // four independent loads in flight; few partials = few rounds
+      float v[4];
 #pragma unroll
-    for (int k = 0; k < 20; ++k) {
-      const int b = slice + 8 * k;
-      v[k] = b < p.nparts ? __ldcg(src + (size_t)b * per) : 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const int b = b0 + 8 * k;
+        v[k] = b < p.nparts ? __ldcg(src + (size_t)b * per) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += v[k];
     }
-#pragma unroll
-    for (int k = 0; k < 20; ++k) s += v[k];
   }
   red[slice][lane] = s;
   __syncthreads();
@@ -512,15 +518,15 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const WgradFinishPara
   }
 }
 
-template <int CO, int CI, int TAPS>
+template <int CO, int CI, int TAPS, int KSPLIT = 1>
 static int launch_wgrad(const WgradParams &p, int grid_x, int smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<CO, CI, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<CO, CI, TAPS, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail((int)e, "bc_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  launch_kernel(conv_wgrad_kernel<CO, CI, TAPS>, dim3((unsigned)grid_x, (unsigned)(p.ksize * p.ksize / TAPS)), dim3(kWgThreads),
+  launch_kernel(conv_wgrad_kernel<CO, CI, TAPS, KSPLIT>, dim3((unsigned)grid_x, (unsigned)(p.ksize * p.ksize / TAPS)), dim3(kWgThreads),
                 (size_t)smem, stream, 1, p);
   return check_launch("bc_conv_wgrad");
 }
@@ -547,26 +553,32 @@ int conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, con
   p.WR = (p.TR - 1) * stride + ksize; p.WC = (p.TC - 1) * stride + ksize;
   p.tiles_y = (p.Ho + p.TR - 1) / p.TR; p.tiles_x = (p.Wo + p.TC - 1) / p.TC;
   p.ntiles = N * p.tiles_y * p.tiles_x;
-  const int stage = 64 * (Cout_p * 2 + 16) + p.WR * p.WC * (Cin_p * 2 + 16);
+  // channel counts the kernel works on: the planes' padded counts, or 32 x 32 when the real counts fit (the policy net's
+  // 256x512-pixel layers: a quarter of the padded flops, half of the operand bytes)
+  const bool small = ksize == 3 && Cout <= 32 && Cin <= 32;
+  const int co = small ? 32 : Cout_p, ci = small ? 32 : Cin_p, ksplit = small ? 2 : 1;
+  p.co_pitch = Cout_p; p.ci_pitch = Cin_p;
+  const int stage = 64 * (co * 2 + 16) + p.WR * p.WC * (ci * 2 + 16);
   p.stages = 2 * stage <= 200 * 1024 ? 2 : 1;
   BC_REQUIRE(stage <= 200 * 1024, BC_ERR_UNSUPPORTED, "bc_conv_wgrad: tile of %d bytes", stage);
   const int taps = ksize * ksize;
-  const int taps_per_cta = (Cout_p == 64) ? taps : (Cin_p == 64 ? (ksize == 3 ? 3 : 1) : 1);
+  const int taps_per_cta = (co <= 64) ? taps : (ci == 64 ? (ksize == 3 ? 3 : 1) : 1);
   int grid_x = kNumSMs / (taps / taps_per_cta);  // ~one CTA per SM over both grid dimensions: few partials to add
   if (grid_x > p.ntiles) grid_x = p.ntiles;
-  const long long need = (long long)grid_x * taps * Cout_p * Cin_p * (long long)sizeof(float);
+  const long long need = (long long)grid_x * ksplit * taps * co * ci * (long long)sizeof(float);
   BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_conv_wgrad: workspace of %lld bytes, %lld needed", workspace_bytes, need);
   const int smem = p.stages * stage;
   int rc;
-  if (Cout_p == 64 && Cin_p == 64) rc = ksize == 3 ? launch_wgrad<64, 64, 9>(p, grid_x, smem, stream) : launch_wgrad<64, 64, 1>(p, grid_x, smem, stream);
-  else if (Cout_p == 128 && Cin_p == 64) rc = ksize == 3 ? launch_wgrad<128, 64, 3>(p, grid_x, smem, stream) : launch_wgrad<128, 64, 1>(p, grid_x, smem, stream);
+  if (small) rc = launch_wgrad<32, 32, 9, 2>(p, grid_x, smem, stream);
+  else if (co == 64 && ci == 64) rc = ksize == 3 ? launch_wgrad<64, 64, 9>(p, grid_x, smem, stream) : launch_wgrad<64, 64, 1>(p, grid_x, smem, stream);
+  else if (co == 128 && ci == 64) rc = ksize == 3 ? launch_wgrad<128, 64, 3>(p, grid_x, smem, stream) : launch_wgrad<128, 64, 1>(p, grid_x, smem, stream);
   else rc = launch_wgrad<128, 128, 1>(p, grid_x, smem, stream);
   if (rc) return rc;
   WgradFinishParams f;
   f.partial = p.partial; f.grad = grad_w;
   for (int i = 0; i < 4; ++i) f.gs[i] = grad_strides[i];
   f.inv_scale = inv_scale; f.bn_sums = bn_sums; f.dgamma = dgamma; f.dbeta = dbeta;
-  f.nparts = grid_x; f.ksize = ksize; f.CO = Cout_p; f.CI = Cin_p; f.Cout = Cout; f.Cin = Cin;
+  f.nparts = grid_x * ksplit; f.ksize = ksize; f.CO = co; f.CI = ci; f.Cout = Cout; f.Cin = Cin;
   f.bn_C = bn_sums ? Cout : 0; f.bn_Cp = Cout_p;
   const int blocks = (taps * Cout * Cin + 31) / 32 + (f.bn_C + 31) / 32;
   launch_kernel(wgrad_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, f);

@@ -1,4 +1,4 @@
-"""rl_semseg (bench.bench_rl) with training frames on the native kernels vs torch autograd over cuDNN graph replays."""
+"""rl_semseg (bench.bench_rl): policy inference / training frames on the native kernels vs torch (cuDNN graph replays)."""
 import json
 import os
 import subprocess
