@@ -53,7 +53,8 @@ def build_policy_from_settings(settings: dict):
                              optimizer=optimizer, complexity_weight=settings["block_complexity_weight"],
                              quantize_number_exec=quantize, policy_net=net, information_gain=ig,
                              shared_across_ranks=bool(settings.get("block_policy_shared", False)),
-                             device_sampling=bool(settings.get("block_policy_device_sampling", True)), **common)
+                             device_sampling=bool(settings.get("block_policy_device_sampling", True)),
+                             strict_checks=bool(settings.get("block_policy_strict_checks", False)), **common)
     raise NotImplementedError(f"Policy {name} not implemented")
 
 
@@ -216,7 +217,8 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
     def __init__(self, block_size: int, block_target: float, optimizer: torch.optim.Optimizer,
                  complexity_weight: float, policy_net: PolicyNet, information_gain: InformationGain,
                  cost_momentum: float = 0.9, at_least_one: bool = False, quantize_number_exec: float = 0,
-                 verbose: bool = False, shared_across_ranks: bool = False, device_sampling: bool = True):
+                 verbose: bool = False, shared_across_ranks: bool = False, device_sampling: bool = True,
+                 strict_checks: bool = False):
         super().__init__(block_size, verbose, quantize_number_exec)
         # Bernoulli draw + count quantisation in one kernel (bc_sample_grid), the only host round trip of the frame
         # being the executed-block count the API exposes anyway.  False: the reference's host procedure
@@ -237,6 +239,8 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
         self.complexity_weight_gamma = complexity_weight
         self.optimizer = optimizer
         self.at_least_one = at_least_one
+        self.strict_checks = strict_checks
+        self._deferred = []
 
     def forward(self, policy_meta: dict):
         shape = self._grid_shape(policy_meta)
@@ -256,8 +260,7 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     no_grad = policy_meta.get("policy_will_train", True) is False and \
                         getattr(self.net, "fused_inference", False)
                     grid_logits = self.net(policy_meta, no_grad=no_grad) if no_grad else self.net(policy_meta)
-                    assert torch.all(~torch.isnan(grid_logits)), \
-                        "Policy net returned NaN's, maybe optimization problem?"
+                    self._check(torch.isnan(grid_logits).any(), "Policy net returned NaN's, maybe optimization problem?")
                 sampled = None
                 if self.device_sampling and grid_logits.is_cuda and grid_logits.numel() <= 8192:
                     with timings.env("policy/sample", 3):
@@ -280,6 +283,7 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                         probs = dist.probs
                 if self.at_least_one and grid.sum() == 0:
                     grid[0, 0, 0, 0] = 1
+                self.flush_checks()  # this path talks to the host anyway
                 grid = self.quantize_number_exec_grid(grid)
                 policy_meta["grid_log_probs"] = dist.log_prob(grid) if dist is not None else None
                 policy_meta["grid_probs"] = probs
@@ -298,15 +302,54 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
         if no_grad:
             dist, probs = None, torch.sigmoid(grid_logits.detach())
         else:
-            dist = Bernoulli(logits=grid_logits)
+            # argument / sample validation of torch.distributions is a host sync each (torch._is_all_true); NaN logits are
+            # caught by the (deferred) check in forward()
+            dist = Bernoulli(logits=grid_logits, validate_args=self.strict_checks)
             probs = dist.probs
         p32 = probs.detach().float().contiguous()
         G = p32.numel()
         uniforms = torch.rand(2 * G, device=p32.device, dtype=torch.float32)  # torch's generator: torch.manual_seed
         multiple = int(G * self.quantize_number_exec) if self.quantize_number_exec > 0 else 0
         grid, counts = _C.sample_grid(p32, uniforms, multiple, self.at_least_one)
-        set_num_exec_hint(grid, int(counts[0]))  # the one host sync of the frame (the API's num_exec is a Python int)
+        # the one host sync of the frame (the API's num_exec is a Python int); checks deferred since the last one
+        # (NaN asserts, the "not well trained" diagnostic) ride on the same device -> host read
+        set_num_exec_hint(grid, self._read_count_and_checks(counts))
         return grid, probs, dist
+
+    # ------------------------------------------------------------------ device-side checks without extra host syncs
+    def _check(self, bad: torch.Tensor, message: str, warn: bool = False):
+        """`bad` (0-d bool tensor) must be False.  On the GPU the verdict is not read here -- that would stall the host
+        until the frame's kernels have run, once per check -- but together with the next executed-block count (the one
+        device -> host read every rl frame needs anyway): an AssertionError (the reference asserts in place,
+        policy.py:253,335,345) or, with `warn`, a printed warning arrives at most one frame later.
+        ``strict_checks`` (settings['block_policy_strict_checks']) restores the immediate behaviour."""
+        if not bad.is_cuda or self.strict_checks:
+            if bool(bad):
+                if not warn:
+                    raise AssertionError(message)
+                print(message)
+            return
+        self._deferred.append((bad.detach().reshape(1).to(torch.int32), message, warn))
+        if len(self._deferred) > 32:  # nobody is reading counts (host-side sampling path): do not pile up
+            self.flush_checks()
+
+    def _read_count_and_checks(self, counts: torch.Tensor) -> int:
+        """int(counts[0]) plus every deferred check, in one device -> host copy."""
+        if not self._deferred:
+            return int(counts[0])
+        pending, self._deferred = self._deferred, []
+        vals = torch.cat([counts[:1]] + [f for f, _, _ in pending]).tolist()
+        for v, (_, message, warn) in zip(vals[1:], pending):
+            if v:
+                if not warn:
+                    raise AssertionError(message)
+                print(message)
+        return int(vals[0])
+
+    def flush_checks(self):
+        """Read the deferred checks now (end of a clip / before saving a checkpoint)."""
+        if self._deferred:
+            self._read_count_and_checks(torch.zeros(1, dtype=torch.int32, device=self._deferred[0][0].device))
 
     def _shared_world(self):
         import torch.distributed as dist
@@ -369,7 +412,7 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                 reward_complexity_weighted = self._get_reward_complexity(policy_meta) * self.complexity_weight_gamma
                 reward = ig + reward_complexity_weighted
                 assert reward.dim() == 4
-                assert not torch.any(torch.isnan(reward))
+                self._check(torch.isnan(reward).any(), "PolicyTrainRL.optim: NaN in the reward")
                 log_probs = policy_meta["grid_log_probs"]
                 if log_probs is None:
                     raise RuntimeError(
@@ -380,7 +423,7 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                 reward = F.adaptive_max_pool2d(reward, output_size=log_probs.shape[2:])
                 reward = torch.where(grid, reward, -reward)  # skipped blocks: negated reward
                 loss_policy = (-log_probs * reward.detach()).mean()
-                assert not torch.isnan(loss_policy)
+                self._check(torch.isnan(loss_policy), "PolicyTrainRL.optim: the policy loss is NaN")
                 with timings.env("policy/optimizer_backward", 3):
                     loss_policy.backward()
                 if self.shared_across_ranks:
@@ -390,7 +433,17 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
                     self.optimizer.step()
                     self.optimizer.zero_grad(set_to_none=True)
 
-                if self.verbose or self.stats.count_images > 300:
+                if self.stats.count_images > 300 and not self.verbose and not self.strict_checks \
+                        and policy_meta["grid_probs"].is_cuda:
+                    # the reference's diagnostic without its two host round trips (boolean-mask indexing + the comparison):
+                    # masked means on the device, the verdict read with the next frame's executed-block count
+                    probs, g = policy_meta["grid_probs"].detach().float(), grid.to(torch.float32)
+                    n_exec = g.sum()
+                    exec_mean = (probs * g).sum() / n_exec
+                    skip_mean = (probs * (1 - g)).sum() / (g.numel() - n_exec)
+                    self._check(exec_mean - skip_mean < 0.3, "Warning: Block execution policy seems not well trained yet.",
+                                warn=True)
+                elif self.verbose or self.stats.count_images > 300:
                     exec_mean = policy_meta["grid_probs"][grid].mean()
                     skip_mean = policy_meta["grid_probs"][~grid].mean()
                     if self.verbose:

@@ -426,3 +426,29 @@ def test_fused_policy_trunk_updates_bn_running_statistics_like_torch():
             tol = 0.03 * float(ra.abs().max()) + 1e-3
             assert float((ra - rb).abs().max()) <= tol, (float((ra - rb).abs().max()), tol)
         assert not torch.equal(b.running_var, torch.ones_like(b.running_var))
+
+
+def test_deferred_nan_check_raises_within_one_frame():
+    """PolicyTrainRL's NaN asserts (reference policy/policy.py:253) do not stall the host on the GPU any more: the
+    verdict is read with the next executed-block count -- and still arrives, at most one frame later; with
+    block_policy_strict_checks the assert fires in place."""
+    import blockcopy
+    from blockcopy.core.argparser import default_settings
+    from consumers.clips import synthetic_clip
+    from consumers.swiftnet_rn18 import build_swiftnet_rn18
+
+    for strict in (False, True):
+        settings = default_settings(block_policy="rl_semseg", block_size=128, block_train_interval=3)
+        settings["block_policy_strict_checks"] = strict
+        model = blockcopy.BlockCopyModel(build_swiftnet_rn18(), settings).eval().cuda().half()
+        model.policy.net = model.policy.net.float().train()
+        clip = synthetic_clip(4, 512, 1024, seed=0, device="cuda")
+        with torch.no_grad():
+            model(clip[0])
+            model(clip[1])
+            with torch.no_grad():
+                model.policy.net.layers[2][0].bias.fill_(float("nan"))
+            with pytest.raises(AssertionError, match="NaN"):
+                model(clip[2])
+                assert not strict, "strict checks must raise on the frame itself"
+                model(clip[3])
