@@ -674,7 +674,7 @@ struct GnParams {
 // note there); the last CTA adds the per-CTA partials of a (group, statistic) pair with one warp: lane l takes CTAs
 // l, l+32, ... in order, then a fixed shuffle tree -- all loads of the final reduction are in flight at once.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) {
-  __shared__ float red[kGnThreads][2];
+  __shared__ __align__(8) float red[kGnThreads][2];
   __shared__ double fin[2 * 256];
   __shared__ bool last;
   pdl_trigger();
@@ -731,20 +731,38 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const GnParams p) 
   __syncthreads();
   if (!last) return;
   __threadfence();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int pair = warp; pair < 2 * p.groups; pair += kGnThreads / 32) {  // pair = 2 * group + (0: sum | 1: sum of squares)
-    double v[10];  // gridDim.x <= 2 * 148 = 296 <= 320
+  // (group, statistic) pair -> `slices` threads, each adds every slices-th CTA partial (eight loads in flight), then the
+  // slices are added in order: all 256 threads work, the sum order is fixed
+  {
+    const int pairs = 2 * p.groups;  // <= 512
+    double *comb = reinterpret_cast<double *>(red);  // 256 x 2 floats = 256 doubles, free by now
+    for (int base = 0; base < pairs; base += kGnThreads) {
+      const int np = pairs - base < kGnThreads ? pairs - base : kGnThreads;  // pairs handled in this round
+      int slices = 1;
+      while (slices * 2 * np <= kGnThreads) slices *= 2;
+      const int pr = threadIdx.x % np, slice = threadIdx.x / np;
+      double t = 0.0;
+      if (slice < slices) {
+        for (unsigned b0 = (unsigned)slice; b0 < gridDim.x; b0 += 8u * slices) {
+          double v[8];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      const unsigned b = (unsigned)lane + 32u * j;
-      v[j] = b < gridDim.x ? __ldcg(p.partial + (size_t)b * 2 * p.groups + pair) : 0.0;
+          for (int j = 0; j < 8; ++j) {
+            const unsigned b = b0 + (unsigned)(j * slices);
+            v[j] = b < gridDim.x ? __ldcg(p.partial + (size_t)b * pairs + base + pr) : 0.0;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t += v[j];
+        }
+      }
+      __syncthreads();
+      comb[threadIdx.x] = t;
+      __syncthreads();
+      if (threadIdx.x < np) {
+        double sum = 0.0;
+        for (int z = 0; z < slices; ++z) sum += comb[z * np + threadIdx.x];
+        fin[base + threadIdx.x] = sum;
+      }
     }
-    double t = 0.0;
-#pragma unroll
-    for (int j = 0; j < 10; ++j) t += v[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) fin[pair] = t;
   }
   __syncthreads();
   if (threadIdx.x < p.groups) {
@@ -774,7 +792,7 @@ int gn_stats(float *mean, float *invstd, const void *x, long long P, int C, int 
   BC_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, BC_ERR_ALIGN, "bc_gn_stats: 16-byte alignment");
   const int rows = kGnThreads / (C / 8);
   long long grid = (P + 8 * rows - 1) / (8 * rows);
-  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;  // two CTAs per SM: 16 loads in flight per thread pair
   const long long need = 16 + grid * groups * 2 * (long long)sizeof(double);
   BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_gn_stats: workspace of %lld bytes, %lld needed", workspace_bytes, need);
   GnParams p;
