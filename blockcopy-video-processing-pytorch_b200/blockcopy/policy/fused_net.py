@@ -12,8 +12,10 @@ sampled grid is used, so no autograd graph is needed and the trunk runs here as
     relu / add    bc_ew_fused
 
 Channel counts are padded to multiples of 64 (26 -> 64 inputs, 32 -> 64 in the first stage) with zero weights; the
-final 128 -> 1 conv (0.6 MFLOP) stays a torch call.  Weights are re-packed to fp16 from the live fp32 parameters at
-every call (they change with each online optimiser step), inside the same CUDA graph when graphs are on.
+final 128 -> 1 conv goes through bc_conv_fewout.  Weights are re-packed to fp16 from the live fp32 parameters (one
+launch, ahead of the CUDA graph) whenever a parameter changed since the last pack -- in-place updates are seen through the
+tensors' version counters, fused optimiser steps through fused_optim.PARAM_EPOCH, new storage through the pointers; code
+that writes parameters through ``.data`` must bump PARAM_EPOCH itself (policy.py::sync_shared_policy does).
 
 Numerics: fp16 operands / fp32 accumulation / fp16 activations against the reference's fp32 (TF32 on cuDNN)
 trunk -- logits agree to ~1e-2 of their range (tests/test_gpu_policy.py states the bound); the grid is sampled
@@ -100,6 +102,7 @@ class FusedPolicyTrunk:
         self._graph = None   # (key, graph, static input, static output)
         self._pack_key = self._pack_table = None
         self._pack_total = 0
+        self._pack_srcs = self._packed_token = None
         self._run_key = self._run_table = None
 
     def _bns(self) -> List[_BN]:
@@ -149,8 +152,7 @@ class FusedPolicyTrunk:
         return out
 
     def _forward(self) -> torch.Tensor:
-        """Everything after the input plane ``self._x16`` has been filled."""
-        self._pack()
+        """Everything after the input plane ``self._x16`` has been filled and the parameters packed."""
         h = self._bn(self._conv(self._x16, self.stem[0]), self.stem[1], relu=True)
         for c1, b1, c2, b2, ds in self.blocks:
             y = self._bn(self._conv(h, c1), b1, relu=True)
@@ -221,6 +223,22 @@ class FusedPolicyTrunk:
             self._pack_total, self._pack_key = off, key
         _C.pack_params(self._pack_table, self._pack_total)
 
+    def _pack_if_needed(self):
+        """Re-pack the fp16 parameter copies only when a parameter changed since the last pack: an in-place update
+        (`_version` counters), a fused optimiser step (fused_optim.PARAM_EPOCH: raw-pointer updates) or new storage
+        (`_param_key`).  The policy trains every block_train_interval-th frame only, so most frames skip the launch."""
+        from .fused_optim import PARAM_EPOCH
+
+        srcs = self._pack_srcs
+        if srcs is None:
+            srcs = self._pack_srcs = [c.conv.weight for c in [self.stem[0]] + [c for b in self.blocks for c in (b[0], b[2])] +
+                                      [b[4][0] for b in self.blocks if b[4] is not None] + [h[0] for h in self.head]] + \
+                [t for b in self._bns() for t in (b.bn.weight, b.bn.bias)]
+        token = (PARAM_EPOCH[0], sum(t._version for t in srcs))
+        if self._pack_key != self._param_key() or self._packed_token != token:
+            self._pack()
+            self._packed_token = token
+
     def _prepare(self, shape, device):
         N, C, H, W = shape
         if self._ws is None or self._ws.device != device:
@@ -241,6 +259,7 @@ class FusedPolicyTrunk:
         """fill(x16) writes the features (fp16, channels 0..C-1 of the padded NHWC plane x16) -- eagerly, every call;
         everything behind it is one CUDA graph when `use_cuda_graph`."""
         self._prepare(shape, device)
+        self._pack_if_needed()  # eagerly, outside the graph: skipped on frames whose parameters did not change
         fill(self._x16)
         if not use_cuda_graph:
             return self._forward()

@@ -15,6 +15,11 @@ import torch
 from .. import _C
 
 
+# Bumped by every fused step: the kernel updates parameters through raw pointers, which does not touch the tensors'
+# `_version` counters -- consumers that cache values derived from parameters (policy/fused_net.py) watch both.
+PARAM_EPOCH = [0]
+
+
 def _dense(t: torch.Tensor) -> bool:
     return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
 
@@ -94,6 +99,8 @@ class FusedRMSprop(torch.optim.RMSprop):
                     seen[i] = ptr
                 rows[i][1] = ptr
             work.append((group, rows, steps, dev))
+        if work:
+            PARAM_EPOCH[0] += 1
         for group, rows, steps, dev in work:
             torch._foreach_add_(steps, 1)
             _C.rmsprop_step(rows, dev, group["lr"], group["alpha"], group["eps"], group["weight_decay"], group["momentum"])

@@ -126,7 +126,6 @@ class FusedPolicyTrainer(FusedPolicyTrunk):
         return _Unit(c, b, x, z, out, relu)
 
     def _forward(self) -> torch.Tensor:
-        self._pack()
         self._stem_rec = self._unit(self._x16, self.stem[0], self.stem[1], True)
         h = self._stem_rec.out
         self._blocks_rec = []
@@ -238,6 +237,7 @@ class FusedPolicyTrainer(FusedPolicyTrunk):
     # ------------------------------------------------------------------ entry points
     def _run_forward(self, fill, shape, device) -> torch.Tensor:
         self._prepare(shape, device)
+        self._pack_if_needed()
         fill(self._x16)
         self._eager = True
         if not self.use_cuda_graph:

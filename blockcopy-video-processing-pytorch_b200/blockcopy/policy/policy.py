@@ -368,6 +368,9 @@ class PolicyTrainRL(Policy, metaclass=abc.ABCMeta):
         with torch.no_grad():
             for t in list(self.net.parameters()) + list(self.net.buffers()):
                 dist.broadcast(t.data, src=0)
+        from blockcopy.policy.fused_optim import PARAM_EPOCH
+
+        PARAM_EPOCH[0] += 1  # written through .data: the fused trunks must re-pack their fp16 copies
 
     def _allreduce_gradients(self):
         """Average of the policy gradients over all ranks, one flat buffer, in place."""
