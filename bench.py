@@ -731,6 +731,9 @@ def roofline_records(kern, peaks):
                      "traffic": 3.42e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the layer2 "
                      "shape (algorithmic: 6.2 MB; inputs come from L2), ncu --set full: profiles/r02_conv_persist_ncu.md",
                      "per_shape": {k: kern[k] for k in dom_keys},
+                     "same_shapes_8_streams_batched": (lambda b: {
+                         "frac": sum(b[k]["flops"] for k in dom_keys) / sum(b[k]["us"] for k in dom_keys) * 1e-6 / peaks["tf_burst"],
+                         "per_shape": {k: b[k] for k in dom_keys}})(kern["at_8_streams_batched"]) if "at_8_streams_batched" in kern else None,
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                      "algorithmic_flops_per_launch": flops / len(dom_keys), "us_per_launch": us / len(dom_keys)},
         "roofline_l20": {"bound": "tensor", "kernel": "bc_conv_igemm 3x3 128->128 on 32-px blocks, E=40 (SwiftNet layer #20: "
@@ -812,6 +815,9 @@ def microbench(device, peaks, reps=200, sets=8):
         del planes, tiles, padded, outs
     res.update(large_gather_microbench(device, peaks))
     res.update(conv_microbench(device, peaks, me_full=None))
+    # the same conv launches when 8 streams are batched along N (config 4: E = 8 x 40 blocks): how far the kernels get
+    # when the grid fills the GPU
+    res["at_8_streams_batched"] = conv_microbench(device, peaks, me_full=None, reps=20, sets=2, E=320, images=8)
     res.update(io_microbench(device, peaks))
     return res
 
@@ -900,20 +906,20 @@ def large_gather_microbench(device, peaks, reps=100, sets=2):
     return out
 
 
-def conv_microbench(device, peaks, me_full=None, reps=50, sets=4, E=40):
+def conv_microbench(device, peaks, me_full=None, reps=50, sets=4, E=40, images=1):
     """bc_conv_igemm on the four characteristic 3x3 layers of SwiftNet-RN18 at 1024x2048 (grid 8x16,
     E = 40 executed blocks): achieved TFLOP/s = 2*9*Cin*Cout*BS^2*E / time, graph-timed, rotating
     `sets` plane copies (the layer-#20 planes are 33.5 MB each)."""
     from blockcopy import _C
 
     out = {}
-    cells = torch.randperm(128, generator=torch.Generator().manual_seed(0))[:E].sort().values.to(torch.int32).to(device)
+    cells = torch.randperm(128 * images, generator=torch.Generator().manual_seed(0))[:E].sort().values.to(torch.int32).to(device)
     g = torch.Generator(device=device).manual_seed(1)
     for name, Cin, Cout, BS in (("conv3x3_c128_bs32(#20)", 128, 128, 32), ("conv3x3_c64_bs32(layer1)", 64, 64, 32),
                                 ("conv3x3_c128_bs16(layer2)", 128, 128, 16), ("conv3x3_c256_bs8(layer3)", 256, 256, 8),
                                 ("conv3x3_c512_bs4(layer4)", 512, 512, 4)):
         H, W = 8 * BS, 16 * BS
-        planes = [torch.randn(1, Cin, H, W, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=torch.channels_last)
+        planes = [torch.randn(images, Cin, H, W, device=device, dtype=torch.float16, generator=g).contiguous(memory_format=torch.channels_last)
                   for _ in range(sets)]
         w = (torch.randn(Cout, Cin, 3, 3, device=device, dtype=torch.float16, generator=g) * 0.05).contiguous(memory_format=torch.channels_last)
         bias = torch.zeros(Cout, device=device, dtype=torch.float16)
