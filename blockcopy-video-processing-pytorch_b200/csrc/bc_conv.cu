@@ -639,7 +639,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     p.splits = 1;
     p.ksteps_per_split = total_k_steps;
     p.work = nullptr;
-    return launch_conv_persistent(a3_map, b_map, p, n_tile, stream);
+    p.tma_epi = 0;
+    return launch_conv_persistent(a3_map, b_map, a3_map, a3_map, p, n_tile, stream);
   }
   if (persistent) {
     p.tiles_m = tiles;
@@ -647,7 +648,37 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
     p.splits = 1;
     p.ksteps_per_split = total_k_steps;
     p.work = nullptr;
-    return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
+    // Epilogue through TMA stores (BC_CONV_TMA_EPI=0: per-thread stores): a single tile's staging -> global phase took
+    // ~2800 clk of per-thread 16-byte stores (23 B/clk per SM; tools/cta_timeline.py) against ~1700 clk for TMEM -> staging
+    static const int env_tma_epi = getenv("BC_CONV_TMA_EPI") ? atoi(getenv("BC_CONV_TMA_EPI")) : 1;
+    CUtensorMap o_map = a_map, pl_map = a_map;
+    p.tma_epi = env_tma_epi && (out || plane_out) && !(p.debug & 2);
+    if (p.tma_epi) {
+      const int px = BS_out * BS_out;
+      p.st_px = px < 32 ? px : 32;
+      p.st_bw = BS_out < 32 ? BS_out : 32;
+      p.st_bh = p.st_px / p.st_bw;
+      if (out) {  // the packed tile batch as (rows = E * BS_out^2, Cout): a warp's 32 accumulator rows are consecutive rows
+        cuuint64_t gdim[2] = {(cuuint64_t)Cout, (cuuint64_t)E * px};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cout * 2};
+        cuuint32_t box[2] = {64u, 32u};
+        cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&o_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (tile output) failed: CUresult %d", (int)r);
+      }
+      if (plane_out) {
+        cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)p.out_W, (cuuint64_t)p.out_H, (cuuint64_t)out_N};
+        cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)p.out_W * Cout * 2, (cuuint64_t)p.out_H * p.out_W * Cout * 2};
+        cuuint32_t box[4] = {64u, (cuuint32_t)p.st_bw, (cuuint32_t)p.st_bh, 1u};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&pl_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, plane_out, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BC_REQUIRE(r == CUDA_SUCCESS, BC_ERR_UNSUPPORTED, "bc_conv_igemm: tensor map (plane output) failed: CUresult %d", (int)r);
+      }
+    }
+    return launch_conv_persistent(a_map, b_map, o_map, pl_map, p, n_tile, stream);
   }
   if (use_split && env_persist != 0 && p.work != nullptr) {
     // split-K on the persistent kernel: one (tile, k-range) unit per CTA, the S CTAs of a cluster (S,1,1)
@@ -664,7 +695,8 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
       p.splits = S;
       p.d_splits = FastDiv((uint32_t)S);
       p.ksteps_per_split = (total_k_steps + S - 1) / S;
-      return launch_conv_persistent(a_map, b_map, p, n_tile, stream);
+      p.tma_epi = 0;
+      return launch_conv_persistent(a_map, b_map, a_map, a_map, p, n_tile, stream);
     }
   }
   // Variant selection (B200 sweep, profiles/r01b_conv_experiments.md): what counts is how many CTAs an SM can

@@ -50,6 +50,9 @@ struct ConvParams {
   float *work;
   long long work_bytes;
   unsigned long long *trace;  // bc_debug_trace buffer (16 words per CTA) or nullptr
+  // persistent kernel, S = 1: the epilogue leaves through TMA stores (128-byte-swizzled staging rows -> o_map / pl_map)
+  // instead of per-thread global stores.  One store box of the plane = st_px consecutive tile rows = st_bw x st_bh pixels.
+  int tma_epi, st_px, st_bw, st_bh;
   int debug;  // BC_CONV_DEBUG (timing experiments only): bit 0 one k-step, bit 1 no epilogue stores, bit 2 weight producer waits for the previous kernel too
 };
 
@@ -72,8 +75,8 @@ __device__ __forceinline__ void trace_wall(const ConvParams &p, int k) {  // slo
   }
 }
 unsigned long long *debug_trace_buffer();  // bc_api.cu
-int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int n_tile,
-                           cudaStream_t s);  // bc_conv_persist.cu
+int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const CUtensorMap &o_map,
+                           const CUtensorMap &pl_map, const ConvParams &p, int n_tile, cudaStream_t s);  // bc_conv_persist.cu
 
 template <int N_TILE> constexpr int kPartStride = N_TILE + 4;  // floats per parked accumulator row (+4: bank spread)
 

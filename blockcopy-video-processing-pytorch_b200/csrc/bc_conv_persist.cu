@@ -137,6 +137,7 @@ constexpr int kPersistA3Max = 3;
 template <int N_TILE, int STAGES, bool A3 = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                             const __grid_constant__ CUtensorMap o_map, const __grid_constant__ CUtensorMap pl_map,
                              const ConvParams p) {
   constexpr uint32_t kBBytes = N_TILE * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -165,11 +166,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
   // the S CTAs of a cluster own the S k-ranges of one tile; grid = units, one unit per CTA.
   const int S = p.splits;
   const int total_units = total_tiles * S;
+  const bool tma_epi = !A3 && S == 1 && p.tma_epi != 0;
   if (threadIdx.x == 0) { trace_wall(p, 8); trace_mark(p, 0); }
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
+    if (p.tma_epi) {
+      if (p.out) prefetch_map(&o_map);
+      if (p.plane_out) prefetch_map(&pl_map);
+    }
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(&full_bar[s], A3 ? 1 : 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
       mbar_init(&empty_bar[s], 1);
@@ -443,7 +449,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       // this tile's slice of the bias + this warp's 32 plane-row offsets, while the MMAs of the tile run
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
       for (int c = t128; c < N_TILE; c += 128) bias_s[c] = p.bias ? __half2float(__ldg(p.bias + t.n0 + c)) : 0.f;
-      {
+      int bx = 0, by = 0, bn = -1;  // TMA epilogue: plane coordinates of store box `lane` of this warp (bn < 0: none)
+      if (tma_epi) {
+        if (p.plane_out && lane * p.st_px < 32) {
+          int blk, y, x;
+          pixel_of_row(p, q * 32 + lane * p.st_px, t.r0, blk, y, x);
+          if (blk < t.nvalid) {
+            uint32_t n, gh, gw;
+            p.out_cell((uint32_t)__ldg(p.out_mapping + t.b0 + blk), n, gh, gw);
+            bx = (int)gw * p.BS_out + x; by = (int)gh * p.BS_out + y; bn = (int)n;
+          }
+        }
+      } else {
         const int m = q * 32 + lane;
         int blk, y, x;
         pixel_of_row(p, m, t.r0, blk, y, x);
@@ -455,6 +472,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
 
       mbar_wait(&acc_full[buf], buf_parity);
       tc_fence_after_sync();
+      if (S == 1 && threadIdx.x == 64) trace_mark(p, 4);  // accumulator complete (S > 1 marks slot 4 below)
       if (S > 1) {
         // ---- split-K, phase 1: this CTA's fp32 partial -> L2 scratch, whole rows per access (half of the
         //      tile's columns at a time through the staging rows)
@@ -484,8 +502,82 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
         }
         continue;  // one unit per CTA in split mode; phase 2 follows the cluster barrier below
       }
-      // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's staging rows
       const uint32_t acc = tmem_base + buf * N_TILE + ((uint32_t)(q * 32) << 16);
+      if (tma_epi) {
+        // ---- TMA epilogue: TMEM -> + bias -> fp16 (+ residual, ReLU) in registers, one accumulator row per thread, into
+        //      128-byte-swizzled staging rows (per 64-channel half: 32 rows x 128 B); then one bulk tensor store per half
+        //      to the tile batch and one per (half, store box) to the next op's plane: no per-thread global stores
+        constexpr int kHalves = N_TILE / 64;
+        uint8_t *st = staging + (size_t)q * kHalves * 4096;
+        const int m = q * 32 + lane;
+        const bool row_ok = m < m_valid;
+        const __half *res_row = (p.residual && row_ok) ? p.residual + out_base + (size_t)m * p.Cout : nullptr;
+        tma_wait_read<0>();  // this lane's stores of the previous tile have read the staging rows
+        __syncwarp();
+        const int row0 = t.b0 * p.BS_out * p.BS_out + t.r0 * p.BS_out + q * 32;
+        // 32 accumulator columns: (+ bias) -> fp16 (+ residual, ReLU) -> swizzled staging row of this thread
+        auto finish32 = [&](const uint32_t (&v32)[32], const uint4 (&rr)[4], int c0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              oh[u] = __floats2half2_rn(__uint_as_float(v32[8 * j + 2 * u]) + bias_s[c0 + 8 * j + 2 * u],
+                                        __uint_as_float(v32[8 * j + 2 * u + 1]) + bias_s[c0 + 8 * j + 2 * u + 1]);
+            if (p.residual) {  // fp16-rounded conv output + identity, rounded once more (HADD2 == float add + round)
+              const __half2 *rh = reinterpret_cast<const __half2 *>(&rr[j]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
+            }
+            if (p.relu) {
+              const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) oh[u] = __hmax2(oh[u], zero);
+            }
+            const int c = c0 + 8 * j;
+            *reinterpret_cast<uint4 *>(st + (c >> 6) * 4096 + lane * 128 + ((((c & 63) >> 3) ^ (lane & 7)) << 4)) = o;
+          }
+        };
+        auto load_res = [&](uint4 (&rr)[4], int c0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = res_row ? __ldg(reinterpret_cast<const uint4 *>(res_row + c0 + 8 * j)) : make_uint4(0, 0, 0, 0);
+        };
+        // software pipeline over 32-column groups: the TMEM load of group g + 1 is in flight while group g is converted;
+        // every finished 64-channel half leaves at once (its stores overlap the conversion of the next half)
+        uint32_t va[32], vb[32];
+        uint4 ra[4], rb[4];
+        load_res(ra, 0);
+        tmem_ld_32x32(acc, va);
+        bool issued = false;
+#pragma unroll
+        for (int h = 0; h < kHalves; ++h) {
+          const int c0 = 64 * h;
+          tmem_ld_wait();
+          load_res(rb, c0 + 32);
+          tmem_ld_32x32(acc + (uint32_t)(c0 + 32), vb);
+          finish32(va, ra, c0);
+          tmem_ld_wait();
+          if (h + 1 < kHalves) {
+            load_res(ra, c0 + 64);
+            tmem_ld_32x32(acc + (uint32_t)(c0 + 64), va);
+          } else {
+            tc_fence_before_sync();  // the accumulator buffer is in registers: hand it back to the MMA warp
+            mbar_arrive(&acc_empty[buf]);
+          }
+          finish32(vb, rb, c0 + 32);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (p.out && lane == 0) { tma_store_2d(&o_map, st + h * 4096, t.n0 + c0, row0); issued = true; }
+          if (bn >= 0) { tma_store_4d(&pl_map, st + h * 4096 + lane * p.st_px * 128, t.n0 + c0, bx, by, bn); issued = true; }
+        }
+        if (issued) tma_commit();
+        if (threadIdx.x == 64) trace_mark(p, 7);
+        if (buf == 1) buf_parity ^= 1;
+        buf ^= 1;
+        continue;
+      }
+      // ---- phase A: TMEM -> + bias -> fp16, one accumulator row per thread, into this warp's staging rows
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t v32[32];
@@ -506,6 +598,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[buf]);
       __syncwarp();
+      if (threadIdx.x == 64) trace_mark(p, 7);  // phase A done (TMEM -> staging rows)
       // ---- phase B: kTPR lanes cover one pixel's N_TILE channels (16 B each): (+ residual) -> ReLU ->
       //      whole 32-byte sectors to the tile batch and to the next op's plane
       constexpr int kBatch = 4;
@@ -549,6 +642,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
       if (buf == 1) buf_parity ^= 1;
       buf ^= 1;
     }
+    if (tma_epi) tma_wait_read<0>();  // the staging rows must outlive the stores that read them
     if (threadIdx.x == 64) trace_mark(p, 5);
     tc_fence_before_sync();
   }
@@ -583,7 +677,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap a_map, const __
 }
 
 template <int N_TILE, int STAGES>
-static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, cudaStream_t s) {
+static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const CUtensorMap &o_map,
+                             const CUtensorMap &pl_map, const ConvParams &p, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (kABytes + N_TILE * 128) + 4 * 32 * (N_TILE * 2 + 16) + 1024;
   static_assert(smem <= 227 * 1024 - 4096, "operand ring + staging must fit one SM");
   static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_persistent_kernel<N_TILE, STAGES>,
@@ -593,7 +688,7 @@ static int launch_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map,
   const int total = p.tiles_m * p.ntiles_n;
   const unsigned grid = p.splits > 1 ? (unsigned)(total * p.splits) : (unsigned)(total < kNumSMs ? total : kNumSMs);
   const cudaError_t e = launch_kernel_cluster(conv_igemm_persistent_kernel<N_TILE, STAGES>, dim3(grid), dim3(kPersistThreads),
-                                              smem, s, dim3((unsigned)p.splits, 1, 1), a_map, b_map, p);
+                                              smem, s, dim3((unsigned)p.splits, 1, 1), a_map, b_map, o_map, pl_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -615,7 +710,7 @@ static int launch_persistent_a3(const CUtensorMap &a3_map, const CUtensorMap &b_
   const int total = p.tiles_m * p.ntiles_n;
   const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
   const cudaError_t e = launch_kernel_cluster(conv_igemm_persistent_kernel<N_TILE, 2, true>, dim3(grid), dim3(kPersistThreads),
-                                              smem, s, dim3(1, 1, 1), a3_map, b_map, p);
+                                              smem, s, dim3(1, 1, 1), a3_map, b_map, a3_map, a3_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -623,10 +718,11 @@ static int launch_persistent_a3(const CUtensorMap &a3_map, const CUtensorMap &b_
   return check_launch("bc_conv_igemm");
 }
 
-int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const ConvParams &p, int n_tile,
-                           cudaStream_t s) {
+int launch_conv_persistent(const CUtensorMap &a_map, const CUtensorMap &b_map, const CUtensorMap &o_map,
+                           const CUtensorMap &pl_map, const ConvParams &p, int n_tile, cudaStream_t s) {
   if (p.a3_bytes) return n_tile == 128 ? launch_persistent_a3<128>(a_map, b_map, p, s) : launch_persistent_a3<64>(a_map, b_map, p, s);
-  return n_tile == 128 ? launch_persistent<128, 5>(a_map, b_map, p, s) : launch_persistent<64, 8>(a_map, b_map, p, s);
+  return n_tile == 128 ? launch_persistent<128, 5>(a_map, b_map, o_map, pl_map, p, s)
+                       : launch_persistent<64, 8>(a_map, b_map, o_map, pl_map, p, s);
 }
 
 }  // namespace bc

@@ -35,6 +35,12 @@ def report(name, trace, flops=None):
         m = [(t[:, k].double() - c[:, 1]).mean() for k in (11, 13, 14, 12)]
         print(f"   producer 0 after the PDL wait: tile decoded +{m[0]:.0f} clk, block coordinates (mapping loads) +{m[1]:.0f}, "
               f"tap decoded +{m[2]:.0f}, first activation load issued +{m[3]:.0f}, first operands landed +{d[1].mean():.0f}")
+    if (t[:, 7] != 0).any() and (t[:, 4] != 0).any() and not (t[:, 13] != 0).any():
+        d0 = t[:, 4].double() - c[:, 3]
+        a = (t[:, 7] - t[:, 4]).double()
+        b = c[:, 5] - t[:, 7].double()
+        print(f"   epilogue of the last tile: last MMA issue -> accumulator complete {d0.mean():.0f} clk, TMEM -> staging rows "
+              f"{a.mean():.0f} clk, staging -> global {b.mean():.0f} clk")
     if (t[:, 13] != 0).any():
         w = (t[:, 14] - t[:, 13]).double()
         r = c[:, 6] - t[:, 14].double()
