@@ -58,6 +58,7 @@ _SIGNATURES = {
     "bc_conv_wgrad": ([_vp] * 4 + [_i] * 9 + [_vp] * 5 + [ctypes.c_longlong, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
+    "bc_bn_norm": ([_vp] * 6 + [ctypes.c_longlong, _i, ctypes.c_float, _i, _vp, ctypes.c_longlong, _vp], _i),
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
     "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
     "bc_frame_from_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
@@ -777,6 +778,21 @@ def gn_supported(x: torch.Tensor, groups: int) -> bool:
     C = x.shape[1]
     return (x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and C % 8 == 0 and C <= 2048 and 1 <= groups <= 256
             and C % groups == 0 and (C // groups) % 8 == 0)
+
+
+def bn_norm(out: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, weight: Optional[torch.Tensor],
+            shift: Optional[torch.Tensor], eps: float, relu: bool, workspace: torch.Tensor):
+    """out = relu?(weight * (x - mean) * invstd + shift) with the batch statistics of x (train-mode BatchNorm2d), one launch
+    (bc_bn_norm = bn_stats + the normalisation behind a grid-wide barrier); mean / invstd (fp32 [C]) are written too."""
+    _dev(out, x, mean, invstd, weight, shift, workspace)
+    assert x.dtype == torch.float16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    assert out.dtype == torch.float16 and out.shape == x.shape and out.is_contiguous(memory_format=torch.channels_last)
+    N, C, H, W = x.shape
+    _check(lib().bc_bn_norm(out.data_ptr(), mean.data_ptr(), invstd.data_ptr(), x.data_ptr(),
+                            weight.data_ptr() if weight is not None else None, shift.data_ptr() if shift is not None else None,
+                            N * H * W, C, float(eps), int(bool(relu)), workspace.data_ptr(), workspace.numel(), _stream()),
+           "bc_bn_norm")
+    return out
 
 
 def bn_update_running(table: torch.Tensor):

@@ -79,6 +79,8 @@ int conv_wgrad(float *grad_w, const long long *grad_strides, const void *dz, con
                const float *bn_sums, void *workspace, long long workspace_bytes, cudaStream_t stream);
 int blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping, int E, int N,
                    int H, int W, int BS, int dtype, cudaStream_t stream);
+int bn_norm(void *out, float *mean, float *invstd, const void *x, const float *weight, const float *shift, long long P, int C,
+            float eps, int relu, void *workspace, long long workspace_bytes, cudaStream_t stream);
 int raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift, cudaStream_t stream);
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -410,6 +412,11 @@ BC_API int bc_conv_wgrad(float *grad_w, const long long *grad_strides, const voi
 BC_API int bc_blocks_from_u8(void *tiles, const uint8_t *src, const float *mean, const float *std, const int32_t *mapping_exec,
                              int E, int N, int H, int W, int BS, bc_dtype_t dtype, bc_stream_t stream) {
   return blocks_from_u8(tiles, src, mean, std, mapping_exec, E, N, H, W, BS, (int)dtype, (cudaStream_t)stream);
+}
+
+BC_API int bc_bn_norm(void *out, float *mean, float *invstd, const void *x, const float *weight, const float *shift, long long P,
+                      int C, float eps, int relu, void *workspace, long long workspace_bytes, bc_stream_t stream) {
+  return bn_norm(out, mean, invstd, x, weight, shift, P, C, eps, relu, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

@@ -231,6 +231,11 @@ struct StatsParams {
   int C;
   float eps;
   uint32_t zero;         // always 0 (see the note on load batching below)
+  // APPLY form (bc_bn_norm): statistics, a grid-wide barrier, then out = relu?(weight * (x - mean) * invstd + shift)
+  const float *weight, *shift;  // [C] or nullptr
+  __half *out;
+  int relu;
+  unsigned int *done;    // second counter of the barrier (CTAs that have left it); zero between launches
 };
 
 constexpr int kStatsThreads = 512;
@@ -239,9 +244,15 @@ constexpr int kStatsThreads = 512;
 // ~2 loads in flight per thread) to save registers, which bounded the first versions of this kernel at ~1 TB/s.
 // A data dependency keeps a batch together: every value is XOR-ed with (fold of ALL values of the batch) & zero,
 // `zero` being a kernel parameter the compiler cannot fold -- no use can be scheduled before the last load.
+// APPLY = true (bc_bn_norm): the normalisation follows in the SAME launch.  All CTAs (<= one per SM: co-resident) meet
+// at a grid-wide barrier once their partials are written, every CTA then adds the partials itself (same order, same bits
+// as the last-CTA reduction of the plain form) and normalises the pixels it has just read: the policy trunk's
+// conv -> batch norm -> ReLU units are two dependent launches instead of three (~7 us each, mostly launch + latency).
+template <bool APPLY>
 __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsParams p) {
   __shared__ float red[kStatsThreads][17];
   __shared__ double comb[kStatsThreads];
+  __shared__ float s_mean[128], s_istd[128];
   __shared__ bool last;
   pdl_trigger();
   pdl_wait();
@@ -299,12 +310,23 @@ __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsPara
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!last) return;
+  if (APPLY) {
+    if (threadIdx.x == 0) {
+      atomicAdd(p.ticket, 1u);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ticket) : "memory");
+      } while (seen < gridDim.x);
+    }
+    __syncthreads();
+  } else {
+    if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+  }
   __threadfence();
   {
-    // the last CTA: item -> `slices` threads, each adds every slices-th CTA partial (8 loads in flight) in order
+    // the last CTA (APPLY: every CTA): item -> `slices` threads, each adds every slices-th CTA partial in order
     const int slices = kStatsThreads / items, item = threadIdx.x % items, slice = threadIdx.x / items;
     double t = 0.0;
     // all of this thread's partials in flight at once (<= 148 CTAs / slices, padded to batches of 40)
@@ -332,11 +354,68 @@ __global__ void __launch_bounds__(kStatsThreads) bn_stats_kernel(const StatsPara
       const double m = sum / (double)p.P;
       double var = sq / (double)p.P - m * m;
       var = var < 0.0 ? 0.0 : var;
-      p.mean[threadIdx.x] = (float)m;
-      p.invstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
+      const float mf = (float)m, isf = (float)(1.0 / sqrt(var + (double)p.eps));
+      if (!APPLY || blockIdx.x == 0) {
+        p.mean[threadIdx.x] = mf;
+        p.invstd[threadIdx.x] = isf;
+      }
+      if (APPLY) { s_mean[threadIdx.x] = mf; s_istd[threadIdx.x] = isf; }
     }
   }
-  if (threadIdx.x == 0) *p.ticket = 0u;
+  if (!APPLY) {
+    if (threadIdx.x == 0) *p.ticket = 0u;
+    return;
+  }
+  __syncthreads();
+  // ---- normalise the pixels this CTA read for the statistics (ATen's eval-BN expression, as bc_ew_fused)
+  {
+    float mean[8], istd[8], w[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mean[k] = s_mean[sub * 8 + k];
+      istd[k] = s_istd[sub * 8 + k];
+      w[k] = p.weight ? __ldg(p.weight + sub * 8 + k) : 1.f;
+      sh[k] = p.shift ? __ldg(p.shift + sub * 8 + k) : 0.f;
+    }
+    __half *obase = p.out + sub * 8;
+    for (px = blockIdx.x * rows + row; px < p.P; px += 8 * step) {
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t pj = px + j * step;
+        u[j] = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(pj < p.P ? pj : p.P - 1) * p.C));
+      }
+      uint32_t fold = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fold ^= u[j].x;
+      fold &= p.zero;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (px + j * step >= p.P) continue;
+        u[j].x ^= fold;
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u[j]);
+        uint4 o;
+        __half2 *oh = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h[k]);
+          float a = __half2float(__float2half_rn(w[2 * k] * (f.x - mean[2 * k]) * istd[2 * k] + sh[2 * k]));
+          float b = __half2float(__float2half_rn(w[2 * k + 1] * (f.y - mean[2 * k + 1]) * istd[2 * k + 1] + sh[2 * k + 1]));
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          oh[k] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4 *>(obase + (size_t)(px + j * step) * p.C) = o;
+      }
+    }
+  }
+  // leave the barrier: the last CTA out resets both counters for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(p.done, 1u) == gridDim.x - 1) {
+      *p.ticket = 0u;
+      *p.done = 0u;
+    }
+  }
 }
 
 int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, float eps, void *workspace,
@@ -357,8 +436,32 @@ int bn_stats(float *mean, float *invstd, const void *x, long long P, int C, floa
   p.ticket = (unsigned int *)workspace;
   p.partial = (float *)((char *)workspace + 16);
   p.P = (uint32_t)P; p.C = C; p.eps = eps; p.zero = 0u;
-  launch_kernel(bn_stats_kernel, dim3((unsigned)grid), dim3(kStatsThreads), 0, stream, 1, p);
+  p.weight = p.shift = nullptr; p.out = nullptr; p.relu = 0; p.done = nullptr;
+  launch_kernel(bn_stats_kernel<false>, dim3((unsigned)grid), dim3(kStatsThreads), 0, stream, 1, p);
   return check_launch("bc_bn_stats");
+}
+
+int bn_norm(void *out, float *mean, float *invstd, const void *x, const float *weight, const float *shift, long long P, int C,
+            float eps, int relu, void *workspace, long long workspace_bytes, cudaStream_t stream) {
+  BC_REQUIRE(out && mean && invstd && x && workspace, BC_ERR_NULL, "bc_bn_norm: NULL pointer");
+  BC_REQUIRE(P > 0 && P < (1ll << 31), BC_ERR_SHAPE, "bc_bn_norm: %lld pixels", P);
+  BC_REQUIRE(C >= 8 && C <= 128 && C % 8 == 0 && kStatsThreads % (2 * C) == 0, BC_ERR_UNSUPPORTED,
+             "bc_bn_norm: C=%d (8, 16, 32, 64 or 128 channels)", C);
+  BC_REQUIRE((((uintptr_t)x | (uintptr_t)out | (uintptr_t)workspace) & 15) == 0, BC_ERR_ALIGN, "bc_bn_norm: 16-byte alignment");
+  const int rows = kStatsThreads / (C / 8);
+  long long grid = (P + 16 * rows - 1) / (16 * rows);
+  if (grid > kNumSMs) grid = kNumSMs;  // one CTA per SM at most: the grid-wide barrier needs every CTA resident
+  const long long need = 16 + grid * 2 * C * (long long)sizeof(float);
+  BC_REQUIRE(workspace_bytes >= need, BC_ERR_RANGE, "bc_bn_norm: workspace of %lld bytes, %lld needed", workspace_bytes, need);
+  StatsParams p;
+  p.x = (const __half *)x; p.mean = mean; p.invstd = invstd;
+  p.ticket = (unsigned int *)workspace;
+  p.done = (unsigned int *)workspace + 1;
+  p.partial = (float *)((char *)workspace + 16);
+  p.P = (uint32_t)P; p.C = C; p.eps = eps; p.zero = 0u;
+  p.weight = weight; p.shift = shift; p.out = (__half *)out; p.relu = relu;
+  launch_kernel(bn_stats_kernel<true>, dim3((unsigned)grid), dim3(kStatsThreads), 0, stream, 1, p);
+  return check_launch("bc_bn_norm");
 }
 
 // ---------------------------------------------------------------------------------------------------

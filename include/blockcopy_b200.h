@@ -293,6 +293,16 @@ BC_API int bc_gn_stats(float *mean, float *invstd, const void *x, long long P, i
  */
 BC_API int bc_depth_to_space(void *out, const void *in, int E, int C, int h, int w, int r, bc_stream_t stream);
 
+/* ---- train-mode batch norm in ONE launch: bc_bn_stats + the normalisation (policy/net.py:115-125, policy/resnet.py) ----
+ * out (P, C) fp16 = relu?(weight * (x - mean) * invstd + shift) with the batch statistics of x itself; mean / invstd are
+ * also written out (running-statistics update, backward pass).  The kernel's CTAs (at most one per SM) meet at a grid-wide
+ * barrier between the two phases.  Arguments as bc_bn_stats; workspace: same size, first 8 bytes zero before the first call
+ * (left at zero), private to the stream.  Same bits as bc_bn_stats followed by bc_ew_fused; measured SLOWER than those two
+ * launches on the policy trunk (330 vs 308 us per forward), so the Python host uses it only with BLOCKCOPY_BN_NORM=1.
+ */
+BC_API int bc_bn_norm(void *out, float *mean, float *invstd, const void *x, const float *weight, const float *shift, long long P,
+                      int C, float eps, int relu, void *workspace, long long workspace_bytes, bc_stream_t stream);
+
 /* ---- running statistics of train-mode batch norms (policy/net.py:115-125 runs the policy net in train mode) ----
  * For every row l < n of the DEVICE table (8 x int64 per row: batch mean fp32*, batch invstd fp32* -- the outputs of
  * bc_bn_stats --, running_mean fp32* | 0, running_var fp32* | 0, num_batches_tracked int64* | 0, C, count = N*H*W,

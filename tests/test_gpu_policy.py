@@ -452,3 +452,28 @@ def test_deferred_nan_check_raises_within_one_frame():
                 model(clip[2])
                 assert not strict, "strict checks must raise on the frame itself"
                 model(clip[3])
+
+
+@pytest.mark.parametrize("N,C,H,W,relu,affine", [(1, 64, 256, 512, True, True), (2, 128, 16, 32, False, True), (1, 64, 5, 7, True, False),
+                                                   (1, 8, 64, 128, True, True)])
+def test_bn_norm_equals_bn_stats_plus_ew_fused(N, C, H, W, relu, affine):
+    """bc_bn_norm (statistics, grid-wide barrier, normalisation: one launch) == bc_bn_stats followed by bc_ew_fused, bit for
+    bit, and leaves its barrier counters at zero (repeated launches on one workspace)."""
+    from blockcopy import _C
+
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = (1.5 * torch.randn(N, C, H, W, device="cuda", generator=g) + 0.7).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.rand(C, device="cuda", generator=g) + 0.5) if affine else None
+    sh = (torch.randn(C, device="cuda", generator=g) * 0.3) if affine else None
+    ws = torch.zeros(_C.BN_STATS_WORKSPACE, dtype=torch.uint8, device="cuda")
+    mean, invstd = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    _C.bn_stats(x, mean, invstd, 1e-5, ws)
+    want = torch.empty_like(x)
+    _C.ew_fused(want, x, None, (mean, invstd, w, sh), relu=relu)
+    for _ in range(3):
+        m2, i2 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        got = torch.full_like(x, float("nan"))
+        _C.bn_norm(got, x, m2, i2, w, sh, 1e-5, relu, ws)
+        assert torch.equal(m2, mean) and torch.equal(i2, invstd)
+        assert torch.equal(got, want)
+        assert int(ws[:8].view(torch.int32).abs().sum()) == 0
