@@ -731,7 +731,7 @@ def roofline_records(kern, peaks):
                                "(512ch, 4-px, split-K), E=40",
                      "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
                      "traffic": 3.42e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the layer2 "
-                     "shape (algorithmic: 6.2 MB; inputs come from L2), ncu --set full: profiles/r02_conv_persist_ncu.md",
+                     "shape (algorithmic: 6.2 MB; inputs come from L2), ncu --set full: profiles/r02b_conv_persist_ncu.md",
                      "per_shape": {k: kern[k] for k in dom_keys},
                      "same_shapes_8_streams_batched": (lambda b: {
                          "frac": sum(b[k]["flops"] for k in dom_keys) / sum(b[k]["us"] for k in dom_keys) * 1e-6 / peaks["tf_burst"],
