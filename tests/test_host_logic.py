@@ -494,3 +494,19 @@ def test_non_inplace_combine_reuses_the_previous_plane_only_when_nobody_can_see_
         del out2, view1
         out3, st = step(frames[3], part, st)
         assert out3.data_ptr() == ptr2 and torch.equal(out3, want3)
+
+
+def test_policy_checks_on_cpu_are_immediate_and_deferred_queue_is_bounded(capsys):
+    """PolicyTrainRL._check: on CPU tensors (no sync to save) the reference's in-place behaviour -- AssertionError, or a
+    printed warning -- and flush_checks() on an empty queue is a no-op."""
+    import blockcopy
+
+    policy = blockcopy.build_policy_from_settings(_settings(block_policy="rl_semseg", block_size=64))
+    policy._check(torch.tensor(False), "never shown")
+    with pytest.raises(AssertionError, match="boom"):
+        policy._check(torch.tensor(True), "boom")
+    policy._check(torch.tensor(True), "only a warning", warn=True)
+    assert "only a warning" in capsys.readouterr().out
+    assert policy._deferred == []
+    policy.flush_checks()
+    assert policy._read_count_and_checks(torch.tensor([7, 5], dtype=torch.int32)) == 7
