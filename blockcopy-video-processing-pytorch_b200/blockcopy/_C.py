@@ -58,6 +58,11 @@ _SIGNATURES = {
     "bc_conv_wgrad": ([_vp] * 4 + [_i] * 9 + [_vp] * 5 + [ctypes.c_longlong, _vp], _i),
     "bc_bn_stats": ([_vp, _vp, _vp, ctypes.c_longlong, _i, ctypes.c_float, _vp, ctypes.c_longlong, _vp], _i),
     "bc_pack_params": ([_vp, _i, ctypes.c_longlong, _vp], _i),
+    "bc_graph_record": ([_i], _i),
+    "bc_graph_last_node": ([_vp, _vp], _i),
+    "bc_graph_patch_next": ([_vp, _vp, _vp], _i),
+    "bc_graph_memcpy": ([_vp, _vp, ctypes.c_longlong, _vp, _vp], _i),
+    "bc_graph_patch_memcpy": ([_vp, _vp, _vp, _vp, ctypes.c_longlong], _i),
     "bc_bn_norm": ([_vp] * 6 + [ctypes.c_longlong, _i, ctypes.c_float, _i, _vp, ctypes.c_longlong, _vp], _i),
     "bc_rmsprop_step": ([_vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_vp], _i),
     "bc_conv_fewout": ([_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp], _i),
@@ -393,6 +398,46 @@ def maxpool_halo(out: torch.Tensor, plane: torch.Tensor, mapping_exec: torch.Ten
                                  plane.data_ptr(), mapping_exec.data_ptr(), E, N, C, H, W, BS_in, k, stride, padding,
                                  _stream()), "bc_maxpool_halo")
     return out
+
+
+# ------------------------------------------------------------------------------------------- CUDA-graph node patching
+def graph_record(on: bool):
+    """While on, every launch of this library on a CAPTURING stream remembers the graph node it created
+    (graph_last_node); see bc_graph_record."""
+    _rc(lib().bc_graph_record(int(bool(on))), "bc_graph_record")
+
+
+def graph_last_node():
+    """(node handle, kernel handle) of the last recorded launch."""
+    node, func = ctypes.c_void_p(), ctypes.c_void_p()
+    _rc(lib().bc_graph_last_node(ctypes.byref(node), ctypes.byref(func)), "bc_graph_last_node")
+    return node.value, func.value
+
+
+def graph_patch_next(graph_exec: int, node, func):
+    """The NEXT launch of this library on this thread re-points `node` of the instantiated graph instead of running."""
+    _rc(lib().bc_graph_patch_next(graph_exec, node, func), "bc_graph_patch_next")
+
+
+def graph_memcpy(dst: torch.Tensor, src: torch.Tensor):
+    """dst <- src (same dense layout) as a device-to-device copy on the current stream; returns the memcpy node's handle
+    when the stream is capturing, else None."""
+    _dev(dst, src)
+    assert dst.shape == src.shape and dst.dtype == src.dtype and dst.stride() == src.stride()
+    node = ctypes.c_void_p()
+    _rc(lib().bc_graph_memcpy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(), _stream(), ctypes.byref(node)),
+        "bc_graph_memcpy")
+    return node.value
+
+
+def graph_patch_memcpy(graph_exec: int, node, dst: torch.Tensor, src: torch.Tensor):
+    _rc(lib().bc_graph_patch_memcpy(graph_exec, node, dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size()),
+        "bc_graph_patch_memcpy")
+
+
+def _rc(rc: int, what: str):
+    if rc != 0:
+        raise BlockCopyNativeError(f"{what} failed with status {rc}: {lib().bc_last_error_string().decode()}")
 
 
 # ------------------------------------------------------------------------------------------- derived-parameter cache

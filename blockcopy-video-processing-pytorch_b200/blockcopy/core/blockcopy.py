@@ -119,7 +119,7 @@ class BlockCopyModel(nn.Module):
 
 
     # ------------------------------------------------------------------ CUDA-graph mode
-    def _block_frame_inplace(self, inputs, grid, graph=None):
+    def _block_frame_inplace(self, inputs, grid, graph=None, patch=False):
         """One block-sparse frame with every combine IN PLACE into persistent planes (what a graph
         can replay): returns (frame_state plane, output plane, prefix), both persistent tensors.
 
@@ -135,6 +135,8 @@ class BlockCopyModel(nn.Module):
             # address the graph bakes in belongs to this model, not to the (shared) capture stream
             gs.splitk_ws = torch.empty(_C.SPLITK_WS_BYTES, dtype=torch.uint8, device=inputs.device)
             gs.splitk_ws_side = torch.empty(_C.SPLITK_WS_BYTES // 2, dtype=torch.uint8, device=inputs.device)
+        if graph is not None and patch:
+            return self._capture_whole_frame(inputs, grid, graph)
         x = to_tensorwrapper(as_tensor(inputs))
         self.block_temporal_features = feats = x.process_temporal_features(self.block_temporal_features)
         feats.track_transfer_idx = False
@@ -159,6 +161,76 @@ class BlockCopyModel(nn.Module):
         with torch.cuda.graph(graph, pool=gs.pool, stream=gs.capture_stream):
             res = body()
         return res + (prefix,)
+
+    def _capture_whole_frame(self, inputs, grid, graph):
+        """Graph-patch mode: index compaction, the input gather and the copy into the output buffer are captured too;
+        before every replay their nodes are re-pointed at that frame's grid / frame / output buffer
+        (``_C.graph_patch_next``), so that a steady frame is ONE graph launch and nothing else on the stream."""
+        from .. import _C
+
+        gs = self._graphs
+        if gs.capture_stream is None or gs.capture_stream.device != inputs.device:
+            gs.capture_stream = torch.cuda.Stream(device=inputs.device, priority=-1)
+        image = inputs.as_subclass(torch.Tensor)
+        with torch.cuda.graph(graph, pool=gs.pool, stream=gs.capture_stream):
+            x = to_tensorwrapper(image)
+            self.block_temporal_features = feats = x.process_temporal_features(self.block_temporal_features)
+            feats.track_transfer_idx = False
+            _C.graph_record(True)
+            try:
+                feats._process_grid(grid, x._features_prev)          # bc_compact_mask
+                cm = _C.graph_last_node()
+                blocks = x._split(image.shape[2] // grid.shape[2])   # bc_gather
+                ga = _C.graph_last_node()
+            finally:
+                _C.graph_record(False)
+            assert cm[0] != ga[0], "graph patching: the input gather created no node of its own"
+            tiles = blocks.as_subclass(torch.Tensor)
+            with _C.splitk_workspace_scope(gs.splitk_ws), side_stream_scope(gs.splitk_ws_side):
+                frame_state = run_on_side_stream(lambda: blocks.combine_().to_tensor(), keep=(blocks,))
+                dense = self.base_model(blocks).combine_().to_tensor()
+            if gs.out_bufs is None or gs.out_bufs[0].shape != dense.shape:
+                gs.out_bufs = [torch.empty_like(dense), torch.empty_like(dense)]
+            cp = _C.graph_memcpy(gs.out_bufs[0], dense)
+        graph.instantiate()
+        prefix = (feats._grid_idx, feats._index_buf, tiles, tuple(inputs.shape), inputs.dtype, _C.layout_of(tiles))
+        info = dict(exec=graph.raw_cuda_graph_exec(), cm=cm, ga=ga, cp=cp)
+        return frame_state, dense, prefix, info
+
+    def _patch_and_replay(self, entry, inputs, grid, num_exec):
+        """Re-point the three per-frame nodes of a whole-frame graph, then launch it."""
+        from .. import _C
+
+        gs = self._graphs
+        graph, frame_state, dense, launches, prefix, info = entry
+        grid_idx, buf, tiles, shape, dtype, layout = prefix
+        assert tuple(inputs.shape) == shape and inputs.dtype == dtype, \
+            "input shape / dtype changed after CUDA graphs were captured"
+        g = grid if (grid.dtype == torch.bool and grid.is_contiguous() and grid.device == tiles.device) else \
+            grid.to(tiles.device, dtype=torch.bool).contiguous()
+        G = g.numel()
+        image = inputs.as_subclass(torch.Tensor)
+        fmt = torch.channels_last if layout == _C.BC_NHWC else torch.contiguous_format
+        if not image.is_contiguous(memory_format=fmt):
+            image = image.contiguous(memory_format=fmt)
+        try:
+            _C.graph_patch_next(info["exec"], *info["cm"])
+            _C.compact_mask(g.view(torch.uint8), grid_idx, buf[:G], buf[2 * G:])
+            _C.graph_patch_next(info["exec"], *info["ga"])
+            _C.gather(tiles, image, buf[:num_exec], num_exec)
+        except _C.BlockCopyNativeError:
+            # this frame's tensors would take another kernel variant than the captured one (other layout / alignment):
+            # the caller drops the graph and runs the frame eagerly
+            return None
+        finally:
+            _C.graph_record(False)  # disarm the hook should a call have failed before it reached its launch
+        gs.flip ^= 1
+        out = gs.out_bufs[gs.flip]
+        _C.graph_patch_memcpy(info["exec"], info["cp"], out, dense)
+        gs.keep = (g, image)  # what the re-pointed nodes read stays alive until the next frame's nodes are re-pointed
+        graph.replay()
+        _C.add_launches(launches)
+        return frame_state, out
 
     @staticmethod
     def _refill_prefix(prefix, inputs, grid, num_exec):
@@ -195,14 +267,30 @@ class BlockCopyModel(nn.Module):
         num_exec = hint
         if num_exec == 0:
             raise AssertionError("policy_meta['num_exec'] says blocks execute but the grid is empty")
-        entry = gs.graphs.get(num_exec)
+        # whole-frame graphs with re-pointed nodes (graph-patch mode) for plain tensors whose grid needs no conversion;
+        # a U8Frame keeps the eager prefix (its first gather is another kernel: graphs are keyed by the input kind)
+        patch = gs.patch and not isinstance(inputs, U8Frame) and grid.dtype == torch.bool and grid.is_contiguous() \
+            and grid.device == inputs.device
+        key = (num_exec, patch)
+        entry = gs.graphs.get(key)
         if entry is None:
-            seen = gs.seen.get(num_exec, 0)
-            gs.seen[num_exec] = seen + 1
-            if seen == 0:
+            seen = gs.seen.get(key, 0)
+            gs.seen[key] = seen + 1
+            if seen == 0 and not any(k[0] == num_exec for k in gs.graphs):
                 # first time this block count shows up: run eagerly (allocates planes on the first
                 # frame of the first clip, lets cuDNN pick its algorithms)
                 frame_state, dense, _ = self._block_frame_inplace(inputs, grid)
+            elif patch:
+                graph = torch.cuda.CUDAGraph(keep_graph=True)
+                n0 = _C.launch_count()
+                frame_state, dense, prefix, info = self._block_frame_inplace(inputs, grid, graph=graph, patch=True)
+                if gs.pool is None:
+                    gs.pool = graph.pool()
+                entry = gs.graphs[key] = (graph, frame_state, dense, _C.launch_count() - n0 - 2, prefix, info)
+                # capturing does not execute: replay now (the nodes already point at this frame's grid and pixels; the
+                # output node is re-pointed at the ping-pong buffer whose turn it is)
+                self.block_temporal_features._was_reset = False
+                return self._patch_and_replay(entry, inputs, grid, num_exec)
             else:
                 graph = torch.cuda.CUDAGraph()
                 n0 = _C.launch_count()
@@ -210,17 +298,27 @@ class BlockCopyModel(nn.Module):
                 if gs.pool is None:
                     gs.pool = graph.pool()
                 # kernels of ours inside the graph (the eager prefix = 2 launches counts itself)
-                entry = gs.graphs[num_exec] = (graph, frame_state, dense, _C.launch_count() - n0 - 2, prefix)
+                entry = gs.graphs[key] = (graph, frame_state, dense, _C.launch_count() - n0 - 2, prefix, None)
                 graph.replay()  # capturing does not execute; the prefix of THIS frame has just run eagerly
                 _C.add_launches(0)
         else:
-            graph, frame_state, dense, launches, prefix = entry
+            graph, frame_state, dense, launches, prefix, info = entry
             if self.block_temporal_features._was_reset:
                 # same contract as the eager path (tensorwrapper.py:164-165): the planes still hold the previous clip
                 assert num_exec == grid.numel(), "No previous features known, first run should execute all blocks!"
-            self._refill_prefix(prefix, inputs, grid, num_exec)
-            graph.replay()
-            _C.add_launches(launches)
+            if info is not None:
+                res = self._patch_and_replay(entry, inputs, grid, num_exec)
+                if res is not None:
+                    self.block_temporal_features._was_reset = False
+                    return res
+                gs.graphs.pop(key)  # captured for tensors of another layout: this frame eagerly, a new graph next time
+                gs.seen[key] = 1
+                frame_state, dense, _ = self._block_frame_inplace(inputs, grid)
+                entry = None
+            else:
+                self._refill_prefix(prefix, inputs, grid, num_exec)
+                graph.replay()
+                _C.add_launches(launches)
         if entry is not None:
             frame_state, dense = entry[1], entry[2]
             # a replayed frame creates no new BlockFeatures: the kept one now holds this frame's history
@@ -245,6 +343,9 @@ class _GraphState:
         self.splitk_ws = None  # this model's split-K scratch (see _block_frame_inplace)
         self.splitk_ws_side = None  # ... and the one of convs issued on the side stream
         self.capture_stream = None  # high-priority stream the graphs are captured on
+        # whole-frame graphs whose per-frame nodes are re-pointed before each replay (see _capture_whole_frame)
+        self.patch = __import__("os").environ.get("BLOCKCOPY_GRAPH_PATCH", "1") != "0"
+        self.keep = None
 
 
 def _try_fused_dense(module, x):

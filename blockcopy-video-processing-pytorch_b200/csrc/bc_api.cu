@@ -29,6 +29,13 @@ int fail(int code, const char *fmt, ...) {
 }
 
 int check_launch(const char *what) {
+  GraphHook &h = graph_hook();
+  if (h.patch_error != cudaSuccess) {  // the launch was a graph-node update (bc_graph_patch_next) and it failed
+    const cudaError_t pe = h.patch_error;
+    h.patch_error = cudaSuccess;
+    set_error("%s: graph node update failed: %s (%s)", what, cudaGetErrorName(pe), cudaGetErrorString(pe));
+    return (int)pe;
+  }
   const cudaError_t e = cudaPeekAtLastError();
   if (e == cudaSuccess) return BC_OK;
   cudaGetLastError();  // clear the sticky launch-configuration error
@@ -105,6 +112,28 @@ int head_1x1(void *tiles_out, void *dense_out, const void *dense_prev, const voi
              const void *bias, const float *bn_mean, const float *bn_invstd, const float *bn_weight,
              const float *bn_shift, int relu_in, const int32_t *grid_idx, const int32_t *mapping, int E, int N, int GH,
              int GW, int BS, int Cin, int Cout, int tiles_layout, int dense_layout, cudaStream_t stream);
+
+GraphHook &graph_hook() {
+  static thread_local GraphHook h;
+  return h;
+}
+
+cudaError_t graph_record_after_launch(GraphHook &h, const void *func, cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  cudaGraph_t g = nullptr;
+  const cudaGraphNode_t *deps = nullptr;
+  const cudaGraphEdgeData *edges = nullptr;
+  size_t n = 0;
+  const cudaError_t e = cudaStreamGetCaptureInfo_v3(stream, &st, &id, &g, &deps, &edges, &n);
+  if (e != cudaSuccess) return e;
+  if (st == cudaStreamCaptureStatusActive && n >= 1) {  // the stream's only dependency now is the node just created
+    h.node = deps[n - 1];
+    h.func = func;
+    ++h.recorded;
+  }
+  return cudaSuccess;
+}
 
 bool pdl_enabled() {
   // programmatic dependent launch: the next kernel's prologue (barrier init, TMEM alloc, descriptor prefetch)
@@ -417,6 +446,56 @@ BC_API int bc_blocks_from_u8(void *tiles, const uint8_t *src, const float *mean,
 BC_API int bc_bn_norm(void *out, float *mean, float *invstd, const void *x, const float *weight, const float *shift, long long P,
                       int C, float eps, int relu, void *workspace, long long workspace_bytes, bc_stream_t stream) {
   return bn_norm(out, mean, invstd, x, weight, shift, P, C, eps, relu, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+BC_API int bc_graph_record(int on) {
+  GraphHook &h = graph_hook();
+  h.mode = on ? 1 : 0;
+  h.node = nullptr;
+  h.func = nullptr;
+  h.recorded = 0;
+  h.patch_error = cudaSuccess;
+  return BC_OK;
+}
+
+BC_API int bc_graph_last_node(void **node, const void **func) {
+  GraphHook &h = graph_hook();
+  BC_REQUIRE(node && func, BC_ERR_NULL, "bc_graph_last_node: NULL pointer");
+  BC_REQUIRE(h.node != nullptr, BC_ERR_RANGE, "bc_graph_last_node: no launch was recorded (stream not capturing?)");
+  *node = (void *)h.node;
+  *func = h.func;
+  return BC_OK;
+}
+
+BC_API int bc_graph_patch_next(void *exec, void *node, const void *func) {
+  BC_REQUIRE(exec && node && func, BC_ERR_NULL, "bc_graph_patch_next: NULL handle");
+  GraphHook &h = graph_hook();
+  h.mode = 2;
+  h.exec = (cudaGraphExec_t)exec;
+  h.node = (cudaGraphNode_t)node;
+  h.func = func;
+  return BC_OK;
+}
+
+BC_API int bc_graph_memcpy(void *dst, const void *src, long long bytes, bc_stream_t stream, void **node) {
+  BC_REQUIRE(dst && src && bytes > 0, BC_ERR_NULL, "bc_graph_memcpy: NULL pointer / empty copy");
+  const cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail((int)e, "bc_graph_memcpy: %s", cudaGetErrorString(e));
+  if (node) {
+    GraphHook h;
+    const cudaError_t r = graph_record_after_launch(h, nullptr, (cudaStream_t)stream);
+    if (r != cudaSuccess) return fail((int)r, "bc_graph_memcpy: %s", cudaGetErrorString(r));
+    *node = (void *)h.node;  // NULL when the stream is not capturing
+  }
+  return BC_OK;
+}
+
+BC_API int bc_graph_patch_memcpy(void *exec, void *node, void *dst, const void *src, long long bytes) {
+  BC_REQUIRE(exec && node && dst && src && bytes > 0, BC_ERR_NULL, "bc_graph_patch_memcpy: NULL handle / pointer");
+  const cudaError_t e = cudaGraphExecMemcpyNodeSetParams1D((cudaGraphExec_t)exec, (cudaGraphNode_t)node, dst, src, (size_t)bytes,
+                                                           cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) return fail((int)e, "bc_graph_patch_memcpy: %s", cudaGetErrorString(e));
+  return BC_OK;
 }
 
 BC_API int bc_raster_boxes(float *out, const int32_t *rects, const float *values, int n, int H, int W, int shift,

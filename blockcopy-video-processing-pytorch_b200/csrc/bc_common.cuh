@@ -4,6 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <tuple>
+#include <type_traits>
+#include <utility>
+
 #include "blockcopy_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -98,6 +102,29 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 bool pdl_enabled();  // BC_PDL=0 disables the launch attribute (bc_api.cu)
 
+// ------------------------------------------------------------------ CUDA-graph node recording / patching (bc_api.cu)
+// The Python host replays one captured graph per frame; what differs between frames is a handful of POINTERS (the
+// caller's frame, its grid, the output buffer).  Instead of launching those kernels eagerly in front of the graph
+// (a launch gap each), the host captures them too and re-points their nodes before every replay:
+//   mode 1 (record): after a launch on a capturing stream, remember the graph node the launch created;
+//   mode 2 (patch, one shot): the next launch does not run -- its grid / block / arguments are written into `node` of
+//   the instantiated graph `exec` (cudaGraphExecKernelNodeSetParams).
+struct GraphHook {
+  int mode = 0;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node = nullptr;
+  const void *func = nullptr;  // record: kernel of the recorded node; patch: kernel the node was captured with (checked)
+  int recorded = 0;
+  cudaError_t patch_error = cudaSuccess;  // result of the last node update, reported by check_launch()
+};
+GraphHook &graph_hook();
+cudaError_t graph_record_after_launch(GraphHook &h, const void *func, cudaStream_t stream);
+
+template <typename Tuple, size_t... I>
+inline void fill_arg_pointers(Tuple &t, void **argv, std::index_sequence<I...>) {
+  ((argv[I] = (void *)&std::get<I>(t)), ...);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                          dim3 cluster, Args &&...args) {
@@ -122,7 +149,29 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   }
   cfg.attrs = at;
   cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  GraphHook &h = graph_hook();
+  if (h.mode == 2) {  // re-point an existing graph node instead of launching
+    h.mode = 0;
+    if (h.func != (const void *)kernel) {  // another kernel variant than the captured one
+      h.patch_error = cudaErrorInvalidDeviceFunction;
+      return h.patch_error;
+    }
+    std::tuple<std::remove_cv_t<std::remove_reference_t<KArgs>>...> copies{static_cast<KArgs>(args)...};
+    void *argv[sizeof...(KArgs) > 0 ? sizeof...(KArgs) : 1];
+    fill_arg_pointers(copies, argv, std::index_sequence_for<KArgs...>{});
+    cudaKernelNodeParams np = {};
+    np.func = (void *)kernel;
+    np.gridDim = grid;
+    np.blockDim = block;
+    np.sharedMemBytes = (unsigned int)smem;
+    np.kernelParams = argv;
+    np.extra = nullptr;
+    h.patch_error = cudaGraphExecKernelNodeSetParams(h.exec, h.node, &np);
+    return h.patch_error;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (h.mode == 1 && e == cudaSuccess) return graph_record_after_launch(h, (const void *)kernel, stream);
+  return e;
 }
 
 template <typename... KArgs, typename... Args>

@@ -344,6 +344,24 @@ BC_API int bc_conv_wgrad(float *grad_w, const long long *grad_strides, const voi
                          int Cin_p, int Cout_p, int Cin, int Cout, int ksize, int stride, const float *inv_scale, float *dgamma,
                          float *dbeta, const float *bn_sums, void *workspace, long long workspace_bytes, bc_stream_t stream);
 
+/* ---- CUDA-graph node recording / patching (used by the Python host's block_cuda_graphs mode) -------------------
+ * The host replays one captured graph per frame.  The kernels whose ARGUMENTS differ between frames (index compaction of
+ * the caller's grid, the gather from the caller's frame, the copy into the output buffer) are captured as well and
+ * re-pointed before every replay instead of being launched eagerly in front of the graph:
+ *   bc_graph_record(1) ... launch on a capturing stream ... bc_graph_last_node(&node, &func) ... bc_graph_record(0)
+ *   per replay: bc_graph_patch_next(exec, node, func); <the same entry point with this frame's pointers>  -- that call
+ *   does not launch: it writes its grid / block / arguments into `node` of the instantiated graph `exec`
+ *   (cudaGraphExecKernelNodeSetParams) and fails if it would have chosen another kernel variant than the captured one.
+ * bc_graph_memcpy: device-to-device copy on `stream` (captured as a memcpy node; *node = its handle while capturing, else
+ * NULL); bc_graph_patch_memcpy re-points such a node.  exec / node are cudaGraphExec_t / cudaGraphNode_t as void*.
+ * State is per host thread.
+ */
+BC_API int bc_graph_record(int on);
+BC_API int bc_graph_last_node(void **node, const void **func);
+BC_API int bc_graph_patch_next(void *exec, void *node, const void *func);
+BC_API int bc_graph_memcpy(void *dst, const void *src, long long bytes, bc_stream_t stream, void **node);
+BC_API int bc_graph_patch_memcpy(void *exec, void *node, void *dst, const void *src, long long bytes);
+
 /* ---- box rasteriser of the object-detection information gain (policy/information_gain.py:56-108) ----
  * Replaces the reference's per-box torch slice assignments `mask[y1:y2, x1:x2] = max(mask[...], value)`
  * (build_instance_mask :56-66, build_instance_mask_iou_gain :68-108): out (H,W) fp32 <- for every pixel the

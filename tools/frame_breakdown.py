@@ -20,7 +20,7 @@ with torch.no_grad():
         for f in clip:
             model(f)
     torch.cuda.synchronize()
-    for E, entry in model._graphs.graphs.items():
+    for (E, _patch), entry in model._graphs.graphs.items():
         if E != model.policy.num_exec_for(128):
             continue
         g = entry[0]

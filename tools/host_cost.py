@@ -38,7 +38,7 @@ for rep in range(3):
     t2 = time.perf_counter()
     print(f"issue {1e6 * (t1 - t0) / n:.1f} us/frame   issue+drain {1e6 * (t2 - t0) / n:.1f} us/frame")
 # the graph replay alone
-g = m._graphs.graphs[40][0]
+g = next(v for k, v in m._graphs.graphs.items() if k[0] == 40)[0]
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
