@@ -26,11 +26,13 @@ class BlockCopyModel(nn.Module):
     Optional extra keys (absent => reference behaviour):
       block_channels_last (bool, default True): store conv weights channels_last so that packed
           tiles and planes are NHWC, the layout the sm_100a kernels are written for.
-      block_cuda_graphs (bool, default False): capture the block-sparse frame behind the split (every
-          layer, the combines) into one CUDA graph per executed-block count and replay it; index
-          compaction and the gather of the executed input blocks run eagerly, straight from the caller's
-          frame; side branches of the model (skip bottlenecks, residual downsamples, the frame_state
-          scatter) are parallel branches of the graph.  The Python interception layer then runs only while
+      block_cuda_graphs (bool, default False): capture the block-sparse frame (index compaction, the gather of
+          the executed input blocks, every layer, the combines, the copy into the output buffer) into one CUDA
+          graph per executed-block count and replay it; the nodes that read the caller's grid and frame or write
+          the output buffer are re-pointed before each replay (``_capture_whole_frame``; for ``U8Frame`` inputs and
+          grids that need a conversion those steps run eagerly in front of the graph instead); side branches of
+          the model (skip bottlenecks, residual downsamples, the frame_state scatter) are parallel branches of
+          the graph.  The Python interception layer then runs only while
           capturing.  Differences to the eager mode: feature planes persist across ``reset_temporal`` (the
           first frame of a clip rewrites all of them), and the returned output tensor is one of two
           alternating buffers -- it stays valid until the next-but-one call (clone it to keep it longer).
@@ -270,7 +272,8 @@ class BlockCopyModel(nn.Module):
         # whole-frame graphs with re-pointed nodes (graph-patch mode) for plain tensors whose grid needs no conversion;
         # a U8Frame keeps the eager prefix (its first gather is another kernel: graphs are keyed by the input kind)
         patch = gs.patch and not isinstance(inputs, U8Frame) and grid.dtype == torch.bool and grid.is_contiguous() \
-            and grid.device == inputs.device
+            and grid.device == inputs.device and inputs.dim() == 4 \
+            and (inputs.is_contiguous() or inputs.is_contiguous(memory_format=torch.channels_last))
         key = (num_exec, patch)
         entry = gs.graphs.get(key)
         if entry is None:
