@@ -96,7 +96,7 @@ __device__ __forceinline__ void splitk_reduce_l2(const ConvParams &p, uint32_t r
 template <int N_TILE, int STAGES, bool SPLITK>
 __global__ void __launch_bounds__(kConvThreadsV1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap bmc_map, const ConvParams p) {
   const bool is_split = SPLITK && p.splits > 1;
   constexpr uint32_t kBBytes = N_TILE * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -128,6 +128,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     r0 = 0;
     nvalid = min(p.blocks_per_tile, p.E - b0);
   }
+  const int mca = (!is_split && p.mc > 1) ? p.mc : 1;    // activation multicast (cluster along blockIdx.y)
+  const int mcb = (!is_split && p.mcb > 1) ? p.mcb : 1;  // weight multicast (cluster along blockIdx.x)
+  const int mc = mca > mcb ? mca : mcb;                   // CTAs per cluster (one of the two is 1)
+  const uint16_t mc_mask = (uint16_t)((1u << mc) - 1u);
+  const int mc_rank = mc > 1 ? (int)cluster_ctarank() : 0;
   const int total_k = p.ksize * p.ksize * p.kc_per_tap;
   const int k_begin = (int)blockIdx.z * p.ksteps_per_split;
   const int num_k = (p.debug & 1) ? 1 : min(p.ksteps_per_split, total_k - k_begin);
@@ -142,6 +147,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_map(&a_map);
     prefetch_map(&b_map);
+    if (mcb > 1) prefetch_map(&bmc_map);
     for (int i = 0; i < nvalid; ++i) {
       const uint32_t cell = p.mapping ? (uint32_t)__ldg(p.mapping + b0 + i) : (uint32_t)(b0 + i);
       uint32_t n, gh, gw;
@@ -152,7 +158,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);  // activations (warp 0) + weights (warp 6), one arrive.expect_tx each
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)mc);  // multicast: a stage is free once EVERY CTA of the cluster has read it
     }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
@@ -160,6 +166,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   if (warp == 1) tmem_alloc(&tmem_base_slot, N_TILE);
   tc_fence_before_sync();
   __syncthreads();
+  if (mc > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast to / arrives on them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
   pdl_trigger();
@@ -185,7 +192,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       for (int ks = 0; ks < num_k; ++ks) {
         mbar_wait(&empty_bar[s], parity);
         mbar_expect_tx(&full_bar[s], tx_bytes);
-        if (nvalid == 1) {
+        if (mca > 1) {  // this CTA's share of the tile's boxes, delivered to every CTA of the cluster
+          for (int i = mc_rank; i < nvalid; i += mca) {
+            const int4 c = blk_coord_s[i];
+            tma_load_4d_multicast(sa + (size_t)i * p.box_bytes, &a_map, &full_bar[s], cc * kChunkK, c.x + kw * p.dil,
+                                  c.y + kh * p.dil, c.z, mc_mask);
+          }
+        } else if (nvalid == 1) {
           tma_load_4d(sa, &a_map, &full_bar[s], cc * kChunkK, cx0 + kw * p.dil, cy0 + kh * p.dil, cn0);
         } else {
           for (int i = 0; i < nvalid; ++i) {
@@ -210,7 +223,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
       for (int ks = 0; ks < num_k; ++ks) {
         mbar_wait(&empty_bar[s], parity);
         mbar_expect_tx(&full_bar[s], kBBytes);
-        tma_load_2d(sb, &b_map, &full_bar[s], kcoord, n0);
+        if (mcb > 1) {  // this CTA's rows of the weight tile, delivered to every CTA of the cluster
+          const int rows = N_TILE / mcb;
+          tma_load_2d_multicast(sb + (size_t)mc_rank * rows * 128, &bmc_map, &full_bar[s], kcoord, n0 + mc_rank * rows, mc_mask);
+        } else {
+          tma_load_2d(sb, &b_map, &full_bar[s], kcoord, n0);
+        }
         kcoord += kChunkK;
         sb += kStageBytes;
         if (++s == STAGES) { s = 0; parity ^= 1; sb = smem + kABytes; }
@@ -231,7 +249,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
 #pragma unroll
         for (int k = 0; k < kChunkK / 16; ++k)
           umma_f16_ss(tmem_base, a_desc0 + stage_off + 2 * k, b_desc0 + stage_off + 2 * k, idesc, (uint32_t)((ks | k) != 0));
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        // frees the stage once these MMAs have read it -- in every CTA of the cluster when the activations are multicast
+        if (mc > 1) umma_commit_multicast(&empty_bar[s], mc_mask);
+        else umma_commit(&empty_bar[s]);
         stage_off += kStageBytes >> 4;
         if (++s == STAGES) { s = 0; parity ^= 1; stage_off = 0; }
       }
@@ -435,6 +455,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_consta
   }
 
   __syncthreads();
+  if (mc > 1) cluster_sync_all();  // no CTA leaves while a peer may still arrive on its barriers
   if (threadIdx.x == 0) { trace_mark(p, 6); trace_wall(p, 10); }
   if (warp == 1) {
     tc_fence_after_sync();
@@ -494,9 +515,36 @@ static int launch_conv(const CUtensorMap &a_map, const CUtensorMap &b_map, ConvP
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const cudaError_t attr = attr1 != cudaSuccess ? attr1 : attr2;
   BC_REQUIRE(attr == cudaSuccess, (int)attr, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(attr));
-  const cudaError_t e = launch_kernel(p.splits > 1 ? conv_igemm_kernel<N_TILE, STAGES, true> : conv_igemm_kernel<N_TILE, STAGES, false>,
-                                      dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits),
-                                      dim3(kConvThreadsV1), smem, s, (unsigned)p.splits, a_map, b_map, p);
+  // activation multicast (see ConvParams::mc): the channel slices of a pixel tile as one cluster, when the tile consists of
+  // several boxes that divide evenly among them and the grid is big enough to be bound by operand delivery
+  // bit 0: activation multicast (default on); bit 1: weight multicast -- bit-identical but MEASURED SLOWER (E = 320: layer #20
+  // 127.8 vs 107.7 us, layer1 58.8 vs 49.6, layer2 38.6 vs 32.5: four CTAs in lockstep on a 2-3 stage ring for an operand that
+  // is small and L2-hot anyway), so it is an experiment switch only (BC_CONV_MULTICAST=3)
+  static const int env_mc = getenv("BC_CONV_MULTICAST") ? atoi(getenv("BC_CONV_MULTICAST")) : 1;
+  p.mc = p.mcb = 1;
+  // (two channel slices sharing a 2-box tile measured slower than no sharing: 32.5 vs 29.8 us on the 8-px layer at E = 320)
+  if ((env_mc & 1) && p.splits == 1 && ntiles_n == 4 && p.blocks_per_tile > 1 && p.blocks_per_tile % ntiles_n == 0 && ctas >= kNumSMs)
+    p.mc = ntiles_n;
+  // weight multicast: pixel tiles of one channel slice as a cluster along x (tiles whose activations are a single box)
+  CUtensorMap bmc_map = b_map;
+  if ((env_mc & 2) && p.mc == 1 && p.splits == 1 && p.blocks_per_tile == 1 && ctas >= kNumSMs && p.w_ptr != nullptr) {
+    const int mcb = tiles % 4 == 0 ? 4 : (tiles % 2 == 0 ? 2 : 1);
+    if (mcb > 1) {
+      cuuint64_t gdim[2] = {(cuuint64_t)p.w_K, (cuuint64_t)p.Cout};
+      cuuint64_t gstr[1] = {(cuuint64_t)p.w_K * 2};
+      cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)(N_TILE / mcb)};
+      cuuint32_t estr[2] = {1, 1};
+      const CUresult r = tensor_map_encoder()(&bmc_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(p.w_ptr), gdim, gstr,
+                                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) p.mcb = mcb;
+    }
+  }
+  const dim3 cluster = p.mc > 1 ? dim3(1, (unsigned)p.mc, 1) : (p.mcb > 1 ? dim3((unsigned)p.mcb, 1, 1) : dim3(1, 1, (unsigned)p.splits));
+  const cudaError_t e = launch_kernel_cluster(
+      p.splits > 1 ? conv_igemm_kernel<N_TILE, STAGES, true> : conv_igemm_kernel<N_TILE, STAGES, false>,
+      dim3((unsigned)tiles, (unsigned)ntiles_n, (unsigned)p.splits), dim3(kConvThreadsV1), smem, s, cluster, a_map, b_map,
+      bmc_map, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail((int)e, "bc_conv_igemm: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -544,6 +592,10 @@ int conv_igemm(void *out, const void *plane, const void *weight, const void *bia
   {
     static const char *dbg = getenv("BC_CONV_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+    p.mc = p.mcb = 1;
+    p.tma_epi = 0;
+    p.w_ptr = weight;
+    p.w_K = (long long)ksize * ksize * Cin;
     p.trace = debug_trace_buffer();
   }
   p.work = (((uintptr_t)workspace & 15) == 0 && workspace_bytes > 0) ? (float *)workspace : nullptr;

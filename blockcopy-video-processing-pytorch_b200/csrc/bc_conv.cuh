@@ -53,6 +53,15 @@ struct ConvParams {
   // persistent kernel, S = 1: the epilogue leaves through TMA stores (128-byte-swizzled staging rows -> o_map / pl_map)
   // instead of per-thread global stores.  One store box of the plane = st_px consecutive tile rows = st_bw x st_bh pixels.
   int tma_epi, st_px, st_bw, st_bh;
+  // one-tile kernel: the `mc` CTAs of a cluster (1, mc, 1) compute the mc channel slices of ONE pixel tile; each loads
+  // 1/mc of the tile's activation boxes and multicasts them to all (TMA .multicast::cluster), so the activations cross
+  // the L2 -> SM path once per cluster instead of once per CTA.  1 = off.
+  int mc;
+  // ... or the `mcb` CTAs of a cluster (mcb, 1, 1) compute mcb PIXEL tiles of one channel slice and share the WEIGHT tile:
+  // each loads N_TILE / mcb of its rows (bmc_map) and multicasts them.  At most one of mc / mcb is > 1.
+  int mcb;
+  const void *w_ptr;        // host side only: weights and their row length (elements), for the multicast weight map
+  long long w_K;
   int debug;  // BC_CONV_DEBUG (timing experiments only): bit 0 one k-step, bit 1 no epilogue stores, bit 2 weight producer waits for the previous kernel too
 };
 

@@ -376,3 +376,52 @@ def test_head_1x1_matches_op_by_op(bn, relu, dense_cl, with_prev):
     O.combine_(tiles.cpu().contiguous(), want, me)
     assert torch.equal(dense.cpu().contiguous(), want)
 
+
+
+_MULTICAST_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
+from blockcopy import _C
+Cin, Cout, BS, E = int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), int(sys.argv[7])
+g = torch.Generator().manual_seed(Cin + BS)
+N, GH, GW = 2, 16, 16
+plane = torch.randn(N, Cin, GH * BS, GW * BS, generator=g).half().cuda().contiguous(memory_format=torch.channels_last)
+w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).half().cuda().contiguous(memory_format=torch.channels_last)
+b = (0.1 * torch.randn(Cout, generator=g)).half().cuda()
+me = torch.randperm(N * GH * GW, generator=g)[:E].sort().values.to(torch.int32).cuda()
+res = torch.randn(E, Cout, BS, BS, generator=g).half().cuda().contiguous(memory_format=torch.channels_last)
+nxt = torch.zeros(N, Cout, GH * BS, GW * BS, dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+out = torch.full((E, Cout, BS, BS), float("nan"), dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+for _ in range(3):
+    _C.conv_igemm(out, plane, w, b, res, me, E, BS, 1, 1, relu=True, plane_out=nxt)
+torch.cuda.synchronize()
+torch.save({"out": out.cpu(), "nxt": nxt.cpu(), "plane": plane.cpu(), "w": w.cpu(), "b": b.cpu(), "res": res.cpu(), "me": me.cpu()}, sys.argv[1])
+'''
+
+
+@pytest.mark.parametrize("Cin,Cout,BS,E", [(512, 512, 4, 325), (256, 256, 8, 301), (512, 512, 2, 509), (256, 512, 4, 320),
+                                           (128, 128, 32, 41), (64, 64, 32, 37), (128, 128, 16, 301), (64, 128, 32, 40)])
+def test_multicast_forms_are_bit_identical(tmp_path, Cin, Cout, BS, E):
+    """Big grids run the one-tile kernel as thread-block clusters that share an operand through TMA multicast
+    (BC_CONV_MULTICAST=0: every CTA loads everything itself): small blocks (4- / 2-px, 8 streams batched) -- the four channel
+    slices of a pixel tile share its activation boxes; big blocks (16- / 32-px) -- four (two) pixel tiles of a channel slice
+    share the weight tile.  The same MMA sequence, so the same bits -- incl. a last tile that is only partly filled (E not
+    a multiple of the blocks per tile) -- and within tolerance of the fp32 torch conv."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "blockcopy-video-processing-pytorch_b200")
+    outs = {}
+    for mc in ("3", "0"):
+        path = str(tmp_path / f"mc{mc}.pt")
+        subprocess.run([sys.executable, "-c", _MULTICAST_SCRIPT, path, root, pkg, str(Cin), str(Cout), str(BS), str(E)], check=True,
+                       env=dict(os.environ, BC_CONV_MULTICAST=mc), timeout=120)
+        outs[mc] = torch.load(path)
+    a, b = outs["3"], outs["0"]
+    assert torch.isfinite(a["out"].float()).all()
+    assert torch.equal(a["out"], b["out"]) and torch.equal(a["nxt"], b["nxt"])
+    ref = (O.split(F.conv2d(a["plane"].float(), a["w"].float(), a["b"].float(), padding=1).contiguous(), a["me"], BS)
+           .half().float() + a["res"].float()).relu()
+    assert (a["out"].float() - ref).abs().max().item() <= 2 ** -9 * float(ref.abs().max()) + 2e-3

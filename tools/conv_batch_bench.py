@@ -10,7 +10,7 @@ r = bench.conv_microbench(dev, bench.load_peaks(), reps=20, sets=2, E=int(sys.ar
 print({k.split("(")[1][:-1]: (round(v["us"], 1), round(v["frac_of_tensor_peak"], 3)) for k, v in r.items()})
 '''
 for E, images in ((40, 1), (320, 8), (160, 4), (80, 2)):
-    for env in ({}, {"BC_CONV_PERSIST": "2"}, {"BC_CONV_PERSIST": "0"}, {"BC_CONV_A3": "1"}):
+    for env in ({"BC_CONV_MULTICAST": "3"}, {"BC_CONV_MULTICAST": "1"}, {"BC_CONV_MULTICAST": "0"}):
         r = subprocess.run([sys.executable, "-c", CHILD, str(E), str(images)], capture_output=True, text=True,
                            env=dict(os.environ, **env), cwd=ROOT, timeout=600)
         print(f"E={E} {env}:", r.stdout.strip() or r.stderr.strip()[-300:], flush=True)
