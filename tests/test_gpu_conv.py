@@ -399,8 +399,8 @@ torch.save({"out": out.cpu(), "nxt": nxt.cpu(), "plane": plane.cpu(), "w": w.cpu
 '''
 
 
-@pytest.mark.parametrize("Cin,Cout,BS,E", [(512, 512, 4, 325), (256, 256, 8, 301), (512, 512, 2, 509), (256, 512, 4, 320),
-                                           (128, 128, 32, 41), (64, 64, 32, 37), (128, 128, 16, 301), (64, 128, 32, 40)])
+@pytest.mark.parametrize("Cin,Cout,BS,E", [(512, 512, 4, 325), (512, 512, 2, 509), (256, 512, 4, 320), (128, 128, 32, 41),
+                                           (64, 64, 32, 37), (128, 128, 16, 301)])
 def test_multicast_forms_are_bit_identical(tmp_path, Cin, Cout, BS, E):
     """Big grids run the one-tile kernel as thread-block clusters that share an operand through TMA multicast
     (BC_CONV_MULTICAST=0: every CTA loads everything itself): small blocks (4- / 2-px, 8 streams batched) -- the four channel
