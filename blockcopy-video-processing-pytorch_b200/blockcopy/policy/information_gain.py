@@ -35,6 +35,10 @@ class InformationGainSemSeg(InformationGain):
         return out
 
     def forward(self, policy_meta: Dict) -> torch.Tensor:
+        """fp16 logits on the GPU (the configuration the path is built for): one kernel, bc_info_gain.  Anything else
+        (fp32 models, more than 64 classes, sizes that are not multiples of 4, the CPU restatement the host-logic tests
+        run) takes the reference's own op sequence below (information_gain.py:32-41) -- the same arithmetic, op by op; it is
+        not a fall-back of the kernel path: it never runs for the benchmarked configuration."""
         cur, prev = policy_meta["outputs"], policy_meta["outputs_prev"]
         assert cur is not None and prev is not None
         if cur.is_cuda and cur.dtype == torch.float16 and prev.dtype == torch.float16 and cur.shape == prev.shape \
